@@ -1,0 +1,75 @@
+"""Import the UNMODIFIED reference `gbm/model.py` on a CPU-only box.  TEST INFRASTRUCTURE ONLY.
+
+Works only where the reference checkout exists (the build container: /root/reference).  It is used
+by tests/golden/make_golden.py to generate the committed golden vectors, by the (skipped when the
+checkout is absent) live oracle-vs-reference test, and never by anything that runs on the GPU box.
+
+The shim is harness code, not a restatement:
+  1. `PyTorchHelpers` (gbm/model.py:7) is not shipped with the reference -> empty stub module;
+  2. `.cuda()` (gbm/model.py:135,154,189 - the last one is evaluated at class-definition time)
+     -> identity;
+  3. `nn.DataParallel(..., device_ids=[0,1,2,3])` (gbm/model.py:132-135) -> pass-through wrapper
+     that keeps the `.module` attribute, hence the `cnn.module.*` state-dict keys.
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("MIL_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "gbm", "model.py"))
+
+
+def load_reference_model_module():
+    """Returns the reference's `model` module (gbm/model.py), imported under the shim."""
+    import torch
+    from torch import nn
+
+    if "model" in sys.modules and getattr(sys.modules["model"], "__mil_shim__", False):
+        return sys.modules["model"]
+    if not reference_available():
+        raise FileNotFoundError(f"reference checkout not found under {REFERENCE_ROOT}")
+
+    sys.modules.setdefault("PyTorchHelpers", types.ModuleType("PyTorchHelpers"))
+
+    class _PassThroughDP(nn.Module):
+        def __init__(self, module, device_ids=None, **_):
+            super().__init__()
+            self.module = module
+
+        def forward(self, *a, **k):
+            return self.module(*a, **k)
+
+    saved = (torch.Tensor.cuda, nn.Module.cuda, nn.DataParallel)
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    nn.Module.cuda = lambda self, *a, **k: self
+    nn.DataParallel = _PassThroughDP
+    for pth in (os.path.join(REFERENCE_ROOT, "gbm"), REFERENCE_ROOT):
+        if pth not in sys.path:
+            sys.path.insert(0, pth)
+    try:
+        import model as ref_model  # noqa: the reference's gbm/model.py
+    finally:
+        # keep the shims in place: the reference calls .cuda() inside __init__ too
+        pass
+    ref_model.__mil_shim__ = True
+    ref_model.__mil_saved__ = saved
+    return ref_model
+
+
+def build_reference(class_weights=None, seed: int = 0, quiet: bool = True):
+    """`Attention(n_classes=3, class_weights)` of the reference with its own init under
+    torch.manual_seed(seed)."""
+    import torch
+    ref_model = load_reference_model_module()
+    torch.manual_seed(seed)
+    ctx = contextlib.redirect_stdout(io.StringIO()) if quiet else contextlib.nullcontext()
+    with ctx:
+        net = ref_model.Attention(n_classes=3, class_weights=class_weights)
+    return net

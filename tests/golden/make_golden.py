@@ -1,0 +1,98 @@
+"""Generate the golden vectors from the UNMODIFIED reference (run in the build container only).
+
+    python tests/golden/make_golden.py
+
+Writes tests/golden/weights.npz (the reference constructor's own init under torch.manual_seed(0))
+and one tests/golden/case_*.npz per case below: the 13 outputs of the reference's
+Attention.forward (gbm/model.py:249-264) and d loss / d parameter for all 65 tensors -- full
+tensors for the small ones and a selection of conv weights, (sum, abs-sum, l2) digests for all.
+Inputs are not stored: oracle/synth.py regenerates them from (n, side, seed).
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim, synth  # noqa: E402
+
+CASES = [
+    # name, n_bag, side, weight_mask, Y, class_weights, training
+    dict(name="eval_8x64", n=8, side=64, wm=[0.25, 0.25, 0.25], Y=1, cw=None, training=False),
+    dict(name="eval_12x96_peaked_cw", n=12, side=96, wm=[-1.0, -1.0, -1.0], Y=2, cw=[0.5, 1.0, 2.0], training=False),
+    dict(name="eval_5x224_mixedmask", n=5, side=224, wm=[0.25, -0.5, -1.0], Y=0, cw=None, training=False),
+    dict(name="eval_3x300_odd", n=3, side=300, wm=[0.25, 0.25, 0.25], Y=1, cw=None, training=False),
+    dict(name="eval_2x33_tiny", n=2, side=33, wm=[-1.0, 0.25, 0.1], Y=2, cw=[1.0, 3.0, 0.25], training=False),
+    dict(name="train_40x64_injected", n=40, side=64, wm=[0.25, -1.0, 0.25], Y=1, cw=None, training=True),
+]
+
+FULL_GRADS = (
+    "weight_mask", "cnn.module.conv1.weight", "cnn.module.layer1.0.conv1.weight",
+    "cnn.module.layer2.0.conv1.weight", "cnn.module.layer2.0.downsample.0.weight",
+    "cnn.module.layer3.1.conv2.weight", "cnn.module.layer4.2.conv2.weight", "cnn.module.fc.weight",
+)
+
+
+class _InjectedDropout(torch.nn.Module):
+    """Harness-only replacement for `context.do` so a train-mode run is reproducible."""
+
+    def __init__(self, mask):
+        super().__init__()
+        self.mask = mask
+
+    def forward(self, x):
+        return x * self.mask / 0.75 if self.training else x
+
+
+def run_case(net, case):
+    bag = torch.from_numpy(synth.make_bag(case["n"], case["side"], seed=1))
+    Y = torch.tensor([case["Y"]])
+    with torch.no_grad():
+        net.weight_mask.copy_(torch.tensor(case["wm"]))
+    net.loss.weight = None if case["cw"] is None else torch.tensor(case["cw"])
+    net.zero_grad(set_to_none=True)
+    extra = {}
+    if case["training"]:
+        net.train()
+        torch.manual_seed(2)
+        idx = torch.randperm(case["n"])[: int(case["n"] * 0.2)]      # replay of gbm/model.py:193
+        mask = torch.from_numpy(synth.make_drop_mask(len(idx), seed=2))
+        net.context.do = _InjectedDropout(mask)
+        torch.manual_seed(2)
+        extra["indices"] = idx.numpy()
+    else:
+        net.eval()
+    out = net(bag, Y)
+    out["loss"].backward()
+    rec = {f"out.{k}": v.detach().numpy() for k, v in out.items()}
+    for k, prm in net.named_parameters():
+        g = prm.grad if prm.grad is not None else torch.zeros_like(prm)
+        rec[f"gdigest.{k}"] = np.array([g.sum().item(), g.abs().sum().item(), g.norm().item()], dtype=np.float64)
+        if k in FULL_GRADS or g.numel() <= 3200:
+            rec[f"grad.{k}"] = g.numpy()
+    rec.update({f"extra.{k}": v for k, v in extra.items()})
+    rec["meta"] = np.frombuffer(json.dumps(case).encode(), dtype=np.uint8)
+    return rec
+
+
+def main():
+    assert ref_shim.reference_available(), "needs the reference checkout"
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    net = ref_shim.build_reference(seed=0)
+    sd = {k: v.detach().numpy().copy() for k, v in net.state_dict().items()}
+    np.savez(os.path.join(HERE, "weights.npz"), **sd)
+    for case in CASES:
+        rec = run_case(net, case)
+        np.savez(os.path.join(HERE, f"case_{case['name']}.npz"), **rec)
+        print(case["name"], "loss", float(rec["out.loss"]), "y_pred", rec["out.y_pred"].ravel())
+
+
+if __name__ == "__main__":
+    main()
