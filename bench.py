@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""Benchmark of the ResNet-26 + attention-MIL hot path (BASELINE.json metric: tiles/sec fwd+bwd).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--tiles T] [--side S]
+
+A step = one forward + backward of `Attention` over one bag (BASELINE.json configs[1]: 4,096 RGB 224x224 tiles,
+bf16, all tiles through the CNN).  With N > 1 (torchrun, one rank per GPU) the bag is N x 4,096 tiles sharded
+over the ranks (configs[2]-style; weak scaling), the head's bag-wide sums and the weight gradients are
+all-reduced over NCCL.  Prints ONE JSON line (rank 0).
+
+  value  : tiles/s, bag resident in HBM, CUDA-event timed, max over ranks
+  e2e    : same metric through the public API with the bag in pinned HOST memory: the fp32 NCHW bag is copied
+           host->device every step and the loss is read back, inside the timed region
+  roofline: the dominant kernel (the 3x3 convolution of layer1, 31 % of the FLOPs) timed alone with CUDA events;
+           achieved = algorithmic FLOPs per launch / duration, against MEASURED_PEAKS.json's bf16 burst peak
+  cpu_baseline: the CPU oracle port of the reference path (torch CPU, all host threads) on a bounded sample
+
+--impl reference times that CPU path alone (the reference is pure Python + torch and cannot travel to the GPU
+box, so the oracle port -- pinned to the reference's golden vectors -- stands in: kind "port").
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "deep-convolutional-neural-network-resnet-26-and-attention-network_b200"
+
+FLOP_FWD_BWD = {224: 1247.7e6, 256: 1629.9e6}      # algorithmic FLOP per tile
+L1_CONV_FLOP_224 = 22.58e6                         # one layer1 3x3 conv, per tile
+METRIC = "tiles/sec fwd+bwd ResNet-26+attention-MIL"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_reference_throughput(side, sample_tiles, reps, seed=1):
+    """fwd+bwd tiles/s of the CPU oracle port of the reference path on all host threads."""
+    import torch
+    from oracle import mil_oracle
+    mil = importlib.import_module(PKG)
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    p = mil_oracle.init_params(seed=0)
+    bag = torch.from_numpy(mil.synth.make_bag(sample_tiles, side, seed=seed))
+    Y = torch.tensor([1])
+    mil_oracle.forward_backward(p, bag[: max(2, sample_tiles // 8)], Y)      # warm-up
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        mil_oracle.forward_backward(p, bag, Y)
+        times.append(time.perf_counter() - t0)
+    best = min(times)
+    return sample_tiles / best, cores, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = args.ref_tiles
+    t_all0 = time.perf_counter()
+    import torch
+    from oracle import mil_oracle
+    mil = importlib.import_module(PKG)
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    p = mil_oracle.init_params(seed=0)
+    bag = torch.from_numpy(mil.synth.make_bag(sample, args.side, seed=1))
+    Y = torch.tensor([1])
+    for _ in range(args.warmup):
+        mil_oracle.forward_backward(p, bag, Y)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        mil_oracle.forward_backward(p, bag, Y)
+    dt = time.perf_counter() - t0
+    v = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "tiles/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"bag of {args.tiles} RGB {args.side}x{args.side} tiles, all tiles through the CNN, "
+                               f"fwd+bwd, 3 classes (BASELINE.json configs[1])",
+                   "tiles_per_step_timed": sample},
+        "cpu_baseline": {"value": v, "unit": "tiles/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} of the {args.tiles} tiles per step, fp32, torch CPU {torch.__version__}"},
+        "e2e": {"value": v, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t_all0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def make_device_bag(mil, n, side, device, seed=1):
+    """n diverse tiles on the device: 64 closed-form base tiles (package synth) x per-tile contrast/offset
+    jitter, clamped to the [-1,1] range of the reference's normalisation (RoiBuilder.py:201-202)."""
+    import torch
+    base = torch.from_numpy(mil.synth.make_bag(64, side, seed=seed)).to(device)
+    g = torch.Generator(device=device).manual_seed(seed)
+    bag = torch.empty((n, 3, side, side), dtype=torch.float32, device=device)
+    for s in range(0, n, 64):
+        m = min(64, n - s)
+        c = 0.6 + 0.4 * torch.rand((m, 3, 1, 1), device=device, generator=g)
+        o = 0.3 * (torch.rand((m, 3, 1, 1), device=device, generator=g) - 0.5)
+        perm = torch.randperm(64, device=device, generator=g)[:m]
+        bag[s:s + m] = (base[perm] * c + o).clamp_(-1, 1)
+    return bag
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    mil = importlib.import_module(PKG)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = mil.BagGroup()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = mil.BagGroup(dist.group.WORLD, seed=0, grad_buckets=1)
+    lib = mil._lib.load()
+
+    torch.manual_seed(0)
+    net = mil.Attention(n_classes=3).to(dev).eval()      # eval => every tile goes through the CNN (gbm/model.py:196)
+    net.precision = args.precision
+    net.bag_group = group
+    n, side = args.tiles, args.side
+    bag = make_device_bag(mil, n, side, dev, seed=1 + rank)
+    Y = torch.tensor([1], device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(x):
+        net.zero_grad(set_to_none=True)
+        out = net(x, Y)
+        out["loss"].backward()
+        return out
+
+    # ---------------- device-resident ----------------
+    for _ in range(args.warmup):
+        step(bag)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.mil_kernel_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        out = step(bag)
+    ev1.record()
+    barrier()
+    launches = lib.mil_kernel_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = float(ms) / args.steps
+    value = n * world / (ms_step * 1e-3)
+    loss_val = float(out["loss"])
+
+    # ---------------- end to end from pinned host memory ----------------
+    host = torch.empty((n, 3, side, side), dtype=torch.float32).pin_memory()
+    host.copy_(bag)
+    dbuf = torch.empty_like(bag)
+    del bag
+    def e2e_step():
+        dbuf.copy_(host, non_blocking=True)
+        o = step(dbuf)
+        return float(o["loss"])                     # device -> host read of the step's result
+    for _ in range(max(1, min(args.warmup, 2))):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    ems = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+    e2e_value = n * world / (float(ems) / args.steps * 1e-3)
+    del host, dbuf
+
+    # ---------------- dominant kernel alone: layer1 3x3 conv (rank 0) ----------------
+    roofline = None
+    if rank == 0:
+        import ctypes as C
+        burst, sustained, hbm, how = peaks()
+        h1 = ((side - 1) // 2 + 1 - 1) // 2 + 1
+        nk = min(n, 1024)
+        dt = mil.model.DTYPE_CODES[args.precision]
+        P = lambda t: C.c_void_p(t.data_ptr())
+        nb = int(lib.mil_pf8_bytes(nk, 20, h1, h1, dt))
+        xin = torch.randn(nk, 20, h1, h1, device=dev)
+        X = torch.zeros(nb, dtype=torch.uint8, device=dev)
+        O = torch.zeros(nb, dtype=torch.uint8, device=dev)
+        mil._lib.check(lib.mil_to_pf8(dt, P(xin), P(X), nk, 20, h1, h1, None), "mil_to_pf8")
+        w = torch.randn(20, 20, 3, 3, device=dev) * 0.1
+        bias = torch.zeros(20, device=dev)
+        wsb = int(lib.mil_conv_workspace_bytes(nk, 20, h1, h1, 20, h1, h1, 3))
+        wsk = torch.zeros(wsb, dtype=torch.uint8, device=dev)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+        def conv_once():      # one weight-pack launch (~2 us) + the convolution kernel
+            mil._lib.check(lib.mil_conv_pf8(dt, 0, 0, P(X), nk, 20, h1, h1, P(w), 20, 20, 3, 1, P(bias), P(X), None,
+                                            P(O), h1, h1, 0, P(wsk), wsb, st), "mil_conv_pf8")
+        for _ in range(3):
+            conv_once()
+        reps = 10
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        k0.record()
+        for _ in range(reps):
+            conv_once()
+        k1.record()
+        torch.cuda.synchronize()
+        kms = k0.elapsed_time(k1) / reps
+        flop = 2.0 * 20 * 20 * 9 * h1 * h1 * nk
+        ach = flop / (kms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "conv3x3 20->20 (layer1), fused bias+residual+LeakyReLU",
+                    "achieved": ach, "peak": burst, "unit": "TFLOP/s", "frac": ach / burst, "traffic": None,
+                    "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({how}, burst)",
+                    "tiles_per_launch": nk, "ms_per_launch": kms,
+                    "whole_step_frac_of_sustained": value * FLOP_FWD_BWD.get(side, 0) / 1e12 / sustained}
+
+    # ---------------- CPU baseline (rank 0, N=1 only) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, cores, times = cpu_reference_throughput(side, args.ref_tiles, reps=2)
+        cpu = {"value": v, "unit": "tiles/s", "cores": cores, "kind": "port",
+               "sample": f"{args.ref_tiles} tiles of the same synthetic workload, fwd+bwd, fp32, best of {len(times)}"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "tiles/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": f"bag of {n} RGB {side}x{side} tiles per GPU, all tiles through the CNN, fwd+bwd, "
+                                   f"3 classes (BASELINE.json configs[1]; N>1: one {n * world}-tile bag sharded "
+                                   f"over the ranks, configs[2])",
+                       "tiles_per_gpu": n, "side": side, "parallelism": f"bag-sharded x{world}",
+                       "l2": f"inputs larger than L2 ({n * 3 * side * side * 4 / 1e6:.0f} MB bag per step)",
+                       "slides_per_s": value / (n * world), "loss": loss_val},
+            "e2e": {"value": e2e_value, "unit": "tiles/s", "h2d_bytes_per_step": n * 3 * side * side * 4,
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--tiles", type=int, default=4096, help="tiles per GPU per step")
+    ap.add_argument("--side", type=int, default=224)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--ref-tiles", type=int, default=64, help="tiles per step of the CPU arm (bounded sample)")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

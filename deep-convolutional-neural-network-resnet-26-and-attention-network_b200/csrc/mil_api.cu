@@ -1,0 +1,297 @@
+// extern "C" entry points of libmil_b200.so (declared in include/mil_b200.h).  Thin: argument checks,
+// plan construction, launch sequences.  Errors never cross the boundary as exceptions.
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+#include <exception>
+
+#include "../../include/mil_b200.h"
+#include "mil_extractor.cuh"
+#include "mil_head.cuh"
+
+static thread_local char g_err[1024] = "";
+void mil_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static std::atomic<long long> g_launches{0};
+void mil_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+#define MIL_API_BEGIN try {
+#define MIL_API_END                                        \
+  }                                                        \
+  catch (const std::exception& e) {                        \
+    mil_set_error("internal C++ exception: %s", e.what()); \
+    return 3;                                              \
+  }                                                        \
+  catch (...) {                                            \
+    mil_set_error("internal C++ exception");               \
+    return 3;                                              \
+  }
+
+static int require_device() {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    mil_set_error("no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+    return 4;
+  }
+  static thread_local int checked_dev = -1;
+  if (checked_dev != dev) {
+    cudaDeviceProp p;
+    MIL_CHECK_CUDA(cudaGetDeviceProperties(&p, dev));
+    MIL_REQUIRE(p.major == 10, "device %d is sm_%d%d; libmil_b200 is built for sm_100a only", dev, p.major, p.minor);
+    checked_dev = dev;
+  }
+  return 0;
+}
+
+static MilHeadParams head_params(const void* const* params) {
+  MilHeadParams P;
+  auto f = [&](const char* n) { return reinterpret_cast<const float*>(params[mil_param_index(n)]); };
+  P.weight_mask = f("weight_mask");
+  P.bn_w = f("context.bn.weight");
+  P.bn_b = f("context.bn.bias");
+  P.att_w1 = f("attention.lin1.weight");
+  P.att_b1 = f("attention.lin1.bias");
+  P.att_w2 = f("attention.lin2.weight");
+  P.att_b2 = f("attention.lin2.bias");
+  P.buf_w1 = f("buffer.lin1.weight");
+  P.buf_b1 = f("buffer.lin1.bias");
+  P.buf_w2 = f("buffer.classifier.weight");
+  P.buf_b2 = f("buffer.classifier.bias");
+  return P;
+}
+static MilHeadGrads head_grads(float* grads) {
+  MilHeadGrads G;
+  const auto& t = mil_param_table();
+  auto f = [&](const char* n) { return grads + t[mil_param_index(n)].offset; };
+  G.weight_mask = f("weight_mask");
+  G.bn_w = f("context.bn.weight");
+  G.bn_b = f("context.bn.bias");
+  G.att_w1 = f("attention.lin1.weight");
+  G.att_b1 = f("attention.lin1.bias");
+  G.att_w2 = f("attention.lin2.weight");
+  G.att_b2 = f("attention.lin2.bias");
+  G.buf_w1 = f("buffer.lin1.weight");
+  G.buf_b1 = f("buffer.lin1.bias");
+  G.buf_w2 = f("buffer.classifier.weight");
+  G.buf_b2 = f("buffer.classifier.bias");
+  return G;
+}
+
+extern "C" {
+
+int mil_abi_version(void) { return MIL_ABI_VERSION; }
+const char* mil_last_error(void) { return g_err; }
+long long mil_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+int mil_param_count(void) { return (int)mil_param_table().size(); }
+const char* mil_param_name(int i) {
+  const auto& t = mil_param_table();
+  return (i >= 0 && i < (int)t.size()) ? t[i].name.c_str() : nullptr;
+}
+int mil_param_shape(int i, int* ndim, long long shape4[4]) {
+  const auto& t = mil_param_table();
+  MIL_REQUIRE(i >= 0 && i < (int)t.size(), "mil_param_shape: index %d out of range", i);
+  *ndim = t[i].ndim;
+  for (int k = 0; k < 4; ++k) shape4[k] = t[i].shape[k];
+  return 0;
+}
+long long mil_param_offset(int i) {
+  const auto& t = mil_param_table();
+  return (i >= 0 && i < (int)t.size()) ? t[i].offset : -1;
+}
+long long mil_param_total(void) {
+  const auto& t = mil_param_table();
+  return t.back().offset + t.back().numel;
+}
+
+// ---- extractor ---------------------------------------------------------------------------------------
+size_t mil_extractor_workspace_bytes(int n_tiles, int side, int dtype) {
+  try {
+    MilPlan pl;
+    if (mil_make_plan(n_tiles, side, dtype, &pl) != 0) return 0;
+    return pl.total_bytes;
+  } catch (...) {
+    mil_set_error("internal C++ exception");
+    return 0;
+  }
+}
+
+int mil_extractor_read_activation(int n_tiles, int side, int dtype, const void* ws, int which, float* nchw,
+                                  void* stream) {
+  MIL_API_BEGIN
+  MIL_TRY(require_device());
+  MilPlan pl;
+  MIL_TRY(mil_make_plan(n_tiles, side, dtype, &pl));
+  MIL_REQUIRE(which >= -1 && which < 24, "mil_extractor_read_activation: which=%d out of range", which);
+  const char* base = reinterpret_cast<const char*>(ws);
+  if (which < 0) {
+    const MilPF8& g = pl.g[0];
+    return mil_launch_from_pf8(dtype, base + pl.off_pooled, nchw, g.n, g.c, g.h, g.w, (cudaStream_t)stream);
+  }
+  const int lb = which / 2;
+  const MilPF8& g = pl.g[lb / 3];
+  const size_t off = (which & 1) ? pl.off_y[lb] : pl.off_h[lb];
+  return mil_launch_from_pf8(dtype, base + off, nchw, g.n, g.c, g.h, g.w, (cudaStream_t)stream);
+  MIL_API_END
+}
+
+int mil_extractor_forward(const void* const* params, const float* bag, const int32_t* idx, int n_tiles, int side,
+                          int dtype, void* ws, size_t ws_bytes, float* H, void* stream) {
+  MIL_API_BEGIN
+  MIL_TRY(require_device());
+  MIL_REQUIRE(params && bag && ws && H, "mil_extractor_forward: null pointer argument");
+  MilPlan pl;
+  MIL_TRY(mil_make_plan(n_tiles, side, dtype, &pl));
+  MIL_REQUIRE(ws_bytes >= pl.total_bytes, "mil_extractor_forward: workspace too small (%zu < %zu)", ws_bytes,
+              pl.total_bytes);
+  return mil_extractor_forward_impl(params, bag, idx, pl, ws, H, (cudaStream_t)stream);
+  MIL_API_END
+}
+
+int mil_extractor_backward(const void* const* params, const float* bag, const int32_t* idx, int n_tiles, int side,
+                           int dtype, void* ws, size_t ws_bytes, const float* dH, float* grads_flat, void* stream) {
+  MIL_API_BEGIN
+  MIL_TRY(require_device());
+  MIL_REQUIRE(params && bag && ws && dH && grads_flat, "mil_extractor_backward: null pointer argument");
+  MilPlan pl;
+  MIL_TRY(mil_make_plan(n_tiles, side, dtype, &pl));
+  MIL_REQUIRE(ws_bytes >= pl.total_bytes, "mil_extractor_backward: workspace too small (%zu < %zu)", ws_bytes,
+              pl.total_bytes);
+  return mil_extractor_backward_impl(params, bag, idx, pl, ws, dH, grads_flat, (cudaStream_t)stream);
+  MIL_API_END
+}
+
+// ---- head ----------------------------------------------------------------------------------------------
+size_t mil_head_workspace_bytes(int n) {
+  if (n < 1) n = 1;
+  return mil_head_part_doubles(n) * sizeof(double) + mil_head_bwd_partial_floats(n) * sizeof(float) + 256;
+}
+static int head_check(int n, long long n_global, size_t ws_bytes) {
+  MIL_TRY(require_device());
+  MIL_REQUIRE(n >= 0 && n_global >= n, "head: bad tile counts n=%d n_global=%lld", n, n_global);
+  // nn.BatchNorm1d(track_running_stats=False) refuses a single row in train AND eval (reference behaviour;
+  // the Python binding raises ValueError before reaching this point)
+  MIL_REQUIRE(n_global >= 2, "Expected more than 1 value per channel when training, got input size (%lld, 80)",
+              n_global);
+  MIL_REQUIRE(ws_bytes >= mil_head_workspace_bytes(n), "head: workspace too small (%zu < %zu)", ws_bytes,
+              mil_head_workspace_bytes(n));
+  return 0;
+}
+
+int mil_head_stats(const float* H, int n, void* ws, size_t ws_bytes, double* stats, void* stream) {
+  MIL_API_BEGIN
+  MIL_TRY(require_device());
+  MIL_REQUIRE(H && ws && stats, "mil_head_stats: null pointer argument");
+  MIL_REQUIRE(ws_bytes >= mil_head_workspace_bytes(n), "mil_head_stats: workspace too small");
+  return mil_launch_head_stats(H, n, (double*)ws, stats, (cudaStream_t)stream);
+  MIL_API_END
+}
+
+int mil_head_scores(const void* const* params, const float* H, const float* drop, int n, long long n_global,
+                    const double* stats, float* raw, float* g, float* b, void* ws, size_t ws_bytes, double* sums,
+                    void* stream) {
+  MIL_API_BEGIN
+  MIL_TRY(head_check(n, n_global, ws_bytes));
+  MIL_REQUIRE(params && H && stats && raw && g && b && ws && sums, "mil_head_scores: null pointer argument");
+  return mil_launch_head_scores(head_params(params), H, drop, n, n_global, stats, raw, g, b, (double*)ws, sums,
+                                (cudaStream_t)stream);
+  MIL_API_END
+}
+
+int mil_head_finalize(const double* sums, const double* stats, long long n_global, const long long* Y,
+                      const float* class_w, int n, const float* g, const float* b, float* A, float* wroi,
+                      float* scal, void* stream) {
+  MIL_API_BEGIN
+  MIL_TRY(require_device());
+  MIL_REQUIRE(sums && stats && Y && g && b && A && wroi && scal, "mil_head_finalize: null pointer argument");
+  return mil_launch_head_finalize(sums, stats, n_global, Y, class_w, n, g, b, A, wroi, scal, (cudaStream_t)stream);
+  MIL_API_END
+}
+
+int mil_head_backward_a(const void* const* params, const float* H, const float* drop, int n, long long n_global,
+                        const double* stats, const float* raw, const float* g, const float* b, const float* scal,
+                        const float* gloss, float* dHz, float* dHi, float* grads_flat, void* ws, size_t ws_bytes,
+                        double* bnsums, void* stream) {
+  MIL_API_BEGIN
+  MIL_TRY(head_check(n, n_global, ws_bytes));
+  MIL_REQUIRE(params && H && stats && raw && g && b && scal && dHz && dHi && grads_flat && ws && bnsums,
+              "mil_head_backward_a: null pointer argument");
+  float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + mil_head_part_doubles(n) * sizeof(double));
+  return mil_launch_head_bwd_a(head_params(params), head_grads(grads_flat), H, drop, n, n_global, stats, raw, g, b,
+                               scal, gloss, dHz, dHi, part, bnsums, (cudaStream_t)stream);
+  MIL_API_END
+}
+
+int mil_head_backward_b(const void* const* params, const float* H, int n, long long n_global, const double* stats,
+                        const double* bnsums, const float* dHz, const float* dHi, float* dH, void* stream) {
+  MIL_API_BEGIN
+  MIL_TRY(require_device());
+  MIL_REQUIRE(params && H && stats && bnsums && dHz && dHi && dH, "mil_head_backward_b: null pointer argument");
+  return mil_launch_head_bwd_b(head_params(params).bn_w, H, n, n_global, stats, bnsums, dHz, dHi, dH,
+                               (cudaStream_t)stream);
+  MIL_API_END
+}
+
+// ---- layer-level operators -----------------------------------------------------------------------------
+size_t mil_pf8_bytes(int n, int c, int h, int w, int dtype) { return mil_pf8_bytes(mil_pf8(n, c, h, w), dtype); }
+
+int mil_to_pf8(int dtype, const float* nchw, void* pf8, int n, int c, int h, int w, void* stream) {
+  MIL_API_BEGIN
+  MIL_TRY(require_device());
+  return mil_launch_to_pf8(dtype, nchw, pf8, n, c, h, w, (cudaStream_t)stream);
+  MIL_API_END
+}
+int mil_from_pf8(int dtype, const void* pf8, float* nchw, int n, int c, int h, int w, void* stream) {
+  MIL_API_BEGIN
+  MIL_TRY(require_device());
+  return mil_launch_from_pf8(dtype, pf8, nchw, n, c, h, w, (cudaStream_t)stream);
+  MIL_API_END
+}
+
+size_t mil_conv_workspace_bytes(int n, int cin, int hi, int wi, int cout, int ho, int wo, int ks) {
+  const MilPF8 gi = mil_pf8(n, cin, hi, wi), go = mil_pf8(n, cout, ho, wo);
+  const size_t wp = (size_t)ks * ks * gi.cb * 8 * go.cb * 8 * sizeof(float);
+  return 2 * wp + mil_wgrad_direct_partial_floats(gi, go, ks) * sizeof(float) + 1024;
+}
+
+int mil_conv_pf8(int dtype, int impl, int transposed, const void* x, int n, int cx, int hx, int wx, const float* w,
+                 int cout, int cin, int ks, int stride, const float* bias, const void* res, const void* act,
+                 void* out, int ho, int wo, int epi, void* ws, size_t ws_bytes, void* stream) {
+  MIL_API_BEGIN
+  MIL_TRY(require_device());
+  MIL_REQUIRE(x && w && out && ws, "mil_conv_pf8: null pointer argument");
+  MIL_REQUIRE(cx == (transposed ? cout : cin), "mil_conv_pf8: x has %d channels, expected %d", cx,
+              transposed ? cout : cin);
+  const MilPF8 gx = mil_pf8(n, cx, hx, wx);
+  const MilPF8 go = mil_pf8(n, transposed ? cin : cout, ho, wo);
+  const size_t wp_bytes = (size_t)ks * ks * ((cin + 7) / 8 * 8) * ((cout + 7) / 8 * 8) * sizeof(float);
+  MIL_REQUIRE(ws_bytes >= wp_bytes, "mil_conv_pf8: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  MIL_TRY(mil_launch_pack_conv_w(w, (float*)ws, cout, cin, ks, transposed, s));
+  if (impl == 1)
+    return mil_launch_conv_direct(dtype, transposed, x, gx, (const float*)ws, bias, res, act, out, go, ks, stride,
+                                  epi, s);
+  return mil_conv_dispatch(dtype, transposed, x, gx, (const float*)ws, bias, res, act, out, go, ks, stride, epi, s);
+  MIL_API_END
+}
+
+int mil_conv_wgrad_pf8(int dtype, int impl, const void* x, int n, int cin, int hi, int wi, const void* dz, int cout,
+                       int ho, int wo, int ks, int stride, float* dw, float* db, void* ws, size_t ws_bytes,
+                       void* stream) {
+  MIL_API_BEGIN
+  MIL_TRY(require_device());
+  MIL_REQUIRE(x && dz && dw && ws, "mil_conv_wgrad_pf8: null pointer argument");
+  const MilPF8 gi = mil_pf8(n, cin, hi, wi), go = mil_pf8(n, cout, ho, wo);
+  MIL_REQUIRE(ws_bytes >= mil_wgrad_direct_partial_floats(gi, go, ks) * sizeof(float),
+              "mil_conv_wgrad_pf8: workspace too small");
+  (void)impl;
+  return mil_launch_wgrad_direct(dtype, x, gi, dz, go, (float*)ws, dw, db, ks, stride, (cudaStream_t)stream);
+  MIL_API_END
+}
+
+}  // extern "C"

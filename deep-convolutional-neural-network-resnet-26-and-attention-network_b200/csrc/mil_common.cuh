@@ -1,0 +1,172 @@
+// Shared definitions for the B200 (sm_100a) ResNet-26 + attention-MIL kernels.
+//
+// Activation layout in HBM -- "PF8" (padded-flat, 8-channel chunks):
+//
+//     [channel chunk cb][ lead guard G | image 0 | image 1 | ... | image n-1 | tail guard GT ][8 channels]
+//
+// Every image is stored as (H+1) x (W+1) pixels: one zero column on the right of every row and one
+// zero row below every image.  With that single shared halo, "pixel (y-1, x-1)" of a 3x3 window is
+// simply "flat pixel index - (W+1) - 1" -- the left neighbour of column 0 is the zero column of the
+// row above, the row above row 0 is the zero row of the previous image (or the lead guard).  So a
+// convolution tap is a CONSTANT shift of the flat pixel index, no bounds checks anywhere, and an
+// implicit-GEMM M-tile is any run of 128 consecutive flat pixels (tiles may straddle images).
+// A pixel's 8-channel chunk is one 16-byte unit in bf16: the unit a bulk-TMA copy moves, one row of
+// a tcgen05 "core matrix" (8 pixels x 16 B = 128 contiguous bytes), and one vector load/store per
+// thread.  Channel counts 20/40/60/80 are stored as 24/40/64/80; pad channels, pad pixels and
+// guards are always exactly zero (every kernel that writes a PF8 tensor writes zeros there).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define MIL_SLOPE 0.1f
+
+enum MilDtype { MIL_F32 = 0, MIL_BF16 = 1 };
+enum MilEpilogue {
+  MIL_EPI_FWD = 0,    // out = lrelu(acc + bias [+ res])
+  MIL_EPI_DGRAD = 1,  // out = (acc [+ res]) * lrelu'(act)
+  MIL_EPI_PLAIN = 2   // out = acc [+ bias] [+ res]
+};
+
+void mil_set_error(const char* fmt, ...);
+#define MIL_CHECK_CUDA(expr)                                                               \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      mil_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return 1;                                                                            \
+    }                                                                                      \
+  } while (0)
+// one per kernel launch: counts the launch (mil_kernel_launch_count) and surfaces launch errors
+void mil_count_launch();
+#define MIL_LAUNCH_OK()                 \
+  do {                                  \
+    mil_count_launch();                 \
+    MIL_CHECK_CUDA(cudaGetLastError()); \
+  } while (0)
+#define MIL_REQUIRE(cond, ...)    \
+  do {                            \
+    if (!(cond)) {                \
+      mil_set_error(__VA_ARGS__); \
+      return 2;                   \
+    }                             \
+  } while (0)
+#define MIL_TRY(expr)         \
+  do {                        \
+    int _rc = (expr);         \
+    if (_rc != 0) return _rc; \
+  } while (0)
+
+__host__ __device__ static inline long long mil_cdiv(long long a, long long b) { return (a + b - 1) / b; }
+__host__ __device__ static inline long long mil_rup(long long a, long long b) { return mil_cdiv(a, b) * b; }
+static inline size_t mil_esize(int dtype) { return dtype == MIL_BF16 ? 2 : 4; }
+
+__host__ __device__ __forceinline__ float mil_lrelu(float v) { return v > 0.f ? v : MIL_SLOPE * v; }
+__host__ __device__ __forceinline__ float mil_lrelu_grad(float act) { return act > 0.f ? 1.f : MIL_SLOPE; }
+
+// ---- PF8 tensor geometry -----------------------------------------------------------------------
+struct MilPF8 {
+  int n, c, cb;      // images, channels, 8-channel chunks
+  int h, w, hp, wp;  // spatial size and padded spatial size (h+1, w+1)
+  long long P;       // pixels per image plane = hp*wp
+  long long Q;       // flat pixels = n*P
+  long long G, GT;   // lead / tail guard, in pixels
+  long long PS;      // chunk-plane stride in pixels = G + Q + GT
+};
+#define MIL_TILE_M 128  // flat pixels per implicit-GEMM tile
+static inline MilPF8 mil_pf8(int n, int c, int h, int w) {
+  MilPF8 t;
+  t.n = n; t.c = c; t.cb = (c + 7) / 8;
+  t.h = h; t.w = w; t.hp = h + 1; t.wp = w + 1;
+  t.P = (long long)t.hp * t.wp;
+  t.Q = (long long)n * t.P;
+  t.G = mil_rup(t.wp + 1, 8);
+  t.GT = mil_rup(MIL_TILE_M + t.wp + 1, 8) + 8;
+  t.PS = mil_rup(t.G + t.Q + t.GT, 8);
+  return t;
+}
+static inline size_t mil_pf8_bytes(const MilPF8& t, int dtype) {
+  return (size_t)t.cb * (size_t)t.PS * 8 * mil_esize(dtype);
+}
+// element offset of (chunk cb, flat pixel q, lane 0)
+__host__ __device__ __forceinline__ long long mil_pf8_off(const MilPF8& t, int cb, long long q) {
+  return ((long long)cb * t.PS + t.G + q) * 8;
+}
+
+// ---- 8-channel chunk load/store ----------------------------------------------------------------
+__device__ __forceinline__ void mil_load8(const float* p, float v[8]) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void mil_load8(const __nv_bfloat16* p, float v[8]) {
+  uint4 r = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void mil_store8(float* p, const float v[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void mil_store8(__nv_bfloat16* p, const float v[8]) {
+  uint4 r;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = r;
+}
+__device__ __forceinline__ float mil_to_float(float v) { return v; }
+__device__ __forceinline__ float mil_to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ void mil_from_float(float* p, float v) { *p = v; }
+__device__ __forceinline__ void mil_from_float(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// ---- geometry of the extractor (reference gbm/model.py:24-32) ------------------------------------
+struct MilGeom {
+  int side;  // input tile side S
+  int hc;    // conv1 output side  (7x7, stride 2, pad 3)
+  int h[4];  // h[0] = after maxpool (= layer1 side), h[1..3] = layer2..4 sides
+};
+static inline MilGeom mil_geom(int side) {
+  MilGeom g;
+  g.side = side;
+  g.hc = (side - 1) / 2 + 1;
+  g.h[0] = (g.hc - 1) / 2 + 1;
+  for (int i = 1; i < 4; ++i) g.h[i] = (g.h[i - 1] - 1) / 2 + 1;
+  return g;
+}
+static const int kMilWidths[4] = {20, 40, 60, 80};
+
+// ---- launchers implemented in the .cu files (host side, C++ linkage) -----------------------------
+// mil_layout.cu
+int mil_launch_pack_conv_w(const float* w, float* wp, int cout, int cin, int ks, int transposed, cudaStream_t s);
+int mil_launch_to_pf8(int dtype, const float* nchw, void* pf8, int n, int c, int h, int w, cudaStream_t s);
+int mil_launch_from_pf8(int dtype, const void* pf8, float* nchw, int n, int c, int h, int w, cudaStream_t s);
+int mil_launch_reduce_partials(const float* partial, int nblk, long long stride, float* out, long long count,
+                               cudaStream_t s);
+int mil_launch_reduce_conv_w(const float* partial, int nblk, long long stride, float* dw, float* db, int cout,
+                             int cin, int ks, cudaStream_t s);
+// mil_conv_direct.cu
+int mil_launch_conv_direct(int dtype, int transposed, const void* x, const MilPF8& gi, const float* wp,
+                           const float* bias, const void* res, const void* act, void* out, const MilPF8& go, int ks,
+                           int stride, int epi, cudaStream_t s);
+int mil_wgrad_direct_blocks(const MilPF8& go);
+size_t mil_wgrad_direct_partial_floats(const MilPF8& gi, const MilPF8& go, int ks);
+int mil_launch_wgrad_direct(int dtype, const void* x, const MilPF8& gi, const void* dz, const MilPF8& go,
+                            float* partial, float* dw, float* db, int ks, int stride, cudaStream_t s);
+// mil_stem.cu
+int mil_launch_stem_fwd(int dtype, const float* x, const int* idx, int n, int side, const float* w, const float* b,
+                        void* pooled, const MilPF8& gp, uint8_t* argmax, cudaStream_t s);
+size_t mil_stem_bwd_partial_floats();
+int mil_launch_stem_bwd(int dtype, const float* x, const int* idx, int n, int side, const void* g, const MilPF8& gp,
+                        const uint8_t* argmax, float* partial, float* dw, float* db, cudaStream_t s);
+// mil_tail.cu
+int mil_launch_tail_fwd(int dtype, const void* y4, const MilPF8& g4, const float* wfc, float* avg, float* H,
+                        cudaStream_t s);
+size_t mil_tail_bwd_partial_floats();
+int mil_launch_tail_bwd(int dtype, const void* y4, const MilPF8& g4, const float* wfc, const float* avg,
+                        const float* dH, void* dz4, float* partial, float* dwfc, cudaStream_t s);

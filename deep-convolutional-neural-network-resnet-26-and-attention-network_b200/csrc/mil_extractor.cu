@@ -1,0 +1,368 @@
+// Whole-network drivers of the ResNet-26 tile feature extractor (reference gbm/model.py:14-61,
+// nnBlocks.py:157-189): parameter table, workspace plan, forward and backward launch sequences.
+// Everything is enqueued on the caller's stream; nothing is allocated here (the caller owns the workspace).
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "mil_extractor.cuh"
+
+// ---------------------------------------------------------------------------------------------------
+// parameter table (reference state-dict order)
+// ---------------------------------------------------------------------------------------------------
+static std::vector<MilParamInfo> build_param_table() {
+  std::vector<MilParamInfo> t;
+  long long off = 0;
+  auto add = [&](const std::string& name, std::initializer_list<long long> shape) {
+    MilParamInfo p;
+    p.name = name;
+    p.ndim = (int)shape.size();
+    p.numel = 1;
+    int i = 0;
+    for (long long d : shape) { p.shape[i++] = d; p.numel *= d; }
+    for (; i < 4; ++i) p.shape[i] = 1;
+    p.offset = off;
+    off += p.numel;
+    t.push_back(p);
+  };
+  add("weight_mask", {3});
+  add("cnn.module.conv1.weight", {20, 3, 7, 7});
+  add("cnn.module.conv1.bias", {20});
+  int inpl = 20;
+  for (int l = 0; l < 4; ++l) {
+    const int w = kMilWidths[l];
+    for (int b = 0; b < 3; ++b) {
+      const int cin = (b == 0) ? inpl : w;
+      const std::string p = "cnn.module.layer" + std::to_string(l + 1) + "." + std::to_string(b);
+      add(p + ".conv1.weight", {w, cin, 3, 3});
+      add(p + ".conv1.bias", {w});
+      add(p + ".conv2.weight", {w, w, 3, 3});
+      add(p + ".conv2.bias", {w});
+      if (b == 0 && l > 0) add(p + ".downsample.0.weight", {w, cin, 1, 1});
+    }
+    inpl = w;
+  }
+  add("cnn.module.fc.weight", {80, 80});
+  add("context.bn.weight", {80});
+  add("context.bn.bias", {80});
+  add("attention.lin1.weight", {40, 80});
+  add("attention.lin1.bias", {40});
+  add("attention.lin2.weight", {3, 40});
+  add("attention.lin2.bias", {3});
+  add("buffer.lin1.weight", {40, 80});
+  add("buffer.lin1.bias", {40});
+  add("buffer.classifier.weight", {1, 40});
+  add("buffer.classifier.bias", {1});
+  return t;
+}
+const std::vector<MilParamInfo>& mil_param_table() {
+  static const std::vector<MilParamInfo> t = build_param_table();
+  return t;
+}
+int mil_param_index(const char* name) {
+  const auto& t = mil_param_table();
+  for (size_t i = 0; i < t.size(); ++i)
+    if (t[i].name == name) return (int)i;
+  return -1;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------------------
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int mil_make_plan(int n, int side, int dtype, MilPlan* plan) {
+  MIL_REQUIRE(n >= 1, "extractor: need at least one tile (got %d)", n);
+  MIL_REQUIRE(side >= 8, "extractor: tile side %d too small", side);
+  MIL_REQUIRE(dtype == MIL_F32 || dtype == MIL_BF16, "extractor: unknown dtype %d", dtype);
+  MilPlan& pl = *plan;
+  pl.n = n; pl.side = side; pl.dtype = dtype;
+  pl.geo = mil_geom(side);
+  for (int l = 0; l < 4; ++l) pl.g[l] = mil_pf8(n, kMilWidths[l], pl.geo.h[l], pl.geo.h[l]);
+  pl.convs.clear();
+  size_t wofs = 0;
+  int inpl = 20;
+  for (int l = 0; l < 4; ++l) {
+    const int w = kMilWidths[l];
+    for (int b = 0; b < 3; ++b) {
+      const int cin = (b == 0) ? inpl : w;
+      const std::string p = "cnn.module.layer" + std::to_string(l + 1) + "." + std::to_string(b);
+      for (int which = 0; which < 3; ++which) {
+        if (which == 2 && !(b == 0 && l > 0)) continue;
+        MilConvDesc c;
+        c.layer = l; c.block = b; c.which = which;
+        c.cin = (which == 1) ? w : cin;
+        c.cout = w;
+        c.ks = (which == 2) ? 1 : 3;
+        c.stride = (which != 1 && b == 0 && l > 0) ? 2 : 1;
+        const char* nm = which == 0 ? ".conv1" : (which == 1 ? ".conv2" : ".downsample.0");
+        c.p_w = mil_param_index((p + nm + ".weight").c_str());
+        c.p_b = which == 2 ? -1 : mil_param_index((p + nm + ".bias").c_str());
+        const size_t sz = (size_t)c.ks * c.ks * ((c.cin + 7) / 8 * 8) * ((c.cout + 7) / 8 * 8);
+        c.wp_off = wofs; wofs += sz;
+        c.wpt_off = wofs; wofs += sz;
+        pl.convs.push_back(c);
+      }
+    }
+    inpl = w;
+  }
+  pl.wpack_floats = wofs;
+
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  pl.off_pooled = take(mil_pf8_bytes(pl.g[0], dtype));
+  pl.off_argmax = take((size_t)n * pl.geo.h[0] * pl.geo.h[0] * 20);
+  for (int l = 0; l < 4; ++l)
+    for (int b = 0; b < 3; ++b) {
+      pl.off_h[l * 3 + b] = take(mil_pf8_bytes(pl.g[l], dtype));
+      pl.off_y[l * 3 + b] = take(mil_pf8_bytes(pl.g[l], dtype));
+    }
+  pl.off_avg = take((size_t)n * 80 * sizeof(float));
+  pl.grad_bytes = 0;
+  for (int l = 0; l < 4; ++l) pl.grad_bytes = std::max(pl.grad_bytes, mil_pf8_bytes(pl.g[l], dtype));
+  for (int i = 0; i < 3; ++i) pl.off_grad[i] = take(pl.grad_bytes);
+  pl.off_wpack = take(pl.wpack_floats * sizeof(float));
+  size_t pf = std::max(mil_stem_bwd_partial_floats(), mil_tail_bwd_partial_floats());
+  for (const auto& c : pl.convs) {
+    const MilPF8& go = pl.g[c.layer];
+    const MilPF8 gi = (c.stride == 2) ? pl.g[c.layer - 1] : mil_pf8(n, c.cin, go.h, go.w);
+    pf = std::max(pf, mil_wgrad_direct_partial_floats(gi, go, c.ks));
+  }
+  pl.partial_floats = pf;
+  pl.off_partial = take(pf * sizeof(float));
+  pl.total_bytes = off;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// table-driven helpers: pack all conv weights in one launch, zero all guards in one launch
+// ---------------------------------------------------------------------------------------------------
+#define MIL_MAX_PACK 54
+struct PackTable {
+  const float* src[MIL_MAX_PACK];
+  float* dst[MIL_MAX_PACK];
+  short cout[MIL_MAX_PACK], cin[MIL_MAX_PACK];
+  unsigned char ks[MIL_MAX_PACK], transposed[MIL_MAX_PACK];
+  int count;
+};
+__global__ void pack_all_kernel(PackTable t) {
+  const int e = blockIdx.x;
+  const int cout = t.cout[e], cin = t.cin[e], ks = t.ks[e], tr = t.transposed[e];
+  const int cip = (cin + 7) / 8 * 8, cop = (cout + 7) / 8 * 8, taps = ks * ks;
+  const int A = tr ? cop : cip, B = tr ? cip : cop;
+  const int total = taps * A * B;
+  const float* w = t.src[e];
+  float* wp = t.dst[e];
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < total; i += gridDim.y * blockDim.x) {
+    const int b = i % B, a = (i / B) % A, tp = i / (A * B);
+    const int co = tr ? a : b, ci = tr ? b : a;
+    wp[i] = (co < cout && ci < cin) ? w[((size_t)co * cin + ci) * taps + tp] : 0.f;
+  }
+}
+
+#define MIL_MAX_GUARD 32
+struct GuardTable {
+  void* base[MIL_MAX_GUARD];
+  long long PS[MIL_MAX_GUARD], G[MIL_MAX_GUARD], Q[MIL_MAX_GUARD];
+  int cb[MIL_MAX_GUARD];
+  int count, esize;
+};
+__global__ void zero_guards_kernel(GuardTable t) {
+  const int e = blockIdx.x;
+  const long long PS = t.PS[e], G = t.G[e], Q = t.Q[e];
+  const long long unit = 8 * t.esize / 16;  // 16-byte words per pixel chunk
+  uint4* base = reinterpret_cast<uint4*>(t.base[e]);
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  for (int cb = blockIdx.y; cb < t.cb[e]; cb += gridDim.y) {
+    uint4* plane = base + (size_t)cb * PS * unit;
+    for (long long i = threadIdx.x; i < G * unit; i += blockDim.x) plane[i] = z;
+    for (long long i = (G + Q) * unit + threadIdx.x; i < PS * unit; i += blockDim.x) plane[i] = z;
+  }
+}
+static int launch_guards(GuardTable& t, cudaStream_t s) {
+  if (t.count == 0) return 0;
+  zero_guards_kernel<<<dim3(t.count, 10), 128, 0, s>>>(t);
+  MIL_LAUNCH_OK();
+  return 0;
+}
+static void guard_add(GuardTable& t, void* buf, const MilPF8& g) {
+  t.base[t.count] = buf; t.PS[t.count] = g.PS; t.G[t.count] = g.G; t.Q[t.count] = g.Q; t.cb[t.count] = g.cb;
+  ++t.count;
+}
+int mil_zero_guards(int dtype, void* buf, const MilPF8& g, cudaStream_t s) {
+  GuardTable t;
+  t.count = 0;
+  t.esize = (int)mil_esize(dtype);
+  guard_add(t, buf, g);
+  return launch_guards(t, s);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// conv dispatch
+// ---------------------------------------------------------------------------------------------------
+int mil_conv_dispatch(int dtype, int transposed, const void* x, const MilPF8& gi, const float* wp, const float* bias,
+                      const void* res, const void* act, void* out, const MilPF8& go, int ks, int stride, int epi,
+                      cudaStream_t s) {
+  return mil_launch_conv_direct(dtype, transposed, x, gi, wp, bias, res, act, out, go, ks, stride, epi, s);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------
+static inline char* wsp(void* ws, size_t off) { return reinterpret_cast<char*>(ws) + off; }
+
+static int pack_weights(const void* const* params, const MilPlan& pl, void* ws, bool transposed, cudaStream_t s) {
+  PackTable t;
+  t.count = 0;
+  float* area = reinterpret_cast<float*>(wsp(ws, pl.off_wpack));
+  for (const auto& c : pl.convs) {
+    const int e = t.count++;
+    t.src[e] = reinterpret_cast<const float*>(params[c.p_w]);
+    t.dst[e] = area + (transposed ? c.wpt_off : c.wp_off);
+    t.cout[e] = (short)c.cout; t.cin[e] = (short)c.cin; t.ks[e] = (unsigned char)c.ks;
+    t.transposed[e] = transposed ? 1 : 0;
+  }
+  pack_all_kernel<<<dim3(t.count, 8), 256, 0, s>>>(t);
+  MIL_LAUNCH_OK();
+  return 0;
+}
+
+int mil_extractor_forward_impl(const void* const* params, const float* bag, const int* idx, const MilPlan& pl,
+                               void* ws, float* H, cudaStream_t s) {
+  const int dt = pl.dtype;
+  // guards of every saved activation buffer (cheap, makes the workspace self-initialising)
+  {
+    GuardTable t;
+    t.count = 0;
+    t.esize = (int)mil_esize(dt);
+    guard_add(t, wsp(ws, pl.off_pooled), pl.g[0]);
+    for (int l = 0; l < 4; ++l)
+      for (int b = 0; b < 3; ++b) {
+        guard_add(t, wsp(ws, pl.off_h[l * 3 + b]), pl.g[l]);
+        guard_add(t, wsp(ws, pl.off_y[l * 3 + b]), pl.g[l]);
+      }
+    MIL_TRY(launch_guards(t, s));
+  }
+  MIL_TRY(pack_weights(params, pl, ws, false, s));
+  const float* wpack = reinterpret_cast<const float*>(wsp(ws, pl.off_wpack));
+  const int p_c1w = mil_param_index("cnn.module.conv1.weight"), p_c1b = mil_param_index("cnn.module.conv1.bias");
+  MIL_TRY(mil_launch_stem_fwd(dt, bag, idx, pl.n, pl.side, (const float*)params[p_c1w], (const float*)params[p_c1b],
+                              wsp(ws, pl.off_pooled), pl.g[0], (uint8_t*)wsp(ws, pl.off_argmax), s));
+  const void* X = wsp(ws, pl.off_pooled);
+  MilPF8 gx = pl.g[0];
+  size_t ci = 0;
+  for (int l = 0; l < 4; ++l) {
+    for (int b = 0; b < 3; ++b) {
+      const MilPF8& go = pl.g[l];
+      void* h = wsp(ws, pl.off_h[l * 3 + b]);
+      void* y = wsp(ws, pl.off_y[l * 3 + b]);
+      const MilConvDesc& c1 = pl.convs[ci++];
+      const MilConvDesc& c2 = pl.convs[ci++];
+      MIL_TRY(mil_conv_dispatch(dt, 0, X, gx, wpack + c1.wp_off, (const float*)params[c1.p_b], nullptr, nullptr, h,
+                                go, 3, c1.stride, MIL_EPI_FWD, s));
+      const void* res = X;
+      if (b == 0 && l > 0) {
+        const MilConvDesc& cd = pl.convs[ci++];
+        // projection shortcut (1x1 / stride 2, no bias) written into y, then consumed in place as the residual
+        MIL_TRY(mil_conv_dispatch(dt, 0, X, gx, wpack + cd.wp_off, nullptr, nullptr, nullptr, y, go, 1, 2,
+                                  MIL_EPI_PLAIN, s));
+        res = y;
+      }
+      MIL_TRY(mil_conv_dispatch(dt, 0, h, go, wpack + c2.wp_off, (const float*)params[c2.p_b], res, nullptr, y, go,
+                                3, 1, MIL_EPI_FWD, s));
+      X = y;
+      gx = go;
+    }
+  }
+  const int p_fc = mil_param_index("cnn.module.fc.weight");
+  return mil_launch_tail_fwd(dt, X, pl.g[3], (const float*)params[p_fc], (float*)wsp(ws, pl.off_avg), H, s);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// backward (weight gradients are ACCUMULATED into `grads`, the flat state-dict-ordered buffer)
+// ---------------------------------------------------------------------------------------------------
+int mil_extractor_backward_impl(const void* const* params, const float* bag, const int* idx, const MilPlan& pl,
+                                void* ws, const float* dH, float* grads, cudaStream_t s) {
+  const int dt = pl.dtype;
+  const auto& pt = mil_param_table();
+  MIL_TRY(pack_weights(params, pl, ws, true, s));
+  const float* wpack = reinterpret_cast<const float*>(wsp(ws, pl.off_wpack));
+  float* partial = reinterpret_cast<float*>(wsp(ws, pl.off_partial));
+  void* gb[3] = {wsp(ws, pl.off_grad[0]), wsp(ws, pl.off_grad[1]), wsp(ws, pl.off_grad[2])};
+  auto gptr = [&](int p) { return grads + pt[p].offset; };
+
+  const int p_fc = mil_param_index("cnn.module.fc.weight");
+  void* dz = gb[0];
+  void* dpre = gb[1];
+  void* dnew = gb[2];
+
+  {
+    GuardTable t;
+    t.count = 0;
+    t.esize = (int)mil_esize(dt);
+    for (int i = 0; i < 3; ++i) guard_add(t, gb[i], pl.g[3]);
+    MIL_TRY(launch_guards(t, s));
+  }
+  MIL_TRY(mil_launch_tail_bwd(dt, wsp(ws, pl.off_y[11]), pl.g[3], (const float*)params[p_fc],
+                              (const float*)wsp(ws, pl.off_avg), dH, dz, partial, gptr(p_fc), s));
+  // index of the first conv descriptor of (l, b)
+  auto conv_base = [&](int l, int b) {
+    size_t i = 0;
+    for (; i < pl.convs.size(); ++i)
+      if (pl.convs[i].layer == l && pl.convs[i].block == b) break;
+    return i;
+  };
+  for (int l = 3; l >= 0; --l) {
+    for (int b = 2; b >= 0; --b) {
+      const MilPF8& go = pl.g[l];
+      const bool down = (b == 0 && l > 0);
+      const void* xin = (b > 0) ? wsp(ws, pl.off_y[l * 3 + b - 1])
+                                : (l > 0 ? wsp(ws, pl.off_y[(l - 1) * 3 + 2]) : wsp(ws, pl.off_pooled));
+      const MilPF8& gi = down ? pl.g[l - 1] : pl.g[l];
+      const void* h = wsp(ws, pl.off_h[l * 3 + b]);
+      const size_t cb = conv_base(l, b);
+      const MilConvDesc& c1 = pl.convs[cb];
+      const MilConvDesc& c2 = pl.convs[cb + 1];
+      // conv2: weight gradient, then data gradient through conv2 and the first LeakyReLU
+      MIL_TRY(mil_launch_wgrad_direct(dt, h, go, dz, go, partial, gptr(c2.p_w), gptr(c2.p_b), 3, 1, s));
+      MIL_TRY(mil_conv_dispatch(dt, 1, dz, go, wpack + c2.wpt_off, nullptr, nullptr, h, dpre, go, 3, 1,
+                                MIL_EPI_DGRAD, s));
+      // conv1: weight gradient
+      MIL_TRY(mil_launch_wgrad_direct(dt, xin, gi, dpre, go, partial, gptr(c1.p_w), gptr(c1.p_b), 3, c1.stride, s));
+      if (down) {
+        const MilConvDesc& cd = pl.convs[cb + 2];
+        MIL_TRY(mil_launch_wgrad_direct(dt, xin, gi, dz, go, partial, gptr(cd.p_w), nullptr, 1, 2, s));
+        // the gradient buffers change geometry here: re-zero their guards for the larger map
+        {
+          GuardTable t;
+          t.count = 0;
+          t.esize = (int)mil_esize(dt);
+          guard_add(t, dnew, gi);
+          MIL_TRY(launch_guards(t, s));
+        }
+        MIL_TRY(mil_conv_dispatch(dt, 1, dz, go, wpack + cd.wpt_off, nullptr, nullptr, nullptr, dnew, gi, 1, 2,
+                                  MIL_EPI_PLAIN, s));
+        MIL_TRY(mil_conv_dispatch(dt, 1, dpre, go, wpack + c1.wpt_off, nullptr, dnew, xin, dnew, gi, 3, 2,
+                                  MIL_EPI_DGRAD, s));
+        // dz / dpre will next be written with the geometry of layer l-1
+        {
+          GuardTable t;
+          t.count = 0;
+          t.esize = (int)mil_esize(dt);
+          guard_add(t, dz, gi);
+          guard_add(t, dpre, gi);
+          MIL_TRY(launch_guards(t, s));
+        }
+
+      } else {
+        MIL_TRY(mil_conv_dispatch(dt, 1, dpre, go, wpack + c1.wpt_off, nullptr, dz, xin, dnew, gi, 3, 1,
+                                  MIL_EPI_DGRAD, s));
+      }
+      std::swap(dz, dnew);
+    }
+  }
+
+  const int p_c1w = mil_param_index("cnn.module.conv1.weight"), p_c1b = mil_param_index("cnn.module.conv1.bias");
+  return mil_launch_stem_bwd(dt, bag, idx, pl.n, pl.side, dz, pl.g[0], (const uint8_t*)wsp(ws, pl.off_argmax),
+                             partial, gptr(p_c1w), gptr(p_c1b), s);
+}

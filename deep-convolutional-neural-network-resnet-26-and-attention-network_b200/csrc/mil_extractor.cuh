@@ -1,0 +1,49 @@
+// Host-side model description of the ResNet-26 extractor + head parameters (reference gbm/model.py:14-61,
+// 118-159): the 65 tensors of the reference state dict in its own order, the workspace plan, and the
+// whole-network forward / backward drivers (mil_extractor.cu).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "mil_common.cuh"
+
+struct MilParamInfo {
+  std::string name;
+  int ndim;
+  long long shape[4];
+  long long numel;
+  long long offset;  // float offset inside the flat gradient buffer (state-dict order, densely packed)
+};
+const std::vector<MilParamInfo>& mil_param_table();
+int mil_param_index(const char* name);  // -1 if unknown
+
+// one convolution of the extractor
+struct MilConvDesc {
+  int layer, block;   // 0..3, 0..2
+  int which;          // 0 = conv1, 1 = conv2, 2 = downsample
+  int cin, cout, ks, stride;
+  int p_w, p_b;       // parameter indices (p_b = -1: no bias)
+  size_t wp_off, wpt_off;  // float offsets of the packed normal / transposed weights inside the pack area
+};
+
+struct MilPlan {
+  int n, side, dtype;
+  MilGeom geo;
+  MilPF8 g[4];                  // activation geometry of layer1..4
+  std::vector<MilConvDesc> convs;  // 27 entries, forward order
+  size_t off_pooled, off_argmax, off_h[12], off_y[12], off_avg, off_grad[3], off_wpack, off_partial;
+  size_t wpack_floats, partial_floats, grad_bytes;
+  size_t total_bytes;
+};
+int mil_make_plan(int n, int side, int dtype, MilPlan* plan);
+
+int mil_extractor_forward_impl(const void* const* params, const float* bag, const int* idx, const MilPlan& pl,
+                               void* ws, float* H, cudaStream_t s);
+int mil_extractor_backward_impl(const void* const* params, const float* bag, const int* idx, const MilPlan& pl,
+                                void* ws, const float* dH, float* grads, cudaStream_t s);
+
+// conv dispatch: tcgen05 implicit GEMM where supported (bf16), CUDA-core direct kernel otherwise
+int mil_conv_dispatch(int dtype, int transposed, const void* x, const MilPF8& gi, const float* wp, const float* bias,
+                      const void* res, const void* act, void* out, const MilPF8& go, int ks, int stride, int epi,
+                      cudaStream_t s);
+int mil_zero_guards(int dtype, void* buf, const MilPF8& g, cudaStream_t s);

@@ -1,0 +1,132 @@
+// Layout helpers: weight packing, NCHW <-> PF8 conversion (used by the layer-wise parity tests), and the
+// deterministic second-stage reductions of split-K weight-gradient partials.
+#include "mil_common.cuh"
+
+// ---- conv weight packing ---------------------------------------------------------------------------
+// PyTorch layout w[cout][cin][ks][ks] (reference nnBlocks.py:160-168 nn.Conv2d) ->
+//   normal     : wp[tap][cin_pad ][cout_pad]   (forward conv: contraction over cin)
+//   transposed : wp[tap][cout_pad][cin_pad ]   (dgrad: contraction over cout)
+// zero padded to multiples of 8 channels.
+__global__ void pack_conv_w_kernel(const float* __restrict__ w, float* __restrict__ wp, int cout, int cin, int ks,
+                                   int transposed) {
+  const int cip = (cin + 7) / 8 * 8, cop = (cout + 7) / 8 * 8;
+  const int taps = ks * ks;
+  const int A = transposed ? cop : cip, B = transposed ? cip : cop;
+  const int total = taps * A * B;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int b = i % B, a = (i / B) % A, t = i / (A * B);
+    int co = transposed ? a : b, ci = transposed ? b : a;
+    float v = 0.f;
+    if (co < cout && ci < cin) v = w[((size_t)co * cin + ci) * taps + t];
+    wp[i] = v;
+  }
+}
+int mil_launch_pack_conv_w(const float* w, float* wp, int cout, int cin, int ks, int transposed, cudaStream_t s) {
+  const int cip = (cin + 7) / 8 * 8, cop = (cout + 7) / 8 * 8;
+  const int total = ks * ks * cip * cop;
+  pack_conv_w_kernel<<<(int)mil_cdiv(total, 256), 256, 0, s>>>(w, wp, cout, cin, ks, transposed);
+  MIL_LAUNCH_OK();
+  return 0;
+}
+
+// ---- NCHW fp32 <-> PF8 -------------------------------------------------------------------------------
+template <typename T>
+__global__ void to_pf8_kernel(const float* __restrict__ src, T* __restrict__ dst, MilPF8 g) {
+  // one thread per (chunk, flat pixel): writes 8 channels (zeros on pad pixels / pad channels)
+  const long long total = (long long)g.cb * g.Q;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cb = (int)(i / g.Q);
+    const long long q = i % g.Q;
+    const int n = (int)(q / g.P);
+    const int r = (int)(q % g.P);
+    const int y = r / g.wp, x = r % g.wp;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cb * 8 + j;
+      v[j] = (y < g.h && x < g.w && c < g.c) ? src[(((size_t)n * g.c + c) * g.h + y) * g.w + x] : 0.f;
+    }
+    mil_store8(dst + mil_pf8_off(g, cb, q), v);
+  }
+}
+template <typename T>
+__global__ void from_pf8_kernel(const T* __restrict__ src, float* __restrict__ dst, MilPF8 g) {
+  const long long total = (long long)g.n * g.c * g.h * g.w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % g.w);
+    const int y = (int)((i / g.w) % g.h);
+    const int c = (int)((i / ((long long)g.w * g.h)) % g.c);
+    const int n = (int)(i / ((long long)g.w * g.h * g.c));
+    const long long q = (long long)n * g.P + (long long)y * g.wp + x;
+    dst[i] = mil_to_float(src[mil_pf8_off(g, c >> 3, q) + (c & 7)]);
+  }
+}
+int mil_launch_to_pf8(int dtype, const float* nchw, void* pf8, int n, int c, int h, int w, cudaStream_t s) {
+  MilPF8 g = mil_pf8(n, c, h, w);
+  const int blocks = (int)std::min<long long>(mil_cdiv((long long)g.cb * g.Q, 256), 148 * 32);
+  if (dtype == MIL_BF16)
+    to_pf8_kernel<<<blocks, 256, 0, s>>>(nchw, (__nv_bfloat16*)pf8, g);
+  else
+    to_pf8_kernel<<<blocks, 256, 0, s>>>(nchw, (float*)pf8, g);
+  MIL_LAUNCH_OK();
+  return 0;
+}
+int mil_launch_from_pf8(int dtype, const void* pf8, float* nchw, int n, int c, int h, int w, cudaStream_t s) {
+  MilPF8 g = mil_pf8(n, c, h, w);
+  const int blocks = (int)std::min<long long>(mil_cdiv((long long)n * c * h * w, 256), 148 * 32);
+  if (dtype == MIL_BF16)
+    from_pf8_kernel<<<blocks, 256, 0, s>>>((const __nv_bfloat16*)pf8, nchw, g);
+  else
+    from_pf8_kernel<<<blocks, 256, 0, s>>>((const float*)pf8, nchw, g);
+  MIL_LAUNCH_OK();
+  return 0;
+}
+
+// ---- deterministic second-stage reductions ----------------------------------------------------------
+// out[i] += sum_b partial[b*stride + i]   (fixed summation order: bit-reproducible run to run)
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int nblk, long long stride,
+                                       float* __restrict__ out, long long count) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float acc = 0.f;
+  for (int b = 0; b < nblk; ++b) acc += partial[(size_t)b * stride + i];
+  out[i] += acc;
+}
+int mil_launch_reduce_partials(const float* partial, int nblk, long long stride, float* out, long long count,
+                               cudaStream_t s) {
+  reduce_partials_kernel<<<(int)mil_cdiv(count, 128), 128, 0, s>>>(partial, nblk, stride, out, count);
+  MIL_LAUNCH_OK();
+  return 0;
+}
+
+// partial[b][tap][cin_pad][cout_pad] (+ [cout_pad] bias sums at the end of each record) ->
+//   dw[cout][cin][tap] += ... ,  db[cout] += ...      (PyTorch parameter layout)
+__global__ void reduce_conv_w_kernel(const float* __restrict__ partial, int nblk, long long stride,
+                                     float* __restrict__ dw, float* __restrict__ db, int cout, int cin, int ks) {
+  const int cip = (cin + 7) / 8 * 8, cop = (cout + 7) / 8 * 8;
+  const int taps = ks * ks;
+  const int nw = cout * cin * taps;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nw) {
+    const int t = i % taps, ci = (i / taps) % cin, co = i / (taps * cin);
+    const size_t src = ((size_t)t * cip + ci) * cop + co;
+    float acc = 0.f;
+    for (int b = 0; b < nblk; ++b) acc += partial[(size_t)b * stride + src];
+    dw[i] += acc;
+  } else if (db != nullptr && i < nw + cout) {
+    const int co = i - nw;
+    const size_t src = (size_t)taps * cip * cop + co;
+    float acc = 0.f;
+    for (int b = 0; b < nblk; ++b) acc += partial[(size_t)b * stride + src];
+    db[co] += acc;
+  }
+}
+int mil_launch_reduce_conv_w(const float* partial, int nblk, long long stride, float* dw, float* db, int cout,
+                             int cin, int ks, cudaStream_t s) {
+  const int total = cout * cin * ks * ks + cout;
+  reduce_conv_w_kernel<<<(int)mil_cdiv(total, 128), 128, 0, s>>>(partial, nblk, stride, dw, db, cout, cin, ks);
+  MIL_LAUNCH_OK();
+  return 0;
+}

@@ -1,0 +1,128 @@
+/* mil_b200.h -- C ABI of the B200-native ResNet-26 + attention-MIL hot path (libmil_b200.so).
+ *
+ * The reference (frankenz/Deep-convolutional-neural-network-ResNet-26-and-Attention-network) is pure Python
+ * and has no FFI; the drop-in boundary is its `model.Attention` nn.Module (gbm/model.py:114-264) as used by
+ * gbm/classify_combined.py:432,446-447,518.  This header is the native interface a binding for that class
+ * calls; each entry point names the reference lines it replaces.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`; the library allocates nothing and
+ *     keeps no state between calls: the caller owns inputs, outputs, parameters, gradients and workspaces;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no call synchronises;
+ *   - return value 0 = success; non-zero = error, message available from mil_last_error() (thread local);
+ *     nothing throws across this boundary;
+ *   - parameters are the reference's 65 state-dict tensors, fp32, PyTorch layouts, passed as an array of 65
+ *     device pointers in state-dict order (mil_param_name(i) lists them);  gradients are ACCUMULATED (+=)
+ *     into one flat fp32 buffer of mil_param_total() floats, tensor i at float offset mil_param_offset(i);
+ *   - dtype: MIL_DTYPE_F32 = fp32 storage + FFMA kernels (the 1e-4 check mode),
+ *            MIL_DTYPE_BF16 = bf16 activations, fp32 accumulation, tcgen05 tensor-core convolutions.
+ *   - there is NO CPU fallback: every compute entry point needs an sm_100a device.
+ */
+#ifndef MIL_B200_H_
+#define MIL_B200_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIL_ABI_VERSION 1
+#define MIL_DTYPE_F32 0
+#define MIL_DTYPE_BF16 1
+#define MIL_NUM_PARAMS 65
+#define MIL_FEATURES 80     /* L, gbm/model.py:120 */
+#define MIL_HEAD_SUMS 16    /* doubles exchanged by AR-2 (see mil_head_scores) */
+#define MIL_HEAD_SCALARS 32 /* floats written by mil_head_finalize */
+/* offsets inside the MIL_HEAD_SCALARS block */
+#define MIL_SCAL_MTERM 0   /* [3] Mterm == slide logits (gbm/model.py:227-233) */
+#define MIL_SCAL_YPRED 3   /* [3] softmax(logits)         (gbm/model.py:235) */
+#define MIL_SCAL_DM 6      /* [3] d loss / d Mterm (kept for the backward pass) */
+#define MIL_SCAL_SUMG 9    /* [3] sum_n g_nk (the L1 normaliser of F.normalize, gbm/model.py:213) */
+#define MIL_SCAL_LOSS 12   /* label-smoothed weighted CE (gbm/model.py:241, nnBlocks.py:87-138) */
+#define MIL_SCAL_ATERM_MU 13
+#define MIL_SCAL_ATERM_VAR 14
+#define MIL_SCAL_KLD 15
+#define MIL_SCAL_YHAT 16   /* argmax class as float */
+#define MIL_SCAL_ERROR 17  /* 1 - [yhat == Y] */
+
+/* ---- library / model description ------------------------------------------------------------------ */
+int mil_abi_version(void);
+const char* mil_last_error(void);
+long long mil_kernel_launch_count(void);          /* kernels this library has launched in this process so far */
+int mil_param_count(void);                        /* 65 */
+const char* mil_param_name(int i);                /* reference state-dict key, e.g. "cnn.module.layer1.0.conv1.weight" */
+int mil_param_shape(int i, int* ndim, long long shape4[4]);
+long long mil_param_offset(int i);                /* float offset inside the flat gradient buffer */
+long long mil_param_total(void);                  /* 640967 */
+
+/* ---- feature extractor: ResNet.forward (gbm/model.py:50-61) + BasicResBlock (nnBlocks.py:175-189) ----
+ * bag   : fp32 NCHW [n_bag,3,side,side], the caller's tensor as handed to Attention.forward (gbm/model.py:189)
+ * idx   : optional int32[n_tiles] gather list = the train-mode 20 % subsample (gbm/model.py:193-194);
+ *         NULL => tiles 0..n_tiles-1
+ * H     : fp32 [n_tiles,80] features ('Fterm')
+ * ws    : workspace of mil_extractor_workspace_bytes() bytes; forward leaves the activations backward needs in
+ *         it, so pass the SAME workspace (untouched) to mil_extractor_backward.                              */
+size_t mil_extractor_workspace_bytes(int n_tiles, int side, int dtype);
+int mil_extractor_forward(const void* const* params_host, const float* bag, const int32_t* idx, int n_tiles, int side,
+                          int dtype, void* ws, size_t ws_bytes, float* H, void* stream);
+/* autograd of the above (gbm/classify_combined.py:447): dH fp32 [n_tiles,80] -> grads_flat += d/d(params).
+ * No gradient flows to `bag` (it is detached, gbm/model.py:194,196).                                         */
+int mil_extractor_backward(const void* const* params_host, const float* bag, const int32_t* idx, int n_tiles, int side,
+                           int dtype, void* ws, size_t ws_bytes, const float* dH, float* grads_flat, void* stream);
+
+/* test / debugging aid: copy one saved activation out of a forward workspace as fp32 NCHW.
+ * which = -1: stem output (after max-pool); 2*(3*layer+block): the block's inner activation h;
+ * 2*(3*layer+block)+1: the block's output y  (layer 0..3, block 0..2).                                        */
+int mil_extractor_read_activation(int n_tiles, int side, int dtype, const void* ws, int which, float* nchw,
+                                  void* stream);
+
+/* ---- MIL head: Attention.forward after the CNN (gbm/model.py:200-246) ------------------------------
+ * The head works on the LOCAL shard (n tiles) of a bag of n_global tiles; between the phases the caller
+ * all-reduces (sum) the small double arrays across the ranks that share the bag (single GPU: nothing to do).
+ *   stats  double[160] : sum_n x, sum_n x^2 per feature        (BatchNorm1d batch statistics, gbm/model.py:105-109)
+ *   sums   double[16]  : sum g[3], sum g*b[3], sum raw[3], Gram(raw) upper triangle[6]  (gbm/model.py:211-229)
+ *   bnsums double[160] : sum dHz, sum dHz*xhat per feature     (BatchNorm1d backward)                         */
+size_t mil_head_workspace_bytes(int n);
+int mil_head_stats(const float* H, int n, void* ws, size_t ws_bytes, double* stats, void* stream);
+/* drop: optional fp32 {0,1} keep mask [n,80] of Dropout(0.25) (gbm/model.py:107,110); NULL in eval mode.
+ * raw,g: fp32 [n,3] (attention scores before / after softplus+mask mix); b: fp32 [n] ('Bterm').              */
+int mil_head_scores(const void* const* params_host, const float* H, const float* drop, int n, long long n_global,
+                    const double* stats, float* raw, float* g, float* b, void* ws, size_t ws_bytes, double* sums,
+                    void* stream);
+/* Y: int64[1] label; class_w: optional fp32[3] (CrossEntropyWithProbs weight, gbm/model.py:127);
+ * A ('Aterm'), wroi ('wROIs'): fp32 [3,n]; scal: fp32[MIL_HEAD_SCALARS].                                     */
+int mil_head_finalize(const double* sums, const double* stats, long long n_global, const long long* Y,
+                      const float* class_w, int n, const float* g, const float* b, float* A, float* wroi,
+                      float* scal, void* stream);
+/* gloss: optional fp32[1] upstream gradient of the loss (NULL => 1).  Accumulates the head's parameter
+ * gradients (local contributions) into grads_flat; writes dHz, dHi fp32 [n,80] and bnsums.                   */
+int mil_head_backward_a(const void* const* params_host, const float* H, const float* drop, int n, long long n_global,
+                        const double* stats, const float* raw, const float* g, const float* b, const float* scal,
+                        const float* gloss, float* dHz, float* dHi, float* grads_flat, void* ws, size_t ws_bytes,
+                        double* bnsums, void* stream);
+int mil_head_backward_b(const void* const* params_host, const float* H, int n, long long n_global, const double* stats,
+                        const double* bnsums, const float* dHz, const float* dHi, float* dH, void* stream);
+
+/* ---- layer-level operators on PF8 activation buffers (used by the layer-wise parity tests) ------------
+ * PF8 = padded-flat 8-channel-chunk layout, see csrc/mil_common.cuh.  Buffers must be zero-filled once by the
+ * caller (guards) and are mil_pf8_bytes() large.  impl: 0 = auto, 1 = CUDA-core direct, 2 = tcgen05.        */
+size_t mil_pf8_bytes(int n, int c, int h, int w, int dtype);
+int mil_to_pf8(int dtype, const float* nchw, void* pf8, int n, int c, int h, int w, void* stream);
+int mil_from_pf8(int dtype, const void* pf8, float* nchw, int n, int c, int h, int w, void* stream);
+size_t mil_conv_workspace_bytes(int n, int cin, int hi, int wi, int cout, int ho, int wo, int ks);
+/* out = epilogue(conv(x, w)):  epi 0: lrelu(acc+bias+res), 1: (acc+res)*lrelu'(act), 2: acc+bias+res.
+ * transposed=1 computes the data gradient (x has the conv's OUTPUT geometry, out its INPUT geometry).
+ * w is the PyTorch [cout,cin,ks,ks] fp32 weight.                                                            */
+int mil_conv_pf8(int dtype, int impl, int transposed, const void* x, int n, int cx, int hx, int wx, const float* w,
+                 int cout, int cin, int ks, int stride, const float* bias, const void* res, const void* act,
+                 void* out, int ho, int wo, int epi, void* ws, size_t ws_bytes, void* stream);
+/* dw += wgrad(x, dz), db += sum dz (db may be NULL) */
+int mil_conv_wgrad_pf8(int dtype, int impl, const void* x, int n, int cin, int hi, int wi, const void* dz, int cout,
+                       int ho, int wo, int ks, int stride, float* dw, float* db, void* ws, size_t ws_bytes,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIL_B200_H_ */
