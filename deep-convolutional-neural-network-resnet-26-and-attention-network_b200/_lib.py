@@ -33,6 +33,7 @@ PROTOTYPES = {
     "mil_extractor_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t,
                                        c_void_p, c_void_p, c_void_p]),
     "mil_extractor_read_activation": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "mil_debug_dump_gradient": (c_int, [c_int, c_int, c_int, c_void_p]),
     "mil_head_workspace_bytes": (c_size_t, [c_int]),
     "mil_head_stats": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "mil_head_scores": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_ll, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -140,6 +140,11 @@ int mil_extractor_read_activation(int n_tiles, int side, int dtype, const void* 
   MIL_API_END
 }
 
+int mil_debug_dump_gradient(int layer, int block, int which, float* nchw) {
+  mil_debug_request_dump(layer, block, which, nchw);
+  return 0;
+}
+
 int mil_extractor_forward(const void* const* params, const float* bag, const int32_t* idx, int n_tiles, int side,
                           int dtype, void* ws, size_t ws_bytes, float* H, void* stream) {
   MIL_API_BEGIN

@@ -281,6 +281,12 @@ int mil_extractor_forward_impl(const void* const* params, const float* bag, cons
 // ---------------------------------------------------------------------------------------------------
 // backward (weight gradients are ACCUMULATED into `grads`, the flat state-dict-ordered buffer)
 // ---------------------------------------------------------------------------------------------------
+// test / debugging aid: dump one intermediate gradient of the next backward pass as fp32 NCHW
+static struct { int layer, block, which; float* dst; } g_dump = {-1, -1, 0, nullptr};
+void mil_debug_request_dump(int layer, int block, int which, float* dst) {
+  g_dump.layer = layer; g_dump.block = block; g_dump.which = which; g_dump.dst = dst;
+}
+
 int mil_extractor_backward_impl(const void* const* params, const float* bag, const int* idx, const MilPlan& pl,
                                 void* ws, const float* dH, float* grads, cudaStream_t s) {
   const int dt = pl.dtype;
@@ -327,6 +333,9 @@ int mil_extractor_backward_impl(const void* const* params, const float* bag, con
       MIL_TRY(mil_launch_wgrad_direct(dt, h, go, dz, go, partial, gptr(c2.p_w), gptr(c2.p_b), 3, 1, s));
       MIL_TRY(mil_conv_dispatch(dt, 1, dz, go, wpack + c2.wpt_off, nullptr, nullptr, h, dpre, go, 3, 1,
                                 MIL_EPI_DGRAD, s));
+      // which 1: gradient w.r.t. the pre-activation of this block's first conv (geometry go)
+      if (g_dump.dst != nullptr && g_dump.layer == l && g_dump.block == b && g_dump.which == 1)
+        MIL_TRY(mil_launch_from_pf8(dt, dpre, g_dump.dst, go.n, go.c, go.h, go.w, s));
       // conv1: weight gradient
       MIL_TRY(mil_launch_wgrad_direct(dt, xin, gi, dpre, go, partial, gptr(c1.p_w), gptr(c1.p_b), 3, c1.stride, s));
       if (down) {
@@ -358,6 +367,9 @@ int mil_extractor_backward_impl(const void* const* params, const float* bag, con
         MIL_TRY(mil_conv_dispatch(dt, 1, dpre, go, wpack + c1.wpt_off, nullptr, dz, xin, dnew, gi, 3, 1,
                                   MIL_EPI_DGRAD, s));
       }
+      // which 0: gradient w.r.t. the pre-activation feeding this block's input (geometry gi)
+      if (g_dump.dst != nullptr && g_dump.layer == l && g_dump.block == b && g_dump.which == 0)
+        MIL_TRY(mil_launch_from_pf8(dt, dnew, g_dump.dst, gi.n, gi.c, gi.h, gi.w, s));
       std::swap(dz, dnew);
     }
   }

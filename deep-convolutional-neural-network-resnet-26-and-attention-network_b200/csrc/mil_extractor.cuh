@@ -42,6 +42,8 @@ int mil_extractor_forward_impl(const void* const* params, const float* bag, cons
 int mil_extractor_backward_impl(const void* const* params, const float* bag, const int* idx, const MilPlan& pl,
                                 void* ws, const float* dH, float* grads, cudaStream_t s);
 
+void mil_debug_request_dump(int layer, int block, int which, float* dst);
+
 // conv dispatch: tcgen05 implicit GEMM where supported (bf16), CUDA-core direct kernel otherwise
 int mil_conv_dispatch(int dtype, int transposed, const void* x, const MilPF8& gi, const float* wp, const float* bias,
                       const void* res, const void* act, void* out, const MilPF8& go, int ks, int stride, int epi,

@@ -77,6 +77,11 @@ int mil_extractor_backward(const void* const* params_host, const float* bag, con
 int mil_extractor_read_activation(int n_tiles, int side, int dtype, const void* ws, int which, float* nchw,
                                   void* stream);
 
+/* test / debugging aid: the NEXT mil_extractor_backward calls on this thread also write one intermediate
+ * gradient as fp32 NCHW to `nchw` (NULL switches it off).  which = 0: gradient w.r.t. the pre-activation that
+ * produced the input of block (layer, block); which = 1: w.r.t. the pre-activation of its first convolution. */
+int mil_debug_dump_gradient(int layer, int block, int which, float* nchw);
+
 /* ---- MIL head: Attention.forward after the CNN (gbm/model.py:200-246) ------------------------------
  * The head works on the LOCAL shard (n tiles) of a bag of n_global tiles; between the phases the caller
  * all-reduces (sum) the small double arrays across the ranks that share the bag (single GPU: nothing to do).

@@ -105,24 +105,36 @@ def init_params(seed: int = 0, dtype=torch.float32) -> "OrderedDict[str, torch.T
 # --------------------------------------------------------------------------------------------
 # feature extractor (gbm/model.py:50-61, nnBlocks.py:175-189)
 # --------------------------------------------------------------------------------------------
+def _bf16(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
 def resnet26_forward(p: Dict[str, torch.Tensor], x: torch.Tensor, prefix: str = "cnn.module.",
-                     taps: Optional[dict] = None) -> torch.Tensor:
-    """x [N,3,S,S] -> H [N,80].  `taps` (optional dict) receives every block output."""
+                     taps: Optional[dict] = None, emulate_bf16: str = "") -> torch.Tensor:
+    """x [N,3,S,S] -> H [N,80].  `taps` (optional dict) receives every block output.
+
+    emulate_bf16: "" = the reference arithmetic.  "act" = additionally round every STORED activation
+    (stem output, each block's inner activation and output) to bf16, which is where the CUDA bf16 mode
+    rounds; "act+w" = also round the 3x3 / 1x1 conv weights to bf16 (tensor-core operands).  Used by the
+    tests to separate kernel defects (must match the emulation tightly) from the conditioning of the
+    head with respect to bf16 features (the distance between the emulation and the fp32 reference)."""
     lr = lambda t: F.leaky_relu(t, SLOPE)
+    ra = _bf16 if emulate_bf16 else (lambda t: t)
+    rw = _bf16 if emulate_bf16 == "act+w" else (lambda t: t)
     y = F.conv2d(x, p[prefix + "conv1.weight"], p[prefix + "conv1.bias"], stride=2, padding=3)
-    y = F.max_pool2d(lr(y), kernel_size=3, stride=2, padding=1)
+    y = ra(F.max_pool2d(lr(y), kernel_size=3, stride=2, padding=1))
     if taps is not None:
         taps["stem"] = y
     for li in range(1, 5):
         for b in range(3):
             q = f"{prefix}layer{li}.{b}"
             stride = 2 if (b == 0 and li > 1) else 1
-            h = lr(F.conv2d(y, p[q + ".conv1.weight"], p[q + ".conv1.bias"], stride=stride, padding=1))
-            z = F.conv2d(h, p[q + ".conv2.weight"], p[q + ".conv2.bias"], stride=1, padding=1)
+            h = ra(lr(F.conv2d(y, rw(p[q + ".conv1.weight"]), p[q + ".conv1.bias"], stride=stride, padding=1)))
+            z = F.conv2d(h, rw(p[q + ".conv2.weight"]), p[q + ".conv2.bias"], stride=1, padding=1)
             ident = y
             if q + ".downsample.0.weight" in p:
-                ident = F.conv2d(y, p[q + ".downsample.0.weight"], None, stride=2)
-            y = lr(z + ident)
+                ident = ra(F.conv2d(y, rw(p[q + ".downsample.0.weight"]), None, stride=2))
+            y = ra(lr(z + ident))
             if taps is not None:
                 taps[f"layer{li}.{b}.y1"] = h
                 taps[f"layer{li}.{b}"] = y

@@ -21,7 +21,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
-from oracle import ref_shim, synth  # noqa: E402
+from oracle import mil_oracle, ref_shim, synth  # noqa: E402
 
 CASES = [
     # name, n_bag, side, weight_mask, Y, class_weights, training
@@ -30,6 +30,10 @@ CASES = [
     dict(name="eval_5x224_mixedmask", n=5, side=224, wm=[0.25, -0.5, -1.0], Y=0, cw=None, training=False),
     dict(name="eval_3x300_odd", n=3, side=300, wm=[0.25, 0.25, 0.25], Y=1, cw=None, training=False),
     dict(name="eval_2x33_tiny", n=2, side=33, wm=[-1.0, 0.25, 0.1], Y=2, cw=[1.0, 3.0, 0.25], training=False),
+    # BASELINE.json configs[0]: one bag of 64 RGB 224x224 tiles, 3 classes (default init, and the peaked stress mask)
+    dict(name="eval_64x224_config0", n=64, side=224, wm=[0.25, 0.25, 0.25], Y=1, cw=None, training=False),
+    dict(name="eval_64x224_peaked", n=64, side=224, wm=[-1.0, -1.0, -1.0], Y=0, cw=None, training=False),
+    dict(name="eval_256x64", n=256, side=64, wm=[0.25, 0.25, 0.25], Y=2, cw=[1.0, 2.0, 0.5], training=False),
     dict(name="train_40x64_injected", n=40, side=64, wm=[0.25, -1.0, 0.25], Y=1, cw=None, training=True),
 ]
 
@@ -52,7 +56,7 @@ class _InjectedDropout(torch.nn.Module):
 
 
 def run_case(net, case):
-    bag = torch.from_numpy(synth.make_bag(case["n"], case["side"], seed=1))
+    bag = torch.from_numpy(synth.make_bag(case["n"], case["side"], seed=case.get("seed", 1)))
     Y = torch.tensor([case["Y"]])
     with torch.no_grad():
         net.weight_mask.copy_(torch.tensor(case["wm"]))
@@ -78,7 +82,24 @@ def run_case(net, case):
         if k in FULL_GRADS or g.numel() <= 3200:
             rec[f"grad.{k}"] = g.numpy()
     rec.update({f"extra.{k}": v for k, v in extra.items()})
-    rec["meta"] = np.frombuffer(json.dumps(case).encode(), dtype=np.uint8)
+    # How far is the fp32 reference itself from exact arithmetic?  LeakyReLU / max-pool are not smooth: an
+    # element whose pre-activation is ~1e-7 can take the other branch in a different fp32 summation order and
+    # move a gradient by percents.  gnoise = worst normwise distance between the reference's fp32 gradients and
+    # the fp64 restatement on the same inputs; the parity tests scale their gradient tolerance with it.
+    p64 = {k: v.detach().double() for k, v in net.state_dict().items()}
+    kw = {}
+    if case["training"]:
+        kw = dict(training=True, indices=torch.from_numpy(extra["indices"]),
+                  drop_mask=torch.from_numpy(synth.make_drop_mask(len(extra["indices"]), seed=2)).double())
+    cw = None if case["cw"] is None else torch.tensor(case["cw"]).double()
+    _, g64 = mil_oracle.forward_backward(p64, bag.double(), Y, cw, **kw)
+    gnoise = 0.0
+    for k, prm in net.named_parameters():
+        ref = g64[k]
+        if ref.abs().max() > 1e-5:
+            gnoise = max(gnoise, float((prm.grad.double() - ref).abs().max() / ref.abs().max()))
+    meta = dict(case, gnoise=gnoise)
+    rec["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
     return rec
 
 
@@ -89,7 +110,14 @@ def main():
     sd = {k: v.detach().numpy().copy() for k, v in net.state_dict().items()}
     np.savez(os.path.join(HERE, "weights.npz"), **sd)
     for case in CASES:
-        rec = run_case(net, case)
+        rec = None
+        for seed in range(1, 40):        # small cases: pick a data seed whose bag has no element on a kink
+            case["seed"] = seed
+            rec = run_case(net, case)
+            gnoise = json.loads(bytes(rec["meta"]).decode())["gnoise"]
+            if gnoise < 3e-5 or case["n"] * case["side"] ** 2 > 150000:
+                break
+        print("   seed", case["seed"], "gnoise %.2e" % gnoise)
         np.savez(os.path.join(HERE, f"case_{case['name']}.npz"), **rec)
         print(case["name"], "loss", float(rec["out.loss"]), "y_pred", rec["out.y_pred"].ravel())
 

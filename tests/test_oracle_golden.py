@@ -14,7 +14,7 @@ TOL = 2e-5          # fp32 restatement vs fp32 reference: summation-order noise 
 def _run_oracle(meta, rec):
     p = golden_weights()
     p["weight_mask"] = torch.tensor(meta["wm"])
-    bag = torch.from_numpy(synth.make_bag(meta["n"], meta["side"], seed=1))
+    bag = torch.from_numpy(synth.make_bag(meta["n"], meta["side"], seed=meta.get("seed", 1)))
     cw = None if meta["cw"] is None else torch.tensor(meta["cw"])
     kw = {}
     if meta["training"]:

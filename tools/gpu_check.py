@@ -155,13 +155,26 @@ def activations(precision, n=3, side=64):
     report(f"{precision} Fterm", G.relerr(H, Href), tol)
 
 
+def l2rel(a, b):
+    a = a.detach().double().cpu().flatten()
+    b = torch.as_tensor(b).double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def cosine(a, b):
+    a = a.detach().double().cpu().flatten()
+    b = torch.as_tensor(b).double().flatten()
+    return float((a * b).sum() / (a.norm() * b.norm()).clamp_min(1e-30))
+
+
 @section
 def golden(precision):
     tol_o = 1e-4 if precision == "fp32" else 1e-2
-    tol_g = 1e-3 if precision == "fp32" else 5e-2
     for meta, rec in golden_cases():
         net = build_net(precision, wm=meta["wm"], cw=None if meta["cw"] is None else torch.tensor(meta["cw"]))
-        bag = torch.from_numpy(synth.make_bag(meta["n"], meta["side"], seed=1)).cuda()
+        bag_cpu = torch.from_numpy(synth.make_bag(meta["n"], meta["side"], seed=meta.get("seed", 1)))
+        bag = bag_cpu.cuda()
+        idx = None
         if meta["training"]:
             net.train()
             idx = torch.from_numpy(rec["extra.indices"])
@@ -171,25 +184,39 @@ def golden(precision):
         out["loss"].backward()
         torch.cuda.synchronize()
         tag = f"{precision} {meta['name']}"
+        tol_g = max(1e-3, 5 * meta.get("gnoise", 0.0)) if precision == "fp32" else 1.0
         for k in ("Fterm", "Aterm", "wROIs", "Bterm", "Mterm", "y_pred", "loss", "Aterm_mu", "Aterm_var", "KLD", "l2"):
             assert tuple(out[k].shape) == tuple(rec[f"out.{k}"].shape), (k, out[k].shape, rec[f"out.{k}"].shape)
-            report(f"{tag} {k}", G.relerr(out[k], torch.from_numpy(rec[f"out.{k}"])), tol_o)
+            r = torch.from_numpy(rec[f"out.{k}"])
+            report(f"{tag} {k} (l2rel {l2rel(out[k], r):.1e})", G.relerr(out[k], r), tol_o)
         report(f"{tag} y_pred_hat", float(int(out["y_pred_hat"]) != int(rec["out.y_pred_hat"])), 0.5)
         report(f"{tag} error", float(float(out["error"]) != float(rec["out.error"])), 0.5)
-        worst, worst_k = 0.0, ""
+        if precision == "bf16":
+            # kernel check proper: against the oracle that rounds stored activations to bf16 at the same points
+            p = golden_weights()
+            p["weight_mask"] = torch.tensor(meta["wm"])
+            x = bag_cpu if idx is None else bag_cpu[idx]
+            He = mil_oracle.resnet26_forward(p, x, emulate_bf16="act")
+            report(f"{tag} Fterm vs bf16-emulating oracle (l2rel {l2rel(out['Fterm'], He):.1e})",
+                   G.relerr(out["Fterm"], He), 4e-3)
+        worst, worst_k, wcos, wcos_k, wnr, wnr_k = 0.0, "", 1.0, "", 0.0, ""
         for k, prm in net.named_parameters():
-            if f"grad.{k}" in rec and np.abs(rec[f"grad.{k}"]).max() > 1e-5:
-                e = G.relerr(prm.grad, torch.from_numpy(rec[f"grad.{k}"]))
-                if e > worst:
-                    worst, worst_k = e, k
-                if e >= tol_g:
-                    report(f"{tag} grad {k}", e, tol_g)
             dig = rec[f"gdigest.{k}"]
             if dig[2] > 1e-5:
-                e = abs(float(prm.grad.double().norm()) - dig[2]) / dig[2]
-                if e >= tol_g:
-                    report(f"{tag} |grad| {k}", e, tol_g)
-        report(f"{tag} worst full-tensor grad ({worst_k})", worst, tol_g)
+                nr = abs(float(prm.grad.double().norm()) - dig[2]) / dig[2]
+                if nr > wnr:
+                    wnr, wnr_k = nr, k
+            if f"grad.{k}" in rec and np.abs(rec[f"grad.{k}"]).max() > 1e-5:
+                r = torch.from_numpy(rec[f"grad.{k}"])
+                e = G.relerr(prm.grad, r)
+                c = cosine(prm.grad, r)
+                if e > worst:
+                    worst, worst_k = e, k
+                if c < wcos:
+                    wcos, wcos_k = c, k
+        report(f"{tag} worst grad max-norm err ({worst_k}) gnoise={meta.get('gnoise', 0):.1e}", worst, tol_g)
+        report(f"{tag} worst grad 1-cosine ({wcos_k})", 1 - wcos, 1e-5 if precision == "fp32" else 2e-2)
+        report(f"{tag} worst grad norm ratio err ({wnr_k})", wnr, tol_g if precision == "fp32" else 1e-1)
 
 
 @section
@@ -221,16 +248,24 @@ def timing(precision, n=256, side=224, iters=3):
 
 def main():
     quick = "--quick" in sys.argv
+    only = sys.argv[sys.argv.index("--only") + 1].split(",") if "--only" in sys.argv else None
+    want = lambda name: only is None or name in only
     say(torch.cuda.get_device_name(0), torch.__version__)
     for dt in ("fp32", "bf16"):
-        layout(dt)
+        if want("layout"):
+            layout(dt)
     for dt in ("fp32", "bf16"):
-        conv_ops(dt, 1)
+        if want("conv"):
+            conv_ops(dt, 1)
+    if want("tc"):
+        conv_ops("bf16", 2)
     for dt in ("fp32", "bf16"):
-        activations(dt)
+        if want("act"):
+            activations(dt)
     for dt in ("fp32", "bf16"):
-        golden(dt)
-    if not quick:
+        if want("golden"):
+            golden(dt)
+    if not quick and want("timing"):
         for dt in ("fp32", "bf16"):
             timing(dt)
     say(f"\n{len(FAIL)} failures" + ("" if not FAIL else ":\n  " + "\n  ".join(FAIL)))
