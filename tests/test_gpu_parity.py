@@ -204,26 +204,35 @@ def test_forward_backward_vs_reference_golden(precision, meta, rec):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_topk_attended_tiles_match_oracle(precision):
-    """Peaked attention (weight_mask = -1) on a 48-tile bag: same top-8 tiles per attention map."""
-    n, side, k = 96, 64, 8
-    wm = [-1.0, -1.0, -1.0]
-    net = build_net(precision, wm=wm)
-    bag = torch.from_numpy(synth.make_bag(n, side, seed=11))
-    p = golden_weights()
-    p["weight_mask"] = torch.tensor(wm)
-    ref = mil_oracle.attention_forward(p, bag, torch.tensor([1]))
+@pytest.mark.parametrize("case", ["eval_64x224_peaked", "eval_64x224_config0", "eval_256x64"])
+def test_topk_attended_tiles_match_reference(precision, case):
+    """Identical predicted class and identical top-8 attended tiles per attention map (north_star), on the
+    reference's own outputs for BASELINE-sized bags; the peaked mask (weight_mask = -1) is the case where the
+    ranking is well separated, at the default init the attention is almost uniform."""
+    meta, rec = next(c for c in CASES if c[0]["name"] == case)
+    k = 8
+    net = build_net(precision, wm=meta["wm"], cw=None if meta["cw"] is None else torch.tensor(meta["cw"]))
+    bag = torch.from_numpy(synth.make_bag(meta["n"], meta["side"], seed=meta.get("seed", 1))).cuda()
     with torch.no_grad():
-        out = net(bag.cuda(), torch.tensor([1]).cuda())
-    assert l2rel(out["Aterm"], ref["Aterm"]) < TOL_OUT[precision]
+        out = net(bag, torch.tensor([meta["Y"]]).cuda())
+    a_ref_all = torch.from_numpy(rec["out.Aterm"])
+    tol = gates(precision, meta, meta["n"])["named"]
+    assert G.relerr(out["Aterm"], a_ref_all) < tol
+    checked = 0
     for m in range(3):
-        a_ref = ref["Aterm"][m]
+        a_ref = a_ref_all[m]
         top_ref = torch.topk(a_ref, k + 1).values
-        if float(top_ref[k - 1] - top_ref[k]) < 4 * TOL_OUT[precision] * float(a_ref.max()):
-            continue  # k-th and (k+1)-th tile closer than the tolerance: ordering not decidable
+        if float(top_ref[k - 1] - top_ref[k]) < 2 * tol * float(a_ref.max()):
+            continue  # k-th and (k+1)-th tile closer than the tolerance: the set is not decidable
         got = set(torch.topk(out["Aterm"][m].cpu(), k).indices.tolist())
         assert got == set(torch.topk(a_ref, k).indices.tolist()), m
-    assert int(out["y_pred_hat"]) == int(ref["y_pred_hat"])
+        checked += 1
+    # the strongest tile of every map is always decidable in the peaked case
+    if min(meta["wm"]) < 0:
+        assert checked >= 1
+        for m in range(3):
+            assert int(out["Aterm"][m].argmax()) == int(a_ref_all[m].argmax())
+    assert int(out["y_pred_hat"]) == int(rec["out.y_pred_hat"])
 
 
 def test_single_tile_bag_raises_value_error_like_reference():
