@@ -1,6 +1,7 @@
 // extern "C" entry points of libmil_b200.so (declared in include/mil_b200.h).  Thin: argument checks,
 // plan construction, launch sequences.  Errors never cross the boundary as exceptions.
 #include <atomic>
+#include <algorithm>
 #include <cstdarg>
 #include <cstring>
 #include <exception>
@@ -258,10 +259,24 @@ int mil_from_pf8(int dtype, const void* pf8, float* nchw, int n, int c, int h, i
   MIL_API_END
 }
 
-size_t mil_conv_workspace_bytes(int n, int cin, int hi, int wi, int cout, int ho, int wo, int ks) {
+static size_t conv_ws_layout(int n, int cin, int hi, int wi, int cout, int ho, int wo, int ks, size_t* off_tc,
+                             size_t* off_partial) {
   const MilPF8 gi = mil_pf8(n, cin, hi, wi), go = mil_pf8(n, cout, ho, wo);
-  const size_t wp = (size_t)ks * ks * gi.cb * 8 * go.cb * 8 * sizeof(float);
-  return 2 * wp + mil_wgrad_direct_partial_floats(gi, go, ks) * sizeof(float) + 1024;
+  const size_t wp = ((size_t)ks * ks * gi.cb * 8 * go.cb * 8 * sizeof(float) + 255) / 256 * 256;
+  size_t tc = 0;
+  if (ks == 3 && cin >= 9) {
+    MilTcShape a, b;
+    if (mil_tc_shape(cin, cout, &a) == 0 && mil_tc_shape(cout, cin, &b) == 0)
+      tc = (std::max(mil_tc_wpack_bytes(a), mil_tc_wpack_bytes(b)) + 255) / 256 * 256;
+  }
+  *off_tc = wp;
+  *off_partial = wp + tc;
+  return wp + tc + mil_wgrad_direct_partial_floats(gi, go, ks) * sizeof(float) + 1024;
+}
+
+size_t mil_conv_workspace_bytes(int n, int cin, int hi, int wi, int cout, int ho, int wo, int ks) {
+  size_t a, b;
+  return conv_ws_layout(n, cin, hi, wi, cout, ho, wo, ks, &a, &b);
 }
 
 int mil_conv_pf8(int dtype, int impl, int transposed, const void* x, int n, int cx, int hx, int wx, const float* w,
@@ -274,14 +289,23 @@ int mil_conv_pf8(int dtype, int impl, int transposed, const void* x, int n, int 
               transposed ? cout : cin);
   const MilPF8 gx = mil_pf8(n, cx, hx, wx);
   const MilPF8 go = mil_pf8(n, transposed ? cin : cout, ho, wo);
-  const size_t wp_bytes = (size_t)ks * ks * ((cin + 7) / 8 * 8) * ((cout + 7) / 8 * 8) * sizeof(float);
-  MIL_REQUIRE(ws_bytes >= wp_bytes, "mil_conv_pf8: workspace too small");
+  size_t off_tc, off_partial;
+  const size_t need = transposed ? conv_ws_layout(n, cin, ho, wo, cout, hx, wx, ks, &off_tc, &off_partial)
+                                 : conv_ws_layout(n, cin, hx, wx, cout, ho, wo, ks, &off_tc, &off_partial);
+  MIL_REQUIRE(ws_bytes >= need, "mil_conv_pf8: workspace too small (%zu < %zu)", ws_bytes, need);
   cudaStream_t s = (cudaStream_t)stream;
   MIL_TRY(mil_launch_pack_conv_w(w, (float*)ws, cout, cin, ks, transposed, s));
-  if (impl == 1)
+  const bool tc_ok = mil_tc_supported(dtype, ks, stride, gx.c, go.c) && gx.h == go.h && gx.w == go.w;
+  MIL_REQUIRE(impl != 2 || tc_ok, "mil_conv_pf8: impl=2 (tcgen05) does not support dtype=%d ks=%d stride=%d", dtype, ks,
+              stride);
+  if (impl == 1 || !tc_ok || (impl == 0 && !mil_tc_enabled()))
     return mil_launch_conv_direct(dtype, transposed, x, gx, (const float*)ws, bias, res, act, out, go, ks, stride,
                                   epi, s);
-  return mil_conv_dispatch(dtype, transposed, x, gx, (const float*)ws, bias, res, act, out, go, ks, stride, epi, s);
+  MilTcShape sh;
+  MIL_TRY(mil_tc_shape(gx.c, go.c, &sh));
+  void* wtc = reinterpret_cast<char*>(ws) + off_tc;
+  MIL_TRY(mil_launch_pack_tc((const float*)ws, wtc, sh, s));
+  return mil_launch_conv_tc(transposed, x, gx, wtc, sh, bias, res, act, out, go, epi, s);
   MIL_API_END
 }
 
@@ -292,10 +316,12 @@ int mil_conv_wgrad_pf8(int dtype, int impl, const void* x, int n, int cin, int h
   MIL_TRY(require_device());
   MIL_REQUIRE(x && dz && dw && ws, "mil_conv_wgrad_pf8: null pointer argument");
   const MilPF8 gi = mil_pf8(n, cin, hi, wi), go = mil_pf8(n, cout, ho, wo);
-  MIL_REQUIRE(ws_bytes >= mil_wgrad_direct_partial_floats(gi, go, ks) * sizeof(float),
-              "mil_conv_wgrad_pf8: workspace too small");
+  size_t off_tc, off_partial;
+  const size_t need = conv_ws_layout(n, cin, hi, wi, cout, ho, wo, ks, &off_tc, &off_partial);
+  MIL_REQUIRE(ws_bytes >= need, "mil_conv_wgrad_pf8: workspace too small (%zu < %zu)", ws_bytes, need);
   (void)impl;
-  return mil_launch_wgrad_direct(dtype, x, gi, dz, go, (float*)ws, dw, db, ks, stride, (cudaStream_t)stream);
+  float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + off_partial);
+  return mil_launch_wgrad_direct(dtype, x, gi, dz, go, partial, dw, db, ks, stride, (cudaStream_t)stream);
   MIL_API_END
 }
 

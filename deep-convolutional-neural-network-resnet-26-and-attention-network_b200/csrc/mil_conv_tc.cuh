@@ -1,0 +1,23 @@
+// Host-side declarations of the tcgen05 implicit-GEMM convolution (mil_conv_tc.cu).
+#pragma once
+#include "mil_common.cuh"
+
+#define MIL_TC_MAX_MMA 46  // ceil(9 taps * 10 chunks / 2) + 1
+
+// K-loop description shared by the weight pre-pack and the kernel: MMA j multiplies K-groups order[2j], order[2j+1]
+struct MilTcShape {
+  int cbin, cbout;  // 8-channel chunks of the kernel's input / output
+  int npad;         // UMMA N (output channels padded to a multiple of 16)
+  int nmma;         // number of K=16 MMAs per tile
+  unsigned char g_tap[2 * MIL_TC_MAX_MMA];    // tap (0..8) of each K-group, 0xFF = zero padding group
+  unsigned char g_chunk[2 * MIL_TC_MAX_MMA];  // input chunk of each K-group
+};
+
+bool mil_tc_supported(int dtype, int ks, int stride, int cin, int cout);
+int mil_tc_shape(int cin, int cout, MilTcShape* out);  // cin/cout = the KERNEL's input/output channels
+size_t mil_tc_wpack_bytes(const MilTcShape& sh);
+// wp: fp32 packed weights [tap][kin_pad][nout_pad] (mil_launch_pack_conv_w, normal or transposed)
+int mil_launch_pack_tc(const float* wp, void* wtc, const MilTcShape& sh, cudaStream_t s);
+int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const void* wtc, const MilTcShape& sh,
+                       const float* bias, const void* res, const void* act, void* out, const MilPF8& go, int epi,
+                       cudaStream_t s);

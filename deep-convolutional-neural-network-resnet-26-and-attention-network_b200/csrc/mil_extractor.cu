@@ -80,7 +80,7 @@ int mil_make_plan(int n, int side, int dtype, MilPlan* plan) {
   pl.geo = mil_geom(side);
   for (int l = 0; l < 4; ++l) pl.g[l] = mil_pf8(n, kMilWidths[l], pl.geo.h[l], pl.geo.h[l]);
   pl.convs.clear();
-  size_t wofs = 0;
+  size_t wofs = 0, tcofs = 0;
   int inpl = 20;
   for (int l = 0; l < 4; ++l) {
     const int w = kMilWidths[l];
@@ -101,12 +101,22 @@ int mil_make_plan(int n, int side, int dtype, MilPlan* plan) {
         const size_t sz = (size_t)c.ks * c.ks * ((c.cin + 7) / 8 * 8) * ((c.cout + 7) / 8 * 8);
         c.wp_off = wofs; wofs += sz;
         c.wpt_off = wofs; wofs += sz;
+        c.tc = mil_tc_enabled() && mil_tc_supported(dtype, c.ks, c.stride, c.cin, c.cout);
+        c.wtc_off = c.wtct_off = 0;
+        if (c.tc) {
+          MilTcShape sf, sb;
+          MIL_TRY(mil_tc_shape(c.cin, c.cout, &sf));
+          MIL_TRY(mil_tc_shape(c.cout, c.cin, &sb));
+          c.wtc_off = tcofs; tcofs += align_up(mil_tc_wpack_bytes(sf), 256);
+          c.wtct_off = tcofs; tcofs += align_up(mil_tc_wpack_bytes(sb), 256);
+        }
         pl.convs.push_back(c);
       }
     }
     inpl = w;
   }
   pl.wpack_floats = wofs;
+  pl.wtc_bytes = tcofs;
 
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
@@ -122,6 +132,7 @@ int mil_make_plan(int n, int side, int dtype, MilPlan* plan) {
   for (int l = 0; l < 4; ++l) pl.grad_bytes = std::max(pl.grad_bytes, mil_pf8_bytes(pl.g[l], dtype));
   for (int i = 0; i < 3; ++i) pl.off_grad[i] = take(pl.grad_bytes);
   pl.off_wpack = take(pl.wpack_floats * sizeof(float));
+  pl.off_wtc = take(pl.wtc_bytes + 256);
   size_t pf = std::max(mil_stem_bwd_partial_floats(), mil_tail_bwd_partial_floats());
   for (const auto& c : pl.convs) {
     const MilPF8& go = pl.g[c.layer];
@@ -200,9 +211,22 @@ int mil_zero_guards(int dtype, void* buf, const MilPF8& g, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------------
 // conv dispatch
 // ---------------------------------------------------------------------------------------------------
-int mil_conv_dispatch(int dtype, int transposed, const void* x, const MilPF8& gi, const float* wp, const float* bias,
-                      const void* res, const void* act, void* out, const MilPF8& go, int ks, int stride, int epi,
-                      cudaStream_t s) {
+bool mil_tc_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MIL_B200_DISABLE_TC");
+    return !(e != nullptr && e[0] == '1');
+  }();
+  return on;
+}
+
+int mil_conv_dispatch(int dtype, int transposed, const void* x, const MilPF8& gi, const float* wp, const void* wtc,
+                      const float* bias, const void* res, const void* act, void* out, const MilPF8& go, int ks,
+                      int stride, int epi, cudaStream_t s) {
+  if (wtc != nullptr && mil_tc_supported(dtype, ks, stride, gi.c, go.c)) {
+    MilTcShape sh;
+    MIL_TRY(mil_tc_shape(gi.c, go.c, &sh));
+    return mil_launch_conv_tc(transposed, x, gi, wtc, sh, bias, res, act, out, go, epi, s);
+  }
   return mil_launch_conv_direct(dtype, transposed, x, gi, wp, bias, res, act, out, go, ks, stride, epi, s);
 }
 
@@ -224,6 +248,15 @@ static int pack_weights(const void* const* params, const MilPlan& pl, void* ws, 
   }
   pack_all_kernel<<<dim3(t.count, 8), 256, 0, s>>>(t);
   MIL_LAUNCH_OK();
+  char* tca = wsp(ws, pl.off_wtc);
+  for (const auto& c : pl.convs) {
+    if (!c.tc) continue;
+    MilTcShape sh;
+    // the kernel's input/output channels: (cin, cout) forward, (cout, cin) for the data gradient
+    MIL_TRY(mil_tc_shape(transposed ? c.cout : c.cin, transposed ? c.cin : c.cout, &sh));
+    MIL_TRY(mil_launch_pack_tc(area + (transposed ? c.wpt_off : c.wp_off), tca + (transposed ? c.wtct_off : c.wtc_off),
+                               sh, s));
+  }
   return 0;
 }
 
@@ -245,6 +278,9 @@ int mil_extractor_forward_impl(const void* const* params, const float* bag, cons
   }
   MIL_TRY(pack_weights(params, pl, ws, false, s));
   const float* wpack = reinterpret_cast<const float*>(wsp(ws, pl.off_wpack));
+  auto TCW = [&](const MilConvDesc& c, bool tr) -> const void* {
+    return c.tc ? wsp(ws, pl.off_wtc) + (tr ? c.wtct_off : c.wtc_off) : nullptr;
+  };
   const int p_c1w = mil_param_index("cnn.module.conv1.weight"), p_c1b = mil_param_index("cnn.module.conv1.bias");
   MIL_TRY(mil_launch_stem_fwd(dt, bag, idx, pl.n, pl.side, (const float*)params[p_c1w], (const float*)params[p_c1b],
                               wsp(ws, pl.off_pooled), pl.g[0], (uint8_t*)wsp(ws, pl.off_argmax), s));
@@ -258,17 +294,17 @@ int mil_extractor_forward_impl(const void* const* params, const float* bag, cons
       void* y = wsp(ws, pl.off_y[l * 3 + b]);
       const MilConvDesc& c1 = pl.convs[ci++];
       const MilConvDesc& c2 = pl.convs[ci++];
-      MIL_TRY(mil_conv_dispatch(dt, 0, X, gx, wpack + c1.wp_off, (const float*)params[c1.p_b], nullptr, nullptr, h,
+      MIL_TRY(mil_conv_dispatch(dt, 0, X, gx, wpack + c1.wp_off, TCW(c1, false), (const float*)params[c1.p_b], nullptr, nullptr, h,
                                 go, 3, c1.stride, MIL_EPI_FWD, s));
       const void* res = X;
       if (b == 0 && l > 0) {
         const MilConvDesc& cd = pl.convs[ci++];
         // projection shortcut (1x1 / stride 2, no bias) written into y, then consumed in place as the residual
-        MIL_TRY(mil_conv_dispatch(dt, 0, X, gx, wpack + cd.wp_off, nullptr, nullptr, nullptr, y, go, 1, 2,
+        MIL_TRY(mil_conv_dispatch(dt, 0, X, gx, wpack + cd.wp_off, TCW(cd, false), nullptr, nullptr, nullptr, y, go, 1, 2,
                                   MIL_EPI_PLAIN, s));
         res = y;
       }
-      MIL_TRY(mil_conv_dispatch(dt, 0, h, go, wpack + c2.wp_off, (const float*)params[c2.p_b], res, nullptr, y, go,
+      MIL_TRY(mil_conv_dispatch(dt, 0, h, go, wpack + c2.wp_off, TCW(c2, false), (const float*)params[c2.p_b], res, nullptr, y, go,
                                 3, 1, MIL_EPI_FWD, s));
       X = y;
       gx = go;
@@ -293,6 +329,9 @@ int mil_extractor_backward_impl(const void* const* params, const float* bag, con
   const auto& pt = mil_param_table();
   MIL_TRY(pack_weights(params, pl, ws, true, s));
   const float* wpack = reinterpret_cast<const float*>(wsp(ws, pl.off_wpack));
+  auto TCW = [&](const MilConvDesc& c, bool tr) -> const void* {
+    return c.tc ? wsp(ws, pl.off_wtc) + (tr ? c.wtct_off : c.wtc_off) : nullptr;
+  };
   float* partial = reinterpret_cast<float*>(wsp(ws, pl.off_partial));
   void* gb[3] = {wsp(ws, pl.off_grad[0]), wsp(ws, pl.off_grad[1]), wsp(ws, pl.off_grad[2])};
   auto gptr = [&](int p) { return grads + pt[p].offset; };
@@ -331,7 +370,7 @@ int mil_extractor_backward_impl(const void* const* params, const float* bag, con
       const MilConvDesc& c2 = pl.convs[cb + 1];
       // conv2: weight gradient, then data gradient through conv2 and the first LeakyReLU
       MIL_TRY(mil_launch_wgrad_direct(dt, h, go, dz, go, partial, gptr(c2.p_w), gptr(c2.p_b), 3, 1, s));
-      MIL_TRY(mil_conv_dispatch(dt, 1, dz, go, wpack + c2.wpt_off, nullptr, nullptr, h, dpre, go, 3, 1,
+      MIL_TRY(mil_conv_dispatch(dt, 1, dz, go, wpack + c2.wpt_off, TCW(c2, true), nullptr, nullptr, h, dpre, go, 3, 1,
                                 MIL_EPI_DGRAD, s));
       // which 1: gradient w.r.t. the pre-activation of this block's first conv (geometry go)
       if (g_dump.dst != nullptr && g_dump.layer == l && g_dump.block == b && g_dump.which == 1)
@@ -349,9 +388,9 @@ int mil_extractor_backward_impl(const void* const* params, const float* bag, con
           guard_add(t, dnew, gi);
           MIL_TRY(launch_guards(t, s));
         }
-        MIL_TRY(mil_conv_dispatch(dt, 1, dz, go, wpack + cd.wpt_off, nullptr, nullptr, nullptr, dnew, gi, 1, 2,
+        MIL_TRY(mil_conv_dispatch(dt, 1, dz, go, wpack + cd.wpt_off, TCW(cd, true), nullptr, nullptr, nullptr, dnew, gi, 1, 2,
                                   MIL_EPI_PLAIN, s));
-        MIL_TRY(mil_conv_dispatch(dt, 1, dpre, go, wpack + c1.wpt_off, nullptr, dnew, xin, dnew, gi, 3, 2,
+        MIL_TRY(mil_conv_dispatch(dt, 1, dpre, go, wpack + c1.wpt_off, TCW(c1, true), nullptr, dnew, xin, dnew, gi, 3, 2,
                                   MIL_EPI_DGRAD, s));
         // dz / dpre will next be written with the geometry of layer l-1
         {
@@ -364,7 +403,7 @@ int mil_extractor_backward_impl(const void* const* params, const float* bag, con
         }
 
       } else {
-        MIL_TRY(mil_conv_dispatch(dt, 1, dpre, go, wpack + c1.wpt_off, nullptr, dz, xin, dnew, gi, 3, 1,
+        MIL_TRY(mil_conv_dispatch(dt, 1, dpre, go, wpack + c1.wpt_off, TCW(c1, true), nullptr, dz, xin, dnew, gi, 3, 1,
                                   MIL_EPI_DGRAD, s));
       }
       // which 0: gradient w.r.t. the pre-activation feeding this block's input (geometry gi)

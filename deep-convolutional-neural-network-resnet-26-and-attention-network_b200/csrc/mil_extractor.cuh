@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "mil_common.cuh"
+#include "mil_conv_tc.cuh"
 
 struct MilParamInfo {
   std::string name;
@@ -24,6 +25,8 @@ struct MilConvDesc {
   int cin, cout, ks, stride;
   int p_w, p_b;       // parameter indices (p_b = -1: no bias)
   size_t wp_off, wpt_off;  // float offsets of the packed normal / transposed weights inside the pack area
+  bool tc;                 // forward and data gradient run on the tcgen05 kernel (bf16 mode, 3x3 stride 1)
+  size_t wtc_off, wtct_off;  // byte offsets of the bf16 UMMA-layout weights (normal / transposed) in the tc area
 };
 
 struct MilPlan {
@@ -31,8 +34,8 @@ struct MilPlan {
   MilGeom geo;
   MilPF8 g[4];                  // activation geometry of layer1..4
   std::vector<MilConvDesc> convs;  // 27 entries, forward order
-  size_t off_pooled, off_argmax, off_h[12], off_y[12], off_avg, off_grad[3], off_wpack, off_partial;
-  size_t wpack_floats, partial_floats, grad_bytes;
+  size_t off_pooled, off_argmax, off_h[12], off_y[12], off_avg, off_grad[3], off_wpack, off_wtc, off_partial;
+  size_t wpack_floats, wtc_bytes, partial_floats, grad_bytes;
   size_t total_bytes;
 };
 int mil_make_plan(int n, int side, int dtype, MilPlan* plan);
@@ -45,7 +48,10 @@ int mil_extractor_backward_impl(const void* const* params, const float* bag, con
 void mil_debug_request_dump(int layer, int block, int which, float* dst);
 
 // conv dispatch: tcgen05 implicit GEMM where supported (bf16), CUDA-core direct kernel otherwise
-int mil_conv_dispatch(int dtype, int transposed, const void* x, const MilPF8& gi, const float* wp, const float* bias,
+// wtc: bf16 UMMA-layout weights (mil_launch_pack_tc) or NULL -> CUDA-core kernel
+int mil_conv_dispatch(int dtype, int transposed, const void* x, const MilPF8& gi, const float* wp, const void* wtc,
+                      const float* bias,
                       const void* res, const void* act, void* out, const MilPF8& go, int ks, int stride, int epi,
                       cudaStream_t s);
+bool mil_tc_enabled();  // false when MIL_B200_DISABLE_TC=1 (debugging aid: CUDA-core kernels only)
 int mil_zero_guards(int dtype, void* buf, const MilPF8& g, cudaStream_t s);

@@ -86,7 +86,10 @@ CONV_CASES = [  # cin, cout, ks, stride, H, n
 def conv_ops(dtype, impl=0):
     tol = 1e-5 if dtype == "fp32" else 1.2e-2
     gen = torch.Generator(device="cuda").manual_seed(5)
-    for (cin, cout, ks, stride, H, n) in CONV_CASES:
+    for (cin, cout, ks, stride, H, n) in CONV_CASES + ([(40, 40, 3, 1, 28, 9), (60, 60, 3, 1, 14, 40), (80, 80, 3, 1, 7, 64),
+                                                       (20, 20, 3, 1, 75, 2)] if impl == 2 else []):
+        if impl == 2 and not (ks == 3 and stride == 1):
+            continue
         pad = ks // 2
         x = q(torch.randn(n, cin, H, H, device="cuda", generator=gen), dtype)
         w = torch.randn(cout, cin, ks, ks, device="cuda", generator=gen) * (1.0 / (cin * ks * ks) ** 0.5)
