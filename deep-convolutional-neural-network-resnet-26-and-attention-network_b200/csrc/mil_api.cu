@@ -271,7 +271,9 @@ static size_t conv_ws_layout(int n, int cin, int hi, int wi, int cout, int ho, i
   }
   *off_tc = wp;
   *off_partial = wp + tc;
-  return wp + tc + mil_wgrad_direct_partial_floats(gi, go, ks) * sizeof(float) + 1024;
+  size_t pf = mil_wgrad_direct_partial_floats(gi, go, ks);
+  if (hi == ho && wi == wo) pf = std::max(pf, mil_wgrad_tc_partial_floats(gi, go, ks));
+  return wp + tc + pf * sizeof(float) + 1024;
 }
 
 size_t mil_conv_workspace_bytes(int n, int cin, int hi, int wi, int cout, int ho, int wo, int ks) {
@@ -319,9 +321,13 @@ int mil_conv_wgrad_pf8(int dtype, int impl, const void* x, int n, int cin, int h
   size_t off_tc, off_partial;
   const size_t need = conv_ws_layout(n, cin, hi, wi, cout, ho, wo, ks, &off_tc, &off_partial);
   MIL_REQUIRE(ws_bytes >= need, "mil_conv_wgrad_pf8: workspace too small (%zu < %zu)", ws_bytes, need);
-  (void)impl;
   float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + off_partial);
-  return mil_launch_wgrad_direct(dtype, x, gi, dz, go, partial, dw, db, ks, stride, (cudaStream_t)stream);
+  const bool tc_ok = mil_wgrad_tc_supported(dtype, ks, stride, cin, cout);
+  MIL_REQUIRE(impl != 2 || tc_ok, "mil_conv_wgrad_pf8: impl=2 (tcgen05) does not support dtype=%d ks=%d stride=%d",
+              dtype, ks, stride);
+  if (impl == 1 || !tc_ok || (impl == 0 && !mil_tc_enabled()))
+    return mil_launch_wgrad_direct(dtype, x, gi, dz, go, partial, dw, db, ks, stride, (cudaStream_t)stream);
+  return mil_launch_wgrad_tc(x, gi, dz, go, partial, dw, db, ks, (cudaStream_t)stream);
   MIL_API_END
 }
 

@@ -21,3 +21,9 @@ int mil_launch_pack_tc(const float* wp, void* wtc, const MilTcShape& sh, cudaStr
 int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const void* wtc, const MilTcShape& sh,
                        const float* bias, const void* res, const void* act, void* out, const MilPF8& go, int epi,
                        cudaStream_t s);
+
+// tcgen05 weight gradient (mil_wgrad_tc.cu): 3x3 / 1x1, stride 1, bf16
+bool mil_wgrad_tc_supported(int dtype, int ks, int stride, int cin, int cout);
+size_t mil_wgrad_tc_partial_floats(const MilPF8& gx, const MilPF8& gz, int ks);
+int mil_launch_wgrad_tc(const void* x, const MilPF8& gx, const void* dz, const MilPF8& gz, float* partial, float* dw,
+                        float* db, int ks, cudaStream_t s);

@@ -138,6 +138,8 @@ int mil_make_plan(int n, int side, int dtype, MilPlan* plan) {
     const MilPF8& go = pl.g[c.layer];
     const MilPF8 gi = (c.stride == 2) ? pl.g[c.layer - 1] : mil_pf8(n, c.cin, go.h, go.w);
     pf = std::max(pf, mil_wgrad_direct_partial_floats(gi, go, c.ks));
+    if (mil_wgrad_tc_supported(dtype, c.ks, c.stride, c.cin, c.cout))
+      pf = std::max(pf, mil_wgrad_tc_partial_floats(gi, go, c.ks));
   }
   pl.partial_floats = pf;
   pl.off_partial = take(pf * sizeof(float));
@@ -211,6 +213,13 @@ int mil_zero_guards(int dtype, void* buf, const MilPF8& g, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------------
 // conv dispatch
 // ---------------------------------------------------------------------------------------------------
+int mil_wgrad_dispatch(int dtype, const void* x, const MilPF8& gi, const void* dz, const MilPF8& go, float* partial,
+                       float* dw, float* db, int ks, int stride, cudaStream_t s) {
+  if (mil_tc_enabled() && mil_wgrad_tc_supported(dtype, ks, stride, gi.c, go.c))
+    return mil_launch_wgrad_tc(x, gi, dz, go, partial, dw, db, ks, s);
+  return mil_launch_wgrad_direct(dtype, x, gi, dz, go, partial, dw, db, ks, stride, s);
+}
+
 bool mil_tc_enabled() {
   static const bool on = [] {
     const char* e = getenv("MIL_B200_DISABLE_TC");
@@ -369,17 +378,17 @@ int mil_extractor_backward_impl(const void* const* params, const float* bag, con
       const MilConvDesc& c1 = pl.convs[cb];
       const MilConvDesc& c2 = pl.convs[cb + 1];
       // conv2: weight gradient, then data gradient through conv2 and the first LeakyReLU
-      MIL_TRY(mil_launch_wgrad_direct(dt, h, go, dz, go, partial, gptr(c2.p_w), gptr(c2.p_b), 3, 1, s));
+      MIL_TRY(mil_wgrad_dispatch(dt, h, go, dz, go, partial, gptr(c2.p_w), gptr(c2.p_b), 3, 1, s));
       MIL_TRY(mil_conv_dispatch(dt, 1, dz, go, wpack + c2.wpt_off, TCW(c2, true), nullptr, nullptr, h, dpre, go, 3, 1,
                                 MIL_EPI_DGRAD, s));
       // which 1: gradient w.r.t. the pre-activation of this block's first conv (geometry go)
       if (g_dump.dst != nullptr && g_dump.layer == l && g_dump.block == b && g_dump.which == 1)
         MIL_TRY(mil_launch_from_pf8(dt, dpre, g_dump.dst, go.n, go.c, go.h, go.w, s));
       // conv1: weight gradient
-      MIL_TRY(mil_launch_wgrad_direct(dt, xin, gi, dpre, go, partial, gptr(c1.p_w), gptr(c1.p_b), 3, c1.stride, s));
+      MIL_TRY(mil_wgrad_dispatch(dt, xin, gi, dpre, go, partial, gptr(c1.p_w), gptr(c1.p_b), 3, c1.stride, s));
       if (down) {
         const MilConvDesc& cd = pl.convs[cb + 2];
-        MIL_TRY(mil_launch_wgrad_direct(dt, xin, gi, dz, go, partial, gptr(cd.p_w), nullptr, 1, 2, s));
+        MIL_TRY(mil_wgrad_dispatch(dt, xin, gi, dz, go, partial, gptr(cd.p_w), nullptr, 1, 2, s));
         // the gradient buffers change geometry here: re-zero their guards for the larger map
         {
           GuardTable t;

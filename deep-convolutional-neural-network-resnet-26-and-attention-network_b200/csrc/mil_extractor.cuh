@@ -53,5 +53,7 @@ int mil_conv_dispatch(int dtype, int transposed, const void* x, const MilPF8& gi
                       const float* bias,
                       const void* res, const void* act, void* out, const MilPF8& go, int ks, int stride, int epi,
                       cudaStream_t s);
+int mil_wgrad_dispatch(int dtype, const void* x, const MilPF8& gi, const void* dz, const MilPF8& go, float* partial,
+                       float* dw, float* db, int ks, int stride, cudaStream_t s);
 bool mil_tc_enabled();  // false when MIL_B200_DISABLE_TC=1 (debugging aid: CUDA-core kernels only)
 int mil_zero_guards(int dtype, void* buf, const MilPF8& g, cudaStream_t s);

@@ -1,0 +1,204 @@
+// tcgen05 weight gradient of the 3x3 / 1x1 stride-1 convolutions on the PF8 layout (bf16 operands, fp32
+// accumulation in TMEM), with the bias gradient as one extra accumulator column block.
+// Reference semantics: autograd of nnBlocks.py:178-181 (gbm/classify_combined.py:447).
+//
+//   dW[t][ci][co] = sum over flat pixels q of  x[q + shift_t][ci] * dz[q][co]         db[co] = sum_q dz[q][co]
+//
+// GEMM view per tap t:  D_t[co][ci] += A[co][k] * B_t[ci][k],  k = flat pixel.  Both operands are used exactly
+// as PF8 stores them -- [pixel][8 channels], i.e. "MN-major" core matrices of 8 pixels x 16 B -- so a 128-pixel
+// K-tile needs one bulk-TMA copy per channel chunk and NO transposition: A = the dz planes, B_t = the x planes
+// read from the start address (halo + shift_t) pixels into the span, like the forward kernel does.
+// The nine D_t (and the bias block, B = a constant all-ones block) stay in TMEM for the whole kernel: every CTA
+// accumulates its share of the pixel tiles (split-K over CTAs), then writes ONE partial record; the fixed-order
+// reduction mil_launch_reduce_conv_w sums the records -> deterministic.  TMEM holds 512 columns, so layers
+// with 9 * Cin_pad > 496 split the taps over two CTA groups (blockIdx.y).
+#include <algorithm>
+
+#include "mil_common.cuh"
+#include "mil_conv_tc.cuh"
+#include "mil_tc_ptx.cuh"
+
+#define WG_TK 128
+#define WG_STAGES 3
+#define WG_THREADS 192  // warp 0 producer, warp 1 MMA issuer, warps 2..5 epilogue
+#define WG_A_PLANE (WG_TK * 16)
+#define WG_SLACK (40 * 1024)
+
+struct WgSmemHeader {
+  uint64_t full[WG_STAGES], empty[WG_STAGES], done;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat16* __restrict__ dz, MilPF8 gz,
+                float* __restrict__ partial, long long rec_stride, int ks, int taps_per_group, int npad) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  WgSmemHeader* hd = reinterpret_cast<WgSmemHeader*>(smem);
+  unsigned char* ones = smem + 128;            // 512 B of bf16 1.0: the B operand of the bias-gradient MMA
+  unsigned char* stage0 = smem + 128 + 512;
+  const int ntaps = ks * ks;
+  const int halo = ks == 3 ? gx.wp + 1 : 0;
+  const int span = WG_TK + 2 * halo;
+  const uint32_t b_plane = (uint32_t)span * 16;
+  const uint32_t a_bytes = (uint32_t)gz.cb * WG_A_PLANE;
+  const uint32_t stage_bytes = a_bytes + (uint32_t)gx.cb * b_plane;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tap_lo = blockIdx.y * taps_per_group;
+  const int tap_hi = min(ntaps, tap_lo + taps_per_group);
+  const int ntl = tap_hi - tap_lo;
+  const bool with_bias = (blockIdx.y == gridDim.y - 1);
+  const long long n_tiles = mil_cdiv(gz.Q, WG_TK);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&hd->full[s], 1); mbar_init(&hd->empty[s], 1); }
+    mbar_init(&hd->done, 1);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 128; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;  // two bf16 1.0
+  fence_proxy_async();
+  if (warp == 1) tmem_alloc(&hd->tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = hd->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        mbar_wait(&hd->empty[stage], phase ^ 1);
+        mbar_expect_tx(&hd->full[stage], stage_bytes);
+        const long long q0 = t * WG_TK;
+        unsigned char* dst = stage0 + (size_t)stage * stage_bytes;
+        for (int c = 0; c < gz.cb; ++c)
+          bulk_g2s(dst + (size_t)c * WG_A_PLANE, dz + mil_pf8_off(gz, c, q0), WG_A_PLANE, &hd->full[stage]);
+        for (int c = 0; c < gx.cb; ++c)
+          bulk_g2s(dst + a_bytes + (size_t)c * b_plane, x + mil_pf8_off(gx, c, q0 - halo), b_plane, &hd->full[stage]);
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // D = f32, A = B = bf16, both MN-major (bits 15, 16), M = 128
+      const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t idesc = idesc_base | ((uint32_t)(npad >> 3) << 17);
+      const uint32_t idesc_b = idesc_base | ((uint32_t)(16 >> 3) << 17);
+      const uint64_t ones_desc = make_desc(smem_u32(ones), 128, 256);
+      int stage = 0;
+      uint32_t phase = 0;
+      bool first = true;
+      for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        mbar_wait(&hd->full[stage], phase);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(stage0 + (size_t)stage * stage_bytes);
+        const uint32_t b_base = a_base + a_bytes;
+        for (int tl = 0; tl < ntl; ++tl) {
+          const int tap = tap_lo + tl;
+          const int s = ks == 3 ? ((tap / 3 - 1) * gx.wp + (tap % 3 - 1)) : 0;
+          const uint32_t b_tap = b_base + (uint32_t)(halo + s) * 16;
+#pragma unroll
+          for (int kk = 0; kk < WG_TK / 16; ++kk) {
+            const uint64_t ad = make_desc(a_base + kk * 256, 128, WG_A_PLANE);
+            const uint64_t bd = make_desc(b_tap + kk * 256, 128, b_plane);
+            umma_bf16(tmem_base + tl * npad, ad, bd, idesc, !(first && kk == 0));
+          }
+        }
+        if (with_bias) {
+#pragma unroll
+          for (int kk = 0; kk < WG_TK / 16; ++kk) {
+            const uint64_t ad = make_desc(a_base + kk * 256, 128, WG_A_PLANE);
+            umma_bf16(tmem_base + ntl * npad, ad, ones_desc, idesc_b, !(first && kk == 0));
+          }
+        }
+        umma_commit(&hd->empty[stage]);
+        first = false;
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&hd->done);
+    }
+  } else {
+    // epilogue: TMEM lane = output channel co, columns = (local tap, ci)
+    const int quarter = warp & 3;
+    const int co = quarter * 32 + lane;
+    const int coutp = gz.cb * 8, cinp = gx.cb * 8;
+    mbar_wait(&hd->done, 0);
+    tc_fence_after();
+    if (quarter * 32 < coutp) {  // warp-uniform
+      float* rec = partial + (size_t)blockIdx.x * rec_stride;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      for (int tl = 0; tl < ntl; ++tl) {
+        for (int c = 0; c < gx.cb; ++c) {
+          float v[8];
+          tmem_ld8(taddr + tl * npad + c * 8, v);
+          tmem_ld_wait();
+          if (co < coutp) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rec[((size_t)(tap_lo + tl) * cinp + c * 8 + j) * coutp + co] = v[j];
+          }
+        }
+      }
+      if (with_bias) {
+        float v[8];
+        tmem_ld8(taddr + ntl * npad, v);
+        tmem_ld_wait();
+        if (co < coutp) rec[(size_t)ntaps * cinp * coutp + co] = v[0];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+static int wg_sm_count() {
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      n_sm = 148;
+  }
+  return n_sm;
+}
+
+static void wg_config(const MilPF8& gx, const MilPF8& gz, int ks, int* npad, int* groups, int* tpg, int* ctas) {
+  *npad = (gx.c + 15) / 16 * 16;
+  const int ntaps = ks * ks;
+  *groups = (ntaps * *npad + 16 <= 512) ? 1 : 2;
+  *tpg = (ntaps + *groups - 1) / *groups;
+  const long long n_tiles = mil_cdiv(gz.Q, WG_TK);
+  *ctas = (int)std::max<long long>(1, std::min<long long>(n_tiles, wg_sm_count() / *groups));
+}
+
+bool mil_wgrad_tc_supported(int dtype, int ks, int stride, int cin, int cout) {
+  return dtype == MIL_BF16 && (ks == 3 || ks == 1) && stride == 1 && cin <= 80 && cout <= 80;
+}
+
+size_t mil_wgrad_tc_partial_floats(const MilPF8& gx, const MilPF8& gz, int ks) {
+  int npad, groups, tpg, ctas;
+  wg_config(gx, gz, ks, &npad, &groups, &tpg, &ctas);
+  return (size_t)ctas * ((size_t)ks * ks * gx.cb * 8 * gz.cb * 8 + gz.cb * 8);
+}
+
+int mil_launch_wgrad_tc(const void* x, const MilPF8& gx, const void* dz, const MilPF8& gz, float* partial, float* dw,
+                        float* db, int ks, cudaStream_t s) {
+  MIL_REQUIRE(gx.n == gz.n && gx.h == gz.h && gx.w == gz.w, "wgrad_tc: geometry mismatch");
+  int npad, groups, tpg, ctas;
+  wg_config(gx, gz, ks, &npad, &groups, &tpg, &ctas);
+  const int halo = ks == 3 ? gx.wp + 1 : 0;
+  const size_t stage = (size_t)gz.cb * WG_A_PLANE + (size_t)gx.cb * (WG_TK + 2 * halo) * 16;
+  const size_t smem = 128 + 512 + WG_STAGES * stage + WG_SLACK;
+  MIL_REQUIRE(smem <= 227 * 1024, "wgrad_tc: tile width %d needs %zu bytes of shared memory", gx.w, smem);
+  MIL_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long rec = (long long)ks * ks * gx.cb * 8 * gz.cb * 8 + gz.cb * 8;
+  wgrad_tc_kernel<<<dim3(ctas, groups), WG_THREADS, smem, s>>>((const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)dz,
+                                                             gz, partial, rec, ks, tpg, npad);
+  MIL_LAUNCH_OK();
+  return mil_launch_reduce_conv_w(partial, ctas, rec, dw, db, gz.c, gx.c, ks, s);
+}
