@@ -48,6 +48,7 @@ PROTOTYPES = {
     "mil_pf8_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "mil_to_pf8": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mil_from_pf8": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mil_upsample2_pf8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "mil_conv_workspace_bytes": (c_size_t, [c_int] * 8),
     "mil_conv_pf8": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
                              c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,

@@ -264,9 +264,9 @@ static size_t conv_ws_layout(int n, int cin, int hi, int wi, int cout, int ho, i
   const MilPF8 gi = mil_pf8(n, cin, hi, wi), go = mil_pf8(n, cout, ho, wo);
   const size_t wp = ((size_t)ks * ks * gi.cb * 8 * go.cb * 8 * sizeof(float) + 255) / 256 * 256;
   size_t tc = 0;
-  if (ks == 3 && cin >= 9) {
+  if (cin >= 9 && cout >= 9) {
     MilTcShape a, b;
-    if (mil_tc_shape(cin, cout, &a) == 0 && mil_tc_shape(cout, cin, &b) == 0)
+    if (mil_tc_shape(cin, cout, ks, &a) == 0 && mil_tc_shape(cout, cin, ks, &b) == 0)
       tc = (std::max(mil_tc_wpack_bytes(a), mil_tc_wpack_bytes(b)) + 255) / 256 * 256;
   }
   *off_tc = wp;
@@ -274,6 +274,14 @@ static size_t conv_ws_layout(int n, int cin, int hi, int wi, int cout, int ho, i
   size_t pf = mil_wgrad_direct_partial_floats(gi, go, ks);
   if (hi == ho && wi == wo) pf = std::max(pf, mil_wgrad_tc_partial_floats(gi, go, ks));
   return wp + tc + pf * sizeof(float) + 1024;
+}
+
+int mil_upsample2_pf8(const void* in, int n, int c, int h, int w, void* out, int ho, int wo, void* stream) {
+  MIL_API_BEGIN
+  MIL_TRY(require_device());
+  MIL_REQUIRE(in && out, "mil_upsample2_pf8: null pointer argument");
+  return mil_launch_upsample2(in, mil_pf8(n, c, h, w), out, mil_pf8(n, c, ho, wo), (cudaStream_t)stream);
+  MIL_API_END
 }
 
 size_t mil_conv_workspace_bytes(int n, int cin, int hi, int wi, int cout, int ho, int wo, int ks) {
@@ -297,17 +305,17 @@ int mil_conv_pf8(int dtype, int impl, int transposed, const void* x, int n, int 
   MIL_REQUIRE(ws_bytes >= need, "mil_conv_pf8: workspace too small (%zu < %zu)", ws_bytes, need);
   cudaStream_t s = (cudaStream_t)stream;
   MIL_TRY(mil_launch_pack_conv_w(w, (float*)ws, cout, cin, ks, transposed, s));
-  const bool tc_ok = mil_tc_supported(dtype, ks, stride, gx.c, go.c) && gx.h == go.h && gx.w == go.w;
+  const bool tc_ok = mil_tc_supported(dtype, ks, stride, gx.c, go.c) && !(stride == 2 && transposed);
   MIL_REQUIRE(impl != 2 || tc_ok, "mil_conv_pf8: impl=2 (tcgen05) does not support dtype=%d ks=%d stride=%d", dtype, ks,
               stride);
   if (impl == 1 || !tc_ok || (impl == 0 && !mil_tc_enabled()))
     return mil_launch_conv_direct(dtype, transposed, x, gx, (const float*)ws, bias, res, act, out, go, ks, stride,
                                   epi, s);
   MilTcShape sh;
-  MIL_TRY(mil_tc_shape(gx.c, go.c, &sh));
+  MIL_TRY(mil_tc_shape(gx.c, go.c, ks, &sh));
   void* wtc = reinterpret_cast<char*>(ws) + off_tc;
   MIL_TRY(mil_launch_pack_tc((const float*)ws, wtc, sh, s));
-  return mil_launch_conv_tc(transposed, x, gx, wtc, sh, bias, res, act, out, go, epi, s);
+  return mil_launch_conv_tc(transposed, x, gx, wtc, sh, bias, res, act, out, go, epi, stride == 2, s);
   MIL_API_END
 }
 

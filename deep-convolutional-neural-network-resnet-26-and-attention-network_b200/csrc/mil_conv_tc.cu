@@ -55,19 +55,19 @@ struct TcSmemHeader {
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat16* __restrict__ wtc,
                const float* __restrict__ bias, const __nv_bfloat16* res, const __nv_bfloat16* __restrict__ act,
-               __nv_bfloat16* out, MilPF8 go, MilTcShape sh, int epi, int transposed) {
+               __nv_bfloat16* out, MilPF8 go, MilTcShape sh, int epi, int transposed, int sub) {
   extern __shared__ __align__(128) unsigned char smem[];
   TcSmemHeader* hd = reinterpret_cast<TcSmemHeader*>(smem);
   const uint32_t hdr_bytes = (uint32_t)((sizeof(TcSmemHeader) + 127) / 128 * 128);
   unsigned char* bsm = smem + hdr_bytes;                      // B operand blocks
   const uint32_t b_bytes = (uint32_t)sh.nmma * 2 * sh.npad * 16;
-  const int halo = gx.wp + 1;
+  const int halo = sh.ks == 3 ? gx.wp + 1 : 0;
   const int span = TC_M + 2 * halo;
   const uint32_t plane = (uint32_t)span * 16;                 // one channel-chunk plane of a stage
   const uint32_t stage_bytes = plane * (sh.cbin + 1);         // + one all-zero plane (odd K-group count)
   unsigned char* asm0 = bsm + ((b_bytes + 127) / 128 * 128);  // A stages
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long n_tiles = mil_cdiv(go.Q, TC_M);
+  const long long n_tiles = mil_cdiv(gx.Q, TC_M);  // tiles run over the INPUT resolution (== output unless sub)
   const uint32_t acc_stride = (uint32_t)((sh.npad + 31) / 32 * 32);
   uint32_t tmem_cols = 32;
   while (tmem_cols < acc_stride * TC_ACC) tmem_cols <<= 1;
@@ -88,7 +88,8 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
         off[h] = -1;
       } else {
         const int dy = tap / 3, dx = tap % 3;
-        const int s = transposed ? ((1 - dy) * gx.wp + (1 - dx)) : ((dy - 1) * gx.wp + (dx - 1));
+        int s = transposed ? ((1 - dy) * gx.wp + (1 - dx)) : ((dy - 1) * gx.wp + (dx - 1));
+        if (sh.ks == 1) s = 0;
         off[h] = chunk * (int)plane + (halo + s) * 16;
       }
     }
@@ -164,13 +165,24 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
     long long it = 0;
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       if ((it & 1) != eg) continue;
+      // this thread's pixel: flat index q at the input resolution; qo = where it is stored.  sub: the stride-2
+      // convolutions are evaluated at full resolution and only the even (y, x) positions are kept.
       const long long q = t * TC_M + row;
-      const bool in_range = q < go.Q;
+      long long qo = q;
+      bool in_range = q < gx.Q;
       bool is_pad = true;
       if (in_range) {
-        const int r = (int)(q % go.P);
-        const int y = r / go.wp, xo = r - y * go.wp;
-        is_pad = (y == go.h) || (xo == go.w);
+        const int n = (int)(q / gx.P);
+        const int r = (int)(q - (long long)n * gx.P);
+        const int y = r / gx.wp, xo = r - y * gx.wp;
+        if (!sub) {
+          is_pad = (y == gx.h) || (xo == gx.w);
+        } else {
+          const int yh = y >> 1, xh = xo >> 1;
+          in_range = !(y & 1) && !(xo & 1) && yh <= go.h && xh <= go.w;
+          is_pad = (yh == go.h) || (xh == go.w);
+          qo = (long long)n * go.P + (long long)yh * go.wp + xh;
+        }
       }
       mbar_wait(&hd->acc_full[eg], acc_phase);
       tc_fence_after();
@@ -180,7 +192,7 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
         tmem_ld8(taddr + c * 8, v);
         tmem_ld_wait();
         if (in_range) {
-          const long long o = mil_pf8_off(go, c, q);
+          const long long o = mil_pf8_off(go, c, qo);
           if (is_pad) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = 0.f;
@@ -224,16 +236,20 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------
+// stride 2 is supported for the FORWARD direction only (full-resolution evaluation + subsampled store); the
+// stride-2 data gradient is the stride-1 data gradient of the zero-stuffed output gradient (mil_launch_upsample2)
 bool mil_tc_supported(int dtype, int ks, int stride, int cin, int cout) {
-  return dtype == MIL_BF16 && ks == 3 && stride == 1 && cin <= 80 && cout <= 80;
+  return dtype == MIL_BF16 && (ks == 3 || ks == 1) && (stride == 1 || stride == 2) && cin >= 9 && cin <= 80 &&
+         cout <= 80;
 }
 
-int mil_tc_shape(int cin, int cout, MilTcShape* out) {
+int mil_tc_shape(int cin, int cout, int ks, MilTcShape* out) {
   MilTcShape& sh = *out;
+  sh.ks = ks;
   sh.cbin = (cin + 7) / 8;
   sh.cbout = (cout + 7) / 8;
   sh.npad = (cout + 15) / 16 * 16;
-  const int ng = 9 * sh.cbin;
+  const int ng = ks * ks * sh.cbin;
   sh.nmma = (ng + 1) / 2;
   MIL_REQUIRE(sh.nmma <= MIL_TC_MAX_MMA, "conv_tc: too many K groups (%d)", ng);
   for (int g = 0; g < 2 * sh.nmma; ++g) {
@@ -264,14 +280,18 @@ int mil_launch_pack_tc(const float* wp, void* wtc, const MilTcShape& sh, cudaStr
 static size_t tc_smem_bytes(const MilPF8& gx, const MilTcShape& sh) {
   const size_t hdr = (sizeof(TcSmemHeader) + 127) / 128 * 128;
   const size_t b = ((size_t)sh.nmma * 2 * sh.npad * 16 + 127) / 128 * 128;
-  const size_t span = TC_M + 2 * (gx.wp + 1);
+  const size_t span = TC_M + 2 * (sh.ks == 3 ? gx.wp + 1 : 0);
   return hdr + b + (size_t)TC_STAGES * span * 16 * (sh.cbin + 1);
 }
 
 int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const void* wtc, const MilTcShape& sh,
                        const float* bias, const void* res, const void* act, void* out, const MilPF8& go, int epi,
-                       cudaStream_t s) {
-  MIL_REQUIRE(gx.n == go.n && gx.h == go.h && gx.w == go.w, "conv_tc: geometry mismatch");
+                       int sub, cudaStream_t s) {
+  if (sub)
+    MIL_REQUIRE(gx.n == go.n && go.h == (gx.h - 1) / 2 + 1 && go.w == (gx.w - 1) / 2 + 1 && !transposed,
+                "conv_tc: stride-2 geometry mismatch");
+  else
+    MIL_REQUIRE(gx.n == go.n && gx.h == go.h && gx.w == go.w, "conv_tc: geometry mismatch");
   MIL_REQUIRE(gx.cb == sh.cbin && go.cb == sh.cbout, "conv_tc: channel chunks do not match the packed weights");
   MIL_REQUIRE(epi != MIL_EPI_DGRAD || act != nullptr, "conv_tc: DGRAD epilogue needs the activation tensor");
   const size_t smem = tc_smem_bytes(gx, sh);
@@ -286,11 +306,11 @@ int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const vo
     MIL_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   }
   MIL_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long n_tiles = mil_cdiv(go.Q, TC_M);
+  const long long n_tiles = mil_cdiv(gx.Q, TC_M);
   const int grid = (int)std::min<long long>(n_tiles, n_sm);
   conv_tc_kernel<<<grid, TC_THREADS, smem, s>>>((const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)wtc, bias,
                                                 (const __nv_bfloat16*)res, (const __nv_bfloat16*)act,
-                                                (__nv_bfloat16*)out, go, sh, epi, transposed);
+                                                (__nv_bfloat16*)out, go, sh, epi, transposed, sub);
   MIL_LAUNCH_OK();
   return 0;
 }

@@ -6,6 +6,7 @@
 
 // K-loop description shared by the weight pre-pack and the kernel: MMA j multiplies K-groups order[2j], order[2j+1]
 struct MilTcShape {
+  int ks;           // 3 (nine taps) or 1 (pointwise)
   int cbin, cbout;  // 8-channel chunks of the kernel's input / output
   int npad;         // UMMA N (output channels padded to a multiple of 16)
   int nmma;         // number of K=16 MMAs per tile
@@ -14,13 +15,15 @@ struct MilTcShape {
 };
 
 bool mil_tc_supported(int dtype, int ks, int stride, int cin, int cout);
-int mil_tc_shape(int cin, int cout, MilTcShape* out);  // cin/cout = the KERNEL's input/output channels
+int mil_tc_shape(int cin, int cout, int ks, MilTcShape* out);  // cin/cout = the KERNEL's input/output channels
 size_t mil_tc_wpack_bytes(const MilTcShape& sh);
 // wp: fp32 packed weights [tap][kin_pad][nout_pad] (mil_launch_pack_conv_w, normal or transposed)
 int mil_launch_pack_tc(const float* wp, void* wtc, const MilTcShape& sh, cudaStream_t s);
 int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const void* wtc, const MilTcShape& sh,
                        const float* bias, const void* res, const void* act, void* out, const MilPF8& go, int epi,
-                       cudaStream_t s);
+                       int sub, cudaStream_t s);
+// out (geometry 2x) = zero-stuffed copy of in: out(n, 2y, 2x) = in(n, y, x), zero elsewhere (bf16)
+int mil_launch_upsample2(const void* in, const MilPF8& gin, void* out, const MilPF8& gout, cudaStream_t s);
 
 // tcgen05 weight gradient (mil_wgrad_tc.cu): 3x3 / 1x1, stride 1, bf16
 bool mil_wgrad_tc_supported(int dtype, int ks, int stride, int cin, int cout);

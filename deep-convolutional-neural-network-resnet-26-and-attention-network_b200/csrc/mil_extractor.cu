@@ -105,8 +105,8 @@ int mil_make_plan(int n, int side, int dtype, MilPlan* plan) {
         c.wtc_off = c.wtct_off = 0;
         if (c.tc) {
           MilTcShape sf, sb;
-          MIL_TRY(mil_tc_shape(c.cin, c.cout, &sf));
-          MIL_TRY(mil_tc_shape(c.cout, c.cin, &sb));
+          MIL_TRY(mil_tc_shape(c.cin, c.cout, c.ks, &sf));
+          MIL_TRY(mil_tc_shape(c.cout, c.cin, c.ks, &sb));
           c.wtc_off = tcofs; tcofs += align_up(mil_tc_wpack_bytes(sf), 256);
           c.wtct_off = tcofs; tcofs += align_up(mil_tc_wpack_bytes(sb), 256);
         }
@@ -131,6 +131,13 @@ int mil_make_plan(int n, int side, int dtype, MilPlan* plan) {
   pl.grad_bytes = 0;
   for (int l = 0; l < 4; ++l) pl.grad_bytes = std::max(pl.grad_bytes, mil_pf8_bytes(pl.g[l], dtype));
   for (int i = 0; i < 3; ++i) pl.off_grad[i] = take(pl.grad_bytes);
+  // zero-stuffed output gradients of the three stride-2 blocks (tcgen05 path only): Cout channels at the
+  // block's INPUT resolution
+  pl.up_bytes = 0;
+  if (dtype == MIL_BF16 && mil_tc_enabled())
+    for (int l = 1; l < 4; ++l)
+      pl.up_bytes = std::max(pl.up_bytes, mil_pf8_bytes(mil_pf8(n, kMilWidths[l], pl.geo.h[l - 1], pl.geo.h[l - 1]), dtype));
+  for (int i = 0; i < 2; ++i) pl.off_up[i] = take(pl.up_bytes);
   pl.off_wpack = take(pl.wpack_floats * sizeof(float));
   pl.off_wtc = take(pl.wtc_bytes + 256);
   size_t pf = std::max(mil_stem_bwd_partial_floats(), mil_tail_bwd_partial_floats());
@@ -138,8 +145,8 @@ int mil_make_plan(int n, int side, int dtype, MilPlan* plan) {
     const MilPF8& go = pl.g[c.layer];
     const MilPF8 gi = (c.stride == 2) ? pl.g[c.layer - 1] : mil_pf8(n, c.cin, go.h, go.w);
     pf = std::max(pf, mil_wgrad_direct_partial_floats(gi, go, c.ks));
-    if (mil_wgrad_tc_supported(dtype, c.ks, c.stride, c.cin, c.cout))
-      pf = std::max(pf, mil_wgrad_tc_partial_floats(gi, go, c.ks));
+    if (mil_tc_enabled() && mil_wgrad_tc_supported(dtype, c.ks, 1, c.cin, c.cout))
+      pf = std::max(pf, mil_wgrad_tc_partial_floats(gi, mil_pf8(n, c.cout, gi.h, gi.w), c.ks));
   }
   pl.partial_floats = pf;
   pl.off_partial = take(pf * sizeof(float));
@@ -231,10 +238,10 @@ bool mil_tc_enabled() {
 int mil_conv_dispatch(int dtype, int transposed, const void* x, const MilPF8& gi, const float* wp, const void* wtc,
                       const float* bias, const void* res, const void* act, void* out, const MilPF8& go, int ks,
                       int stride, int epi, cudaStream_t s) {
-  if (wtc != nullptr && mil_tc_supported(dtype, ks, stride, gi.c, go.c)) {
+  if (wtc != nullptr && mil_tc_supported(dtype, ks, stride, gi.c, go.c) && !(stride == 2 && transposed)) {
     MilTcShape sh;
-    MIL_TRY(mil_tc_shape(gi.c, go.c, &sh));
-    return mil_launch_conv_tc(transposed, x, gi, wtc, sh, bias, res, act, out, go, epi, s);
+    MIL_TRY(mil_tc_shape(gi.c, go.c, ks, &sh));
+    return mil_launch_conv_tc(transposed, x, gi, wtc, sh, bias, res, act, out, go, epi, stride == 2, s);
   }
   return mil_launch_conv_direct(dtype, transposed, x, gi, wp, bias, res, act, out, go, ks, stride, epi, s);
 }
@@ -262,7 +269,7 @@ static int pack_weights(const void* const* params, const MilPlan& pl, void* ws, 
     if (!c.tc) continue;
     MilTcShape sh;
     // the kernel's input/output channels: (cin, cout) forward, (cout, cin) for the data gradient
-    MIL_TRY(mil_tc_shape(transposed ? c.cout : c.cin, transposed ? c.cin : c.cout, &sh));
+    MIL_TRY(mil_tc_shape(transposed ? c.cout : c.cin, transposed ? c.cin : c.cout, c.ks, &sh));
     MIL_TRY(mil_launch_pack_tc(area + (transposed ? c.wpt_off : c.wp_off), tca + (transposed ? c.wtct_off : c.wtc_off),
                                sh, s));
   }
@@ -303,6 +310,12 @@ int mil_extractor_forward_impl(const void* const* params, const float* bag, cons
       void* y = wsp(ws, pl.off_y[l * 3 + b]);
       const MilConvDesc& c1 = pl.convs[ci++];
       const MilConvDesc& c2 = pl.convs[ci++];
+      if (c1.stride == 2 && c1.tc && ((gx.h & 1) || (gx.w & 1))) {
+        // the subsampled store of the tcgen05 path reaches the zero row / column of the half-resolution map
+        // only when the input size is even: clear the maps first
+        MIL_CHECK_CUDA(cudaMemsetAsync(h, 0, mil_pf8_bytes(go, dt), s));
+        MIL_CHECK_CUDA(cudaMemsetAsync(y, 0, mil_pf8_bytes(go, dt), s));
+      }
       MIL_TRY(mil_conv_dispatch(dt, 0, X, gx, wpack + c1.wp_off, TCW(c1, false), (const float*)params[c1.p_b], nullptr, nullptr, h,
                                 go, 3, c1.stride, MIL_EPI_FWD, s));
       const void* res = X;
@@ -384,24 +397,32 @@ int mil_extractor_backward_impl(const void* const* params, const float* bag, con
       // which 1: gradient w.r.t. the pre-activation of this block's first conv (geometry go)
       if (g_dump.dst != nullptr && g_dump.layer == l && g_dump.block == b && g_dump.which == 1)
         MIL_TRY(mil_launch_from_pf8(dt, dpre, g_dump.dst, go.n, go.c, go.h, go.w, s));
-      // conv1: weight gradient
-      MIL_TRY(mil_wgrad_dispatch(dt, xin, gi, dpre, go, partial, gptr(c1.p_w), gptr(c1.p_b), 3, c1.stride, s));
-      if (down) {
+      // conv1: weight gradient (the stride-2 blocks do it inside their own branch below)
+      if (!down) MIL_TRY(mil_wgrad_dispatch(dt, xin, gi, dpre, go, partial, gptr(c1.p_w), gptr(c1.p_b), 3, 1, s));
+      if (down && c1.tc) {
+        // stride-2 block on the tensor-core kernels: zero-stuff both output gradients to the input resolution,
+        // after which every gradient of the block is a stride-1 problem
         const MilConvDesc& cd = pl.convs[cb + 2];
-        MIL_TRY(mil_wgrad_dispatch(dt, xin, gi, dz, go, partial, gptr(cd.p_w), nullptr, 1, 2, s));
-        // the gradient buffers change geometry here: re-zero their guards for the larger map
+        const MilPF8 gu = mil_pf8(pl.n, go.c, gi.h, gi.w);
+        void* up_pre = wsp(ws, pl.off_up[0]);
+        void* up_dz = wsp(ws, pl.off_up[1]);
         {
           GuardTable t;
           t.count = 0;
           t.esize = (int)mil_esize(dt);
+          guard_add(t, up_pre, gu);
+          guard_add(t, up_dz, gu);
           guard_add(t, dnew, gi);
           MIL_TRY(launch_guards(t, s));
         }
-        MIL_TRY(mil_conv_dispatch(dt, 1, dz, go, wpack + cd.wpt_off, TCW(cd, true), nullptr, nullptr, nullptr, dnew, gi, 1, 2,
-                                  MIL_EPI_PLAIN, s));
-        MIL_TRY(mil_conv_dispatch(dt, 1, dpre, go, wpack + c1.wpt_off, TCW(c1, true), nullptr, dnew, xin, dnew, gi, 3, 2,
-                                  MIL_EPI_DGRAD, s));
-        // dz / dpre will next be written with the geometry of layer l-1
+        MIL_TRY(mil_launch_upsample2(dpre, go, up_pre, gu, s));
+        MIL_TRY(mil_launch_upsample2(dz, go, up_dz, gu, s));
+        MIL_TRY(mil_wgrad_dispatch(dt, xin, gi, up_pre, gu, partial, gptr(c1.p_w), gptr(c1.p_b), 3, 1, s));
+        MIL_TRY(mil_wgrad_dispatch(dt, xin, gi, up_dz, gu, partial, gptr(cd.p_w), nullptr, 1, 1, s));
+        MIL_TRY(mil_conv_dispatch(dt, 1, up_dz, gu, wpack + cd.wpt_off, TCW(cd, true), nullptr, nullptr, nullptr, dnew,
+                                  gi, 1, 1, MIL_EPI_PLAIN, s));
+        MIL_TRY(mil_conv_dispatch(dt, 1, up_pre, gu, wpack + c1.wpt_off, TCW(c1, true), nullptr, dnew, xin, dnew, gi, 3,
+                                  1, MIL_EPI_DGRAD, s));
         {
           GuardTable t;
           t.count = 0;
@@ -410,7 +431,30 @@ int mil_extractor_backward_impl(const void* const* params, const float* bag, con
           guard_add(t, dpre, gi);
           MIL_TRY(launch_guards(t, s));
         }
-
+      } else if (down) {
+        // CUDA-core path (fp32 check mode): strided weight gradients and transposed stride-2 convolutions
+        const MilConvDesc& cd = pl.convs[cb + 2];
+        MIL_TRY(mil_wgrad_dispatch(dt, xin, gi, dpre, go, partial, gptr(c1.p_w), gptr(c1.p_b), 3, c1.stride, s));
+        MIL_TRY(mil_wgrad_dispatch(dt, xin, gi, dz, go, partial, gptr(cd.p_w), nullptr, 1, 2, s));
+        {
+          GuardTable t;
+          t.count = 0;
+          t.esize = (int)mil_esize(dt);
+          guard_add(t, dnew, gi);
+          MIL_TRY(launch_guards(t, s));
+        }
+        MIL_TRY(mil_conv_dispatch(dt, 1, dz, go, wpack + cd.wpt_off, nullptr, nullptr, nullptr, nullptr, dnew, gi, 1, 2,
+                                  MIL_EPI_PLAIN, s));
+        MIL_TRY(mil_conv_dispatch(dt, 1, dpre, go, wpack + c1.wpt_off, nullptr, nullptr, dnew, xin, dnew, gi, 3, 2,
+                                  MIL_EPI_DGRAD, s));
+        {
+          GuardTable t;
+          t.count = 0;
+          t.esize = (int)mil_esize(dt);
+          guard_add(t, dz, gi);
+          guard_add(t, dpre, gi);
+          MIL_TRY(launch_guards(t, s));
+        }
       } else {
         MIL_TRY(mil_conv_dispatch(dt, 1, dpre, go, wpack + c1.wpt_off, TCW(c1, true), nullptr, dz, xin, dnew, gi, 3, 1,
                                   MIL_EPI_DGRAD, s));

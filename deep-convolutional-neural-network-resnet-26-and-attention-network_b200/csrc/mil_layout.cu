@@ -1,6 +1,9 @@
 // Layout helpers: weight packing, NCHW <-> PF8 conversion (used by the layer-wise parity tests), and the
 // deterministic second-stage reductions of split-K weight-gradient partials.
+#include <algorithm>
+
 #include "mil_common.cuh"
+#include "mil_conv_tc.cuh"
 
 // ---- conv weight packing ---------------------------------------------------------------------------
 // PyTorch layout w[cout][cin][ks][ks] (reference nnBlocks.py:160-168 nn.Conv2d) ->
@@ -127,6 +130,33 @@ int mil_launch_reduce_conv_w(const float* partial, int nblk, long long stride, f
                              int cin, int ks, cudaStream_t s) {
   const int total = cout * cin * ks * ks + cout;
   reduce_conv_w_kernel<<<(int)mil_cdiv(total, 128), 128, 0, s>>>(partial, nblk, stride, dw, db, cout, cin, ks);
+  MIL_LAUNCH_OK();
+  return 0;
+}
+
+// ---- zero-stuffing (bf16): out(n, 2y, 2x) = in(n, y, x), zero elsewhere ------------------------------------
+// Turns the stride-2 convolutions' data / weight gradients into stride-1 problems the tcgen05 kernels handle:
+// conv_transpose_s2(dz) == conv_transpose_s1(zero_stuff(dz)),  wgrad_s2(x, dz) == wgrad_s1(x, zero_stuff(dz)).
+__global__ void upsample2_kernel(const uint4* __restrict__ in, MilPF8 gin, uint4* __restrict__ out, MilPF8 gout) {
+  const long long total = (long long)gout.cb * gout.Q;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cb = (int)(i / gout.Q);
+    const long long q = i - (long long)cb * gout.Q;
+    const int n = (int)(q / gout.P);
+    const int r = (int)(q - (long long)n * gout.P);
+    const int y = r / gout.wp, x = r - y * gout.wp;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (y < gout.h && x < gout.w && !(y & 1) && !(x & 1))
+      v = in[(size_t)cb * gin.PS + gin.G + (size_t)n * gin.P + (size_t)(y >> 1) * gin.wp + (x >> 1)];
+    out[(size_t)cb * gout.PS + gout.G + q] = v;
+  }
+}
+int mil_launch_upsample2(const void* in, const MilPF8& gin, void* out, const MilPF8& gout, cudaStream_t s) {
+  MIL_REQUIRE(gin.n == gout.n && gin.cb == gout.cb && gin.h == (gout.h - 1) / 2 + 1 && gin.w == (gout.w - 1) / 2 + 1,
+              "upsample2: geometry mismatch");
+  const int blocks = (int)std::min<long long>(mil_cdiv((long long)gout.cb * gout.Q, 256), 148 * 16);
+  upsample2_kernel<<<blocks, 256, 0, s>>>((const uint4*)in, gin, (uint4*)out, gout);
   MIL_LAUNCH_OK();
   return 0;
 }

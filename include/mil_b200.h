@@ -115,6 +115,9 @@ int mil_head_backward_b(const void* const* params_host, const float* H, int n, l
 size_t mil_pf8_bytes(int n, int c, int h, int w, int dtype);
 int mil_to_pf8(int dtype, const float* nchw, void* pf8, int n, int c, int h, int w, void* stream);
 int mil_from_pf8(int dtype, const void* pf8, float* nchw, int n, int c, int h, int w, void* stream);
+/* bf16 only: out (ho x wo = the stride-2 convolution's INPUT size) = zero-stuffed copy of in (h x w):
+ * out(n,2y,2x) = in(n,y,x), zero elsewhere.  The stride-2 data / weight gradients are the stride-1 ones of it. */
+int mil_upsample2_pf8(const void* in, int n, int c, int h, int w, void* out, int ho, int wo, void* stream);
 size_t mil_conv_workspace_bytes(int n, int cin, int hi, int wi, int cout, int ho, int wo, int ks);
 /* out = epilogue(conv(x, w)):  epi 0: lrelu(acc+bias+res), 1: (acc+res)*lrelu'(act), 2: acc+bias+res.
  * transposed=1 computes the data gradient (x has the conv's OUTPUT geometry, out its INPUT geometry).

@@ -79,6 +79,13 @@ def conv(x: PF8, w, bias=None, res: PF8 = None, act: PF8 = None, stride=1, epi=0
     return out
 
 
+def upsample2(x: PF8, ho, wo):
+    """Zero-stuffed copy at the stride-2 convolution's input resolution (bf16 only)."""
+    out = PF8(x.n, x.c, ho, wo, x.dtype)
+    check(lib().mil_upsample2_pf8(_p(x.buf), x.n, x.c, x.h, x.w, _p(out.buf), ho, wo, _s()), "mil_upsample2_pf8")
+    return out
+
+
 def wgrad(x: PF8, dz: PF8, ks, stride, with_bias=True, impl=0):
     cin, cout = x.c, dz.c
     dw = torch.zeros((cout, cin, ks, ks), dtype=torch.float32, device="cuda")

@@ -141,17 +141,19 @@ def gates(precision, meta, n_head):
       * bags that leave < 32 tiles for the head: the bag-wide BatchNorm1d (gbm/model.py:105-109) divides by a
         std estimated from a handful of tiles; gate 5e-2.
     Side outputs the north_star does not name (Bterm, wROIs, Aterm_mu, Aterm_var) are held to 5e-2 in bf16.
-    bf16 gradients: per-tensor cosine similarity and norm ratio (bf16 rounding flips ~0.3 % of the LeakyReLU
-    branches, so element-wise gates are meaningless)."""
+    bf16 gradients: per-tensor cosine similarity >= 0.95 and norm within 10 % for bags of >= 32 tiles (bf16
+    rounding flips ~0.3 % of the LeakyReLU branches, so element-wise gates are meaningless; for smaller bags
+    the BatchNorm1d backward cancels almost completely -- for 2 tiles exactly -- and only finiteness is
+    asserted)."""
     if precision == "fp32":
         g = max(1e-3, 5 * meta.get("gnoise", 0.0))
         return dict(named=1e-4, named_l2=1e-4, side=1e-4, feat=1e-4, emu=None, gmax=g, gcos=1e-4, gnorm=g)
     peaked = min(meta["wm"]) < 0
     if n_head < 32:
-        return dict(named=5e-2, named_l2=5e-2, side=1.5e-1, feat=1e-2, emu=8e-3, gmax=None, gcos=1e-1, gnorm=2e-1)
+        return dict(named=5e-2, named_l2=5e-2, side=1.5e-1, feat=1.5e-2, emu=8e-3, gmax=None, gcos=None, gnorm=None)
     if peaked:
-        return dict(named=2e-2, named_l2=1e-2, side=5e-2, feat=1e-2, emu=6e-3, gmax=None, gcos=2e-2, gnorm=1e-1)
-    return dict(named=1e-2, named_l2=1e-2, side=5e-2, feat=1e-2, emu=6e-3, gmax=None, gcos=2e-2, gnorm=1e-1)
+        return dict(named=2e-2, named_l2=1e-2, side=5e-2, feat=1e-2, emu=6e-3, gmax=None, gcos=5e-2, gnorm=1e-1)
+    return dict(named=1e-2, named_l2=1e-2, side=5e-2, feat=1e-2, emu=6e-3, gmax=None, gcos=5e-2, gnorm=1e-1)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
@@ -185,7 +187,7 @@ def test_forward_backward_vs_reference_golden(precision, meta, rec):
         assert G.relerr(out[k], ref[k]) < tol["feat"], (k, G.relerr(out[k], ref[k]))
     if tol["emu"] is not None:     # kernel check proper for the bf16 mode: same rounding points, fp32 arithmetic
         p = golden_weights()
-        He = mil_oracle.resnet26_forward(p, bag_cpu if idx is None else bag_cpu[idx], emulate_bf16="act")
+        He = mil_oracle.resnet26_forward(p, bag_cpu if idx is None else bag_cpu[idx], emulate_bf16="act+w")
         assert G.relerr(out["Fterm"], He) < tol["emu"], G.relerr(out["Fterm"], He)
     if n_head >= 32 or precision == "fp32":
         assert int(out["y_pred_hat"]) == int(ref["y_pred_hat"]) and float(out["error"]) == float(ref["error"])
@@ -194,9 +196,9 @@ def test_forward_backward_vs_reference_golden(precision, meta, rec):
     for k, prm in net.named_parameters():
         assert prm.grad is not None and torch.isfinite(prm.grad).all(), k
         dig = rec[f"gdigest.{k}"]
-        if dig[2] > 1e-5:
+        if dig[2] > 1e-5 and tol["gnorm"] is not None:
             assert abs(float(prm.grad.double().norm()) - dig[2]) <= tol["gnorm"] * dig[2], k
-        if f"grad.{k}" in rec and np.abs(rec[f"grad.{k}"]).max() > 1e-5:
+        if f"grad.{k}" in rec and np.abs(rec[f"grad.{k}"]).max() > 1e-5 and tol["gcos"] is not None:
             r = torch.from_numpy(rec[f"grad.{k}"])
             assert 1 - cosine(prm.grad, r) < tol["gcos"], (k, 1 - cosine(prm.grad, r))
             if tol["gmax"] is not None:
