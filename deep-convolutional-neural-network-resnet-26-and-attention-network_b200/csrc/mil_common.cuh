@@ -68,24 +68,26 @@ __host__ __device__ __forceinline__ float mil_lrelu_grad(float act) { return act
 // ---- PF8 tensor geometry -----------------------------------------------------------------------
 struct MilPF8 {
   int n, c, cb;      // images, channels, 8-channel chunks
-  int h, w, hp, wp;  // spatial size and padded spatial size (h+1, w+1)
+  int h, w, hp, wp;  // spatial size and padded spatial size (h+pad, w+pad); pad = 1 unless stated
   long long P;       // pixels per image plane = hp*wp
   long long Q;       // flat pixels = n*P
   long long G, GT;   // lead / tail guard, in pixels
   long long PS;      // chunk-plane stride in pixels = G + Q + GT
 };
 #define MIL_TILE_M 128  // flat pixels per implicit-GEMM tile
-static inline MilPF8 mil_pf8(int n, int c, int h, int w) {
+// pad = width of the shared zero halo (1 for the 3x3 layers; 2 for the stem's space-to-depth 4x4 window)
+static inline MilPF8 mil_pf8p(int n, int c, int h, int w, int pad) {
   MilPF8 t;
   t.n = n; t.c = c; t.cb = (c + 7) / 8;
-  t.h = h; t.w = w; t.hp = h + 1; t.wp = w + 1;
+  t.h = h; t.w = w; t.hp = h + pad; t.wp = w + pad;
   t.P = (long long)t.hp * t.wp;
   t.Q = (long long)n * t.P;
-  t.G = mil_rup(t.wp + 1, 8);
-  t.GT = mil_rup(MIL_TILE_M + t.wp + 1, 8) + 8;
+  t.G = mil_rup((long long)pad * (t.wp + 1), 8);
+  t.GT = mil_rup(MIL_TILE_M + (long long)pad * (t.wp + 1), 8) + 8;
   t.PS = mil_rup(t.G + t.Q + t.GT, 8);
   return t;
 }
+static inline MilPF8 mil_pf8(int n, int c, int h, int w) { return mil_pf8p(n, c, h, w, 1); }
 static inline size_t mil_pf8_bytes(const MilPF8& t, int dtype) {
   return (size_t)t.cb * (size_t)t.PS * 8 * mil_esize(dtype);
 }

@@ -1,22 +1,27 @@
-// tcgen05 implicit-GEMM 3x3 / stride-1 convolution on the PF8 layout (forward AND data gradient), bf16
-// operands, fp32 accumulation in TMEM, fused epilogue (bias, residual, LeakyReLU / LeakyReLU').
-// Reference semantics: nnBlocks.py:178-187 (conv3x3 + bias -> [+identity] -> LeakyReLU(0.1)) and its autograd.
+// tcgen05 implicit-GEMM convolution on the PF8 layout -- forward AND data gradient of the 3x3 / 1x1 layers
+// (stride 1; stride 2 forward = full-resolution evaluation + subsampled store) and the stem's 7x7 / stride-2
+// convolution in space-to-depth form (4x4 window over 12 channels).  bf16 operands, fp32 accumulation in TMEM,
+// fused epilogue (bias, residual, LeakyReLU / LeakyReLU').
+// Reference semantics: nnBlocks.py:178-187 (conv3x3 + bias -> [+identity] -> LeakyReLU(0.1)), gbm/model.py:24-25,51-52
+// (conv1 + LeakyReLU) and their autograd.
 //
 // GEMM view:  D[128 flat pixels][Cout] = sum over K-groups g = (tap t, 8-channel chunk c) of
 //             A_g[128][8] * B_g[8][Cout],   A_g[i][:] = x[chunk c][q0 + i + shift_t][0..7]
-// Because PF8 turns a tap into a constant shift of the flat pixel index, ALL nine taps read the same
-// shared-memory copy of the input: per tile one bulk-TMA copy per channel chunk brings in the
-// 128 + 2*(W+2) pixels around the tile ("span"), 16 bytes per pixel, and a tap is just a different START
-// ADDRESS of the (un-swizzled, K-major) UMMA descriptor.  8 consecutive pixels x 16 B = one 128-byte core
-// matrix (SBO = 128 B); the two 8-channel halves of a K=16 MMA are two (tap, chunk) groups, LBO = their
-// address distance.  Weights sit in shared memory for the whole kernel in the matching core-matrix layout.
+// Because PF8 turns a tap into a constant shift of the flat pixel index, ALL taps read the same shared-memory
+// copy of the input: per tile one bulk-TMA copy per channel chunk brings in the 128 + 2*halo pixels around the
+// tile ("span"), 16 bytes per pixel, and a tap is just a different START ADDRESS of the (un-swizzled, K-major)
+// UMMA descriptor.  8 consecutive pixels x 16 B = one 128-byte core matrix (SBO = 128 B); the two 8-channel
+// halves of a K=16 MMA are two (tap, chunk) groups, LBO = their address distance.  Weights sit in shared
+// memory for the whole kernel in the matching core-matrix layout.
 //
 // Warp roles (one persistent CTA per SM, tiles strided over CTAs):
 //   warp 0      : producer -- bulk-TMA (cp.async.bulk) of the span planes into a 3-stage ring, mbarrier tx
-//   warp 1      : MMA issuer -- one elected lane issues the tcgen05.mma chain of a tile into one of two
-//                 TMEM accumulator stages, tcgen05.commit releases the smem stage / publishes the accumulator
-//   warps 2..9  : epilogue, two groups of 4 warps (one per accumulator stage): prefetch residual / activation
-//                 chunks, tcgen05.ld the accumulator row (thread = pixel), bias / residual / LeakyReLU,
+//   warp 1      : MMA issuer -- one elected lane issues the tcgen05.mma chain of a tile (descriptors are
+//                 precomputed templates + the stage base) into one of two TMEM accumulator stages;
+//                 tcgen05.commit releases the smem stage / publishes the accumulator
+//   warps 2..9  : epilogue, two groups of 4 warps (one per accumulator stage).  Per tile a thread (= pixel)
+//                 first issues its residual / activation loads, THEN waits for the accumulator, pulls its
+//                 row out of TMEM, hands the accumulator stage back, and only then does the arithmetic and the
 //                 16-byte coalesced stores; pad pixels are written as zeros (PF8 invariant).
 #include <algorithm>
 
@@ -28,6 +33,8 @@
 #define TC_STAGES 3
 #define TC_ACC 2
 #define TC_THREADS 320  // 10 warps
+#define TC_MAXCB 10     // output chunks (80 channels)
+#define TC_HALF 5       // chunks pulled from TMEM per batch
 
 // ---- weight pre-pack: fp32 wp[tap][kin_pad][nout_pad8] -> bf16 B operand blocks --------------------------
 // B block of MMA j: [half h][n (npad rows)][8 k-elements], group (tap,chunk) = order[2j+h]  (0xFF = dummy)
@@ -46,22 +53,33 @@ __global__ void pack_tc_kernel(const float* __restrict__ wp, __nv_bfloat16* __re
 // ---- the kernel ----------------------------------------------------------------------------------------
 struct TcSmemHeader {
   uint64_t full[TC_STAGES], empty[TC_STAGES], acc_full[TC_ACC], acc_empty[TC_ACC], b_full;
+  uint64_t a_desc[MIL_TC_MAX_MMA];  // A descriptor of MMA j relative to the start of an A stage
+  uint64_t b_desc[MIL_TC_MAX_MMA];  // B descriptor of MMA j (absolute)
   uint32_t tmem_base;
-  uint32_t a_off[MIL_TC_MAX_MMA];  // byte offset of the first K-half inside an A stage
-  uint32_t a_lbo[MIL_TC_MAX_MMA];  // byte distance to the second K-half
   float bias[96];
 };
 
+__device__ __forceinline__ uint4 ld_nc16(const __nv_bfloat16* p) {
+  return __ldg(reinterpret_cast<const uint4*>(p));
+}
+__device__ __forceinline__ void unpack8(const uint4& r, float v[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat16* __restrict__ wtc,
-               const float* __restrict__ bias, const __nv_bfloat16* res, const __nv_bfloat16* __restrict__ act,
-               __nv_bfloat16* out, MilPF8 go, MilTcShape sh, int epi, int transposed, int sub) {
+               const float* __restrict__ bias, const __nv_bfloat16* res, const __nv_bfloat16* act,
+               __nv_bfloat16* out, MilPF8 go, MilTcShape sh, int epi, int transposed, int sub, int halo) {
   extern __shared__ __align__(128) unsigned char smem[];
   TcSmemHeader* hd = reinterpret_cast<TcSmemHeader*>(smem);
   const uint32_t hdr_bytes = (uint32_t)((sizeof(TcSmemHeader) + 127) / 128 * 128);
   unsigned char* bsm = smem + hdr_bytes;                      // B operand blocks
   const uint32_t b_bytes = (uint32_t)sh.nmma * 2 * sh.npad * 16;
-  const int halo = sh.ks == 3 ? gx.wp + 1 : 0;
   const int span = TC_M + 2 * halo;
   const uint32_t plane = (uint32_t)span * 16;                 // one channel-chunk plane of a stage
   const uint32_t stage_bytes = plane * (sh.cbin + 1);         // + one all-zero plane (odd K-group count)
@@ -80,27 +98,25 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
     fence_barrier_init();
   }
   for (int j = threadIdx.x; j < sh.nmma; j += blockDim.x) {
-    // shift of tap (dy,dx): forward reads x(q + (dy-1)*wp + dx-1); the data gradient reads dz(q + (1-dy)*wp + 1-dx)
     int off[2];
     for (int h = 0; h < 2; ++h) {
       const int tap = sh.g_tap[2 * j + h], chunk = sh.g_chunk[2 * j + h];
       if (tap == 0xFF) {
         off[h] = -1;
       } else {
-        const int dy = tap / 3, dx = tap % 3;
-        int s = transposed ? ((1 - dy) * gx.wp + (1 - dx)) : ((dy - 1) * gx.wp + (dx - 1));
-        if (sh.ks == 1) s = 0;
+        int s = sh.t_dy[tap] * gx.wp + sh.t_dx[tap];  // forward reads x(q + s); the data gradient reads dz(q - s)
+        if (transposed) s = -s;
         off[h] = chunk * (int)plane + (halo + s) * 16;
       }
     }
     if (off[1] < 0) off[1] = sh.cbin * (int)plane + halo * 16;  // dummy half -> the all-zero plane
-    hd->a_off[j] = (uint32_t)off[0];
-    hd->a_lbo[j] = (uint32_t)(off[1] - off[0]);                 // host guarantees off[1] > off[0]
+    // host guarantees off[1] > off[0] (mil_tc_shape orders the halves)
+    hd->a_desc[j] = make_desc((uint32_t)off[0], (uint32_t)(off[1] - off[0]), 128);
+    hd->b_desc[j] = make_desc(smem_u32(bsm) + (uint32_t)j * 2 * sh.npad * 16, (uint32_t)sh.npad * 16, 128);
   }
   for (int i = threadIdx.x; i < 96; i += blockDim.x)
     hd->bias[i] = (bias != nullptr && i < go.c) ? bias[i] : 0.f;
-  // zero plane of every stage
-  for (int s = 0; s < TC_STAGES; ++s) {
+  for (int s = 0; s < TC_STAGES; ++s) {  // zero plane of every stage
     uint4* zp = reinterpret_cast<uint4*>(asm0 + (size_t)s * stage_bytes + (size_t)sh.cbin * plane);
     for (int i = threadIdx.x; i < span; i += blockDim.x) zp[i] = make_uint4(0, 0, 0, 0);
   }
@@ -137,19 +153,16 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
       mbar_wait(&hd->b_full, 0);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      const uint32_t b_base = smem_u32(bsm);
-      const uint32_t b_blk = (uint32_t)sh.npad * 16;  // one K-half of B
+      const int nmma = sh.nmma;
       for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         mbar_wait(&hd->acc_empty[acc], acc_phase ^ 1);
         mbar_wait(&hd->full[stage], phase);
         tc_fence_after();
-        const uint32_t a_base = smem_u32(asm0 + (size_t)stage * stage_bytes);
+        // the start-address field sits in the low 14 bits of the descriptor: adding the stage base cannot carry
+        const uint64_t a_add = (uint64_t)(smem_u32(asm0 + (size_t)stage * stage_bytes) >> 4);
         const uint32_t d = tmem_base + acc * acc_stride;
-        for (int j = 0; j < sh.nmma; ++j) {
-          const uint64_t ad = make_desc(a_base + hd->a_off[j], hd->a_lbo[j], 128);
-          const uint64_t bd = make_desc(b_base + (uint32_t)j * 2 * b_blk, b_blk, 128);
-          umma_bf16(d, ad, bd, idesc, j > 0);
-        }
+#pragma unroll 2
+        for (int j = 0; j < nmma; ++j) umma_bf16(d, hd->a_desc[j] + a_add, hd->b_desc[j], idesc, j > 0);
         umma_commit(&hd->empty[stage]);   // smem stage reusable once these MMAs have read it
         umma_commit(&hd->acc_full[acc]);  // accumulator complete
         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
@@ -161,6 +174,8 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
     const int eg = (warp - 2) >> 2;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
+    const int cbout = sh.cbout;
+    const bool has_res = res != nullptr, has_act = epi == MIL_EPI_DGRAD;
     uint32_t acc_phase = 0;
     long long it = 0;
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
@@ -176,7 +191,7 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
         const int r = (int)(q - (long long)n * gx.P);
         const int y = r / gx.wp, xo = r - y * gx.wp;
         if (!sub) {
-          is_pad = (y == gx.h) || (xo == gx.w);
+          is_pad = (y >= gx.h) || (xo >= gx.w);
         } else {
           const int yh = y >> 1, xh = xo >> 1;
           in_range = !(y & 1) && !(xo & 1) && yh <= go.h && xh <= go.w;
@@ -184,45 +199,69 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
           qo = (long long)n * go.P + (long long)yh * go.wp + xh;
         }
       }
+      const bool live = in_range && !is_pad;
+      // 1. residual / activation loads go out BEFORE we wait for the tensor core
+      uint4 rres[TC_MAXCB], ract[TC_MAXCB];
+#pragma unroll
+      for (int c = 0; c < TC_MAXCB; ++c) {
+        if (c < cbout && live) {
+          const long long o = mil_pf8_off(go, c, qo);
+          if (has_res) rres[c] = ld_nc16(res + o);
+          if (has_act) ract[c] = ld_nc16(act + o);
+        }
+      }
       mbar_wait(&hd->acc_full[eg], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + eg * acc_stride + ((uint32_t)(quarter * 32) << 16);
-      for (int c = 0; c < sh.cbout; ++c) {
-        float v[8];
-        tmem_ld8(taddr + c * 8, v);
+#pragma unroll
+      for (int half = 0; half < TC_MAXCB / TC_HALF; ++half) {
+        if (half * TC_HALF >= cbout) break;
+        // 2. pull this thread's accumulator row out of TMEM (5 chunks = 40 columns per batch)
+        float acc[TC_HALF][8];
+#pragma unroll
+        for (int k = 0; k < TC_HALF; ++k)
+          if (half * TC_HALF + k < cbout) tmem_ld8(taddr + (half * TC_HALF + k) * 8, acc[k]);
         tmem_ld_wait();
-        if (in_range) {
-          const long long o = mil_pf8_off(go, c, qo);
-          if (is_pad) {
+        if ((half + 1) * TC_HALF >= cbout) {
+          // 3. the accumulator stage is free again: the MMA warp can start the tile after next
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&hd->acc_empty[eg]);
+        }
+        // 4. arithmetic + stores
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = 0.f;
-          } else {
-            if (res != nullptr) {
-              float rv[8];
-              mil_load8(res + o, rv);
+        for (int k = 0; k < TC_HALF; ++k) {
+          const int c = half * TC_HALF + k;
+          if (c < cbout && in_range) {
+            float* v = acc[k];
+            if (is_pad) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] += rv[j];
+              for (int j = 0; j < 8; ++j) v[j] = 0.f;
+            } else {
+              if (has_res) {
+                float rv[8];
+                unpack8(rres[c], rv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] += rv[j];
+              }
+              if (epi != MIL_EPI_DGRAD) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] += hd->bias[c * 8 + j];
+              }
+              if (epi == MIL_EPI_FWD) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = mil_lrelu(v[j]);
+              } else if (epi == MIL_EPI_DGRAD) {
+                float av[8];
+                unpack8(ract[c], av);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] *= mil_lrelu_grad(av[j]);
+              }
             }
-            if (epi != MIL_EPI_DGRAD) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] += hd->bias[c * 8 + j];
-            }
-            if (epi == MIL_EPI_FWD) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = mil_lrelu(v[j]);
-            } else if (epi == MIL_EPI_DGRAD) {
-              float av[8];
-              mil_load8(act + o, av);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] *= mil_lrelu_grad(av[j]);
-            }
+            mil_store8(out + mil_pf8_off(go, c, qo), v);
           }
-          mil_store8(out + o, v);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&hd->acc_empty[eg]);
       acc_phase ^= 1;
     }
   }
@@ -245,11 +284,21 @@ bool mil_tc_supported(int dtype, int ks, int stride, int cin, int cout) {
 
 int mil_tc_shape(int cin, int cout, int ks, MilTcShape* out) {
   MilTcShape& sh = *out;
+  MIL_REQUIRE(ks == 1 || ks == 3 || ks == 7, "conv_tc: unsupported window %d", ks);
   sh.ks = ks;
+  sh.ntaps = 0;
+  if (ks == 7) {  // stem in space-to-depth form: 4x4 window, offsets -2..1 (mil_stem_tc.cu)
+    for (int a = -2; a <= 1; ++a)
+      for (int b = -2; b <= 1; ++b) { sh.t_dy[sh.ntaps] = (signed char)a; sh.t_dx[sh.ntaps] = (signed char)b; ++sh.ntaps; }
+  } else {
+    const int r = ks / 2;
+    for (int a = -r; a <= r; ++a)
+      for (int b = -r; b <= r; ++b) { sh.t_dy[sh.ntaps] = (signed char)a; sh.t_dx[sh.ntaps] = (signed char)b; ++sh.ntaps; }
+  }
   sh.cbin = (cin + 7) / 8;
   sh.cbout = (cout + 7) / 8;
   sh.npad = (cout + 15) / 16 * 16;
-  const int ng = ks * ks * sh.cbin;
+  const int ng = sh.ntaps * sh.cbin;
   sh.nmma = (ng + 1) / 2;
   MIL_REQUIRE(sh.nmma <= MIL_TC_MAX_MMA, "conv_tc: too many K groups (%d)", ng);
   for (int g = 0; g < 2 * sh.nmma; ++g) {
@@ -277,10 +326,10 @@ int mil_launch_pack_tc(const float* wp, void* wtc, const MilTcShape& sh, cudaStr
   return 0;
 }
 
-static size_t tc_smem_bytes(const MilPF8& gx, const MilTcShape& sh) {
+static size_t tc_smem_bytes(int halo, const MilTcShape& sh) {
   const size_t hdr = (sizeof(TcSmemHeader) + 127) / 128 * 128;
   const size_t b = ((size_t)sh.nmma * 2 * sh.npad * 16 + 127) / 128 * 128;
-  const size_t span = TC_M + 2 * (sh.ks == 3 ? gx.wp + 1 : 0);
+  const size_t span = TC_M + 2 * (size_t)halo;
   return hdr + b + (size_t)TC_STAGES * span * 16 * (sh.cbin + 1);
 }
 
@@ -291,10 +340,13 @@ int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const vo
     MIL_REQUIRE(gx.n == go.n && go.h == (gx.h - 1) / 2 + 1 && go.w == (gx.w - 1) / 2 + 1 && !transposed,
                 "conv_tc: stride-2 geometry mismatch");
   else
-    MIL_REQUIRE(gx.n == go.n && gx.h == go.h && gx.w == go.w, "conv_tc: geometry mismatch");
+    MIL_REQUIRE(gx.n == go.n && gx.h == go.h && gx.w == go.w && gx.wp == go.wp && gx.hp == go.hp,
+                "conv_tc: geometry mismatch");
   MIL_REQUIRE(gx.cb == sh.cbin && go.cb == sh.cbout, "conv_tc: channel chunks do not match the packed weights");
   MIL_REQUIRE(epi != MIL_EPI_DGRAD || act != nullptr, "conv_tc: DGRAD epilogue needs the activation tensor");
-  const size_t smem = tc_smem_bytes(gx, sh);
+  const int halo = mil_tc_halo(sh, gx.wp);
+  MIL_REQUIRE(halo <= gx.G, "conv_tc: the window reaches %d pixels back but the map's guard is %lld", halo, gx.G);
+  const size_t smem = tc_smem_bytes(halo, sh);
   MIL_REQUIRE(smem <= 227 * 1024, "conv_tc: tile width %d needs %zu bytes of shared memory", gx.w, smem);
   // the second K-half must sit above the first one (see mil_tc_shape); holds whenever a plane is larger than
   // twice the largest tap shift, i.e. always for cbin >= 2; cbin == 1 would need taps in ascending shift order
@@ -310,7 +362,7 @@ int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const vo
   const int grid = (int)std::min<long long>(n_tiles, n_sm);
   conv_tc_kernel<<<grid, TC_THREADS, smem, s>>>((const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)wtc, bias,
                                                 (const __nv_bfloat16*)res, (const __nv_bfloat16*)act,
-                                                (__nv_bfloat16*)out, go, sh, epi, transposed, sub);
+                                                (__nv_bfloat16*)out, go, sh, epi, transposed, sub, halo);
   MIL_LAUNCH_OK();
   return 0;
 }

@@ -4,15 +4,29 @@
 
 #define MIL_TC_MAX_MMA 46  // ceil(9 taps * 10 chunks / 2) + 1
 
-// K-loop description shared by the weight pre-pack and the kernel: MMA j multiplies K-groups order[2j], order[2j+1]
+#define MIL_TC_MAX_TAPS 16
+// Window + K-loop description shared by the weight pre-pack and the kernels.  A tap is an offset (dy, dx) of the
+// flat pixel index (shift = dy * wp + dx; the data gradient negates it); MMA j multiplies the K-groups
+// (tap, 8-channel chunk) number 2j and 2j+1 of the order below.
 struct MilTcShape {
-  int ks;           // 3 (nine taps) or 1 (pointwise)
+  int ks;           // 3: nine taps -1..1;  1: pointwise;  7: the stem in space-to-depth form, 4x4 taps -2..1
+  int ntaps;
+  signed char t_dy[MIL_TC_MAX_TAPS], t_dx[MIL_TC_MAX_TAPS];
   int cbin, cbout;  // 8-channel chunks of the kernel's input / output
   int npad;         // UMMA N (output channels padded to a multiple of 16)
   int nmma;         // number of K=16 MMAs per tile
-  unsigned char g_tap[2 * MIL_TC_MAX_MMA];    // tap (0..8) of each K-group, 0xFF = zero padding group
+  unsigned char g_tap[2 * MIL_TC_MAX_MMA];    // tap index of each K-group, 0xFF = zero padding group
   unsigned char g_chunk[2 * MIL_TC_MAX_MMA];  // input chunk of each K-group
 };
+// largest |shift| of the window on a map whose padded row length is wp
+static inline int mil_tc_halo(const MilTcShape& sh, int wp) {
+  int m = 0;
+  for (int t = 0; t < sh.ntaps; ++t) {
+    const int s = sh.t_dy[t] * wp + sh.t_dx[t];
+    m = s > m ? s : (-s > m ? -s : m);
+  }
+  return m;
+}
 
 bool mil_tc_supported(int dtype, int ks, int stride, int cin, int cout);
 int mil_tc_shape(int cin, int cout, int ks, MilTcShape* out);  // cin/cout = the KERNEL's input/output channels
@@ -28,5 +42,19 @@ int mil_launch_upsample2(const void* in, const MilPF8& gin, void* out, const Mil
 // tcgen05 weight gradient (mil_wgrad_tc.cu): 3x3 / 1x1, stride 1, bf16
 bool mil_wgrad_tc_supported(int dtype, int ks, int stride, int cin, int cout);
 size_t mil_wgrad_tc_partial_floats(const MilPF8& gx, const MilPF8& gz, int ks);
+int mil_launch_wgrad_tc_partials(const void* x, const MilPF8& gx, const void* dz, const MilPF8& gz, float* partial,
+                                 int ks, int* ctas_out, long long* rec_out, cudaStream_t s);
 int mil_launch_wgrad_tc(const void* x, const MilPF8& gx, const void* dz, const MilPF8& gz, float* partial, float* dw,
                         float* db, int ks, cudaStream_t s);
+
+// stem on the tensor cores (mil_stem_tc.cu)
+MilPF8 mil_stem_tc_geom_in(int n, int side);    // space-to-depth input: 12 channels, conv-output resolution, pad 2
+MilPF8 mil_stem_tc_geom_conv(int n, int side);  // conv1 output: 20 channels, pad 2
+size_t mil_stem_tc_wpack_floats();
+size_t mil_stem_tc_wtc_bytes();
+size_t mil_stem_tc_partial_floats(int n, int side);
+int mil_launch_stem_tc_fwd(const float* x, const int* idx, int n, int side, const float* w, const float* b, void* xs,
+                           void* convout, float* wp, void* wtc, void* pooled, const MilPF8& gp, uint8_t* argmax,
+                           cudaStream_t s);
+int mil_launch_stem_tc_bwd(const void* xs, int n, int side, const void* g, const MilPF8& gp, const uint8_t* argmax,
+                           void* dy, float* partial, float* dw, float* db, cudaStream_t s);

@@ -138,6 +138,14 @@ int mil_make_plan(int n, int side, int dtype, MilPlan* plan) {
     for (int l = 1; l < 4; ++l)
       pl.up_bytes = std::max(pl.up_bytes, mil_pf8_bytes(mil_pf8(n, kMilWidths[l], pl.geo.h[l - 1], pl.geo.h[l - 1]), dtype));
   for (int i = 0; i < 2; ++i) pl.off_up[i] = take(pl.up_bytes);
+  pl.stem_tc = (dtype == MIL_BF16) && mil_tc_enabled();
+  pl.off_xs = pl.off_cv = pl.off_stem_wp = pl.off_stem_wtc = 0;
+  if (pl.stem_tc) {
+    pl.off_xs = take(mil_pf8_bytes(mil_stem_tc_geom_in(n, side), dtype));
+    pl.off_cv = take(mil_pf8_bytes(mil_stem_tc_geom_conv(n, side), dtype));
+    pl.off_stem_wp = take(mil_stem_tc_wpack_floats() * sizeof(float));
+    pl.off_stem_wtc = take(mil_stem_tc_wtc_bytes());
+  }
   pl.off_wpack = take(pl.wpack_floats * sizeof(float));
   pl.off_wtc = take(pl.wtc_bytes + 256);
   size_t pf = std::max(mil_stem_bwd_partial_floats(), mil_tail_bwd_partial_floats());
@@ -148,6 +156,7 @@ int mil_make_plan(int n, int side, int dtype, MilPlan* plan) {
     if (mil_tc_enabled() && mil_wgrad_tc_supported(dtype, c.ks, 1, c.cin, c.cout))
       pf = std::max(pf, mil_wgrad_tc_partial_floats(gi, mil_pf8(n, c.cout, gi.h, gi.w), c.ks));
   }
+  if (pl.stem_tc) pf = std::max(pf, mil_stem_tc_partial_floats(n, side));
   pl.partial_floats = pf;
   pl.off_partial = take(pf * sizeof(float));
   pl.total_bytes = off;
@@ -285,6 +294,10 @@ int mil_extractor_forward_impl(const void* const* params, const float* bag, cons
     t.count = 0;
     t.esize = (int)mil_esize(dt);
     guard_add(t, wsp(ws, pl.off_pooled), pl.g[0]);
+    if (pl.stem_tc) {
+      guard_add(t, wsp(ws, pl.off_xs), mil_stem_tc_geom_in(pl.n, pl.side));
+      guard_add(t, wsp(ws, pl.off_cv), mil_stem_tc_geom_conv(pl.n, pl.side));
+    }
     for (int l = 0; l < 4; ++l)
       for (int b = 0; b < 3; ++b) {
         guard_add(t, wsp(ws, pl.off_h[l * 3 + b]), pl.g[l]);
@@ -298,8 +311,15 @@ int mil_extractor_forward_impl(const void* const* params, const float* bag, cons
     return c.tc ? wsp(ws, pl.off_wtc) + (tr ? c.wtct_off : c.wtc_off) : nullptr;
   };
   const int p_c1w = mil_param_index("cnn.module.conv1.weight"), p_c1b = mil_param_index("cnn.module.conv1.bias");
-  MIL_TRY(mil_launch_stem_fwd(dt, bag, idx, pl.n, pl.side, (const float*)params[p_c1w], (const float*)params[p_c1b],
-                              wsp(ws, pl.off_pooled), pl.g[0], (uint8_t*)wsp(ws, pl.off_argmax), s));
+  if (pl.stem_tc)
+    MIL_TRY(mil_launch_stem_tc_fwd(bag, idx, pl.n, pl.side, (const float*)params[p_c1w], (const float*)params[p_c1b],
+                                   wsp(ws, pl.off_xs), wsp(ws, pl.off_cv), (float*)wsp(ws, pl.off_stem_wp),
+                                   wsp(ws, pl.off_stem_wtc), wsp(ws, pl.off_pooled), pl.g[0],
+                                   (uint8_t*)wsp(ws, pl.off_argmax), s));
+  else
+    MIL_TRY(mil_launch_stem_fwd(dt, bag, idx, pl.n, pl.side, (const float*)params[p_c1w],
+                                (const float*)params[p_c1b], wsp(ws, pl.off_pooled), pl.g[0],
+                                (uint8_t*)wsp(ws, pl.off_argmax), s));
   const void* X = wsp(ws, pl.off_pooled);
   MilPF8 gx = pl.g[0];
   size_t ci = 0;
@@ -467,6 +487,10 @@ int mil_extractor_backward_impl(const void* const* params, const float* bag, con
   }
 
   const int p_c1w = mil_param_index("cnn.module.conv1.weight"), p_c1b = mil_param_index("cnn.module.conv1.bias");
+  if (pl.stem_tc)  // the conv-map buffer of the forward pass is free by now: it takes the dense conv-resolution gradient
+    return mil_launch_stem_tc_bwd(wsp(ws, pl.off_xs), pl.n, pl.side, dz, pl.g[0],
+                                  (const uint8_t*)wsp(ws, pl.off_argmax), wsp(ws, pl.off_cv), partial, gptr(p_c1w),
+                                  gptr(p_c1b), s);
   return mil_launch_stem_bwd(dt, bag, idx, pl.n, pl.side, dz, pl.g[0], (const uint8_t*)wsp(ws, pl.off_argmax),
                              partial, gptr(p_c1w), gptr(p_c1b), s);
 }

@@ -31,13 +31,13 @@ struct WgSmemHeader {
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat16* __restrict__ dz, MilPF8 gz,
-                float* __restrict__ partial, long long rec_stride, int ks, int taps_per_group, int npad) {
+                float* __restrict__ partial, long long rec_stride, MilTcShape sh, int halo, int taps_per_group,
+                int npad) {
   extern __shared__ __align__(128) unsigned char smem[];
   WgSmemHeader* hd = reinterpret_cast<WgSmemHeader*>(smem);
   unsigned char* ones = smem + 128;            // 512 B of bf16 1.0: the B operand of the bias-gradient MMA
   unsigned char* stage0 = smem + 128 + 512;
-  const int ntaps = ks * ks;
-  const int halo = ks == 3 ? gx.wp + 1 : 0;
+  const int ntaps = sh.ntaps;
   const int span = WG_TK + 2 * halo;
   const uint32_t b_plane = (uint32_t)span * 16;
   const uint32_t a_bytes = (uint32_t)gz.cb * WG_A_PLANE;
@@ -94,23 +94,23 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
         tc_fence_after();
         const uint32_t a_base = smem_u32(stage0 + (size_t)stage * stage_bytes);
         const uint32_t b_base = a_base + a_bytes;
+        // descriptors of K-step kk = descriptor of K-step 0 + kk * 256 B (start-address field, 16-byte units)
+        const uint64_t ad0 = make_desc(a_base, 128, WG_A_PLANE);
+        const uint32_t acc0 = first ? 0u : 1u;
         for (int tl = 0; tl < ntl; ++tl) {
           const int tap = tap_lo + tl;
-          const int s = ks == 3 ? ((tap / 3 - 1) * gx.wp + (tap % 3 - 1)) : 0;
-          const uint32_t b_tap = b_base + (uint32_t)(halo + s) * 16;
+          const int s = sh.t_dy[tap] * gx.wp + sh.t_dx[tap];
+          const uint64_t bd0 = make_desc(b_base + (uint32_t)(halo + s) * 16, 128, b_plane);
+          const uint32_t d = tmem_base + tl * npad;
+          umma_bf16(d, ad0, bd0, idesc, acc0);
 #pragma unroll
-          for (int kk = 0; kk < WG_TK / 16; ++kk) {
-            const uint64_t ad = make_desc(a_base + kk * 256, 128, WG_A_PLANE);
-            const uint64_t bd = make_desc(b_tap + kk * 256, 128, b_plane);
-            umma_bf16(tmem_base + tl * npad, ad, bd, idesc, !(first && kk == 0));
-          }
+          for (int kk = 1; kk < WG_TK / 16; ++kk) umma_bf16(d, ad0 + kk * 16, bd0 + kk * 16, idesc, 1u);
         }
         if (with_bias) {
+          const uint32_t d = tmem_base + ntl * npad;
+          umma_bf16(d, ad0, ones_desc, idesc_b, acc0);
 #pragma unroll
-          for (int kk = 0; kk < WG_TK / 16; ++kk) {
-            const uint64_t ad = make_desc(a_base + kk * 256, 128, WG_A_PLANE);
-            umma_bf16(tmem_base + ntl * npad, ad, ones_desc, idesc_b, !(first && kk == 0));
-          }
+          for (int kk = 1; kk < WG_TK / 16; ++kk) umma_bf16(d, ad0 + kk * 16, ones_desc, idesc_b, 1u);
         }
         umma_commit(&hd->empty[stage]);
         first = false;
@@ -169,7 +169,7 @@ static int wg_sm_count() {
 
 static void wg_config(const MilPF8& gx, const MilPF8& gz, int ks, int* npad, int* groups, int* tpg, int* ctas) {
   *npad = (gx.c + 15) / 16 * 16;
-  const int ntaps = ks * ks;
+  const int ntaps = ks == 7 ? 16 : ks * ks;
   *groups = (ntaps * *npad + 16 <= 512) ? 1 : 2;
   *tpg = (ntaps + *groups - 1) / *groups;
   const long long n_tiles = mil_cdiv(gz.Q, WG_TK);
@@ -183,22 +183,38 @@ bool mil_wgrad_tc_supported(int dtype, int ks, int stride, int cin, int cout) {
 size_t mil_wgrad_tc_partial_floats(const MilPF8& gx, const MilPF8& gz, int ks) {
   int npad, groups, tpg, ctas;
   wg_config(gx, gz, ks, &npad, &groups, &tpg, &ctas);
-  return (size_t)ctas * ((size_t)ks * ks * gx.cb * 8 * gz.cb * 8 + gz.cb * 8);
+  const size_t ntaps = ks == 7 ? 16 : (size_t)ks * ks;
+  return (size_t)ctas * (ntaps * gx.cb * 8 * gz.cb * 8 + gz.cb * 8);
 }
 
-int mil_launch_wgrad_tc(const void* x, const MilPF8& gx, const void* dz, const MilPF8& gz, float* partial, float* dw,
-                        float* db, int ks, cudaStream_t s) {
-  MIL_REQUIRE(gx.n == gz.n && gx.h == gz.h && gx.w == gz.w, "wgrad_tc: geometry mismatch");
+// accumulate-only part: writes `*ctas_out` partial records [tap][cin_pad][cout_pad] (+[cout_pad] bias sums)
+int mil_launch_wgrad_tc_partials(const void* x, const MilPF8& gx, const void* dz, const MilPF8& gz, float* partial,
+                                 int ks, int* ctas_out, long long* rec_out, cudaStream_t s) {
+  MIL_REQUIRE(gx.n == gz.n && gx.h == gz.h && gx.w == gz.w && gx.wp == gz.wp && gx.hp == gz.hp,
+              "wgrad_tc: geometry mismatch");
   int npad, groups, tpg, ctas;
   wg_config(gx, gz, ks, &npad, &groups, &tpg, &ctas);
-  const int halo = ks == 3 ? gx.wp + 1 : 0;
+  MilTcShape sh;
+  MIL_TRY(mil_tc_shape(gx.c, gz.c, ks, &sh));
+  const int halo = mil_tc_halo(sh, gx.wp);
+  MIL_REQUIRE(halo <= gx.G, "wgrad_tc: the window reaches %d pixels back but the map's guard is %lld", halo, gx.G);
   const size_t stage = (size_t)gz.cb * WG_A_PLANE + (size_t)gx.cb * (WG_TK + 2 * halo) * 16;
   const size_t smem = 128 + 512 + WG_STAGES * stage + WG_SLACK;
   MIL_REQUIRE(smem <= 227 * 1024, "wgrad_tc: tile width %d needs %zu bytes of shared memory", gx.w, smem);
   MIL_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long rec = (long long)ks * ks * gx.cb * 8 * gz.cb * 8 + gz.cb * 8;
+  const long long rec = (long long)sh.ntaps * gx.cb * 8 * gz.cb * 8 + gz.cb * 8;
   wgrad_tc_kernel<<<dim3(ctas, groups), WG_THREADS, smem, s>>>((const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)dz,
-                                                             gz, partial, rec, ks, tpg, npad);
+                                                             gz, partial, rec, sh, halo, tpg, npad);
   MIL_LAUNCH_OK();
+  *ctas_out = ctas;
+  *rec_out = rec;
+  return 0;
+}
+
+int mil_launch_wgrad_tc(const void* x, const MilPF8& gx, const void* dz, const MilPF8& gz, float* partial, float* dw,
+                        float* db, int ks, cudaStream_t s) {
+  int ctas;
+  long long rec;
+  MIL_TRY(mil_launch_wgrad_tc_partials(x, gx, dz, gz, partial, ks, &ctas, &rec, s));
   return mil_launch_reduce_conv_w(partial, ctas, rec, dw, db, gz.c, gx.c, ks, s);
 }

@@ -121,8 +121,9 @@ def resnet26_forward(p: Dict[str, torch.Tensor], x: torch.Tensor, prefix: str = 
     lr = lambda t: F.leaky_relu(t, SLOPE)
     ra = _bf16 if emulate_bf16 else (lambda t: t)
     rw = _bf16 if emulate_bf16 == "act+w" else (lambda t: t)
-    y = F.conv2d(x, p[prefix + "conv1.weight"], p[prefix + "conv1.bias"], stride=2, padding=3)
-    y = ra(F.max_pool2d(lr(y), kernel_size=3, stride=2, padding=1))
+    # "act+w": the stem runs on the tensor cores too -> bf16 input and conv1 weights, bf16 conv map before the pool
+    y = F.conv2d(rw(x), rw(p[prefix + "conv1.weight"]), p[prefix + "conv1.bias"], stride=2, padding=3)
+    y = ra(F.max_pool2d(rw(lr(y)), kernel_size=3, stride=2, padding=1))
     if taps is not None:
         taps["stem"] = y
     for li in range(1, 5):
