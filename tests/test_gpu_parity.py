@@ -233,11 +233,14 @@ def test_topk_attended_tiles_match_reference(precision, case):
         got = set(torch.topk(out["Aterm"][m].cpu(), k).indices.tolist())
         assert got == set(torch.topk(a_ref, k).indices.tolist()), m
         checked += 1
-    # the strongest tile of every map is always decidable in the peaked case
-    if min(meta["wm"]) < 0:
-        assert checked >= 1
-        for m in range(3):
+    # the strongest tile of every map, whenever it is separated from the runner-up by more than the tolerance
+    for m in range(3):
+        top2 = torch.topk(a_ref_all[m], 2).values
+        if float(top2[0] - top2[1]) > 2 * tol * float(top2[0]):
             assert int(out["Aterm"][m].argmax()) == int(a_ref_all[m].argmax())
+            checked += 1
+    if min(meta["wm"]) < 0 and precision == "fp32":
+        assert checked >= 3
     assert int(out["y_pred_hat"]) == int(rec["out.y_pred_hat"])
 
 
