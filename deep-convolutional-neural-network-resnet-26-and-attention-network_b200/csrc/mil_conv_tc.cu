@@ -30,7 +30,7 @@
 #include "mil_tc_ptx.cuh"
 
 #define TC_M 128
-#define TC_STAGES 3
+#define TC_MAX_STAGES 8  // the ring depth is chosen per launch: as many stages as shared memory holds
 #define TC_ACC 2
 #define TC_THREADS 320  // 10 warps
 #define TC_MAXCB 10     // output chunks (80 channels)
@@ -52,11 +52,17 @@ __global__ void pack_tc_kernel(const float* __restrict__ wp, __nv_bfloat16* __re
 
 // ---- the kernel ----------------------------------------------------------------------------------------
 struct TcSmemHeader {
-  uint64_t full[TC_STAGES], empty[TC_STAGES], acc_full[TC_ACC], acc_empty[TC_ACC], b_full;
-  uint64_t a_desc[MIL_TC_MAX_MMA];  // A descriptor of MMA j relative to the start of an A stage
-  uint64_t b_desc[MIL_TC_MAX_MMA];  // B descriptor of MMA j (absolute)
+  uint64_t full[TC_MAX_STAGES], empty[TC_MAX_STAGES], acc_full[TC_ACC], acc_empty[TC_ACC], b_full;
   uint32_t tmem_base;
   float bias[96];
+};
+
+// per-MMA descriptor templates, precomputed on the host and passed as kernel parameters so that the issuing
+// warp reads them through the uniform datapath (constant bank): A relative to the start of an A stage, B
+// relative to the start of the weight block
+struct TcIssue {
+  uint64_t a_desc[MIL_TC_MAX_MMA];
+  uint64_t b_desc[MIL_TC_MAX_MMA];
 };
 
 __device__ __forceinline__ uint4 ld_nc16(const __nv_bfloat16* p) {
@@ -74,7 +80,8 @@ __device__ __forceinline__ void unpack8(const uint4& r, float v[8]) {
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat16* __restrict__ wtc,
                const float* __restrict__ bias, const __nv_bfloat16* res, const __nv_bfloat16* act,
-               __nv_bfloat16* out, MilPF8 go, MilTcShape sh, int epi, int transposed, int sub, int halo) {
+               __nv_bfloat16* out, MilPF8 go, MilTcShape sh, const __grid_constant__ TcIssue iss, int epi,
+               int sub, int halo, int n_stages) {
   extern __shared__ __align__(128) unsigned char smem[];
   TcSmemHeader* hd = reinterpret_cast<TcSmemHeader*>(smem);
   const uint32_t hdr_bytes = (uint32_t)((sizeof(TcSmemHeader) + 127) / 128 * 128);
@@ -92,31 +99,14 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
 
   // ---- one-time setup ----
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&hd->full[s], 1); mbar_init(&hd->empty[s], 1); }
+    for (int s = 0; s < n_stages; ++s) { mbar_init(&hd->full[s], 1); mbar_init(&hd->empty[s], 1); }
     for (int a = 0; a < TC_ACC; ++a) { mbar_init(&hd->acc_full[a], 1); mbar_init(&hd->acc_empty[a], 4); }
     mbar_init(&hd->b_full, 1);
     fence_barrier_init();
   }
-  for (int j = threadIdx.x; j < sh.nmma; j += blockDim.x) {
-    int off[2];
-    for (int h = 0; h < 2; ++h) {
-      const int tap = sh.g_tap[2 * j + h], chunk = sh.g_chunk[2 * j + h];
-      if (tap == 0xFF) {
-        off[h] = -1;
-      } else {
-        int s = sh.t_dy[tap] * gx.wp + sh.t_dx[tap];  // forward reads x(q + s); the data gradient reads dz(q - s)
-        if (transposed) s = -s;
-        off[h] = chunk * (int)plane + (halo + s) * 16;
-      }
-    }
-    if (off[1] < 0) off[1] = sh.cbin * (int)plane + halo * 16;  // dummy half -> the all-zero plane
-    // host guarantees off[1] > off[0] (mil_tc_shape orders the halves)
-    hd->a_desc[j] = make_desc((uint32_t)off[0], (uint32_t)(off[1] - off[0]), 128);
-    hd->b_desc[j] = make_desc(smem_u32(bsm) + (uint32_t)j * 2 * sh.npad * 16, (uint32_t)sh.npad * 16, 128);
-  }
   for (int i = threadIdx.x; i < 96; i += blockDim.x)
     hd->bias[i] = (bias != nullptr && i < go.c) ? bias[i] : 0.f;
-  for (int s = 0; s < TC_STAGES; ++s) {  // zero plane of every stage
+  for (int s = 0; s < n_stages; ++s) {  // zero plane of every stage
     uint4* zp = reinterpret_cast<uint4*>(asm0 + (size_t)s * stage_bytes + (size_t)sh.cbin * plane);
     for (int i = threadIdx.x; i < span; i += blockDim.x) zp[i] = make_uint4(0, 0, 0, 0);
   }
@@ -128,46 +118,52 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
   const uint32_t tmem_base = hd->tmem_base;
 
   if (warp == 0) {
-    // ===================== producer =====================
-    if (lane == 0) {
+    // ===================== producer (whole warp in uniform control flow, one elected lane issues) ==========
+    if (elect_one()) {
       mbar_expect_tx(&hd->b_full, b_bytes);
       bulk_g2s(bsm, wtc, b_bytes, &hd->b_full);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        mbar_wait(&hd->empty[stage], phase ^ 1);
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      mbar_wait(&hd->empty[stage], phase ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&hd->full[stage], plane * sh.cbin);
         const long long q0 = t * TC_M;
         unsigned char* dst = asm0 + (size_t)stage * stage_bytes;
         for (int c = 0; c < sh.cbin; ++c)
           bulk_g2s(dst + (size_t)c * plane, x + mil_pf8_off(gx, c, q0 - halo), plane, &hd->full[stage]);
-        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == n_stages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      // instruction descriptor: D = f32, A = B = bf16, both K-major, N = npad, M = 128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(sh.npad >> 3) << 17) |
-                             ((uint32_t)(TC_M >> 4) << 24);
-      mbar_wait(&hd->b_full, 0);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      const int nmma = sh.nmma;
-      for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        mbar_wait(&hd->acc_empty[acc], acc_phase ^ 1);
-        mbar_wait(&hd->full[stage], phase);
-        tc_fence_after();
-        // the start-address field sits in the low 14 bits of the descriptor: adding the stage base cannot carry
-        const uint64_t a_add = (uint64_t)(smem_u32(asm0 + (size_t)stage * stage_bytes) >> 4);
-        const uint32_t d = tmem_base + acc * acc_stride;
-#pragma unroll 2
-        for (int j = 0; j < nmma; ++j) umma_bf16(d, hd->a_desc[j] + a_add, hd->b_desc[j], idesc, j > 0);
+    // ===================== MMA issuer (uniform control flow, one elected lane issues) =====================
+    // instruction descriptor: D = f32, A = B = bf16, both K-major, N = npad, M = 128
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(sh.npad >> 3) << 17) |
+                           ((uint32_t)(TC_M >> 4) << 24);
+    mbar_wait(&hd->b_full, 0);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    const int nmma = sh.nmma;
+    const uint64_t b_add = (uint64_t)(smem_u32(bsm) >> 4);
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      mbar_wait(&hd->acc_empty[acc], acc_phase ^ 1);
+      mbar_wait(&hd->full[stage], phase);
+      tc_fence_after();
+      // the start-address field sits in the low 14 bits of the descriptor: adding a base cannot carry
+      const uint64_t a_add = (uint64_t)(smem_u32(asm0 + (size_t)stage * stage_bytes) >> 4);
+      const uint32_t d = tmem_base + acc * acc_stride;
+      if (elect_one()) {
+#pragma unroll 4
+        for (int j = 0; j < nmma; ++j) umma_bf16(d, iss.a_desc[j] + a_add, iss.b_desc[j] + b_add, idesc, j > 0);
         umma_commit(&hd->empty[stage]);   // smem stage reusable once these MMAs have read it
         umma_commit(&hd->acc_full[acc]);  // accumulator complete
-        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
-        if (++acc == TC_ACC) { acc = 0; acc_phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == n_stages) { stage = 0; phase ^= 1; }
+      if (++acc == TC_ACC) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ===================== epilogue: group eg serves accumulator stage eg =====================
@@ -177,19 +173,26 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
     const int cbout = sh.cbout;
     const bool has_res = res != nullptr, has_act = epi == MIL_EPI_DGRAD;
     uint32_t acc_phase = 0;
-    long long it = 0;
-    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-      if ((it & 1) != eg) continue;
-      // this thread's pixel: flat index q at the input resolution; qo = where it is stored.  sub: the stride-2
+    // This thread's pixel as (image n, in-plane offset r), advanced incrementally from tile to tile: the only
+    // 64-bit divisions of the kernel happen here, once (the epilogue's instruction stream is what bounds the
+    // small-channel layers, not the tensor pipe).
+    const long long step_q = 2LL * gridDim.x * TC_M;  // this group takes every second tile of the CTA
+    const int step_n = (int)(step_q / gx.P), step_r = (int)(step_q % gx.P);
+    const long long q_first = ((long long)blockIdx.x + (long long)eg * gridDim.x) * TC_M + row;
+    int n = (int)(q_first / gx.P), r = (int)(q_first % gx.P);
+    const float inv_wp = 1.0f / (float)gx.wp;
+    const int P = (int)gx.P;
+    for (long long t = blockIdx.x + (long long)eg * gridDim.x; t < n_tiles; t += 2LL * gridDim.x) {
+      // flat index q = n * P + r at the input resolution; qo = where the pixel is stored.  sub: the stride-2
       // convolutions are evaluated at full resolution and only the even (y, x) positions are kept.
-      const long long q = t * TC_M + row;
-      long long qo = q;
-      bool in_range = q < gx.Q;
+      bool in_range = n < gx.n;
       bool is_pad = true;
+      long long qo = (long long)n * P + r;
       if (in_range) {
-        const int n = (int)(q / gx.P);
-        const int r = (int)(q - (long long)n * gx.P);
-        const int y = r / gx.wp, xo = r - y * gx.wp;
+        int y = __float2int_rz(((float)r + 0.5f) * inv_wp);  // r / wp for r < 2^22 (exact after the fix-up)
+        if (y * gx.wp > r) --y;
+        else if ((y + 1) * gx.wp <= r) ++y;
+        const int xo = r - y * gx.wp;
         if (!sub) {
           is_pad = (y >= gx.h) || (xo >= gx.w);
         } else {
@@ -199,6 +202,9 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
           qo = (long long)n * go.P + (long long)yh * go.wp + xh;
         }
       }
+      n += step_n;
+      r += step_r;
+      if (r >= P) { r -= P; ++n; }
       const bool live = in_range && !is_pad;
       // 1. residual / activation loads go out BEFORE we wait for the tensor core
       uint4 rres[TC_MAXCB], ract[TC_MAXCB];
@@ -326,11 +332,11 @@ int mil_launch_pack_tc(const float* wp, void* wtc, const MilTcShape& sh, cudaStr
   return 0;
 }
 
-static size_t tc_smem_bytes(int halo, const MilTcShape& sh) {
+static size_t tc_smem_bytes(int halo, const MilTcShape& sh, int n_stages) {
   const size_t hdr = (sizeof(TcSmemHeader) + 127) / 128 * 128;
   const size_t b = ((size_t)sh.nmma * 2 * sh.npad * 16 + 127) / 128 * 128;
   const size_t span = TC_M + 2 * (size_t)halo;
-  return hdr + b + (size_t)TC_STAGES * span * 16 * (sh.cbin + 1);
+  return hdr + b + (size_t)n_stages * span * 16 * (sh.cbin + 1);
 }
 
 int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const void* wtc, const MilTcShape& sh,
@@ -346,7 +352,9 @@ int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const vo
   MIL_REQUIRE(epi != MIL_EPI_DGRAD || act != nullptr, "conv_tc: DGRAD epilogue needs the activation tensor");
   const int halo = mil_tc_halo(sh, gx.wp);
   MIL_REQUIRE(halo <= gx.G, "conv_tc: the window reaches %d pixels back but the map's guard is %lld", halo, gx.G);
-  const size_t smem = tc_smem_bytes(halo, sh);
+  int n_stages = TC_MAX_STAGES;
+  while (n_stages > 2 && tc_smem_bytes(halo, sh, n_stages) > 200 * 1024) --n_stages;
+  const size_t smem = tc_smem_bytes(halo, sh, n_stages);
   MIL_REQUIRE(smem <= 227 * 1024, "conv_tc: tile width %d needs %zu bytes of shared memory", gx.w, smem);
   // the second K-half must sit above the first one (see mil_tc_shape); holds whenever a plane is larger than
   // twice the largest tap shift, i.e. always for cbin >= 2; cbin == 1 would need taps in ascending shift order
@@ -358,11 +366,33 @@ int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const vo
     MIL_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   }
   MIL_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TcIssue iss;
+  {
+    const int plane = (TC_M + 2 * halo) * 16;
+    for (int j = 0; j < sh.nmma; ++j) {
+      int off[2];
+      for (int h = 0; h < 2; ++h) {
+        const int tap = sh.g_tap[2 * j + h], chunk = sh.g_chunk[2 * j + h];
+        if (tap == 0xFF) {
+          off[h] = -1;
+        } else {
+          int sft = sh.t_dy[tap] * gx.wp + sh.t_dx[tap];  // forward reads x(q + s); the data gradient reads dz(q - s)
+          if (transposed) sft = -sft;
+          off[h] = chunk * plane + (halo + sft) * 16;
+        }
+      }
+      if (off[1] < 0) off[1] = sh.cbin * plane + halo * 16;  // dummy half -> the all-zero plane
+      MIL_REQUIRE(off[1] > off[0], "conv_tc: internal error, K-halves out of order");
+      iss.a_desc[j] = make_desc_bits((uint32_t)off[0], (uint32_t)(off[1] - off[0]), 128);
+      iss.b_desc[j] = make_desc_bits((uint32_t)j * 2 * sh.npad * 16, (uint32_t)sh.npad * 16, 128);
+    }
+    for (int j = sh.nmma; j < MIL_TC_MAX_MMA; ++j) iss.a_desc[j] = iss.b_desc[j] = 0;
+  }
   const long long n_tiles = mil_cdiv(gx.Q, TC_M);
   const int grid = (int)std::min<long long>(n_tiles, n_sm);
   conv_tc_kernel<<<grid, TC_THREADS, smem, s>>>((const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)wtc, bias,
                                                 (const __nv_bfloat16*)res, (const __nv_bfloat16*)act,
-                                                (__nv_bfloat16*)out, go, sh, epi, transposed, sub, halo);
+                                                (__nv_bfloat16*)out, go, sh, iss, epi, sub, halo, n_stages);
   MIL_LAUNCH_OK();
   return 0;
 }

@@ -64,6 +64,27 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float v[8]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// one lane of a converged warp (warp-uniform control flow: keeps descriptors / addresses in uniform registers --
+// issuing tcgen05.mma or bulk copies under `if (lane == 0)` instead makes the compiler wrap every instruction in
+// a vector->uniform register shuffle loop, ~130 cycles per MMA)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// host + device: the same descriptor bit layout (the host precomputes per-MMA templates into kernel parameters)
+__host__ __device__ __forceinline__ uint64_t make_desc_bits(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
 // un-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1).
 //   K-major  operand: 8 rows x 16 B core matrices; SBO = next 8 rows (M/N), LBO = next 8 K-elements
 //   MN-major operand: 8 K-rows x 16 B core matrices; SBO = next 8 M/N-elements, LBO = next 8 K-rows

@@ -32,7 +32,7 @@ struct WgSmemHeader {
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat16* __restrict__ dz, MilPF8 gz,
                 float* __restrict__ partial, long long rec_stride, MilTcShape sh, int halo, int taps_per_group,
-                int npad) {
+                int npad, int mma_m) {
   extern __shared__ __align__(128) unsigned char smem[];
   WgSmemHeader* hd = reinterpret_cast<WgSmemHeader*>(smem);
   unsigned char* ones = smem + 128;            // 512 B of bf16 1.0: the B operand of the bias-gradient MMA
@@ -64,11 +64,12 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
   const uint32_t tmem_base = hd->tmem_base;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        mbar_wait(&hd->empty[stage], phase ^ 1);
+    // producer: whole warp in uniform control flow, one elected lane issues the bulk copies
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      mbar_wait(&hd->empty[stage], phase ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&hd->full[stage], stage_bytes);
         const long long q0 = t * WG_TK;
         unsigned char* dst = stage0 + (size_t)stage * stage_bytes;
@@ -76,27 +77,30 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
           bulk_g2s(dst + (size_t)c * WG_A_PLANE, dz + mil_pf8_off(gz, c, q0), WG_A_PLANE, &hd->full[stage]);
         for (int c = 0; c < gx.cb; ++c)
           bulk_g2s(dst + a_bytes + (size_t)c * b_plane, x + mil_pf8_off(gx, c, q0 - halo), b_plane, &hd->full[stage]);
-        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // D = f32, A = B = bf16, both MN-major (bits 15, 16), M = 128
-      const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t idesc = idesc_base | ((uint32_t)(npad >> 3) << 17);
-      const uint32_t idesc_b = idesc_base | ((uint32_t)(16 >> 3) << 17);
-      const uint64_t ones_desc = make_desc(smem_u32(ones), 128, 256);
-      int stage = 0;
-      uint32_t phase = 0;
-      bool first = true;
-      for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        mbar_wait(&hd->full[stage], phase);
-        tc_fence_after();
-        const uint32_t a_base = smem_u32(stage0 + (size_t)stage * stage_bytes);
-        const uint32_t b_base = a_base + a_bytes;
-        // descriptors of K-step kk = descriptor of K-step 0 + kk * 256 B (start-address field, 16-byte units)
-        const uint64_t ad0 = make_desc(a_base, 128, WG_A_PLANE);
-        const uint32_t acc0 = first ? 0u : 1u;
+    // MMA issuer: uniform control flow (descriptors stay in uniform registers), one elected lane issues.
+    // M = 64 when the output channels fit (the accumulator rows then sit in 16 lanes of every lane quarter).
+    // D = f32, A = B = bf16, both MN-major (bits 15, 16)
+    const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(mma_m >> 4) << 24);
+    const uint32_t idesc = idesc_base | ((uint32_t)(npad >> 3) << 17);
+    const uint32_t idesc_b = idesc_base | ((uint32_t)(16 >> 3) << 17);
+    const uint64_t ones_desc = make_desc(smem_u32(ones), 128, 256);
+    int stage = 0;
+    uint32_t phase = 0;
+    bool first = true;
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      mbar_wait(&hd->full[stage], phase);
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(stage0 + (size_t)stage * stage_bytes);
+      const uint32_t b_base = a_base + a_bytes;
+      // descriptors of K-step kk = descriptor of K-step 0 + kk * 256 B (start-address field, 16-byte units)
+      const uint64_t ad0 = make_desc(a_base, 128, WG_A_PLANE);
+      const uint32_t acc0 = first ? 0u : 1u;
+      if (elect_one()) {
         for (int tl = 0; tl < ntl; ++tl) {
           const int tap = tap_lo + tl;
           const int s = sh.t_dy[tap] * gx.wp + sh.t_dx[tap];
@@ -113,19 +117,23 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
           for (int kk = 1; kk < WG_TK / 16; ++kk) umma_bf16(d, ad0 + kk * 16, ones_desc, idesc_b, 1u);
         }
         umma_commit(&hd->empty[stage]);
-        first = false;
-        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
       }
-      umma_commit(&hd->done);
+      __syncwarp();
+      first = false;
+      if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
     }
+    if (elect_one()) umma_commit(&hd->done);
+    __syncwarp();
   } else {
     // epilogue: TMEM lane = output channel co, columns = (local tap, ci)
     const int quarter = warp & 3;
-    const int co = quarter * 32 + lane;
+    // accumulator row -> TMEM lane: M = 128: row i in lane i;  M = 64: row i in lane 32*(i/16) + i%16 (each
+    // lane quarter holds 16 rows)
+    const int co = mma_m == 128 ? quarter * 32 + lane : (lane < 16 ? quarter * 16 + lane : 1 << 20);
     const int coutp = gz.cb * 8, cinp = gx.cb * 8;
     mbar_wait(&hd->done, 0);
     tc_fence_after();
-    if (quarter * 32 < coutp) {  // warp-uniform
+    if ((mma_m == 128 ? quarter * 32 : quarter * 16) < coutp) {  // warp-uniform
       float* rec = partial + (size_t)blockIdx.x * rec_stride;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
       for (int tl = 0; tl < ntl; ++tl) {
@@ -204,7 +212,8 @@ int mil_launch_wgrad_tc_partials(const void* x, const MilPF8& gx, const void* dz
   MIL_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long rec = (long long)sh.ntaps * gx.cb * 8 * gz.cb * 8 + gz.cb * 8;
   wgrad_tc_kernel<<<dim3(ctas, groups), WG_THREADS, smem, s>>>((const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)dz,
-                                                             gz, partial, rec, sh, halo, tpg, npad);
+                                                             gz, partial, rec, sh, halo, tpg, npad,
+                                                             gz.cb * 8 <= 64 ? 64 : 128);
   MIL_LAUNCH_OK();
   *ctas_out = ctas;
   *rec_out = rec;
