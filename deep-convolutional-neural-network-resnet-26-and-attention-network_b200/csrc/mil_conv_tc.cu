@@ -31,10 +31,7 @@
 
 #define TC_M 128
 #define TC_MAX_STAGES 8  // the ring depth is chosen per launch: as many stages as shared memory holds
-#define TC_ACC 2
-#define TC_THREADS 320  // 10 warps
-#define TC_MAXCB 10     // output chunks (80 channels)
-#define TC_HALF 5       // chunks pulled from TMEM per batch
+#define TC_MAX_ACC 4     // accumulator stages = epilogue groups (4 for <= 40 output channels, 2 above)
 
 // ---- weight pre-pack: fp32 wp[tap][kin_pad][nout_pad8] -> bf16 B operand blocks --------------------------
 // B block of MMA j: [half h][n (npad rows)][8 k-elements], group (tap,chunk) = order[2j+h]  (0xFF = dummy)
@@ -52,7 +49,7 @@ __global__ void pack_tc_kernel(const float* __restrict__ wp, __nv_bfloat16* __re
 
 // ---- the kernel ----------------------------------------------------------------------------------------
 struct TcSmemHeader {
-  uint64_t full[TC_MAX_STAGES], empty[TC_MAX_STAGES], acc_full[TC_ACC], acc_empty[TC_ACC], b_full;
+  uint64_t full[TC_MAX_STAGES], empty[TC_MAX_STAGES], acc_full[TC_MAX_ACC], acc_empty[TC_MAX_ACC], b_full;
   uint32_t tmem_base;
   float bias[96];
 };
@@ -77,7 +74,11 @@ __device__ __forceinline__ void unpack8(const uint4& r, float v[8]) {
   }
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// MAXCB: upper bound of the output chunks (sizes the per-thread register arrays exactly); NG: accumulator
+// stages = epilogue groups of 4 warps.  The thin layers are bound by the epilogue's instruction stream, not by
+// the tensor pipe, so they get 4 groups; the wide layers (more registers per thread) get 2.
+template <int MAXCB, int NG>
+__global__ void __launch_bounds__(64 + NG * 128, 1)
 conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat16* __restrict__ wtc,
                const float* __restrict__ bias, const __nv_bfloat16* res, const __nv_bfloat16* act,
                __nv_bfloat16* out, MilPF8 go, MilTcShape sh, const __grid_constant__ TcIssue iss, int epi,
@@ -95,12 +96,12 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
   const long long n_tiles = mil_cdiv(gx.Q, TC_M);  // tiles run over the INPUT resolution (== output unless sub)
   const uint32_t acc_stride = (uint32_t)((sh.npad + 31) / 32 * 32);
   uint32_t tmem_cols = 32;
-  while (tmem_cols < acc_stride * TC_ACC) tmem_cols <<= 1;
+  while (tmem_cols < acc_stride * NG) tmem_cols <<= 1;
 
   // ---- one-time setup ----
   if (threadIdx.x == 0) {
     for (int s = 0; s < n_stages; ++s) { mbar_init(&hd->full[s], 1); mbar_init(&hd->empty[s], 1); }
-    for (int a = 0; a < TC_ACC; ++a) { mbar_init(&hd->acc_full[a], 1); mbar_init(&hd->acc_empty[a], 4); }
+    for (int a = 0; a < NG; ++a) { mbar_init(&hd->acc_full[a], 1); mbar_init(&hd->acc_empty[a], 4); }
     mbar_init(&hd->b_full, 1);
     fence_barrier_init();
   }
@@ -163,7 +164,7 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
       }
       __syncwarp();
       if (++stage == n_stages) { stage = 0; phase ^= 1; }
-      if (++acc == TC_ACC) { acc = 0; acc_phase ^= 1; }
+      if (++acc == NG) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ===================== epilogue: group eg serves accumulator stage eg =====================
@@ -176,13 +177,14 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
     // This thread's pixel as (image n, in-plane offset r), advanced incrementally from tile to tile: the only
     // 64-bit divisions of the kernel happen here, once (the epilogue's instruction stream is what bounds the
     // small-channel layers, not the tensor pipe).
-    const long long step_q = 2LL * gridDim.x * TC_M;  // this group takes every second tile of the CTA
+    constexpr int HALF = MAXCB <= 5 ? MAXCB : 5;           // chunks pulled from TMEM per batch
+    const long long step_q = (long long)NG * gridDim.x * TC_M;  // this group takes every NG-th tile of the CTA
     const int step_n = (int)(step_q / gx.P), step_r = (int)(step_q % gx.P);
     const long long q_first = ((long long)blockIdx.x + (long long)eg * gridDim.x) * TC_M + row;
     int n = (int)(q_first / gx.P), r = (int)(q_first % gx.P);
     const float inv_wp = 1.0f / (float)gx.wp;
     const int P = (int)gx.P;
-    for (long long t = blockIdx.x + (long long)eg * gridDim.x; t < n_tiles; t += 2LL * gridDim.x) {
+    for (long long t = blockIdx.x + (long long)eg * gridDim.x; t < n_tiles; t += (long long)NG * gridDim.x) {
       // flat index q = n * P + r at the input resolution; qo = where the pixel is stored.  sub: the stride-2
       // convolutions are evaluated at full resolution and only the even (y, x) positions are kept.
       bool in_range = n < gx.n;
@@ -207,9 +209,9 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
       if (r >= P) { r -= P; ++n; }
       const bool live = in_range && !is_pad;
       // 1. residual / activation loads go out BEFORE we wait for the tensor core
-      uint4 rres[TC_MAXCB], ract[TC_MAXCB];
+      uint4 rres[MAXCB], ract[MAXCB];
 #pragma unroll
-      for (int c = 0; c < TC_MAXCB; ++c) {
+      for (int c = 0; c < MAXCB; ++c) {
         if (c < cbout && live) {
           const long long o = mil_pf8_off(go, c, qo);
           if (has_res) rres[c] = ld_nc16(res + o);
@@ -220,15 +222,15 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
       tc_fence_after();
       const uint32_t taddr = tmem_base + eg * acc_stride + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll
-      for (int half = 0; half < TC_MAXCB / TC_HALF; ++half) {
-        if (half * TC_HALF >= cbout) break;
+      for (int half = 0; half < (MAXCB + HALF - 1) / HALF; ++half) {
+        if (half * HALF >= cbout) break;
         // 2. pull this thread's accumulator row out of TMEM (5 chunks = 40 columns per batch)
-        float acc[TC_HALF][8];
+        float acc[HALF][8];
 #pragma unroll
-        for (int k = 0; k < TC_HALF; ++k)
-          if (half * TC_HALF + k < cbout) tmem_ld8(taddr + (half * TC_HALF + k) * 8, acc[k]);
+        for (int k = 0; k < HALF; ++k)
+          if (half * HALF + k < cbout) tmem_ld8(taddr + (half * HALF + k) * 8, acc[k]);
         tmem_ld_wait();
-        if ((half + 1) * TC_HALF >= cbout) {
+        if ((half + 1) * HALF >= cbout) {
           // 3. the accumulator stage is free again: the MMA warp can start the tile after next
           tc_fence_before();
           __syncwarp();
@@ -236,8 +238,8 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
         }
         // 4. arithmetic + stores
 #pragma unroll
-        for (int k = 0; k < TC_HALF; ++k) {
-          const int c = half * TC_HALF + k;
+        for (int k = 0; k < HALF; ++k) {
+          const int c = half * HALF + k;
           if (c < cbout && in_range) {
             float* v = acc[k];
             if (is_pad) {
@@ -365,7 +367,6 @@ int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const vo
     MIL_CHECK_CUDA(cudaGetDevice(&dev));
     MIL_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   }
-  MIL_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   TcIssue iss;
   {
     const int plane = (TC_M + 2 * halo) * 16;
@@ -390,9 +391,19 @@ int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const vo
   }
   const long long n_tiles = mil_cdiv(gx.Q, TC_M);
   const int grid = (int)std::min<long long>(n_tiles, n_sm);
-  conv_tc_kernel<<<grid, TC_THREADS, smem, s>>>((const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)wtc, bias,
-                                                (const __nv_bfloat16*)res, (const __nv_bfloat16*)act,
-                                                (__nv_bfloat16*)out, go, sh, iss, epi, sub, halo, n_stages);
+#define MIL_TC_LAUNCH(MAXCB, NG)                                                                                  \
+  do {                                                                                                            \
+    MIL_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<MAXCB, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                        (int)smem));                                                              \
+    conv_tc_kernel<MAXCB, NG><<<grid, 64 + NG * 128, smem, s>>>(                                                  \
+        (const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)wtc, bias, (const __nv_bfloat16*)res,                  \
+        (const __nv_bfloat16*)act, (__nv_bfloat16*)out, go, sh, iss, epi, sub, halo, n_stages);                   \
+  } while (0)
+  if (sh.cbout <= 3) MIL_TC_LAUNCH(3, 4);
+  else if (sh.cbout <= 5) MIL_TC_LAUNCH(5, 4);
+  else if (sh.cbout <= 8) MIL_TC_LAUNCH(8, 2);
+  else MIL_TC_LAUNCH(10, 2);
+#undef MIL_TC_LAUNCH
   MIL_LAUNCH_OK();
   return 0;
 }
