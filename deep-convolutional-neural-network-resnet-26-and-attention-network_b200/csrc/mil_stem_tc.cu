@@ -2,124 +2,141 @@
 // 3 -> 20 channels, + bias, LeakyReLU(0.1), max-pool 3x3 / stride 2 / pad 1; backward = weight / bias gradient
 // only (the bag is detached, gbm/model.py:194,196).
 //
-// A 7x7 stride-2 convolution over 3 channels is a 4x4 stride-1 convolution over the 12 channels of the
-// space-to-depth image  xs[(c,py,px)][Y][X] = x[c][2Y+py][2X+px]  with window offsets a,b in {-2..1}
-// (ky = 2a+py+3, kx = 2b+px+3; the 15 % of taps that fall outside 0..6 carry zero weights).  In PF8 with a
-// 2-pixel shared halo that is exactly the shape conv_tc / wgrad_tc handle: 16 taps x 2 chunks = 16 MMAs (K=16).
+// Space-to-depth by FOUR turns the stem into an ordinary 3x3 / stride-1 convolution at the POOLED resolution:
+//   input   xs[(c, ry, rx)][Y][X] = x[c][4Y+ry][4X+rx]                       3*16 = 48 channels
+//   output  cv[(co, a, b)][Y][X]  = conv1(x)[co][2Y+a][2X+b]                 20*4 = 80 channels (4 phases)
+//   weights W4[(dy,dx)][(c,ry,rx)][(co,a,b)] = w[co][c][4dy+ry-2a+3][4dx+rx-2b+3]   (zero outside 0..6)
+// because conv1 row 2Y+a reads input rows 4Y + (2a+ky-3) and 2a+ky-3 = 4dy+ry has a unique (dy in -1..1, ry in 0..3).
+// So the stem runs on conv_tc / wgrad_tc exactly like a layer (48 -> 80 channels, N = 80 per MMA instead of the
+// 32 a stride-2 formulation gives), the window halo is one row of 57 pixels instead of two rows of 114, and the
+// max-pool becomes a reduction over (neighbour pixel, phase) pairs.
 //
-//   forward : s2d (fp32 NCHW -> bf16 PF8, fused with the train-mode tile gather)  ->  conv_tc (+bias, LeakyReLU)
-//             ->  pool (3x3/2 max, first maximum wins like ATen, 1-byte arg-max per pooled element)
-//   backward: scatter (pooled gradient -> dense conv-resolution gradient through the arg-max, as a gather so that
-//             it is deterministic)  ->  wgrad_tc (16 taps)  ->  fixed-order reduction into the [20][3][7][7] layout
+//   forward : s2d4 (fp32 NCHW -> bf16 PF8, fused with the train-mode tile gather)  ->  conv_tc (+bias, LeakyReLU)
+//             ->  pool (first maximum in window scan order wins like ATen; 1-byte arg-max per pooled element)
+//   backward: unpool (pooled gradient -> the 4-phase conv gradient through the arg-max, as a gather => deterministic)
+//             ->  wgrad_tc (9 taps, 48 x 80)  ->  fixed-order reduction + fold back into the [20][3][7][7] layout
 #include <algorithm>
 
 #include "mil_common.cuh"
 #include "mil_conv_tc.cuh"
 
 #define STC_CO 20
-#define STC_CI 12
+#define STC_CI 48   // 3 * 4 * 4
+#define STC_CO4 80  // 20 * 2 * 2
 
-// ---- 1. space-to-depth --------------------------------------------------------------------------------------
+// ---- 1. space-to-depth by 4 ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-stem_s2d_kernel(const float* __restrict__ x, const int* __restrict__ idx, int side, __nv_bfloat16* __restrict__ xs,
-                MilPF8 g) {
-  const long long total = 2 * g.Q;
+stem_s2d4_kernel(const float* __restrict__ x, const int* __restrict__ idx, int side, __nv_bfloat16* __restrict__ xs,
+                 MilPF8 g) {
+  // one thread per (pixel, (c, ry)) = 12 row-quads: reads one float4 (4 rx) when aligned, writes 4 channels
+  const long long total = 12 * g.Q;
+  const bool vec = (side & 3) == 0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int cb = (int)(i / g.Q);
-    const long long q = i - (long long)cb * g.Q;
+    const int cr = (int)(i / g.Q);  // c*4 + ry
+    const long long q = i - (long long)cr * g.Q;
     const int n = (int)(q / g.P);
     const int r = (int)(q - (long long)n * g.P);
     const int Y = r / g.wp, X = r - Y * g.wp;
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
     if (Y < g.h && X < g.w) {
-      const int src_n = idx ? idx[n] : n;
-      const float* xin = x + (size_t)src_n * 3 * side * side;
+      const int c = cr >> 2, ry = cr & 3;
+      const int iy = 4 * Y + ry;
+      if (iy < side) {
+        const int src_n = idx ? idx[n] : n;
+        const float* row = x + (((size_t)src_n * 3 + c) * side + iy) * side + 4 * X;
+        if (vec) {
+          const float4 f = *reinterpret_cast<const float4*>(row);
+          v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+        } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int cc = cb * 8 + j;  // (c, py, px)
-        if (cc < STC_CI) {
-          const int c = cc >> 2, py = (cc >> 1) & 1, px = cc & 1;
-          const int iy = 2 * Y + py, ix = 2 * X + px;
-          if (iy < side && ix < side) v[j] = xin[((size_t)c * side + iy) * side + ix];
+          for (int rx = 0; rx < 4; ++rx)
+            if (4 * X + rx < side) v[rx] = row[rx];
         }
       }
     }
-    mil_store8(xs + mil_pf8_off(g, cb, q), v);
+    // channel cc = (c*4 + ry)*4 + rx = cr*4 + rx  ->  chunk cr/2, lanes (cr&1)*4 .. +3   (8 bytes)
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&p0);
+    pk.y = *reinterpret_cast<uint32_t*>(&p1);
+    *reinterpret_cast<uint2*>(xs + mil_pf8_off(g, cr >> 1, q) + (cr & 1) * 4) = pk;
   }
 }
 
-// ---- weights: w[20][3][7][7] -> wp[tap(a,b)][kin_pad 16][nout_pad 24] (fp32; mil_launch_pack_tc finishes) -----
-__global__ void stem_pack_w_kernel(const float* __restrict__ w, float* __restrict__ wp) {
-  const int total = 16 * 16 * 24;
+// ---- weights: w[20][3][7][7] -> wp[tap 9][kin 48][nout 80] (fp32; mil_launch_pack_tc finishes), bias4[80] ------
+__global__ void stem_pack_w4_kernel(const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ wp,
+                                    float* __restrict__ bias4) {
+  const int total = 9 * STC_CI * STC_CO4;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int co = i % 24, cc = (i / 24) % 16, t = i / (24 * 16);
+    const int co4 = i % STC_CO4, cc = (i / STC_CO4) % STC_CI, t = i / (STC_CO4 * STC_CI);
+    const int co = co4 >> 2, a = (co4 >> 1) & 1, bb = co4 & 1;
+    const int c = cc >> 4, ry = (cc >> 2) & 3, rx = cc & 3;
+    const int dy = t / 3 - 1, dx = t % 3 - 1;
+    const int ky = 4 * dy + ry - 2 * a + 3, kx = 4 * dx + rx - 2 * bb + 3;
     float v = 0.f;
-    if (co < STC_CO && cc < STC_CI) {
-      const int c = cc >> 2, py = (cc >> 1) & 1, px = cc & 1;
-      const int a = t / 4 - 2, b = t % 4 - 2;
-      const int ky = 2 * a + py + 3, kx = 2 * b + px + 3;
-      if (ky >= 0 && ky < 7 && kx >= 0 && kx < 7) v = w[((co * 3 + c) * 7 + ky) * 7 + kx];
-    }
+    if (ky >= 0 && ky < 7 && kx >= 0 && kx < 7) v = w[((co * 3 + c) * 7 + ky) * 7 + kx];
     wp[i] = v;
   }
+  if (blockIdx.x == 0 && threadIdx.x < STC_CO4) bias4[threadIdx.x] = b[threadIdx.x >> 2];
 }
 
-// ---- 3. max-pool 3x3 / stride 2 / pad 1 over the (already activated) conv map ---------------------------------
+// ---- 3. max-pool 3x3 / stride 2 / pad 1 of the conv1 map held as 4 phases ----------------------------------------
+// pooled (py,px) covers conv rows 2py-1, 2py, 2py+1 = (py-1, a=1), (py, a=0), (py, a=1); same for columns.
+// cv channel = co*4 + a*2 + b  ->  chunk co/2;  thread = (pooled pixel, pair of output channels)
 __global__ void __launch_bounds__(256)
-stem_pool_kernel(const __nv_bfloat16* __restrict__ cv, MilPF8 gc, __nv_bfloat16* __restrict__ pooled, MilPF8 gp,
-                 uint8_t* __restrict__ argmax) {
-  const long long total = (long long)gp.cb * gp.Q;
+stem_pool4_kernel(const __nv_bfloat16* __restrict__ cv, MilPF8 gc, int hc, __nv_bfloat16* __restrict__ pooled,
+                  MilPF8 gp, uint8_t* __restrict__ argmax) {
+  const long long total = 10 * gp.Q;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int cb = (int)(i / gp.Q);
-    const long long q = i - (long long)cb * gp.Q;
+    const int cp = (int)(i / gp.Q);  // channel pair: co = 2cp, 2cp+1
+    const long long q = i - (long long)cp * gp.Q;
     const int n = (int)(q / gp.P);
     const int r = (int)(q - (long long)n * gp.P);
     const int py = r / gp.wp, px = r - py * gp.wp;
-    float best[8];
-    int am[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { best[j] = 0.f; am[j] = 0; }
+    float best[2] = {0.f, 0.f};
+    int am[2] = {0, 0};
     if (py < gp.h && px < gp.w) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) best[j] = -INFINITY;
+      best[0] = best[1] = -INFINITY;
 #pragma unroll
       for (int wy = 0; wy < 3; ++wy) {
+        const int cy = 2 * py - 1 + wy;  // conv row
+        if (cy < 0 || cy >= hc) continue;
+        const int Y = cy >> 1, a = cy & 1;
 #pragma unroll
         for (int wx = 0; wx < 3; ++wx) {
-          const int cy = 2 * py - 1 + wy, cx = 2 * px - 1 + wx;
-          if (cy >= 0 && cy < gc.h && cx >= 0 && cx < gc.w) {
-            float v[8];
-            mil_load8(cv + mil_pf8_off(gc, cb, (long long)n * gc.P + (long long)cy * gc.wp + cx), v);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (v[j] > best[j]) { best[j] = v[j]; am[j] = wy * 3 + wx; }
-          }
+          const int cx = 2 * px - 1 + wx;
+          if (cx < 0 || cx >= hc) continue;
+          const int X = cx >> 1, b = cx & 1;
+          const __nv_bfloat16* p = cv + mil_pf8_off(gc, cp, (long long)n * gc.P + (long long)Y * gc.wp + X) + a * 2 + b;
+          const float v0 = __bfloat162float(p[0]), v1 = __bfloat162float(p[4]);
+          if (v0 > best[0]) { best[0] = v0; am[0] = wy * 3 + wx; }
+          if (v1 > best[1]) { best[1] = v1; am[1] = wy * 3 + wx; }
         }
       }
-      uint8_t* ap = argmax + ((size_t)n * gp.h * gp.w + (size_t)py * gp.w + px) * STC_CO + cb * 8;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (cb * 8 + j < STC_CO) ap[j] = (uint8_t)am[j];
-        else best[j] = 0.f;
-      }
+      uint8_t* ap = argmax + ((size_t)n * gp.h * gp.w + (size_t)py * gp.w + px) * STC_CO + cp * 2;
+      ap[0] = (uint8_t)am[0];
+      ap[1] = (uint8_t)am[1];
     }
-    mil_store8(pooled + mil_pf8_off(gp, cb, q), best);
+    // pooled channel co -> chunk co/8, lane co%8 ; the pair (2cp, 2cp+1) is one 4-byte store
+    __nv_bfloat162 pk = __floats2bfloat162_rn(best[0], best[1]);
+    *reinterpret_cast<__nv_bfloat162*>(pooled + mil_pf8_off(gp, cp >> 2, q) + (cp & 3) * 2) = pk;
+    if (cp == 9) {  // pad channels 20..23 of the last pooled chunk stay zero
+      *reinterpret_cast<uint2*>(pooled + mil_pf8_off(gp, 2, q) + 4) = make_uint2(0, 0);
+    }
   }
 }
 
-// ---- 4. backward scatter as a gather: dY(Y,X)[c] = sum of g(py,px)[c] over the pooled windows whose arg-max is (Y,X)
+// ---- 4. backward: dY4(Y,X)[(co,a,b)] = sum of g(py,px)[co] over the pooled windows whose arg-max is conv (2Y+a, 2X+b)
 __global__ void __launch_bounds__(256)
-stem_unpool_kernel(const __nv_bfloat16* __restrict__ g, MilPF8 gp, const uint8_t* __restrict__ argmax,
-                   __nv_bfloat16* __restrict__ dy, MilPF8 gc) {
-  const long long total = (long long)gc.cb * gc.Q;
+stem_unpool4_kernel(const __nv_bfloat16* __restrict__ g, MilPF8 gp, const uint8_t* __restrict__ argmax,
+                    __nv_bfloat16* __restrict__ dy, MilPF8 gc, int hc) {
+  const long long total = 10 * gc.Q;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int cb = (int)(i / gc.Q);
-    const long long q = i - (long long)cb * gc.Q;
+    const int cp = (int)(i / gc.Q);  // chunk of dY4 = channel pair (co = 2cp, 2cp+1) x 4 phases
+    const long long q = i - (long long)cp * gc.Q;
     const int n = (int)(q / gc.P);
     const int r = (int)(q - (long long)n * gc.P);
     const int Y = r / gc.wp, X = r - Y * gc.wp;
@@ -127,68 +144,81 @@ stem_unpool_kernel(const __nv_bfloat16* __restrict__ g, MilPF8 gp, const uint8_t
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     if (Y < gc.h && X < gc.w) {
-      // pooled windows containing conv row Y: py with 2py-1 <= Y <= 2py+1
-      const int py0 = Y >> 1, py1 = (Y + 1) >> 1, px0 = X >> 1, px1 = (X + 1) >> 1;
-      for (int py = py0; py <= py1; ++py) {
-        if (py >= gp.h) continue;
-        const int wy = Y - (2 * py - 1);
-        for (int px = px0; px <= px1; ++px) {
-          if (px >= gp.w) continue;
-          const int wx = X - (2 * px - 1);
-          const int want = wy * 3 + wx;
-          const uint8_t* ap = argmax + ((size_t)n * gp.h * gp.w + (size_t)py * gp.w + px) * STC_CO + cb * 8;
-          float gv[8];
-          mil_load8(g + mil_pf8_off(gp, cb, (long long)n * gp.P + (long long)py * gp.wp + px), gv);
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (cb * 8 + j < STC_CO && ap[j] == want) acc[j] += gv[j];
+      for (int a = 0; a < 2; ++a) {
+        const int cy = 2 * Y + a;
+        if (cy >= hc) continue;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const int cx = 2 * X + b;
+          if (cx >= hc) continue;
+          // pooled windows containing conv (cy, cx): py in {cy/2, (cy+1)/2}, px in {cx/2, (cx+1)/2}
+          const int py0 = cy >> 1, py1 = (cy + 1) >> 1, px0 = cx >> 1, px1 = (cx + 1) >> 1;
+          for (int py = py0; py <= py1; ++py) {
+            if (py >= gp.h) continue;
+            const int wy = cy - (2 * py - 1);
+            for (int px = px0; px <= px1; ++px) {
+              if (px >= gp.w) continue;
+              const int want = wy * 3 + (cx - (2 * px - 1));
+              const uint8_t* ap = argmax + ((size_t)n * gp.h * gp.w + (size_t)py * gp.w + px) * STC_CO + cp * 2;
+              const __nv_bfloat16* gv =
+                  g + mil_pf8_off(gp, cp >> 2, (long long)n * gp.P + (long long)py * gp.wp + px) + (cp & 3) * 2;
+              if (ap[0] == want) acc[a * 2 + b] += __bfloat162float(gv[0]);
+              if (ap[1] == want) acc[4 + a * 2 + b] += __bfloat162float(gv[1]);
+            }
+          }
         }
       }
     }
-    mil_store8(dy + mil_pf8_off(gc, cb, q), acc);
+    mil_store8(dy + mil_pf8_off(gc, cp, q), acc);
   }
 }
 
-// ---- 5. reduction of the wgrad_tc partial records into the PyTorch layout ------------------------------------
-// record: [tap 16][kin_pad 16][cout_pad 24] + [24] bias sums
-__global__ void stem_reduce_kernel(const float* __restrict__ partial, int nblk, long long stride,
-                                   float* __restrict__ dw, float* __restrict__ db) {
+// ---- 5. reduction of the wgrad_tc partial records + fold back into the PyTorch layout --------------------------
+// record: [tap 9][kin 48][cout 80] + [80] bias sums
+__global__ void stem_reduce4_kernel(const float* __restrict__ partial, int nblk, long long stride,
+                                    float* __restrict__ dw, float* __restrict__ db) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < STC_CO * 147) {
     const int kx = i % 7, ky = (i / 7) % 7, c = (i / 49) % 3, co = i / 147;
-    const int py = (ky + 1) & 1, px = (kx + 1) & 1;           // ky - 3 = 2a + py
-    const int a = (ky - 3 - py) / 2, b = (kx - 3 - px) / 2;   // exact: ky-3-py is even
-    const int t = (a + 2) * 4 + (b + 2), cc = c * 4 + py * 2 + px;
-    const size_t src = ((size_t)t * 16 + cc) * 24 + co;
     float acc = 0.f;
-    for (int k = 0; k < nblk; ++k) acc += partial[(size_t)k * stride + src];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int uy = 2 * a + ky - 3;          // = 4 dy + ry
+      const int dy = (uy + 4) / 4 - 1, ry = uy - 4 * dy;
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int ux = 2 * b + kx - 3;
+        const int dx = (ux + 4) / 4 - 1, rx = ux - 4 * dx;
+        const int t = (dy + 1) * 3 + (dx + 1), cc = (c * 4 + ry) * 4 + rx, co4 = co * 4 + a * 2 + b;
+        const size_t src = ((size_t)t * STC_CI + cc) * STC_CO4 + co4;
+        for (int k = 0; k < nblk; ++k) acc += partial[(size_t)k * stride + src];
+      }
+    }
     dw[i] += acc;
   } else if (i < STC_CO * 147 + STC_CO) {
     const int co = i - STC_CO * 147;
-    const size_t src = (size_t)16 * 16 * 24 + co;
     float acc = 0.f;
-    for (int k = 0; k < nblk; ++k) acc += partial[(size_t)k * stride + src];
+    for (int ph = 0; ph < 4; ++ph) {
+      const size_t src = (size_t)9 * STC_CI * STC_CO4 + co * 4 + ph;
+      for (int k = 0; k < nblk; ++k) acc += partial[(size_t)k * stride + src];
+    }
     db[co] += acc;
   }
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------
-MilPF8 mil_stem_tc_geom_in(int n, int side) {
-  const int hc = (side - 1) / 2 + 1;
-  return mil_pf8p(n, STC_CI, hc, hc, 2);
-}
-MilPF8 mil_stem_tc_geom_conv(int n, int side) {
-  const int hc = (side - 1) / 2 + 1;
-  return mil_pf8p(n, STC_CO, hc, hc, 2);
-}
-size_t mil_stem_tc_wpack_floats() { return 16 * 16 * 24; }
+static int stem_h0(int side) { return (((side - 1) / 2 + 1) - 1) / 2 + 1; }
+MilPF8 mil_stem_tc_geom_in(int n, int side) { return mil_pf8(n, STC_CI, stem_h0(side), stem_h0(side)); }
+MilPF8 mil_stem_tc_geom_conv(int n, int side) { return mil_pf8(n, STC_CO4, stem_h0(side), stem_h0(side)); }
+size_t mil_stem_tc_wpack_floats() { return (size_t)9 * STC_CI * STC_CO4 + STC_CO4; }
 size_t mil_stem_tc_wtc_bytes() {
   MilTcShape sh;
-  mil_tc_shape(STC_CI, STC_CO, 7, &sh);
+  mil_tc_shape(STC_CI, STC_CO4, 3, &sh);
   return mil_tc_wpack_bytes(sh);
 }
 size_t mil_stem_tc_partial_floats(int n, int side) {
-  return mil_wgrad_tc_partial_floats(mil_stem_tc_geom_in(n, side), mil_stem_tc_geom_conv(n, side), 7);
+  return mil_wgrad_tc_partial_floats(mil_stem_tc_geom_in(n, side), mil_stem_tc_geom_conv(n, side), 3);
 }
 
 static int grid_for(long long work) { return (int)std::max<long long>(1, std::min<long long>(mil_cdiv(work, 256), 148 * 16)); }
@@ -197,17 +227,19 @@ int mil_launch_stem_tc_fwd(const float* x, const int* idx, int n, int side, cons
                            void* convout, float* wp, void* wtc, void* pooled, const MilPF8& gp, uint8_t* argmax,
                            cudaStream_t s) {
   const MilPF8 gi = mil_stem_tc_geom_in(n, side), gc = mil_stem_tc_geom_conv(n, side);
-  MIL_REQUIRE(gp.h == (gc.h - 1) / 2 + 1 && gp.c == STC_CO && gp.n == n, "stem_tc_fwd: geometry mismatch");
-  stem_s2d_kernel<<<grid_for(2 * gi.Q), 256, 0, s>>>(x, idx, side, (__nv_bfloat16*)xs, gi);
+  const int hc = (side - 1) / 2 + 1;
+  MIL_REQUIRE(gp.h == gi.h && gp.w == gi.w && gp.c == STC_CO && gp.n == n, "stem_tc_fwd: geometry mismatch");
+  stem_s2d4_kernel<<<grid_for(12 * gi.Q), 256, 0, s>>>(x, idx, side, (__nv_bfloat16*)xs, gi);
   MIL_LAUNCH_OK();
-  stem_pack_w_kernel<<<24, 256, 0, s>>>(w, wp);
+  float* bias4 = wp + (size_t)9 * STC_CI * STC_CO4;
+  stem_pack_w4_kernel<<<64, 256, 0, s>>>(w, b, wp, bias4);
   MIL_LAUNCH_OK();
   MilTcShape sh;
-  MIL_TRY(mil_tc_shape(STC_CI, STC_CO, 7, &sh));
+  MIL_TRY(mil_tc_shape(STC_CI, STC_CO4, 3, &sh));
   MIL_TRY(mil_launch_pack_tc(wp, wtc, sh, s));
-  MIL_TRY(mil_launch_conv_tc(0, xs, gi, wtc, sh, b, nullptr, nullptr, convout, gc, MIL_EPI_FWD, 0, s));
-  stem_pool_kernel<<<grid_for((long long)gp.cb * gp.Q), 256, 0, s>>>((const __nv_bfloat16*)convout, gc,
-                                                                      (__nv_bfloat16*)pooled, gp, argmax);
+  MIL_TRY(mil_launch_conv_tc(0, xs, gi, wtc, sh, bias4, nullptr, nullptr, convout, gc, MIL_EPI_FWD, 0, s));
+  stem_pool4_kernel<<<grid_for(10 * gp.Q), 256, 0, s>>>((const __nv_bfloat16*)convout, gc, hc, (__nv_bfloat16*)pooled,
+                                                        gp, argmax);
   MIL_LAUNCH_OK();
   return 0;
 }
@@ -215,13 +247,14 @@ int mil_launch_stem_tc_fwd(const float* x, const int* idx, int n, int side, cons
 int mil_launch_stem_tc_bwd(const void* xs, int n, int side, const void* g, const MilPF8& gp, const uint8_t* argmax,
                            void* dy, float* partial, float* dw, float* db, cudaStream_t s) {
   const MilPF8 gi = mil_stem_tc_geom_in(n, side), gc = mil_stem_tc_geom_conv(n, side);
-  stem_unpool_kernel<<<grid_for((long long)gc.cb * gc.Q), 256, 0, s>>>((const __nv_bfloat16*)g, gp, argmax,
-                                                                        (__nv_bfloat16*)dy, gc);
+  const int hc = (side - 1) / 2 + 1;
+  stem_unpool4_kernel<<<grid_for(10 * gc.Q), 256, 0, s>>>((const __nv_bfloat16*)g, gp, argmax, (__nv_bfloat16*)dy, gc,
+                                                          hc);
   MIL_LAUNCH_OK();
   int ctas;
   long long rec;
-  MIL_TRY(mil_launch_wgrad_tc_partials(xs, gi, dy, gc, partial, 7, &ctas, &rec, s));
-  stem_reduce_kernel<<<(int)mil_cdiv(STC_CO * 147 + STC_CO, 128), 128, 0, s>>>(partial, ctas, rec, dw, db);
+  MIL_TRY(mil_launch_wgrad_tc_partials(xs, gi, dy, gc, partial, 3, &ctas, &rec, s));
+  stem_reduce4_kernel<<<(int)mil_cdiv(STC_CO * 147 + STC_CO, 128), 128, 0, s>>>(partial, ctas, rec, dw, db);
   MIL_LAUNCH_OK();
   return 0;
 }
