@@ -108,27 +108,27 @@ int mil_launch_reduce_partials(const float* partial, int nblk, long long stride,
 //   dw[cout][cin][tap] += ... ,  db[cout] += ...      (PyTorch parameter layout)
 __global__ void reduce_conv_w_kernel(const float* __restrict__ partial, int nblk, long long stride,
                                      float* __restrict__ dw, float* __restrict__ db, int cout, int cin, int ks) {
+  // threads walk the RECORD layout (coalesced reads of every partial record) and scatter into the parameter layout
   const int cip = (cin + 7) / 8 * 8, cop = (cout + 7) / 8 * 8;
   const int taps = ks * ks;
-  const int nw = cout * cin * taps;
+  const int nrec = taps * cip * cop;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nw) {
-    const int t = i % taps, ci = (i / taps) % cin, co = i / (taps * cin);
-    const size_t src = ((size_t)t * cip + ci) * cop + co;
+  if (i < nrec) {
+    const int co = i % cop, ci = (i / cop) % cip, t = i / (cop * cip);
+    if (co >= cout || ci >= cin) return;
     float acc = 0.f;
-    for (int b = 0; b < nblk; ++b) acc += partial[(size_t)b * stride + src];
-    dw[i] += acc;
-  } else if (db != nullptr && i < nw + cout) {
-    const int co = i - nw;
-    const size_t src = (size_t)taps * cip * cop + co;
+    for (int b = 0; b < nblk; ++b) acc += partial[(size_t)b * stride + i];
+    dw[((size_t)co * cin + ci) * taps + t] += acc;
+  } else if (db != nullptr && i < nrec + cout) {
+    const int co = i - nrec;
     float acc = 0.f;
-    for (int b = 0; b < nblk; ++b) acc += partial[(size_t)b * stride + src];
+    for (int b = 0; b < nblk; ++b) acc += partial[(size_t)b * stride + nrec + co];
     db[co] += acc;
   }
 }
 int mil_launch_reduce_conv_w(const float* partial, int nblk, long long stride, float* dw, float* db, int cout,
                              int cin, int ks, cudaStream_t s) {
-  const int total = cout * cin * ks * ks + cout;
+  const int total = ks * ks * ((cin + 7) / 8 * 8) * ((cout + 7) / 8 * 8) + cout;
   reduce_conv_w_kernel<<<(int)mil_cdiv(total, 128), 128, 0, s>>>(partial, nblk, stride, dw, db, cout, cin, ks);
   MIL_LAUNCH_OK();
   return 0;

@@ -82,11 +82,22 @@ __global__ void stem_pack_w4_kernel(const float* __restrict__ w, const float* __
 }
 
 // ---- 3. max-pool 3x3 / stride 2 / pad 1 of the conv1 map held as 4 phases ----------------------------------------
-// pooled (py,px) covers conv rows 2py-1, 2py, 2py+1 = (py-1, a=1), (py, a=0), (py, a=1); same for columns.
-// cv channel = co*4 + a*2 + b  ->  chunk co/2;  thread = (pooled pixel, pair of output channels)
+// pooled (py,px) covers conv rows 2py-1, 2py, 2py+1 = (py-1, a=1), (py, a=0), (py, a=1); same for columns: the
+// nine window positions live in FOUR neighbouring pixels of the phase map.  cv channel = co*4 + a*2 + b -> chunk
+// co/2; thread = (pooled pixel, pair of output channels) loads those four 16-byte chunks once.
+// arg-max layout: [tile][channel pair cp][py*w + px] as uint16 = (am of co 2cp) | (am of co 2cp+1) << 8.
+__device__ __forceinline__ void unpack8h(const uint4& r, float v[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 stem_pool4_kernel(const __nv_bfloat16* __restrict__ cv, MilPF8 gc, int hc, __nv_bfloat16* __restrict__ pooled,
-                  MilPF8 gp, uint8_t* __restrict__ argmax) {
+                  MilPF8 gp, uint16_t* __restrict__ argmax) {
   const long long total = 10 * gp.Q;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -98,26 +109,35 @@ stem_pool4_kernel(const __nv_bfloat16* __restrict__ cv, MilPF8 gc, int hc, __nv_
     float best[2] = {0.f, 0.f};
     int am[2] = {0, 0};
     if (py < gp.h && px < gp.w) {
+      // the zero halo of PF8 makes (py-1, px-1) readable everywhere; validity is decided on conv coordinates
+      float nb[2][2][8];  // [dy: py-1, py][dx: px-1, px][8 lanes = (co sub-index)*4 + a*2 + b]
+      const long long qc = (long long)n * gc.P + (long long)py * gc.wp + px;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const uint4 raw = __ldg(reinterpret_cast<const uint4*>(
+              cv + mil_pf8_off(gc, cp, qc - (1 - dy) * gc.wp - (1 - dx))));
+          unpack8h(raw, nb[dy][dx]);
+        }
       best[0] = best[1] = -INFINITY;
 #pragma unroll
       for (int wy = 0; wy < 3; ++wy) {
-        const int cy = 2 * py - 1 + wy;  // conv row
-        if (cy < 0 || cy >= hc) continue;
-        const int Y = cy >> 1, a = cy & 1;
+        const int cy = 2 * py - 1 + wy;
+        const bool oky = cy >= 0 && cy < hc;
+        const int dy = wy == 0 ? 0 : 1, a = wy == 1 ? 0 : 1;
 #pragma unroll
         for (int wx = 0; wx < 3; ++wx) {
           const int cx = 2 * px - 1 + wx;
-          if (cx < 0 || cx >= hc) continue;
-          const int X = cx >> 1, b = cx & 1;
-          const __nv_bfloat16* p = cv + mil_pf8_off(gc, cp, (long long)n * gc.P + (long long)Y * gc.wp + X) + a * 2 + b;
-          const float v0 = __bfloat162float(p[0]), v1 = __bfloat162float(p[4]);
-          if (v0 > best[0]) { best[0] = v0; am[0] = wy * 3 + wx; }
-          if (v1 > best[1]) { best[1] = v1; am[1] = wy * 3 + wx; }
+          const int dx = wx == 0 ? 0 : 1, b = wx == 1 ? 0 : 1;
+          if (oky && cx >= 0 && cx < hc) {
+            const float v0 = nb[dy][dx][a * 2 + b], v1 = nb[dy][dx][4 + a * 2 + b];
+            if (v0 > best[0]) { best[0] = v0; am[0] = wy * 3 + wx; }
+            if (v1 > best[1]) { best[1] = v1; am[1] = wy * 3 + wx; }
+          }
         }
       }
-      uint8_t* ap = argmax + ((size_t)n * gp.h * gp.w + (size_t)py * gp.w + px) * STC_CO + cp * 2;
-      ap[0] = (uint8_t)am[0];
-      ap[1] = (uint8_t)am[1];
+      argmax[((size_t)n * 10 + cp) * gp.h * gp.w + (size_t)py * gp.w + px] = (uint16_t)(am[0] | (am[1] << 8));
     }
     // pooled channel co -> chunk co/8, lane co%8 ; the pair (2cp, 2cp+1) is one 4-byte store
     __nv_bfloat162 pk = __floats2bfloat162_rn(best[0], best[1]);
@@ -129,8 +149,10 @@ stem_pool4_kernel(const __nv_bfloat16* __restrict__ cv, MilPF8 gc, int hc, __nv_
 }
 
 // ---- 4. backward: dY4(Y,X)[(co,a,b)] = sum of g(py,px)[co] over the pooled windows whose arg-max is conv (2Y+a, 2X+b)
+// The windows that can point into pixel (Y,X) of the phase map are the pooled pixels (Y,X), (Y,X+1), (Y+1,X),
+// (Y+1,X+1): load their arg-max pairs and gradient pairs once, then test the nine (window, position) combinations.
 __global__ void __launch_bounds__(256)
-stem_unpool4_kernel(const __nv_bfloat16* __restrict__ g, MilPF8 gp, const uint8_t* __restrict__ argmax,
+stem_unpool4_kernel(const __nv_bfloat16* __restrict__ g, MilPF8 gp, const uint16_t* __restrict__ argmax,
                     __nv_bfloat16* __restrict__ dy, MilPF8 gc, int hc) {
   const long long total = 10 * gc.Q;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -144,31 +166,43 @@ stem_unpool4_kernel(const __nv_bfloat16* __restrict__ g, MilPF8 gp, const uint8_
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     if (Y < gc.h && X < gc.w) {
+      int am0[2][2], am1[2][2];
+      float g0[2][2], g1[2][2];
 #pragma unroll
-      for (int a = 0; a < 2; ++a) {
-        const int cy = 2 * Y + a;
-        if (cy >= hc) continue;
+      for (int dyy = 0; dyy < 2; ++dyy)
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          const int cx = 2 * X + b;
-          if (cx >= hc) continue;
-          // pooled windows containing conv (cy, cx): py in {cy/2, (cy+1)/2}, px in {cx/2, (cx+1)/2}
-          const int py0 = cy >> 1, py1 = (cy + 1) >> 1, px0 = cx >> 1, px1 = (cx + 1) >> 1;
-          for (int py = py0; py <= py1; ++py) {
-            if (py >= gp.h) continue;
-            const int wy = cy - (2 * py - 1);
-            for (int px = px0; px <= px1; ++px) {
-              if (px >= gp.w) continue;
-              const int want = wy * 3 + (cx - (2 * px - 1));
-              const uint8_t* ap = argmax + ((size_t)n * gp.h * gp.w + (size_t)py * gp.w + px) * STC_CO + cp * 2;
-              const __nv_bfloat16* gv =
-                  g + mil_pf8_off(gp, cp >> 2, (long long)n * gp.P + (long long)py * gp.wp + px) + (cp & 3) * 2;
-              if (ap[0] == want) acc[a * 2 + b] += __bfloat162float(gv[0]);
-              if (ap[1] == want) acc[4 + a * 2 + b] += __bfloat162float(gv[1]);
-            }
+        for (int dxx = 0; dxx < 2; ++dxx) {
+          const int py = Y + dyy, px = X + dxx;
+          am0[dyy][dxx] = am1[dyy][dxx] = 255;
+          g0[dyy][dxx] = g1[dyy][dxx] = 0.f;
+          if (py < gp.h && px < gp.w) {
+            const uint16_t amv = argmax[((size_t)n * 10 + cp) * gp.h * gp.w + (size_t)py * gp.w + px];
+            am0[dyy][dxx] = amv & 0xFF;
+            am1[dyy][dxx] = amv >> 8;
+            const __nv_bfloat162 gv = *reinterpret_cast<const __nv_bfloat162*>(
+                g + mil_pf8_off(gp, cp >> 2, (long long)n * gp.P + (long long)py * gp.wp + px) + (cp & 3) * 2);
+            const float2 gf = __bfloat1622float2(gv);
+            g0[dyy][dxx] = gf.x;
+            g1[dyy][dxx] = gf.y;
           }
         }
-      }
+      // conv position (2Y+a, 2X+b) seen from pooled window (Y+dyy, X+dxx) is window position
+      //   wy = 2Y+a - (2(Y+dyy)-1) = a + 1 - 2 dyy,  wx = b + 1 - 2 dxx   (valid when 0 <= wy,wx <= 2)
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+          for (int dyy = 0; dyy < 2; ++dyy)
+#pragma unroll
+            for (int dxx = 0; dxx < 2; ++dxx) {
+              const int wy = a + 1 - 2 * dyy, wx = b + 1 - 2 * dxx;
+              if (wy < 0 || wx < 0) continue;  // compile-time after unrolling
+              const int want = wy * 3 + wx;
+              if (am0[dyy][dxx] == want) acc[a * 2 + b] += g0[dyy][dxx];
+              if (am1[dyy][dxx] == want) acc[4 + a * 2 + b] += g1[dyy][dxx];
+            }
+      (void)hc;  // positions beyond the conv map can never be an arg-max: nothing to mask here
     }
     mil_store8(dy + mil_pf8_off(gc, cp, q), acc);
   }
@@ -224,8 +258,9 @@ size_t mil_stem_tc_partial_floats(int n, int side) {
 static int grid_for(long long work) { return (int)std::max<long long>(1, std::min<long long>(mil_cdiv(work, 256), 148 * 16)); }
 
 int mil_launch_stem_tc_fwd(const float* x, const int* idx, int n, int side, const float* w, const float* b, void* xs,
-                           void* convout, float* wp, void* wtc, void* pooled, const MilPF8& gp, uint8_t* argmax,
+                           void* convout, float* wp, void* wtc, void* pooled, const MilPF8& gp, uint8_t* argmax8,
                            cudaStream_t s) {
+  uint16_t* argmax = reinterpret_cast<uint16_t*>(argmax8);  // [tile][10 channel pairs][h0*w0] (same 20 B per pixel)
   const MilPF8 gi = mil_stem_tc_geom_in(n, side), gc = mil_stem_tc_geom_conv(n, side);
   const int hc = (side - 1) / 2 + 1;
   MIL_REQUIRE(gp.h == gi.h && gp.w == gi.w && gp.c == STC_CO && gp.n == n, "stem_tc_fwd: geometry mismatch");
@@ -244,8 +279,9 @@ int mil_launch_stem_tc_fwd(const float* x, const int* idx, int n, int side, cons
   return 0;
 }
 
-int mil_launch_stem_tc_bwd(const void* xs, int n, int side, const void* g, const MilPF8& gp, const uint8_t* argmax,
+int mil_launch_stem_tc_bwd(const void* xs, int n, int side, const void* g, const MilPF8& gp, const uint8_t* argmax8,
                            void* dy, float* partial, float* dw, float* db, cudaStream_t s) {
+  const uint16_t* argmax = reinterpret_cast<const uint16_t*>(argmax8);
   const MilPF8 gi = mil_stem_tc_geom_in(n, side), gc = mil_stem_tc_geom_conv(n, side);
   const int hc = (side - 1) / 2 + 1;
   stem_unpool4_kernel<<<grid_for(10 * gc.Q), 256, 0, s>>>((const __nv_bfloat16*)g, gp, argmax, (__nv_bfloat16*)dy, gc,
