@@ -51,7 +51,7 @@ __global__ void pack_tc_kernel(const float* __restrict__ wp, __nv_bfloat16* __re
 struct TcSmemHeader {
   uint64_t full[TC_MAX_STAGES], empty[TC_MAX_STAGES], acc_full[TC_MAX_ACC], acc_empty[TC_MAX_ACC], b_full;
   uint32_t tmem_base;
-  float bias[96];
+  alignas(16) float bias[96];
 };
 
 // per-MMA descriptor templates, precomputed on the host and passed as kernel parameters so that the issuing
@@ -208,12 +208,13 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
       r += step_r;
       if (r >= P) { r -= P; ++n; }
       const bool live = in_range && !is_pad;
+      const long long o0 = (go.G + qo) * 8, ostride = go.PS * 8;  // element offset of chunk c: o0 + c * ostride
       // 1. residual / activation loads go out BEFORE we wait for the tensor core
       uint4 rres[MAXCB], ract[MAXCB];
 #pragma unroll
       for (int c = 0; c < MAXCB; ++c) {
         if (c < cbout && live) {
-          const long long o = mil_pf8_off(go, c, qo);
+          const long long o = o0 + c * ostride;
           if (has_res) rres[c] = ld_nc16(res + o);
           if (has_act) ract[c] = ld_nc16(act + o);
         }
@@ -253,8 +254,11 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
                 for (int j = 0; j < 8; ++j) v[j] += rv[j];
               }
               if (epi != MIL_EPI_DGRAD) {
+                const float4 b0 = *reinterpret_cast<const float4*>(&hd->bias[c * 8]);
+                const float4 b1 = *reinterpret_cast<const float4*>(&hd->bias[c * 8 + 4]);
+                const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] += hd->bias[c * 8 + j];
+                for (int j = 0; j < 8; ++j) v[j] += bv[j];
               }
               if (epi == MIL_EPI_FWD) {
 #pragma unroll
@@ -266,7 +270,7 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
                 for (int j = 0; j < 8; ++j) v[j] *= mil_lrelu_grad(av[j]);
               }
             }
-            mil_store8(out + mil_pf8_off(go, c, qo), v);
+            mil_store8(out + (o0 + c * ostride), v);
           }
         }
       }

@@ -4,14 +4,20 @@
 //
 //   dW[t][ci][co] = sum over flat pixels q of  x[q + shift_t][ci] * dz[q][co]         db[co] = sum_q dz[q][co]
 //
-// GEMM view per tap t:  D_t[co][ci] += A[co][k] * B_t[ci][k],  k = flat pixel.  Both operands are used exactly
-// as PF8 stores them -- [pixel][8 channels], i.e. "MN-major" core matrices of 8 pixels x 16 B -- so a 128-pixel
-// K-tile needs one bulk-TMA copy per channel chunk and NO transposition: A = the dz planes, B_t = the x planes
-// read from the start address (halo + shift_t) pixels into the span, like the forward kernel does.
-// The nine D_t (and the bias block, B = a constant all-ones block) stay in TMEM for the whole kernel: every CTA
-// accumulates its share of the pixel tiles (split-K over CTAs), then writes ONE partial record; the fixed-order
-// reduction mil_launch_reduce_conv_w sums the records -> deterministic.  TMEM holds 512 columns, so layers
-// with 9 * Cin_pad > 496 split the taps over two CTA groups (blockIdx.y).
+// GEMM view:  D[co][n] += A[co][k] * B[n][k],  k = flat pixel.  Both operands are used exactly as PF8 stores them
+// -- [pixel][8 channels], i.e. "MN-major" core matrices of 8 pixels x 16 B -- so a 128-pixel K-tile needs only
+// bulk-TMA copies and NO transposition: A = the dz planes, B = x planes read from a shifted start address.
+//
+// A thin MMA costs the tensor pipe as much as a wide one (~0.35*M cycles up to N = 64, profiles/r1_mma_cost.txt),
+// so for the 3x3 layers the three dx taps are CONCATENATED along N: the producer loads three copies of every x
+// plane, shifted by -1 / 0 / +1 pixel, as consecutive shared-memory planes; N-group (dx, chunk) then sits at a
+// uniform stride and ONE MMA per (dy, K-step) covers N = 3*Cin columns (72 .. 240) -- 24 + 8 MMAs per K-tile
+// instead of 72 + 8.  The price is 3x the L2 -> shared-memory traffic of x.
+//
+// The tap accumulators (and the bias block, B = a constant all-ones block) stay in TMEM for the whole kernel: every
+// CTA accumulates its share of the pixel tiles (split-K over CTAs), then writes ONE partial record
+// [tap][cin_pad][cout_pad] + [cout_pad]; a fixed-order reduction sums the records -> deterministic.  TMEM holds 512
+// columns, so wide layers split the dy taps over two CTA groups (blockIdx.y).
 #include <algorithm>
 
 #include "mil_common.cuh"
@@ -19,38 +25,42 @@
 #include "mil_tc_ptx.cuh"
 
 #define WG_TK 128
-#define WG_STAGES 3
+#define WG_MAX_STAGES 3
 #define WG_THREADS 192  // warp 0 producer, warp 1 MMA issuer, warps 2..5 epilogue
 #define WG_A_PLANE (WG_TK * 16)
-#define WG_SLACK (40 * 1024)
+#define WG_SLACK (8 * 1024)
 
 struct WgSmemHeader {
-  uint64_t full[WG_STAGES], empty[WG_STAGES], done;
+  uint64_t full[WG_MAX_STAGES], empty[WG_MAX_STAGES], done;
   uint32_t tmem_base;
 };
 
+// dxcat = 1: 3x3 window, taps grouped by dy, N = (dx, chunk) planes;  dxcat = 0: one tap per MMA (1x1 window)
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat16* __restrict__ dz, MilPF8 gz,
                 float* __restrict__ partial, long long rec_stride, MilTcShape sh, int halo, int taps_per_group,
-                int npad, int mma_m) {
+                int npad, int mma_m, int dxcat, int n_stages) {
   extern __shared__ __align__(128) unsigned char smem[];
   WgSmemHeader* hd = reinterpret_cast<WgSmemHeader*>(smem);
   unsigned char* ones = smem + 128;            // 512 B of bf16 1.0: the B operand of the bias-gradient MMA
   unsigned char* stage0 = smem + 128 + 512;
-  const int ntaps = sh.ntaps;
-  const int span = WG_TK + 2 * halo;
+  const int ntaps = sh.ntaps;                  // taps of the record layout (9 or 1)
+  const int ngrp_taps = dxcat ? 3 : ntaps;     // MMA "taps": dy rows when dxcat
+  const int nbp = dxcat ? 3 * gx.cb : gx.cb;   // B planes per stage
+  const int span = dxcat ? WG_TK + 2 * gx.wp : WG_TK + 2 * halo;
+  const int back = dxcat ? gx.wp : halo;       // pixels before q0 held by a plane (of the dx = 0 copy)
   const uint32_t b_plane = (uint32_t)span * 16;
   const uint32_t a_bytes = (uint32_t)gz.cb * WG_A_PLANE;
-  const uint32_t stage_bytes = a_bytes + (uint32_t)gx.cb * b_plane;
+  const uint32_t stage_bytes = a_bytes + (uint32_t)nbp * b_plane;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tap_lo = blockIdx.y * taps_per_group;
-  const int tap_hi = min(ntaps, tap_lo + taps_per_group);
+  const int tap_hi = min(ngrp_taps, tap_lo + taps_per_group);
   const int ntl = tap_hi - tap_lo;
   const bool with_bias = (blockIdx.y == gridDim.y - 1);
   const long long n_tiles = mil_cdiv(gz.Q, WG_TK);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&hd->full[s], 1); mbar_init(&hd->empty[s], 1); }
+    for (int s = 0; s < n_stages; ++s) { mbar_init(&hd->full[s], 1); mbar_init(&hd->empty[s], 1); }
     mbar_init(&hd->done, 1);
     fence_barrier_init();
   }
@@ -75,11 +85,18 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
         unsigned char* dst = stage0 + (size_t)stage * stage_bytes;
         for (int c = 0; c < gz.cb; ++c)
           bulk_g2s(dst + (size_t)c * WG_A_PLANE, dz + mil_pf8_off(gz, c, q0), WG_A_PLANE, &hd->full[stage]);
-        for (int c = 0; c < gx.cb; ++c)
-          bulk_g2s(dst + a_bytes + (size_t)c * b_plane, x + mil_pf8_off(gx, c, q0 - halo), b_plane, &hd->full[stage]);
+        if (dxcat) {
+          for (int dx = 0; dx < 3; ++dx)
+            for (int c = 0; c < gx.cb; ++c)
+              bulk_g2s(dst + a_bytes + (size_t)(dx * gx.cb + c) * b_plane, x + mil_pf8_off(gx, c, q0 - back + dx - 1),
+                       b_plane, &hd->full[stage]);
+        } else {
+          for (int c = 0; c < gx.cb; ++c)
+            bulk_g2s(dst + a_bytes + (size_t)c * b_plane, x + mil_pf8_off(gx, c, q0 - back), b_plane, &hd->full[stage]);
+        }
       }
       __syncwarp();
-      if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      if (++stage == n_stages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
     // MMA issuer: uniform control flow (descriptors stay in uniform registers), one elected lane issues.
@@ -103,8 +120,9 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
       if (elect_one()) {
         for (int tl = 0; tl < ntl; ++tl) {
           const int tap = tap_lo + tl;
-          const int s = sh.t_dy[tap] * gx.wp + sh.t_dx[tap];
-          const uint64_t bd0 = make_desc(b_base + (uint32_t)(halo + s) * 16, 128, b_plane);
+          // pixel offset of this tap's window start inside a B plane
+          const int s = dxcat ? tap * gx.wp : back + sh.t_dy[tap] * gx.wp + sh.t_dx[tap];
+          const uint64_t bd0 = make_desc(b_base + (uint32_t)s * 16, 128, b_plane);
           const uint32_t d = tmem_base + tl * npad;
           umma_bf16(d, ad0, bd0, idesc, acc0);
 #pragma unroll
@@ -120,12 +138,12 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
       }
       __syncwarp();
       first = false;
-      if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      if (++stage == n_stages) { stage = 0; phase ^= 1; }
     }
     if (elect_one()) umma_commit(&hd->done);
     __syncwarp();
   } else {
-    // epilogue: TMEM lane = output channel co, columns = (local tap, ci)
+    // epilogue: TMEM lane = output channel co, columns = (local tap, B plane, 8 ci)
     const int quarter = warp & 3;
     // accumulator row -> TMEM lane: M = 128: row i in lane i;  M = 64: row i in lane 32*(i/16) + i%16 (each
     // lane quarter holds 16 rows)
@@ -137,13 +155,16 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
       float* rec = partial + (size_t)blockIdx.x * rec_stride;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
       for (int tl = 0; tl < ntl; ++tl) {
-        for (int c = 0; c < gx.cb; ++c) {
+        for (int p = 0; p < nbp; ++p) {
           float v[8];
-          tmem_ld8(taddr + tl * npad + c * 8, v);
+          tmem_ld8(taddr + tl * npad + p * 8, v);
           tmem_ld_wait();
+          // record tap and input chunk of this column block
+          const int rtap = dxcat ? (tap_lo + tl) * 3 + p / gx.cb : tap_lo + tl;
+          const int c = dxcat ? p % gx.cb : p;
           if (co < coutp) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) rec[((size_t)(tap_lo + tl) * cinp + c * 8 + j) * coutp + co] = v[j];
+            for (int j = 0; j < 8; ++j) rec[((size_t)rtap * cinp + c * 8 + j) * coutp + co] = v[j];
           }
         }
       }
@@ -175,13 +196,28 @@ static int wg_sm_count() {
   return n_sm;
 }
 
-static void wg_config(const MilPF8& gx, const MilPF8& gz, int ks, int* npad, int* groups, int* tpg, int* ctas) {
-  *npad = (gx.c + 15) / 16 * 16;
-  const int ntaps = ks == 7 ? 16 : ks * ks;
-  *groups = (ntaps * *npad + 16 <= 512) ? 1 : 2;
-  *tpg = (ntaps + *groups - 1) / *groups;
+struct WgConfig {
+  int dxcat, npad, groups, tpg, ctas, mma_m, n_stages;
+  size_t smem;
+};
+
+static WgConfig wg_config(const MilPF8& gx, const MilPF8& gz, int ks) {
+  WgConfig c;
+  c.dxcat = ks == 3 ? 1 : 0;
+  c.mma_m = gz.cb * 8 <= 64 ? 64 : 128;
+  c.npad = c.dxcat ? 3 * gx.cb * 8 : (gx.c + 15) / 16 * 16;
+  const int gtaps = c.dxcat ? 3 : ks * ks;
+  c.groups = (gtaps * c.npad + 16 <= 512) ? 1 : 2;
+  c.tpg = (gtaps + c.groups - 1) / c.groups;
   const long long n_tiles = mil_cdiv(gz.Q, WG_TK);
-  *ctas = (int)std::max<long long>(1, std::min<long long>(n_tiles, wg_sm_count() / *groups));
+  c.ctas = (int)std::max<long long>(1, std::min<long long>(n_tiles, wg_sm_count() / c.groups));
+  const int halo = ks == 3 ? gx.wp + 1 : 0;
+  const size_t span = c.dxcat ? WG_TK + 2 * (size_t)gx.wp : WG_TK + 2 * (size_t)halo;
+  const size_t stage = (size_t)gz.cb * WG_A_PLANE + (size_t)(c.dxcat ? 3 * gx.cb : gx.cb) * span * 16;
+  c.n_stages = WG_MAX_STAGES;
+  while (c.n_stages > 1 && 128 + 512 + c.n_stages * stage + WG_SLACK > 220 * 1024) --c.n_stages;
+  c.smem = 128 + 512 + c.n_stages * stage + WG_SLACK;
+  return c;
 }
 
 bool mil_wgrad_tc_supported(int dtype, int ks, int stride, int cin, int cout) {
@@ -189,10 +225,8 @@ bool mil_wgrad_tc_supported(int dtype, int ks, int stride, int cin, int cout) {
 }
 
 size_t mil_wgrad_tc_partial_floats(const MilPF8& gx, const MilPF8& gz, int ks) {
-  int npad, groups, tpg, ctas;
-  wg_config(gx, gz, ks, &npad, &groups, &tpg, &ctas);
-  const size_t ntaps = ks == 7 ? 16 : (size_t)ks * ks;
-  return (size_t)ctas * (ntaps * gx.cb * 8 * gz.cb * 8 + gz.cb * 8);
+  const WgConfig c = wg_config(gx, gz, ks);
+  return (size_t)c.ctas * ((size_t)ks * ks * gx.cb * 8 * gz.cb * 8 + gz.cb * 8);
 }
 
 // accumulate-only part: writes `*ctas_out` partial records [tap][cin_pad][cout_pad] (+[cout_pad] bias sums)
@@ -200,22 +234,22 @@ int mil_launch_wgrad_tc_partials(const void* x, const MilPF8& gx, const void* dz
                                  int ks, int* ctas_out, long long* rec_out, cudaStream_t s) {
   MIL_REQUIRE(gx.n == gz.n && gx.h == gz.h && gx.w == gz.w && gx.wp == gz.wp && gx.hp == gz.hp,
               "wgrad_tc: geometry mismatch");
-  int npad, groups, tpg, ctas;
-  wg_config(gx, gz, ks, &npad, &groups, &tpg, &ctas);
+  MIL_REQUIRE(ks == 3 || ks == 1, "wgrad_tc: unsupported window %d", ks);
+  const WgConfig c = wg_config(gx, gz, ks);
   MilTcShape sh;
   MIL_TRY(mil_tc_shape(gx.c, gz.c, ks, &sh));
   const int halo = mil_tc_halo(sh, gx.wp);
   MIL_REQUIRE(halo <= gx.G, "wgrad_tc: the window reaches %d pixels back but the map's guard is %lld", halo, gx.G);
-  const size_t stage = (size_t)gz.cb * WG_A_PLANE + (size_t)gx.cb * (WG_TK + 2 * halo) * 16;
-  const size_t smem = 128 + 512 + WG_STAGES * stage + WG_SLACK;
-  MIL_REQUIRE(smem <= 227 * 1024, "wgrad_tc: tile width %d needs %zu bytes of shared memory", gx.w, smem);
-  MIL_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MIL_REQUIRE(c.mma_m == 64 || c.npad % 16 == 0, "wgrad_tc: N = %d is not a multiple of 16 (M = 128)", c.npad);
+  MIL_REQUIRE(c.npad <= 256, "wgrad_tc: N = %d too wide", c.npad);
+  MIL_REQUIRE(c.smem <= 227 * 1024, "wgrad_tc: tile width %d needs %zu bytes of shared memory", gx.w, c.smem);
+  MIL_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
   const long long rec = (long long)sh.ntaps * gx.cb * 8 * gz.cb * 8 + gz.cb * 8;
-  wgrad_tc_kernel<<<dim3(ctas, groups), WG_THREADS, smem, s>>>((const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)dz,
-                                                             gz, partial, rec, sh, halo, tpg, npad,
-                                                             gz.cb * 8 <= 64 ? 64 : 128);
+  wgrad_tc_kernel<<<dim3(c.ctas, c.groups), WG_THREADS, c.smem, s>>>(
+      (const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)dz, gz, partial, rec, sh, halo, c.tpg, c.npad, c.mma_m, c.dxcat,
+      c.n_stages);
   MIL_LAUNCH_OK();
-  *ctas_out = ctas;
+  *ctas_out = c.ctas;
   *rec_out = rec;
   return 0;
 }
