@@ -44,7 +44,10 @@ class BagGroup:
         if n_local_bag not in self._sizes:
             import torch.distributed as dist
             backend = dist.get_backend(self.group)
-            dev = device if backend == "nccl" else torch.device("cpu")
+            if backend == "nccl":
+                dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+            else:
+                dev = torch.device("cpu")
             mine = torch.tensor([n_local_bag], dtype=torch.int64, device=dev)
             out = [torch.zeros_like(mine) for _ in range(self.world)]
             dist.all_gather(out, mine, group=self.group)
