@@ -49,7 +49,7 @@ __global__ void pack_tc_kernel(const float* __restrict__ wp, __nv_bfloat16* __re
 
 // ---- the kernel ----------------------------------------------------------------------------------------
 struct TcSmemHeader {
-  uint64_t full[TC_MAX_STAGES], empty[TC_MAX_STAGES], acc_full[TC_MAX_ACC], acc_empty[TC_MAX_ACC], b_full;
+  uint64_t full[TC_MAX_STAGES], empty[TC_MAX_STAGES], acc_empty[TC_MAX_ACC], b_full;
   uint32_t tmem_base;
   alignas(16) float bias[96];
 };
@@ -78,7 +78,7 @@ __device__ __forceinline__ void unpack8(const uint4& r, float v[8]) {
 // stages = epilogue groups of 4 warps.  The thin layers are bound by the epilogue's instruction stream, not by
 // the tensor pipe, so they get 4 groups; the wide layers (more registers per thread) get 2.
 template <int MAXCB, int NG>
-__global__ void __launch_bounds__(64 + NG * 128, 1)
+__global__ void __launch_bounds__(96 + NG * 128, 1)
 conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat16* __restrict__ wtc,
                const float* __restrict__ bias, const __nv_bfloat16* res, const __nv_bfloat16* act,
                __nv_bfloat16* out, MilPF8 go, MilTcShape sh, const __grid_constant__ TcIssue iss, int epi,
@@ -101,7 +101,7 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
   // ---- one-time setup ----
   if (threadIdx.x == 0) {
     for (int s = 0; s < n_stages; ++s) { mbar_init(&hd->full[s], 1); mbar_init(&hd->empty[s], 1); }
-    for (int a = 0; a < NG; ++a) { mbar_init(&hd->acc_full[a], 1); mbar_init(&hd->acc_empty[a], 4); }
+    for (int a = 0; a < NG; ++a) mbar_init(&hd->acc_empty[a], 4);
     mbar_init(&hd->b_full, 1);
     fence_barrier_init();
   }
@@ -139,19 +139,22 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
       __syncwarp();
       if (++stage == n_stages) { stage = 0; phase ^= 1; }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (uniform control flow, one elected lane issues) =====================
+  } else if (warp <= 2) {
+    // ===================== MMA issuers: two warps take alternate tiles (uniform control flow, one elected lane) ====
+    // The per-tile fixed cost of an issuing warp (two mbarrier waits, fence, elect, commit) is ~1/3 of its loop on
+    // the thin layers; with two warps it overlaps the other warp's MMA issue.  ONE commit per tile: `empty[stage]`
+    // tells the producer that the stage is free AND the epilogue that the accumulator is complete.
     // instruction descriptor: D = f32, A = B = bf16, both K-major, N = npad, M = 128
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(sh.npad >> 3) << 17) |
                            ((uint32_t)(TC_M >> 4) << 24);
     mbar_wait(&hd->b_full, 0);
-    int stage = 0, acc = 0;
-    uint32_t phase = 0, acc_phase = 0;
     const int nmma = sh.nmma;
     const uint64_t b_add = (uint64_t)(smem_u32(bsm) >> 4);
-    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-      mbar_wait(&hd->acc_empty[acc], acc_phase ^ 1);
-      mbar_wait(&hd->full[stage], phase);
+    long long it = warp - 1;  // CTA-local tile counter
+    for (long long t = blockIdx.x + it * gridDim.x; t < n_tiles; t += 2LL * gridDim.x, it += 2) {
+      const int stage = (int)(it % n_stages), acc = (int)(it % NG);
+      mbar_wait(&hd->acc_empty[acc], (uint32_t)((it / NG) & 1) ^ 1);
+      mbar_wait(&hd->full[stage], (uint32_t)((it / n_stages) & 1));
       tc_fence_after();
       // the start-address field sits in the low 14 bits of the descriptor: adding a base cannot carry
       const uint64_t a_add = (uint64_t)(smem_u32(asm0 + (size_t)stage * stage_bytes) >> 4);
@@ -159,21 +162,18 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
       if (elect_one()) {
 #pragma unroll 4
         for (int j = 0; j < nmma; ++j) umma_bf16(d, iss.a_desc[j] + a_add, iss.b_desc[j] + b_add, idesc, j > 0);
-        umma_commit(&hd->empty[stage]);   // smem stage reusable once these MMAs have read it
-        umma_commit(&hd->acc_full[acc]);  // accumulator complete
+        umma_commit(&hd->empty[stage]);
       }
       __syncwarp();
-      if (++stage == n_stages) { stage = 0; phase ^= 1; }
-      if (++acc == NG) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ===================== epilogue: group eg serves accumulator stage eg =====================
-    const int eg = (warp - 2) >> 2;
+    const int eg = (warp - 3) >> 2;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
     const int cbout = sh.cbout;
     const bool has_res = res != nullptr, has_act = epi == MIL_EPI_DGRAD;
-    uint32_t acc_phase = 0;
+    long long it = eg;  // CTA-local tile counter of this group
     // This thread's pixel as (image n, in-plane offset r), advanced incrementally from tile to tile: the only
     // 64-bit divisions of the kernel happen here, once (the epilogue's instruction stream is what bounds the
     // small-channel layers, not the tensor pipe).
@@ -184,7 +184,7 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
     int n = (int)(q_first / gx.P), r = (int)(q_first % gx.P);
     const float inv_wp = 1.0f / (float)gx.wp;
     const int P = (int)gx.P;
-    for (long long t = blockIdx.x + (long long)eg * gridDim.x; t < n_tiles; t += (long long)NG * gridDim.x) {
+    for (long long t = blockIdx.x + (long long)eg * gridDim.x; t < n_tiles; t += (long long)NG * gridDim.x, it += NG) {
       // flat index q = n * P + r at the input resolution; qo = where the pixel is stored.  sub: the stride-2
       // convolutions are evaluated at full resolution and only the even (y, x) positions are kept.
       bool in_range = n < gx.n;
@@ -219,7 +219,7 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
           if (has_act) ract[c] = ld_nc16(act + o);
         }
       }
-      mbar_wait(&hd->acc_full[eg], acc_phase);
+      mbar_wait(&hd->empty[it % n_stages], (uint32_t)((it / n_stages) & 1));
       tc_fence_after();
       const uint32_t taddr = tmem_base + eg * acc_stride + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll
@@ -274,7 +274,6 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
           }
         }
       }
-      acc_phase ^= 1;
     }
   }
   // ---- teardown ----
@@ -358,8 +357,12 @@ int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const vo
   MIL_REQUIRE(epi != MIL_EPI_DGRAD || act != nullptr, "conv_tc: DGRAD epilogue needs the activation tensor");
   const int halo = mil_tc_halo(sh, gx.wp);
   MIL_REQUIRE(halo <= gx.G, "conv_tc: the window reaches %d pixels back but the map's guard is %lld", halo, gx.G);
+  // ring depth: as deep as shared memory allows, and a MULTIPLE of the accumulator ring (the one `empty[stage]`
+  // barrier per tile is waited on by the producer and by the epilogue group of that accumulator: with
+  // n_stages % NG == 0 the next completion of a stage's barrier needs this epilogue group to have moved on)
+  const int ng = sh.cbout <= 5 ? 4 : 2;
   int n_stages = TC_MAX_STAGES;
-  while (n_stages > 2 && tc_smem_bytes(halo, sh, n_stages) > 200 * 1024) --n_stages;
+  while (n_stages > ng && tc_smem_bytes(halo, sh, n_stages) > 200 * 1024) n_stages -= ng;
   const size_t smem = tc_smem_bytes(halo, sh, n_stages);
   MIL_REQUIRE(smem <= 227 * 1024, "conv_tc: tile width %d needs %zu bytes of shared memory", gx.w, smem);
   // the second K-half must sit above the first one (see mil_tc_shape); holds whenever a plane is larger than
@@ -399,7 +402,7 @@ int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const vo
   do {                                                                                                            \
     MIL_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<MAXCB, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                         (int)smem));                                                              \
-    conv_tc_kernel<MAXCB, NG><<<grid, 64 + NG * 128, smem, s>>>(                                                  \
+    conv_tc_kernel<MAXCB, NG><<<grid, 96 + NG * 128, smem, s>>>(                                                  \
         (const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)wtc, bias, (const __nv_bfloat16*)res,                  \
         (const __nv_bfloat16*)act, (__nv_bfloat16*)out, go, sh, iss, epi, sub, halo, n_stages);                   \
   } while (0)
