@@ -32,6 +32,8 @@ PROTOTYPES = {
                                       c_void_p, c_void_p]),
     "mil_extractor_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t,
                                        c_void_p, c_void_p, c_void_p]),
+    "mil_extractor_backward_staged": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t,
+                                              c_void_p, c_void_p, c_void_p, c_void_p]),
     "mil_extractor_read_activation": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "mil_debug_dump_gradient": (c_int, [c_int, c_int, c_int, c_void_p]),
     "mil_head_workspace_bytes": (c_size_t, [c_int]),

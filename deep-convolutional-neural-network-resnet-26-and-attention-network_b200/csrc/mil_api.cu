@@ -159,6 +159,21 @@ int mil_extractor_forward(const void* const* params, const float* bag, const int
   MIL_API_END
 }
 
+int mil_extractor_backward_staged(const void* const* params, const float* bag, const int32_t* idx, int n_tiles,
+                                  int side, int dtype, void* ws, size_t ws_bytes, const float* dH, float* grads_flat,
+                                  void* const* layer_events_host, void* stream) {
+  MIL_API_BEGIN
+  MIL_TRY(require_device());
+  MIL_REQUIRE(params && bag && ws && dH && grads_flat, "mil_extractor_backward_staged: null pointer argument");
+  MilPlan pl;
+  MIL_TRY(mil_make_plan(n_tiles, side, dtype, &pl));
+  MIL_REQUIRE(ws_bytes >= pl.total_bytes, "mil_extractor_backward_staged: workspace too small (%zu < %zu)", ws_bytes,
+              pl.total_bytes);
+  return mil_extractor_backward_impl(params, bag, idx, pl, ws, dH, grads_flat, (cudaStream_t)stream,
+                                     reinterpret_cast<const cudaEvent_t*>(layer_events_host));
+  MIL_API_END
+}
+
 int mil_extractor_backward(const void* const* params, const float* bag, const int32_t* idx, int n_tiles, int side,
                            int dtype, void* ws, size_t ws_bytes, const float* dH, float* grads_flat, void* stream) {
   MIL_API_BEGIN

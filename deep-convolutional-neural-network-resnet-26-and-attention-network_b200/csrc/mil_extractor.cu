@@ -366,7 +366,8 @@ void mil_debug_request_dump(int layer, int block, int which, float* dst) {
 }
 
 int mil_extractor_backward_impl(const void* const* params, const float* bag, const int* idx, const MilPlan& pl,
-                                void* ws, const float* dH, float* grads, cudaStream_t s) {
+                                void* ws, const float* dH, float* grads, cudaStream_t s,
+                                const cudaEvent_t* layer_events) {
   const int dt = pl.dtype;
   const auto& pt = mil_param_table();
   MIL_TRY(pack_weights(params, pl, ws, true, s));
@@ -484,6 +485,8 @@ int mil_extractor_backward_impl(const void* const* params, const float* bag, con
         MIL_TRY(mil_launch_from_pf8(dt, dnew, g_dump.dst, gi.n, gi.c, gi.h, gi.w, s));
       std::swap(dz, dnew);
     }
+    // every gradient of layer l+1 (and, for l = 3, of fc and the head) is final: let the caller start reducing it
+    if (layer_events != nullptr && layer_events[l] != nullptr) MIL_CHECK_CUDA(cudaEventRecord(layer_events[l], s));
   }
 
   const int p_c1w = mil_param_index("cnn.module.conv1.weight"), p_c1b = mil_param_index("cnn.module.conv1.bias");

@@ -35,6 +35,7 @@ class BagGroup:
         self._gen = torch.Generator().manual_seed(int(seed)) if self.world > 1 else None
         self._sizes: Dict[int, List[int]] = {}
         self._n_global_pending: Optional[int] = None
+        self._comm_stream = None
 
     # ---- shard bookkeeping -------------------------------------------------------------------------
     def shard_sizes(self, n_local_bag: int, device=None) -> List[int]:
@@ -97,3 +98,25 @@ class BagGroup:
             works.append(dist.all_reduce(flat[s:s + step], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         for w in works:
             w.wait()
+
+    def all_reduce_grads_staged(self, flat: torch.Tensor, events, bounds) -> None:
+        """Bucketed AR-4 overlapped with backward.  events[l] (l = 3..0) fires when layer l+1's gradients are final
+        (mil_extractor_backward_staged); bounds = float offsets where layer2 / layer3 / layer4 start.  Buckets in
+        completion order: [layer4 .. end] (incl. fc + head), [layer3], [layer2], [start .. layer1]."""
+        if self.world == 1:
+            return
+        import torch.distributed as dist
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=flat.device)
+        b2, b3, b4 = bounds
+        n = flat.numel()
+        buckets = [(events[3], b4, n), (events[2], b3, b4), (events[1], b2, b3), (events[0], 0, b2)]
+        works = []
+        with torch.cuda.stream(self._comm_stream):
+            for ev, lo, hi in buckets:
+                self._comm_stream.wait_event(ev)
+                works.append(dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        cur = torch.cuda.current_stream(flat.device)
+        for w in works:
+            w.wait()                      # makes the current stream wait for the collective
+        cur.wait_stream(self._comm_stream)

@@ -272,10 +272,23 @@ class _MilFunction(torch.autograd.Function):
         _lib.check(lib.mil_head_backward_b(pp, _ptr(H), n, n_global, _ptr(stats), _ptr(bnsums), _ptr(dHz), _ptr(dHi),
                                            _ptr(dH), st), "mil_head_backward_b")
         ws = ctx.lease.ws
-        _lib.check(lib.mil_extractor_backward(pp, _ptr(ctx.bag), _ptr(ctx.idx), n, side, dt, _ptr(ws.buf), nbytes,
-                                              _ptr(dH), _ptr(grads), st), "mil_extractor_backward")
+        if group.world > 1:
+            # AR-4, bucketed and overlapped: the extractor backward records an event per finished layer, the
+            # bucket of that layer is all-reduced on a side stream while the earlier layers are still running
+            events = [torch.cuda.Event() for _ in range(4)]
+            for ev in events:
+                ev.record()                         # materialise the handles (they are re-recorded by the library)
+            evp = (C.c_void_p * 4)(*[ev.cuda_event for ev in events])
+            _lib.check(lib.mil_extractor_backward_staged(pp, _ptr(ctx.bag), _ptr(ctx.idx), n, side, dt, _ptr(ws.buf),
+                                                         nbytes, _ptr(dH), _ptr(grads), evp, st),
+                       "mil_extractor_backward_staged")
+            events[0] = torch.cuda.Event()          # conv1 (stem) gradients come last: final when the call's work is
+            events[0].record()
+            group.all_reduce_grads_staged(grads, events, owner._layer_bucket_bounds())
+        else:
+            _lib.check(lib.mil_extractor_backward(pp, _ptr(ctx.bag), _ptr(ctx.idx), n, side, dt, _ptr(ws.buf), nbytes,
+                                                  _ptr(dH), _ptr(grads), st), "mil_extractor_backward")
         ctx.lease.release()
-        group.all_reduce_grads(grads)                                                   # AR-4
         out = []
         for (nm, shape, off), need in zip(owner._param_table, ctx.needs_input_grad[5:]):
             numel = 1
@@ -382,6 +395,11 @@ class Attention(nn.Module):
     @property
     def _param_names(self):
         return [t[0] for t in self._param_table]
+
+    def _layer_bucket_bounds(self):
+        """Float offsets [start of layer2, layer3, layer4] inside the flat gradient buffer (state-dict order)."""
+        offs = {nm: off for nm, _, off in self._param_table}
+        return [offs[f"cnn.module.layer{k}.0.conv1.weight"] for k in (2, 3, 4)]
 
     def _class_weights(self, device):
         w = self.loss.weight

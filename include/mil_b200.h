@@ -71,6 +71,15 @@ int mil_extractor_forward(const void* const* params_host, const float* bag, cons
 int mil_extractor_backward(const void* const* params_host, const float* bag, const int32_t* idx, int n_tiles, int side,
                            int dtype, void* ws, size_t ws_bytes, const float* dH, float* grads_flat, void* stream);
 
+/* Same, for the bucketed gradient all-reduce overlapped with backward (north_star; replaces DataParallel's
+ * reduce-add onto GPU 0): layer_events_host = 4 cudaEvent_t handles (or NULL entries).  Event [l] is recorded on
+ * `stream` as soon as every gradient of layer l+1 is final -- [3] also covers fc and the head's parameters, which
+ * precede the extractor in backward order -- so the caller can all-reduce that slice of grads_flat on another
+ * stream while the remaining layers are still being processed.  conv1 / layer1 are final when the call's work is. */
+int mil_extractor_backward_staged(const void* const* params_host, const float* bag, const int32_t* idx, int n_tiles,
+                                  int side, int dtype, void* ws, size_t ws_bytes, const float* dH, float* grads_flat,
+                                  void* const* layer_events_host, void* stream);
+
 /* test / debugging aid: copy one saved activation out of a forward workspace as fp32 NCHW.
  * which = -1: stem output (after max-pool); 2*(3*layer+block): the block's inner activation h;
  * 2*(3*layer+block)+1: the block's output y  (layer 0..3, block 0..2).                                        */
