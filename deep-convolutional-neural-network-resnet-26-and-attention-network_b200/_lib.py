@@ -30,6 +30,8 @@ PROTOTYPES = {
     "mil_extractor_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "mil_extractor_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t,
                                       c_void_p, c_void_p]),
+    "mil_extractor_forward_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t,
+                                         c_void_p, c_void_p]),
     "mil_extractor_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t,
                                        c_void_p, c_void_p, c_void_p]),
     "mil_extractor_backward_staged": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t,

@@ -155,7 +155,20 @@ int mil_extractor_forward(const void* const* params, const float* bag, const int
   MIL_TRY(mil_make_plan(n_tiles, side, dtype, &pl));
   MIL_REQUIRE(ws_bytes >= pl.total_bytes, "mil_extractor_forward: workspace too small (%zu < %zu)", ws_bytes,
               pl.total_bytes);
-  return mil_extractor_forward_impl(params, bag, idx, pl, ws, H, (cudaStream_t)stream);
+  return mil_extractor_forward_impl(params, bag, 0, idx, pl, ws, H, (cudaStream_t)stream);
+  MIL_API_END
+}
+
+int mil_extractor_forward_u8(const void* const* params, const uint8_t* bag, const int32_t* idx, int n_tiles, int side,
+                             int dtype, void* ws, size_t ws_bytes, float* H, void* stream) {
+  MIL_API_BEGIN
+  MIL_TRY(require_device());
+  MIL_REQUIRE(params && bag && ws && H, "mil_extractor_forward_u8: null pointer argument");
+  MilPlan pl;
+  MIL_TRY(mil_make_plan(n_tiles, side, dtype, &pl));
+  MIL_REQUIRE(ws_bytes >= pl.total_bytes, "mil_extractor_forward_u8: workspace too small (%zu < %zu)", ws_bytes,
+              pl.total_bytes);
+  return mil_extractor_forward_impl(params, bag, 1, idx, pl, ws, H, (cudaStream_t)stream);
   MIL_API_END
 }
 

@@ -53,7 +53,7 @@ MilPF8 mil_stem_tc_geom_conv(int n, int side);  // conv1 output: 20 channels, pa
 size_t mil_stem_tc_wpack_floats();
 size_t mil_stem_tc_wtc_bytes();
 size_t mil_stem_tc_partial_floats(int n, int side);
-int mil_launch_stem_tc_fwd(const float* x, const int* idx, int n, int side, const float* w, const float* b, void* xs,
+int mil_launch_stem_tc_fwd(const void* x, int x_u8, const int* idx, int n, int side, const float* w, const float* b, void* xs,
                            void* convout, float* wp, void* wtc, void* pooled, const MilPF8& gp, uint8_t* argmax,
                            cudaStream_t s);
 int mil_launch_stem_tc_bwd(const void* xs, int n, int side, const void* g, const MilPF8& gp, const uint8_t* argmax,

@@ -285,8 +285,9 @@ static int pack_weights(const void* const* params, const MilPlan& pl, void* ws, 
   return 0;
 }
 
-int mil_extractor_forward_impl(const void* const* params, const float* bag, const int* idx, const MilPlan& pl,
-                               void* ws, float* H, cudaStream_t s) {
+int mil_extractor_forward_impl(const void* const* params, const void* bag, int bag_u8, const int* idx,
+                               const MilPlan& pl, void* ws, float* H, cudaStream_t s) {
+  MIL_REQUIRE(!bag_u8 || pl.stem_tc, "extractor: 8-bit tiles need the bf16 tensor-core stem (dtype bf16)");
   const int dt = pl.dtype;
   // guards of every saved activation buffer (cheap, makes the workspace self-initialising)
   {
@@ -312,12 +313,12 @@ int mil_extractor_forward_impl(const void* const* params, const float* bag, cons
   };
   const int p_c1w = mil_param_index("cnn.module.conv1.weight"), p_c1b = mil_param_index("cnn.module.conv1.bias");
   if (pl.stem_tc)
-    MIL_TRY(mil_launch_stem_tc_fwd(bag, idx, pl.n, pl.side, (const float*)params[p_c1w], (const float*)params[p_c1b],
+    MIL_TRY(mil_launch_stem_tc_fwd(bag, bag_u8, idx, pl.n, pl.side, (const float*)params[p_c1w], (const float*)params[p_c1b],
                                    wsp(ws, pl.off_xs), wsp(ws, pl.off_cv), (float*)wsp(ws, pl.off_stem_wp),
                                    wsp(ws, pl.off_stem_wtc), wsp(ws, pl.off_pooled), pl.g[0],
                                    (uint8_t*)wsp(ws, pl.off_argmax), s));
   else
-    MIL_TRY(mil_launch_stem_fwd(dt, bag, idx, pl.n, pl.side, (const float*)params[p_c1w],
+    MIL_TRY(mil_launch_stem_fwd(dt, (const float*)bag, idx, pl.n, pl.side, (const float*)params[p_c1w],
                                 (const float*)params[p_c1b], wsp(ws, pl.off_pooled), pl.g[0],
                                 (uint8_t*)wsp(ws, pl.off_argmax), s));
   const void* X = wsp(ws, pl.off_pooled);

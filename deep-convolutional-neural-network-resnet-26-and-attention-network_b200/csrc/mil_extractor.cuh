@@ -42,8 +42,8 @@ struct MilPlan {
 };
 int mil_make_plan(int n, int side, int dtype, MilPlan* plan);
 
-int mil_extractor_forward_impl(const void* const* params, const float* bag, const int* idx, const MilPlan& pl,
-                               void* ws, float* H, cudaStream_t s);
+int mil_extractor_forward_impl(const void* const* params, const void* bag, int bag_u8, const int* idx,
+                               const MilPlan& pl, void* ws, float* H, cudaStream_t s);
 int mil_extractor_backward_impl(const void* const* params, const float* bag, const int* idx, const MilPlan& pl,
                                 void* ws, const float* dH, float* grads, cudaStream_t s,
                                 const cudaEvent_t* layer_events = nullptr);

@@ -25,8 +25,14 @@
 #define STC_CO4 80  // 20 * 2 * 2
 
 // ---- 1. space-to-depth by 4 ---------------------------------------------------------------------------------
+// TIn = float: the reference's normalised fp32 tiles;  TIn = uint8_t: raw 8-bit tiles, normalised on the fly exactly
+// like the reference's transform ToTensor() + Normalize(0.5, 0.5) (RoiBuilder.py:199-202): (u/255 - 0.5) / 0.5
+__device__ __forceinline__ float stem_norm(float v) { return v; }
+__device__ __forceinline__ float stem_norm(uint8_t v) { return ((float)v / 255.0f - 0.5f) / 0.5f; }
+
+template <typename TIn>
 __global__ void __launch_bounds__(256)
-stem_s2d4_kernel(const float* __restrict__ x, const int* __restrict__ idx, int side, __nv_bfloat16* __restrict__ xs,
+stem_s2d4_kernel(const TIn* __restrict__ x, const int* __restrict__ idx, int side, __nv_bfloat16* __restrict__ xs,
                  MilPF8 g) {
   // one thread per (pixel, (c, ry)) = 12 row-quads: reads one float4 (4 rx) when aligned, writes 4 channels
   const long long total = 12 * g.Q;
@@ -44,14 +50,16 @@ stem_s2d4_kernel(const float* __restrict__ x, const int* __restrict__ idx, int s
       const int iy = 4 * Y + ry;
       if (iy < side) {
         const int src_n = idx ? idx[n] : n;
-        const float* row = x + (((size_t)src_n * 3 + c) * side + iy) * side + 4 * X;
+        const TIn* row = x + (((size_t)src_n * 3 + c) * side + iy) * side + 4 * X;
         if (vec) {
-          const float4 f = *reinterpret_cast<const float4*>(row);
-          v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+          struct alignas(4 * sizeof(TIn)) Quad { TIn e[4]; };
+          const Quad f = *reinterpret_cast<const Quad*>(row);
+#pragma unroll
+          for (int rx = 0; rx < 4; ++rx) v[rx] = stem_norm(f.e[rx]);
         } else {
 #pragma unroll
           for (int rx = 0; rx < 4; ++rx)
-            if (4 * X + rx < side) v[rx] = row[rx];
+            if (4 * X + rx < side) v[rx] = stem_norm(row[rx]);
         }
       }
     }
@@ -257,14 +265,17 @@ size_t mil_stem_tc_partial_floats(int n, int side) {
 
 static int grid_for(long long work) { return (int)std::max<long long>(1, std::min<long long>(mil_cdiv(work, 256), 148 * 16)); }
 
-int mil_launch_stem_tc_fwd(const float* x, const int* idx, int n, int side, const float* w, const float* b, void* xs,
+int mil_launch_stem_tc_fwd(const void* x, int x_u8, const int* idx, int n, int side, const float* w, const float* b, void* xs,
                            void* convout, float* wp, void* wtc, void* pooled, const MilPF8& gp, uint8_t* argmax8,
                            cudaStream_t s) {
   uint16_t* argmax = reinterpret_cast<uint16_t*>(argmax8);  // [tile][10 channel pairs][h0*w0] (same 20 B per pixel)
   const MilPF8 gi = mil_stem_tc_geom_in(n, side), gc = mil_stem_tc_geom_conv(n, side);
   const int hc = (side - 1) / 2 + 1;
   MIL_REQUIRE(gp.h == gi.h && gp.w == gi.w && gp.c == STC_CO && gp.n == n, "stem_tc_fwd: geometry mismatch");
-  stem_s2d4_kernel<<<grid_for(12 * gi.Q), 256, 0, s>>>(x, idx, side, (__nv_bfloat16*)xs, gi);
+  if (x_u8)
+    stem_s2d4_kernel<uint8_t><<<grid_for(12 * gi.Q), 256, 0, s>>>((const uint8_t*)x, idx, side, (__nv_bfloat16*)xs, gi);
+  else
+    stem_s2d4_kernel<float><<<grid_for(12 * gi.Q), 256, 0, s>>>((const float*)x, idx, side, (__nv_bfloat16*)xs, gi);
   MIL_LAUNCH_OK();
   float* bias4 = wp + (size_t)9 * STC_CI * STC_CO4;
   stem_pack_w4_kernel<<<64, 256, 0, s>>>(w, b, wp, bias4);

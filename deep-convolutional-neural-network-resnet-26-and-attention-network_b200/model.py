@@ -209,7 +209,8 @@ class _MilFunction(torch.autograd.Function):
         st = _stream()
         f32 = dict(dtype=torch.float32, device=dev)
         H = torch.empty((n, 80), **f32)
-        _lib.check(lib.mil_extractor_forward(pp, _ptr(bag), _ptr(idx), n, side, dt, _ptr(ws.buf), nbytes, _ptr(H), st),
+        fwd = lib.mil_extractor_forward_u8 if bag.dtype == torch.uint8 else lib.mil_extractor_forward
+        _lib.check(fwd(pp, _ptr(bag), _ptr(idx), n, side, dt, _ptr(ws.buf), nbytes, _ptr(H), st),
                    "mil_extractor_forward")
         # ---- head (gbm/model.py:200-246) with the three bag-wide sums reduced across the bag group ----
         hws_bytes = int(lib.mil_head_workspace_bytes(n))
@@ -415,7 +416,13 @@ class Attention(nn.Module):
         if self.precision not in DTYPE_CODES:
             raise ValueError(f"precision must be one of {list(DTYPE_CODES)}, got {self.precision!r}")
         bag = full_input.detach()                                                     # gbm/model.py:194,196
-        if bag.dtype != torch.float32 or not bag.is_contiguous():
+        if bag.dtype == torch.uint8:
+            # raw 8-bit tiles: ToTensor() + Normalize(.5, .5) of the reference's loader (RoiBuilder.py:199-202) is
+            # fused into the stem's load in bf16 mode; the fp32 check mode normalises here with the same fp32 ops
+            bag = bag.contiguous()
+            if self.precision != "bf16":
+                bag = ((bag.float() / 255.0 - 0.5) / 0.5).contiguous()
+        elif bag.dtype != torch.float32 or not bag.is_contiguous():
             bag = bag.float().contiguous()
         dev = bag.device
         if Y is None:

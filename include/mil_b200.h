@@ -66,6 +66,11 @@ long long mil_param_total(void);                  /* 640967 */
 size_t mil_extractor_workspace_bytes(int n_tiles, int side, int dtype);
 int mil_extractor_forward(const void* const* params_host, const float* bag, const int32_t* idx, int n_tiles, int side,
                           int dtype, void* ws, size_t ws_bytes, float* H, void* stream);
+/* Same with raw 8-bit tiles (uint8 NCHW [n_bag,3,side,side]): the reference's CPU transform ToTensor() +
+ * Normalize(0.5, 0.5) (RoiBuilder.py:199-202) is fused into the stem's load -- a quarter of the host->device bytes.
+ * bf16 mode only.  The backward entry points never read the bag in bf16 mode (pass the same pointer).            */
+int mil_extractor_forward_u8(const void* const* params_host, const uint8_t* bag, const int32_t* idx, int n_tiles,
+                             int side, int dtype, void* ws, size_t ws_bytes, float* H, void* stream);
 /* autograd of the above (gbm/classify_combined.py:447): dH fp32 [n_tiles,80] -> grads_flat += d/d(params).
  * No gradient flows to `bag` (it is detached, gbm/model.py:194,196).                                         */
 int mil_extractor_backward(const void* const* params_host, const float* bag, const int32_t* idx, int n_tiles, int side,

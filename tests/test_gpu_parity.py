@@ -244,6 +244,31 @@ def test_topk_attended_tiles_match_reference(precision, case):
     assert int(out["y_pred_hat"]) == int(rec["out.y_pred_hat"])
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_uint8_tiles_equal_reference_normalisation(precision):
+    """Raw 8-bit tiles: the fused (u/255 - .5)/.5 of the stem load gives bit-identical results to feeding the
+    fp32 tensor the reference's ToTensor()+Normalize(.5,.5) would produce (RoiBuilder.py:199-202)."""
+    g = torch.Generator().manual_seed(3)
+    u8 = torch.randint(0, 256, (20, 3, 64, 64), generator=g, dtype=torch.uint8)
+    f32 = (u8.float() / 255.0 - 0.5) / 0.5
+    net = build_net(precision)
+    Y = torch.tensor([1]).cuda()
+    oa = net(u8.cuda(), Y)
+    oa["loss"].backward()
+    ga = [p.grad.clone() for p in net.parameters()]
+    net.zero_grad(set_to_none=True)
+    ob = net(f32.cuda(), Y)
+    ob["loss"].backward()
+    if precision == "bf16":     # the fused normalisation runs the same fp32 operations: bit-identical
+        for k in ("Fterm", "Aterm", "Mterm", "loss"):
+            assert torch.equal(oa[k], ob[k]), k
+        for a, p in zip(ga, net.parameters()):
+            assert torch.equal(a, p.grad)
+    else:                       # fp32 mode normalises with torch on the device (division rounding may differ by 1 ulp)
+        for k in ("Fterm", "Aterm", "Mterm", "loss"):
+            assert G.relerr(oa[k], ob[k]) < 1e-5, k
+
+
 def test_single_tile_bag_raises_value_error_like_reference():
     net = build_net("fp32")
     with pytest.raises(ValueError):
