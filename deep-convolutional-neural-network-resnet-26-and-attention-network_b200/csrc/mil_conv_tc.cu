@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(96 + NG * 128, 1)
 conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat16* __restrict__ wtc,
                const float* __restrict__ bias, const __nv_bfloat16* res, const __nv_bfloat16* act,
                __nv_bfloat16* out, MilPF8 go, MilTcShape sh, const __grid_constant__ TcIssue iss, int epi,
-               int sub, int halo, int n_stages) {
+               int sub, int halo, int n_stages, MilPF8 gr, int res_half) {
   extern __shared__ __align__(128) unsigned char smem[];
   TcSmemHeader* hd = reinterpret_cast<TcSmemHeader*>(smem);
   const uint32_t hdr_bytes = (uint32_t)((sizeof(TcSmemHeader) + 127) / 128 * 128);
@@ -188,8 +188,8 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
       // flat index q = n * P + r at the input resolution; qo = where the pixel is stored.  sub: the stride-2
       // convolutions are evaluated at full resolution and only the even (y, x) positions are kept.
       bool in_range = n < gx.n;
-      bool is_pad = true;
-      long long qo = (long long)n * P + r;
+      bool is_pad = true, res_ok = true;
+      long long qo = (long long)n * P + r, qres = 0;
       if (in_range) {
         int y = __float2int_rz(((float)r + 0.5f) * inv_wp);  // r / wp for r < 2^22 (exact after the fix-up)
         if (y * gx.wp > r) --y;
@@ -197,6 +197,10 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
         const int xo = r - y * gx.wp;
         if (!sub) {
           is_pad = (y >= gx.h) || (xo >= gx.w);
+          if (res_half) {  // the residual lives at HALF resolution and only feeds the even (y, x) positions
+            res_ok = !(y & 1) && !(xo & 1);
+            qres = (long long)n * gr.P + (long long)(y >> 1) * gr.wp + (xo >> 1);
+          }
         } else {
           const int yh = y >> 1, xh = xo >> 1;
           in_range = !(y & 1) && !(xo & 1) && yh <= go.h && xh <= go.w;
@@ -215,7 +219,10 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
       for (int c = 0; c < MAXCB; ++c) {
         if (c < cbout && live) {
           const long long o = o0 + c * ostride;
-          if (has_res) rres[c] = ld_nc16(res + o);
+          if (has_res) {
+            if (!res_half) rres[c] = ld_nc16(res + o);
+            else rres[c] = res_ok ? ld_nc16(res + (gr.G + qres) * 8 + c * (gr.PS * 8)) : make_uint4(0, 0, 0, 0);
+          }
           if (has_act) ract[c] = ld_nc16(act + o);
         }
       }
@@ -346,7 +353,11 @@ static size_t tc_smem_bytes(int halo, const MilTcShape& sh, int n_stages) {
 
 int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const void* wtc, const MilTcShape& sh,
                        const float* bias, const void* res, const void* act, void* out, const MilPF8& go, int epi,
-                       int sub, cudaStream_t s) {
+                       int sub, cudaStream_t s, const MilPF8* gres_half) {
+  if (gres_half != nullptr)
+    MIL_REQUIRE(!sub && res != nullptr && gres_half->cb == go.cb && gres_half->h == (go.h - 1) / 2 + 1 &&
+                    gres_half->w == (go.w - 1) / 2 + 1,
+                "conv_tc: half-resolution residual geometry mismatch");
   if (sub)
     MIL_REQUIRE(gx.n == go.n && go.h == (gx.h - 1) / 2 + 1 && go.w == (gx.w - 1) / 2 + 1 && !transposed,
                 "conv_tc: stride-2 geometry mismatch");
@@ -404,7 +415,8 @@ int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const vo
                                         (int)smem));                                                              \
     conv_tc_kernel<MAXCB, NG><<<grid, 96 + NG * 128, smem, s>>>(                                                  \
         (const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)wtc, bias, (const __nv_bfloat16*)res,                  \
-        (const __nv_bfloat16*)act, (__nv_bfloat16*)out, go, sh, iss, epi, sub, halo, n_stages);                   \
+        (const __nv_bfloat16*)act, (__nv_bfloat16*)out, go, sh, iss, epi, sub, halo, n_stages,                    \
+        gres_half ? *gres_half : go, gres_half ? 1 : 0);                                                          \
   } while (0)
   if (sh.cbout <= 3) MIL_TC_LAUNCH(3, 4);
   else if (sh.cbout <= 5) MIL_TC_LAUNCH(5, 4);

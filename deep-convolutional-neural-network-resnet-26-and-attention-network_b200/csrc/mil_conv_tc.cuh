@@ -35,7 +35,9 @@ size_t mil_tc_wpack_bytes(const MilTcShape& sh);
 int mil_launch_pack_tc(const float* wp, void* wtc, const MilTcShape& sh, cudaStream_t s);
 int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const void* wtc, const MilTcShape& sh,
                        const float* bias, const void* res, const void* act, void* out, const MilPF8& go, int epi,
-                       int sub, cudaStream_t s);
+                       int sub, cudaStream_t s, const MilPF8* gres_half = nullptr);
+// out (half resolution) = in at the even (y, x) positions (bf16): the input of a stride-2 1x1 projection
+int mil_launch_subsample2(const void* in, const MilPF8& gin, void* out, const MilPF8& gout, cudaStream_t s);
 // out (geometry 2x) = zero-stuffed copy of in: out(n, 2y, 2x) = in(n, y, x), zero elsewhere (bf16)
 int mil_launch_upsample2(const void* in, const MilPF8& gin, void* out, const MilPF8& gout, cudaStream_t s);
 

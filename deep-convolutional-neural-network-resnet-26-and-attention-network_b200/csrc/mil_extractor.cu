@@ -138,6 +138,12 @@ int mil_make_plan(int n, int side, int dtype, MilPlan* plan) {
     for (int l = 1; l < 4; ++l)
       pl.up_bytes = std::max(pl.up_bytes, mil_pf8_bytes(mil_pf8(n, kMilWidths[l], pl.geo.h[l - 1], pl.geo.h[l - 1]), dtype));
   for (int i = 0; i < 2; ++i) pl.off_up[i] = take(pl.up_bytes);
+  // inputs of the three stride-2 blocks at their even positions (what the 1x1 / stride-2 projection reads), kept
+  // for the backward pass
+  for (int l = 0; l < 4; ++l) pl.off_xsub[l] = 0;
+  if (dtype == MIL_BF16 && mil_tc_enabled())
+    for (int l = 1; l < 4; ++l)
+      pl.off_xsub[l] = take(mil_pf8_bytes(mil_pf8(n, kMilWidths[l - 1], pl.geo.h[l], pl.geo.h[l]), dtype));
   pl.stem_tc = (dtype == MIL_BF16) && mil_tc_enabled();
   pl.off_xs = pl.off_cv = pl.off_stem_wp = pl.off_stem_wtc = 0;
   if (pl.stem_tc) {
@@ -304,6 +310,9 @@ int mil_extractor_forward_impl(const void* const* params, const void* bag, int b
         guard_add(t, wsp(ws, pl.off_h[l * 3 + b]), pl.g[l]);
         guard_add(t, wsp(ws, pl.off_y[l * 3 + b]), pl.g[l]);
       }
+    if (pl.dtype == MIL_BF16 && mil_tc_enabled())
+      for (int l = 1; l < 4; ++l)
+        guard_add(t, wsp(ws, pl.off_xsub[l]), mil_pf8(pl.n, kMilWidths[l - 1], pl.geo.h[l], pl.geo.h[l]));
     MIL_TRY(launch_guards(t, s));
   }
   MIL_TRY(pack_weights(params, pl, ws, false, s));
@@ -343,8 +352,16 @@ int mil_extractor_forward_impl(const void* const* params, const void* bag, int b
       if (b == 0 && l > 0) {
         const MilConvDesc& cd = pl.convs[ci++];
         // projection shortcut (1x1 / stride 2, no bias) written into y, then consumed in place as the residual
-        MIL_TRY(mil_conv_dispatch(dt, 0, X, gx, wpack + cd.wp_off, TCW(cd, false), nullptr, nullptr, nullptr, y, go, 1, 2,
-                                  MIL_EPI_PLAIN, s));
+        if (cd.tc) {
+          // tensor-core path: gather the even positions once, then a plain 1x1 conv at the OUTPUT resolution
+          const MilPF8 gxs = mil_pf8(pl.n, gx.c, go.h, go.w);
+          void* xsub = wsp(ws, pl.off_xsub[l]);
+          MIL_TRY(mil_launch_subsample2(X, gx, xsub, gxs, s));
+          MIL_TRY(mil_conv_dispatch(dt, 0, xsub, gxs, wpack + cd.wp_off, TCW(cd, false), nullptr, nullptr, nullptr, y, go, 1,
+                                    1, MIL_EPI_PLAIN, s));
+        } else
+          MIL_TRY(mil_conv_dispatch(dt, 0, X, gx, wpack + cd.wp_off, nullptr, nullptr, nullptr, nullptr, y, go, 1, 2,
+                                    MIL_EPI_PLAIN, s));
         res = y;
       }
       MIL_TRY(mil_conv_dispatch(dt, 0, h, go, wpack + c2.wp_off, TCW(c2, false), (const float*)params[c2.p_b], res, nullptr, y, go,
@@ -422,29 +439,35 @@ int mil_extractor_backward_impl(const void* const* params, const float* bag, con
       // conv1: weight gradient (the stride-2 blocks do it inside their own branch below)
       if (!down) MIL_TRY(mil_wgrad_dispatch(dt, xin, gi, dpre, go, partial, gptr(c1.p_w), gptr(c1.p_b), 3, 1, s));
       if (down && c1.tc) {
-        // stride-2 block on the tensor-core kernels: zero-stuff both output gradients to the input resolution,
-        // after which every gradient of the block is a stride-1 problem
+        // stride-2 block on the tensor-core kernels.  The 3x3 conv: zero-stuff its output gradient to the input
+        // resolution, after which its gradients are stride-1 problems.  The 1x1 projection: everything stays at
+        // the OUTPUT resolution (weight gradient against the even-position input saved by the forward pass, data
+        // gradient into t_sub), and the full-resolution dgrad epilogue adds t_sub at the even positions.
         const MilConvDesc& cd = pl.convs[cb + 2];
         const MilPF8 gu = mil_pf8(pl.n, go.c, gi.h, gi.w);
+        const MilPF8 gxs = mil_pf8(pl.n, gi.c, go.h, go.w);
         void* up_pre = wsp(ws, pl.off_up[0]);
-        void* up_dz = wsp(ws, pl.off_up[1]);
+        void* t_sub = wsp(ws, pl.off_up[1]);
         {
           GuardTable t;
           t.count = 0;
           t.esize = (int)mil_esize(dt);
           guard_add(t, up_pre, gu);
-          guard_add(t, up_dz, gu);
+          guard_add(t, t_sub, gxs);
           guard_add(t, dnew, gi);
           MIL_TRY(launch_guards(t, s));
         }
         MIL_TRY(mil_launch_upsample2(dpre, go, up_pre, gu, s));
-        MIL_TRY(mil_launch_upsample2(dz, go, up_dz, gu, s));
         MIL_TRY(mil_wgrad_dispatch(dt, xin, gi, up_pre, gu, partial, gptr(c1.p_w), gptr(c1.p_b), 3, 1, s));
-        MIL_TRY(mil_wgrad_dispatch(dt, xin, gi, up_dz, gu, partial, gptr(cd.p_w), nullptr, 1, 1, s));
-        MIL_TRY(mil_conv_dispatch(dt, 1, up_dz, gu, wpack + cd.wpt_off, TCW(cd, true), nullptr, nullptr, nullptr, dnew,
-                                  gi, 1, 1, MIL_EPI_PLAIN, s));
-        MIL_TRY(mil_conv_dispatch(dt, 1, up_pre, gu, wpack + c1.wpt_off, TCW(c1, true), nullptr, dnew, xin, dnew, gi, 3,
-                                  1, MIL_EPI_DGRAD, s));
+        MIL_TRY(mil_wgrad_dispatch(dt, wsp(ws, pl.off_xsub[l]), gxs, dz, go, partial, gptr(cd.p_w), nullptr, 1, 1, s));
+        MIL_TRY(mil_conv_dispatch(dt, 1, dz, go, wpack + cd.wpt_off, TCW(cd, true), nullptr, nullptr, nullptr, t_sub, gxs,
+                                  1, 1, MIL_EPI_PLAIN, s));
+        {
+          MilTcShape sh;
+          MIL_TRY(mil_tc_shape(gu.c, gi.c, 3, &sh));
+          MIL_TRY(mil_launch_conv_tc(1, up_pre, gu, TCW(c1, true), sh, nullptr, t_sub, xin, dnew, gi, MIL_EPI_DGRAD, 0, s,
+                                     &gxs));
+        }
         {
           GuardTable t;
           t.count = 0;

@@ -34,7 +34,7 @@ struct MilPlan {
   MilGeom geo;
   MilPF8 g[4];                  // activation geometry of layer1..4
   std::vector<MilConvDesc> convs;  // 27 entries, forward order
-  size_t off_pooled, off_argmax, off_h[12], off_y[12], off_avg, off_grad[3], off_up[2], off_wpack, off_wtc, off_partial;
+  size_t off_pooled, off_argmax, off_h[12], off_y[12], off_avg, off_grad[3], off_up[2], off_xsub[4], off_wpack, off_wtc, off_partial;
   bool stem_tc;                 // stem on the tensor cores (bf16 mode)
   size_t off_xs, off_cv, off_stem_wp, off_stem_wtc;
   size_t wpack_floats, wtc_bytes, partial_floats, grad_bytes, up_bytes;

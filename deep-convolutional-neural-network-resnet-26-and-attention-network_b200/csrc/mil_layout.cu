@@ -152,6 +152,31 @@ __global__ void upsample2_kernel(const uint4* __restrict__ in, MilPF8 gin, uint4
     out[(size_t)cb * gout.PS + gout.G + q] = v;
   }
 }
+// ---- even-position subsampling (bf16): out(n, y, x) = in(n, 2y, 2x) -------------------------------------------
+__global__ void subsample2_kernel(const uint4* __restrict__ in, MilPF8 gin, uint4* __restrict__ out, MilPF8 gout) {
+  const long long total = (long long)gout.cb * gout.Q;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cb = (int)(i / gout.Q);
+    const long long q = i - (long long)cb * gout.Q;
+    const int n = (int)(q / gout.P);
+    const int r = (int)(q - (long long)n * gout.P);
+    const int y = r / gout.wp, x = r - y * gout.wp;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (y < gout.h && x < gout.w)
+      v = in[(size_t)cb * gin.PS + gin.G + (size_t)n * gin.P + (size_t)(2 * y) * gin.wp + 2 * x];
+    out[(size_t)cb * gout.PS + gout.G + q] = v;
+  }
+}
+int mil_launch_subsample2(const void* in, const MilPF8& gin, void* out, const MilPF8& gout, cudaStream_t s) {
+  MIL_REQUIRE(gin.n == gout.n && gin.cb == gout.cb && gout.h == (gin.h - 1) / 2 + 1 && gout.w == (gin.w - 1) / 2 + 1,
+              "subsample2: geometry mismatch");
+  const int blocks = (int)std::min<long long>(mil_cdiv((long long)gout.cb * gout.Q, 256), 148 * 16);
+  subsample2_kernel<<<blocks, 256, 0, s>>>((const uint4*)in, gin, (uint4*)out, gout);
+  MIL_LAUNCH_OK();
+  return 0;
+}
+
 int mil_launch_upsample2(const void* in, const MilPF8& gin, void* out, const MilPF8& gout, cudaStream_t s) {
   MIL_REQUIRE(gin.n == gout.n && gin.cb == gout.cb && gin.h == (gout.h - 1) / 2 + 1 && gin.w == (gout.w - 1) / 2 + 1,
               "upsample2: geometry mismatch");
