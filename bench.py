@@ -64,19 +64,31 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def wait_first(self, limit_s=15.0):
+        """nvidia-smi takes a while to start on a fresh box: block until its first sample arrives."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t0 < limit_s:
+            time.sleep(0.01)
+
+    def stop(self, t_begin=None, t_end=None):
+        """Summary of the samples taken inside [t_begin, t_end] (the timed region); if the sampler has none there
+        it falls back to every sample it took under the same load (warm-up included) and says so."""
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.1)
         self.proc.terminate()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        rows = [r for t, r in self.rows if t_begin is None or (t_begin <= t <= t_end + 0.03)]
+        window = "timed region"
+        if not rows:
+            rows, window = [r for _, r in self.rows], "warm-up + timed region (no sample landed inside the timed region)"
+        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [nm for i, nm in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
+        reasons = [nm for i, nm in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(rows), "window": window}
 
 
 def cpu_reference_throughput(side, sample_tiles, reps, seed=1):
@@ -187,12 +199,15 @@ def run_ours(args):
         return out
 
     # ---------------- device-resident ----------------
-    for _ in range(args.warmup):
-        step(bag)
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step(bag)
+    if rank == 0:
+        sampler.wait_first()
+    barrier()
+    t_begin = time.perf_counter()
     l0 = lib.mil_kernel_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -201,7 +216,7 @@ def run_ours(args):
     ev1.record()
     barrier()
     launches = lib.mil_kernel_launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, time.perf_counter()) if rank == 0 else None
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
