@@ -12,7 +12,8 @@ all-reduced over NCCL.  Prints ONE JSON line (rank 0).
   e2e    : same metric through the public API with the bag in pinned HOST memory: the fp32 NCHW bag is copied
            host->device every step and the loss is read back, inside the timed region
   roofline: the dominant kernel (the 3x3 convolution of layer1, 31 % of the FLOPs) timed alone with CUDA events;
-           achieved = algorithmic FLOPs per launch / duration, against MEASURED_PEAKS.json's bf16 burst peak
+           it is HBM-bound (48 FLOP/B): achieved = algorithmic bytes per launch / duration against
+           MEASURED_PEAKS.json's copy bandwidth; the tensor-pipe fraction of the same launch is reported next to it
   cpu_baseline: the CPU oracle port of the reference path (torch CPU, all host threads) on a bounded sample
 
 --impl reference times that CPU path alone (the reference is pure Python + torch and cannot travel to the GPU
@@ -33,6 +34,9 @@ PKG = "deep-convolutional-neural-network-resnet-26-and-attention-network_b200"
 
 FLOP_FWD_BWD = {224: 1247.7e6, 256: 1629.9e6}      # algorithmic FLOP per tile
 L1_CONV_FLOP_224 = 22.58e6                         # one layer1 3x3 conv, per tile
+# dram__bytes_read.sum + dram__bytes_write.sum of that kernel at 1024 tiles per launch, from the ncu --set full
+# capture summarised in profiles/ (filled in from the capture; None = no capture for this launch size)
+L1_CONV_NCU_TRAFFIC = {}
 METRIC = "tiles/sec fwd+bwd ResNet-26+attention-MIL"
 
 
@@ -283,8 +287,10 @@ def run_ours(args):
         nb = int(lib.mil_pf8_bytes(nk, 20, h1, h1, dt))
         xin = torch.randn(nk, 20, h1, h1, device=dev)
         X = torch.zeros(nb, dtype=torch.uint8, device=dev)
+        R = torch.zeros(nb, dtype=torch.uint8, device=dev)     # residual: a separate map, as inside the network
         O = torch.zeros(nb, dtype=torch.uint8, device=dev)
         mil._lib.check(lib.mil_to_pf8(dt, P(xin), P(X), nk, 20, h1, h1, None), "mil_to_pf8")
+        mil._lib.check(lib.mil_to_pf8(dt, P(torch.randn_like(xin)), P(R), nk, 20, h1, h1, None), "mil_to_pf8")
         w = torch.randn(20, 20, 3, 3, device=dev) * 0.1
         bias = torch.zeros(20, device=dev)
         wsb = int(lib.mil_conv_workspace_bytes(nk, 20, h1, h1, 20, h1, h1, 3))
@@ -292,7 +298,7 @@ def run_ours(args):
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
         def conv_once():      # one weight-pack launch (~2 us) + the convolution kernel
-            mil._lib.check(lib.mil_conv_pf8(dt, 0, 0, P(X), nk, 20, h1, h1, P(w), 20, 20, 3, 1, P(bias), P(X), None,
+            mil._lib.check(lib.mil_conv_pf8(dt, 0, 0, P(X), nk, 20, h1, h1, P(w), 20, 20, 3, 1, P(bias), P(R), None,
                                             P(O), h1, h1, 0, P(wsk), wsb, st), "mil_conv_pf8")
         for _ in range(3):
             conv_once()
@@ -307,11 +313,18 @@ def run_ours(args):
         kms = k0.elapsed_time(k1) / reps
         flop = 2.0 * 20 * 20 * 9 * h1 * h1 * nk
         ach = flop / (kms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "conv3x3 20->20 (layer1), fused bias+residual+LeakyReLU",
-                    "achieved": ach, "peak": burst, "unit": "TFLOP/s", "frac": ach / burst, "traffic": None,
-                    "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({how}, burst)",
-                    "tiles_per_launch": nk, "ms_per_launch": kms,
-                    "whole_step_frac_of_sustained": value * FLOP_FWD_BWD.get(side, 0) / 1e12 / sustained}
+        # algorithmic bytes: input map + residual map + output map, 20 channels bf16, un-padded;
+        # at 48 FLOP/B this kernel sits far left of the 253 FLOP/B ridge: HBM is the roofline that binds it
+        elem = 2 if args.precision == "bf16" else 4
+        abytes = 3.0 * 20 * h1 * h1 * elem * nk
+        gbs = abytes / (kms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "conv3x3 20->20 (layer1), fused bias+residual+LeakyReLU",
+                    "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                    "traffic": L1_CONV_NCU_TRAFFIC.get(nk),
+                    "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({how}, burst copy)",
+                    "algorithmic_bytes_per_launch": abytes, "tiles_per_launch": nk, "ms_per_launch": kms,
+                    "tensor": {"achieved": ach, "peak": burst, "unit": "TFLOP/s", "frac": ach / burst},
+                    "whole_step_tensor_frac_of_sustained": value * FLOP_FWD_BWD.get(side, 0) / 1e12 / sustained}
 
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
     cpu = None

@@ -34,41 +34,41 @@ template <typename TIn>
 __global__ void __launch_bounds__(256)
 stem_s2d4_kernel(const TIn* __restrict__ x, const int* __restrict__ idx, int side, __nv_bfloat16* __restrict__ xs,
                  MilPF8 g) {
-  // one thread per (pixel, (c, ry)) = 12 row-quads: reads one float4 (4 rx) when aligned, writes 4 channels
-  const long long total = 12 * g.Q;
+  // one thread per (pixel, chunk k of 6): chunk k = channels (c, ry, rx) with c = k/2, ry = 2(k&1) + {0,1}, rx = 0..3
+  // -> two 4-element row segments in (one vector load each when aligned), ONE 16-byte chunk out
+  const long long total = 6 * g.Q;
   const bool vec = (side & 3) == 0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int cr = (int)(i / g.Q);  // c*4 + ry
-    const long long q = i - (long long)cr * g.Q;
+    const int k = (int)(i / g.Q);
+    const long long q = i - (long long)k * g.Q;
     const int n = (int)(q / g.P);
     const int r = (int)(q - (long long)n * g.P);
     const int Y = r / g.wp, X = r - Y * g.wp;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (Y < g.h && X < g.w) {
-      const int c = cr >> 2, ry = cr & 3;
-      const int iy = 4 * Y + ry;
-      if (iy < side) {
-        const int src_n = idx ? idx[n] : n;
-        const TIn* row = x + (((size_t)src_n * 3 + c) * side + iy) * side + 4 * X;
-        if (vec) {
-          struct alignas(4 * sizeof(TIn)) Quad { TIn e[4]; };
-          const Quad f = *reinterpret_cast<const Quad*>(row);
+      const int c = k >> 1;
+      const int src_n = idx ? idx[n] : n;
 #pragma unroll
-          for (int rx = 0; rx < 4; ++rx) v[rx] = stem_norm(f.e[rx]);
-        } else {
+      for (int h = 0; h < 2; ++h) {
+        const int iy = 4 * Y + 2 * (k & 1) + h;
+        if (iy < side) {
+          const TIn* row = x + (((size_t)src_n * 3 + c) * side + iy) * side + 4 * X;
+          if (vec) {
+            struct alignas(4 * sizeof(TIn)) Quad { TIn e[4]; };
+            const Quad f = *reinterpret_cast<const Quad*>(row);
 #pragma unroll
-          for (int rx = 0; rx < 4; ++rx)
-            if (4 * X + rx < side) v[rx] = stem_norm(row[rx]);
+            for (int rx = 0; rx < 4; ++rx) v[h * 4 + rx] = stem_norm(f.e[rx]);
+          } else {
+#pragma unroll
+            for (int rx = 0; rx < 4; ++rx)
+              if (4 * X + rx < side) v[h * 4 + rx] = stem_norm(row[rx]);
+          }
         }
       }
     }
-    // channel cc = (c*4 + ry)*4 + rx = cr*4 + rx  ->  chunk cr/2, lanes (cr&1)*4 .. +3   (8 bytes)
-    __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
-    uint2 pk;
-    pk.x = *reinterpret_cast<uint32_t*>(&p0);
-    pk.y = *reinterpret_cast<uint32_t*>(&p1);
-    *reinterpret_cast<uint2*>(xs + mil_pf8_off(g, cr >> 1, q) + (cr & 1) * 4) = pk;
+    // channel cc = (c*4 + ry)*4 + rx  ->  chunk cc/8 = k, lane (ry&1)*4 + rx
+    mil_store8(xs + mil_pf8_off(g, k, q), v);
   }
 }
 
@@ -106,53 +106,59 @@ __device__ __forceinline__ void unpack8h(const uint4& r, float v[8]) {
 __global__ void __launch_bounds__(256)
 stem_pool4_kernel(const __nv_bfloat16* __restrict__ cv, MilPF8 gc, int hc, __nv_bfloat16* __restrict__ pooled,
                   MilPF8 gp, uint16_t* __restrict__ argmax) {
-  const long long total = 10 * gp.Q;
+  // one thread per (pooled pixel, pooled chunk pc of 3) = four channel pairs cp = 4pc .. 4pc+3 (cp < 10): every
+  // pooled chunk leaves as ONE 16-byte store
+  const long long total = 3 * gp.Q;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int cp = (int)(i / gp.Q);  // channel pair: co = 2cp, 2cp+1
-    const long long q = i - (long long)cp * gp.Q;
+    const int pc = (int)(i / gp.Q);
+    const long long q = i - (long long)pc * gp.Q;
     const int n = (int)(q / gp.P);
     const int r = (int)(q - (long long)n * gp.P);
     const int py = r / gp.wp, px = r - py * gp.wp;
-    float best[2] = {0.f, 0.f};
-    int am[2] = {0, 0};
+    float out[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (py < gp.h && px < gp.w) {
-      // the zero halo of PF8 makes (py-1, px-1) readable everywhere; validity is decided on conv coordinates
-      float nb[2][2][8];  // [dy: py-1, py][dx: px-1, px][8 lanes = (co sub-index)*4 + a*2 + b]
       const long long qc = (long long)n * gc.P + (long long)py * gc.wp + px;
+      const int ncp = pc == 2 ? 2 : 4;  // channel pairs 8, 9 only in the last chunk (channels 20..23 are padding)
+      for (int j = 0; j < ncp; ++j) {
+        const int cp = pc * 4 + j;
+        // the zero halo of PF8 makes (py-1, px-1) readable everywhere; validity is decided on conv coordinates
+        float nb[2][2][8];  // [dy: py-1, py][dx: px-1, px][8 lanes = (co sub-index)*4 + a*2 + b]
 #pragma unroll
-      for (int dy = 0; dy < 2; ++dy)
+        for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-        for (int dx = 0; dx < 2; ++dx) {
-          const uint4 raw = __ldg(reinterpret_cast<const uint4*>(
-              cv + mil_pf8_off(gc, cp, qc - (1 - dy) * gc.wp - (1 - dx))));
-          unpack8h(raw, nb[dy][dx]);
-        }
-      best[0] = best[1] = -INFINITY;
+          for (int dx = 0; dx < 2; ++dx) {
+            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(
+                cv + mil_pf8_off(gc, cp, qc - (1 - dy) * gc.wp - (1 - dx))));
+            unpack8h(raw, nb[dy][dx]);
+          }
+        float best[2] = {-INFINITY, -INFINITY};
+        int am[2] = {0, 0};
 #pragma unroll
-      for (int wy = 0; wy < 3; ++wy) {
-        const int cy = 2 * py - 1 + wy;
-        const bool oky = cy >= 0 && cy < hc;
-        const int dy = wy == 0 ? 0 : 1, a = wy == 1 ? 0 : 1;
+        for (int wy = 0; wy < 3; ++wy) {
+          const int cy = 2 * py - 1 + wy;
+          const bool oky = cy >= 0 && cy < hc;
+          const int dy = wy == 0 ? 0 : 1, a = wy == 1 ? 0 : 1;
 #pragma unroll
-        for (int wx = 0; wx < 3; ++wx) {
-          const int cx = 2 * px - 1 + wx;
-          const int dx = wx == 0 ? 0 : 1, b = wx == 1 ? 0 : 1;
-          if (oky && cx >= 0 && cx < hc) {
-            const float v0 = nb[dy][dx][a * 2 + b], v1 = nb[dy][dx][4 + a * 2 + b];
-            if (v0 > best[0]) { best[0] = v0; am[0] = wy * 3 + wx; }
-            if (v1 > best[1]) { best[1] = v1; am[1] = wy * 3 + wx; }
+          for (int wx = 0; wx < 3; ++wx) {
+            const int cx = 2 * px - 1 + wx;
+            const int dx = wx == 0 ? 0 : 1, b = wx == 1 ? 0 : 1;
+            if (oky && cx >= 0 && cx < hc) {
+              const float v0 = nb[dy][dx][a * 2 + b], v1 = nb[dy][dx][4 + a * 2 + b];
+              if (v0 > best[0]) { best[0] = v0; am[0] = wy * 3 + wx; }
+              if (v1 > best[1]) { best[1] = v1; am[1] = wy * 3 + wx; }
+            }
           }
         }
+        argmax[((size_t)n * 10 + cp) * gp.h * gp.w + (size_t)py * gp.w + px] = (uint16_t)(am[0] | (am[1] << 8));
+        // pooled channel co = 2cp + {0,1} -> chunk co/8 = pc, lane co%8 = 2j + {0,1}
+        if (j == 0) { out[0] = best[0]; out[1] = best[1]; }
+        if (j == 1) { out[2] = best[0]; out[3] = best[1]; }
+        if (j == 2) { out[4] = best[0]; out[5] = best[1]; }
+        if (j == 3) { out[6] = best[0]; out[7] = best[1]; }
       }
-      argmax[((size_t)n * 10 + cp) * gp.h * gp.w + (size_t)py * gp.w + px] = (uint16_t)(am[0] | (am[1] << 8));
     }
-    // pooled channel co -> chunk co/8, lane co%8 ; the pair (2cp, 2cp+1) is one 4-byte store
-    __nv_bfloat162 pk = __floats2bfloat162_rn(best[0], best[1]);
-    *reinterpret_cast<__nv_bfloat162*>(pooled + mil_pf8_off(gp, cp >> 2, q) + (cp & 3) * 2) = pk;
-    if (cp == 9) {  // pad channels 20..23 of the last pooled chunk stay zero
-      *reinterpret_cast<uint2*>(pooled + mil_pf8_off(gp, 2, q) + 4) = make_uint2(0, 0);
-    }
+    mil_store8(pooled + mil_pf8_off(gp, pc, q), out);
   }
 }
 
@@ -162,57 +168,76 @@ stem_pool4_kernel(const __nv_bfloat16* __restrict__ cv, MilPF8 gc, int hc, __nv_
 __global__ void __launch_bounds__(256)
 stem_unpool4_kernel(const __nv_bfloat16* __restrict__ g, MilPF8 gp, const uint16_t* __restrict__ argmax,
                     __nv_bfloat16* __restrict__ dy, MilPF8 gc, int hc) {
-  const long long total = 10 * gc.Q;
+  // one thread per (phase-map pixel, pooled chunk pc of 3): the four neighbouring pooled gradients are loaded as whole
+  // 16-byte chunks ONCE and serve the (up to) four channel pairs cp = 4pc .. 4pc+3, each one 16-byte chunk of dY4
+  const long long total = 3 * gc.Q;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int cp = (int)(i / gc.Q);  // chunk of dY4 = channel pair (co = 2cp, 2cp+1) x 4 phases
-    const long long q = i - (long long)cp * gc.Q;
+    const int pc = (int)(i / gc.Q);
+    const long long q = i - (long long)pc * gc.Q;
     const int n = (int)(q / gc.P);
     const int r = (int)(q - (long long)n * gc.P);
     const int Y = r / gc.wp, X = r - Y * gc.wp;
-    float acc[8];
+    const bool inside = Y < gc.h && X < gc.w;
+    const int ncp = pc == 2 ? 2 : 4;
+    float gv[2][2][8];
+    bool ok[2][2];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    if (Y < gc.h && X < gc.w) {
-      int am0[2][2], am1[2][2];
-      float g0[2][2], g1[2][2];
+    for (int dyy = 0; dyy < 2; ++dyy)
 #pragma unroll
-      for (int dyy = 0; dyy < 2; ++dyy)
+      for (int dxx = 0; dxx < 2; ++dxx) {
+        const int py = Y + dyy, px = X + dxx;
+        ok[dyy][dxx] = inside && py < gp.h && px < gp.w;
+        uint4 raw = make_uint4(0, 0, 0, 0);
+        if (ok[dyy][dxx])
+          raw = __ldg(reinterpret_cast<const uint4*>(
+              g + mil_pf8_off(gp, pc, (long long)n * gp.P + (long long)py * gp.wp + px)));
+        unpack8h(raw, gv[dyy][dxx]);
+      }
+    for (int j = 0; j < ncp; ++j) {
+      const int cp = pc * 4 + j;  // chunk of dY4 = channel pair (co = 2cp, 2cp+1) x 4 phases
+      float acc[8];
 #pragma unroll
-        for (int dxx = 0; dxx < 2; ++dxx) {
-          const int py = Y + dyy, px = X + dxx;
-          am0[dyy][dxx] = am1[dyy][dxx] = 255;
-          g0[dyy][dxx] = g1[dyy][dxx] = 0.f;
-          if (py < gp.h && px < gp.w) {
-            const uint16_t amv = argmax[((size_t)n * 10 + cp) * gp.h * gp.w + (size_t)py * gp.w + px];
-            am0[dyy][dxx] = amv & 0xFF;
-            am1[dyy][dxx] = amv >> 8;
-            const __nv_bfloat162 gv = *reinterpret_cast<const __nv_bfloat162*>(
-                g + mil_pf8_off(gp, cp >> 2, (long long)n * gp.P + (long long)py * gp.wp + px) + (cp & 3) * 2);
-            const float2 gf = __bfloat1622float2(gv);
-            g0[dyy][dxx] = gf.x;
-            g1[dyy][dxx] = gf.y;
-          }
-        }
-      // conv position (2Y+a, 2X+b) seen from pooled window (Y+dyy, X+dxx) is window position
-      //   wy = 2Y+a - (2(Y+dyy)-1) = a + 1 - 2 dyy,  wx = b + 1 - 2 dxx   (valid when 0 <= wy,wx <= 2)
+      for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+      if (inside) {
+        int am0[2][2], am1[2][2];
+        float g0[2][2], g1[2][2];
 #pragma unroll
-      for (int a = 0; a < 2; ++a)
+        for (int dyy = 0; dyy < 2; ++dyy)
 #pragma unroll
-        for (int b = 0; b < 2; ++b)
-#pragma unroll
-          for (int dyy = 0; dyy < 2; ++dyy)
-#pragma unroll
-            for (int dxx = 0; dxx < 2; ++dxx) {
-              const int wy = a + 1 - 2 * dyy, wx = b + 1 - 2 * dxx;
-              if (wy < 0 || wx < 0) continue;  // compile-time after unrolling
-              const int want = wy * 3 + wx;
-              if (am0[dyy][dxx] == want) acc[a * 2 + b] += g0[dyy][dxx];
-              if (am1[dyy][dxx] == want) acc[4 + a * 2 + b] += g1[dyy][dxx];
+          for (int dxx = 0; dxx < 2; ++dxx) {
+            am0[dyy][dxx] = am1[dyy][dxx] = 255;
+            // lanes 2j, 2j+1 of the pooled chunk (j is not a compile-time constant: select, do not index)
+            const float* v = gv[dyy][dxx];
+            g0[dyy][dxx] = j == 0 ? v[0] : (j == 1 ? v[2] : (j == 2 ? v[4] : v[6]));
+            g1[dyy][dxx] = j == 0 ? v[1] : (j == 1 ? v[3] : (j == 2 ? v[5] : v[7]));
+            if (ok[dyy][dxx]) {
+              const uint16_t amv =
+                  argmax[((size_t)n * 10 + cp) * gp.h * gp.w + (size_t)(Y + dyy) * gp.w + (X + dxx)];
+              am0[dyy][dxx] = amv & 0xFF;
+              am1[dyy][dxx] = amv >> 8;
             }
-      (void)hc;  // positions beyond the conv map can never be an arg-max: nothing to mask here
+          }
+        // conv position (2Y+a, 2X+b) seen from pooled window (Y+dyy, X+dxx) is window position
+        //   wy = 2Y+a - (2(Y+dyy)-1) = a + 1 - 2 dyy,  wx = b + 1 - 2 dxx   (valid when 0 <= wy,wx <= 2)
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int dyy = 0; dyy < 2; ++dyy)
+#pragma unroll
+              for (int dxx = 0; dxx < 2; ++dxx) {
+                const int wy = a + 1 - 2 * dyy, wx = b + 1 - 2 * dxx;
+                if (wy < 0 || wx < 0) continue;  // compile-time after unrolling
+                const int want = wy * 3 + wx;
+                if (am0[dyy][dxx] == want) acc[a * 2 + b] += g0[dyy][dxx];
+                if (am1[dyy][dxx] == want) acc[4 + a * 2 + b] += g1[dyy][dxx];
+              }
+      }
+      mil_store8(dy + mil_pf8_off(gc, cp, q), acc);
     }
-    mil_store8(dy + mil_pf8_off(gc, cp, q), acc);
+    (void)hc;  // positions beyond the conv map can never be an arg-max: nothing to mask here
   }
 }
 
@@ -273,9 +298,9 @@ int mil_launch_stem_tc_fwd(const void* x, int x_u8, const int* idx, int n, int s
   const int hc = (side - 1) / 2 + 1;
   MIL_REQUIRE(gp.h == gi.h && gp.w == gi.w && gp.c == STC_CO && gp.n == n, "stem_tc_fwd: geometry mismatch");
   if (x_u8)
-    stem_s2d4_kernel<uint8_t><<<grid_for(12 * gi.Q), 256, 0, s>>>((const uint8_t*)x, idx, side, (__nv_bfloat16*)xs, gi);
+    stem_s2d4_kernel<uint8_t><<<grid_for(6 * gi.Q), 256, 0, s>>>((const uint8_t*)x, idx, side, (__nv_bfloat16*)xs, gi);
   else
-    stem_s2d4_kernel<float><<<grid_for(12 * gi.Q), 256, 0, s>>>((const float*)x, idx, side, (__nv_bfloat16*)xs, gi);
+    stem_s2d4_kernel<float><<<grid_for(6 * gi.Q), 256, 0, s>>>((const float*)x, idx, side, (__nv_bfloat16*)xs, gi);
   MIL_LAUNCH_OK();
   float* bias4 = wp + (size_t)9 * STC_CI * STC_CO4;
   stem_pack_w4_kernel<<<64, 256, 0, s>>>(w, b, wp, bias4);
@@ -284,7 +309,7 @@ int mil_launch_stem_tc_fwd(const void* x, int x_u8, const int* idx, int n, int s
   MIL_TRY(mil_tc_shape(STC_CI, STC_CO4, 3, &sh));
   MIL_TRY(mil_launch_pack_tc(wp, wtc, sh, s));
   MIL_TRY(mil_launch_conv_tc(0, xs, gi, wtc, sh, bias4, nullptr, nullptr, convout, gc, MIL_EPI_FWD, 0, s));
-  stem_pool4_kernel<<<grid_for(10 * gp.Q), 256, 0, s>>>((const __nv_bfloat16*)convout, gc, hc, (__nv_bfloat16*)pooled,
+  stem_pool4_kernel<<<grid_for(3 * gp.Q), 256, 0, s>>>((const __nv_bfloat16*)convout, gc, hc, (__nv_bfloat16*)pooled,
                                                         gp, argmax);
   MIL_LAUNCH_OK();
   return 0;
@@ -295,7 +320,7 @@ int mil_launch_stem_tc_bwd(const void* xs, int n, int side, const void* g, const
   const uint16_t* argmax = reinterpret_cast<const uint16_t*>(argmax8);
   const MilPF8 gi = mil_stem_tc_geom_in(n, side), gc = mil_stem_tc_geom_conv(n, side);
   const int hc = (side - 1) / 2 + 1;
-  stem_unpool4_kernel<<<grid_for(10 * gc.Q), 256, 0, s>>>((const __nv_bfloat16*)g, gp, argmax, (__nv_bfloat16*)dy, gc,
+  stem_unpool4_kernel<<<grid_for(3 * gc.Q), 256, 0, s>>>((const __nv_bfloat16*)g, gp, argmax, (__nv_bfloat16*)dy, gc,
                                                           hc);
   MIL_LAUNCH_OK();
   int ctas;

@@ -39,7 +39,7 @@ struct WgSmemHeader {
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat16* __restrict__ dz, MilPF8 gz,
                 float* __restrict__ partial, long long rec_stride, MilTcShape sh, int halo, int taps_per_group,
-                int npad, int mma_m, int dxcat, int n_stages) {
+                int npad, int mma_m, int dxcat, int fold, int n_stages) {
   extern __shared__ __align__(128) unsigned char smem[];
   WgSmemHeader* hd = reinterpret_cast<WgSmemHeader*>(smem);
   unsigned char* ones = smem + 128;            // 512 B of bf16 1.0: the B operand of the bias-gradient MMA
@@ -51,7 +51,10 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
   const int back = dxcat ? gx.wp : halo;       // pixels before q0 held by a plane (of the dx = 0 copy)
   const uint32_t b_plane = (uint32_t)span * 16;
   const uint32_t a_bytes = (uint32_t)gz.cb * WG_A_PLANE;
-  const uint32_t stage_bytes = a_bytes + (uint32_t)nbp * b_plane;
+  const uint32_t load_bytes = a_bytes + (uint32_t)nbp * b_plane;
+  // fold = 1: one more B plane per stage, constant 1.0, so the bias gradient is one more N-group of the tap MMAs
+  // (a thin M = 64 MMA costs the tensor pipe 28 cycles whatever its N: profiles/r1_mma_cost.txt)
+  const uint32_t stage_bytes = load_bytes + (fold ? b_plane : 0u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tap_lo = blockIdx.y * taps_per_group;
   const int tap_hi = min(ngrp_taps, tap_lo + taps_per_group);
@@ -66,6 +69,11 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
   }
   for (int i = threadIdx.x; i < 128; i += blockDim.x)
     reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;  // two bf16 1.0
+  if (fold)
+    for (int st = 0; st < n_stages; ++st) {
+      uint32_t* op = reinterpret_cast<uint32_t*>(stage0 + (size_t)st * stage_bytes + load_bytes);
+      for (int i = threadIdx.x; i < (int)(b_plane / 4); i += blockDim.x) op[i] = 0x3F803F80u;
+    }
   fence_proxy_async();
   if (warp == 1) tmem_alloc(&hd->tmem_base, 512);
   tc_fence_before();
@@ -80,7 +88,7 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       mbar_wait(&hd->empty[stage], phase ^ 1);
       if (elect_one()) {
-        mbar_expect_tx(&hd->full[stage], stage_bytes);
+        mbar_expect_tx(&hd->full[stage], load_bytes);
         const long long q0 = t * WG_TK;
         unsigned char* dst = stage0 + (size_t)stage * stage_bytes;
         for (int c = 0; c < gz.cb; ++c)
@@ -128,7 +136,7 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
 #pragma unroll
           for (int kk = 1; kk < WG_TK / 16; ++kk) umma_bf16(d, ad0 + kk * 16, bd0 + kk * 16, idesc, 1u);
         }
-        if (with_bias) {
+        if (with_bias && !fold) {
           const uint32_t d = tmem_base + ntl * npad;
           umma_bf16(d, ad0, ones_desc, idesc_b, acc0);
 #pragma unroll
@@ -170,7 +178,7 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
       }
       if (with_bias) {
         float v[8];
-        tmem_ld8(taddr + ntl * npad, v);
+        tmem_ld8(taddr + (fold ? nbp * 8 : ntl * npad), v);
         tmem_ld_wait();
         if (co < coutp) rec[(size_t)ntaps * cinp * coutp + co] = v[0];
       }
@@ -197,7 +205,7 @@ static int wg_sm_count() {
 }
 
 struct WgConfig {
-  int dxcat, npad, groups, tpg, ctas, mma_m, n_stages;
+  int dxcat, fold, npad, groups, tpg, ctas, mma_m, n_stages;
   size_t smem;
 };
 
@@ -205,15 +213,16 @@ static WgConfig wg_config(const MilPF8& gx, const MilPF8& gz, int ks) {
   WgConfig c;
   c.dxcat = ks == 3 ? 1 : 0;
   c.mma_m = gz.cb * 8 <= 64 ? 64 : 128;
-  c.npad = c.dxcat ? 3 * gx.cb * 8 : (gx.c + 15) / 16 * 16;
+  c.fold = (c.dxcat && c.mma_m == 64) ? 1 : 0;
+  c.npad = c.dxcat ? (3 * gx.cb + c.fold) * 8 : (gx.c + 15) / 16 * 16;
   const int gtaps = c.dxcat ? 3 : ks * ks;
-  c.groups = (gtaps * c.npad + 16 <= 512) ? 1 : 2;
+  c.groups = (gtaps * c.npad + (c.fold ? 0 : 16) <= 512) ? 1 : 2;
   c.tpg = (gtaps + c.groups - 1) / c.groups;
   const long long n_tiles = mil_cdiv(gz.Q, WG_TK);
   c.ctas = (int)std::max<long long>(1, std::min<long long>(n_tiles, wg_sm_count() / c.groups));
   const int halo = ks == 3 ? gx.wp + 1 : 0;
   const size_t span = c.dxcat ? WG_TK + 2 * (size_t)gx.wp : WG_TK + 2 * (size_t)halo;
-  const size_t stage = (size_t)gz.cb * WG_A_PLANE + (size_t)(c.dxcat ? 3 * gx.cb : gx.cb) * span * 16;
+  const size_t stage = (size_t)gz.cb * WG_A_PLANE + (size_t)((c.dxcat ? 3 * gx.cb : gx.cb) + c.fold) * span * 16;
   c.n_stages = WG_MAX_STAGES;
   while (c.n_stages > 1 && 128 + 512 + c.n_stages * stage + WG_SLACK > 220 * 1024) --c.n_stages;
   c.smem = 128 + 512 + c.n_stages * stage + WG_SLACK;
@@ -247,7 +256,7 @@ int mil_launch_wgrad_tc_partials(const void* x, const MilPF8& gx, const void* dz
   const long long rec = (long long)sh.ntaps * gx.cb * 8 * gz.cb * 8 + gz.cb * 8;
   wgrad_tc_kernel<<<dim3(c.ctas, c.groups), WG_THREADS, c.smem, s>>>(
       (const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)dz, gz, partial, rec, sh, halo, c.tpg, c.npad, c.mma_m, c.dxcat,
-      c.n_stages);
+      c.fold, c.n_stages);
   MIL_LAUNCH_OK();
   *ctas_out = c.ctas;
   *rec_out = rec;

@@ -18,8 +18,9 @@ w = torch.randn(c, c, 3, 3, device="cuda") * 0.1
 b = torch.zeros(c, device="cuda")
 X = G.PF8.from_nchw(x, "bf16")
 DZ = G.PF8.from_nchw(torch.randn(n, c, h, h, device="cuda"), "bf16")
+R = G.PF8.from_nchw(torch.randn(n, c, h, h, device="cuda"), "bf16")          # residual: a separate map
 for _ in range(2):
-    out = G.conv(X, w, bias=b, res=X, stride=1, epi=0, impl=2)          # forward conv, full epilogue
+    out = G.conv(X, w, bias=b, res=R, stride=1, epi=0, impl=2)          # forward conv, full epilogue
     dw, db = G.wgrad(X, DZ, 3, 1, impl=2)                                # weight gradient
 torch.cuda.synchronize()
 print("ok", float(out.to_nchw().abs().mean()), float(dw.abs().mean()))
