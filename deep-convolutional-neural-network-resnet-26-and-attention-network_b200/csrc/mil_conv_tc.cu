@@ -77,7 +77,9 @@ __device__ __forceinline__ void unpack8(const uint4& r, float v[8]) {
 // MAXCB: upper bound of the output chunks (sizes the per-thread register arrays exactly); NG: accumulator
 // stages = epilogue groups of 4 warps.  The thin layers are bound by the epilogue's instruction stream, not by
 // the tensor pipe, so they get 4 groups; the wide layers (more registers per thread) get 2.
-template <int MAXCB, int NG>
+enum { TCM_GENERIC = 0, TCM_PLAIN, TCM_FWD, TCM_FWD_RES, TCM_DGRAD, TCM_DGRAD_RES };
+
+template <int MAXCB, int NG, int MODE>
 __global__ void __launch_bounds__(96 + NG * 128, 1)
 conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat16* __restrict__ wtc,
                const float* __restrict__ bias, const __nv_bfloat16* res, const __nv_bfloat16* act,
@@ -168,11 +170,17 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
     }
   } else {
     // ===================== epilogue: group eg serves accumulator stage eg =====================
+    // MODE != TCM_GENERIC: chunk count, epilogue kind and residual are compile-time facts -- the per-chunk branches
+    // fold away (the generic form executes ~540 instructions per pixel on layer 1, the specialised one about a third)
+    constexpr bool SPEC = MODE != TCM_GENERIC;
     const int eg = (warp - 3) >> 2;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
-    const int cbout = sh.cbout;
-    const bool has_res = res != nullptr, has_act = epi == MIL_EPI_DGRAD;
+    const int cbout = SPEC ? MAXCB : sh.cbout;
+    const bool has_res = SPEC ? (MODE == TCM_FWD_RES || MODE == TCM_DGRAD_RES) : res != nullptr;
+    const bool has_act = SPEC ? (MODE == TCM_DGRAD || MODE == TCM_DGRAD_RES) : epi == MIL_EPI_DGRAD;
+    const bool do_bias = SPEC ? (MODE == TCM_FWD || MODE == TCM_FWD_RES) : epi != MIL_EPI_DGRAD;
+    const bool do_lrelu = SPEC ? (MODE == TCM_FWD || MODE == TCM_FWD_RES) : epi == MIL_EPI_FWD;
     long long it = eg;  // CTA-local tile counter of this group
     // This thread's pixel as (image n, in-plane offset r), advanced incrementally from tile to tile: the only
     // 64-bit divisions of the kernel happen here, once (the epilogue's instruction stream is what bounds the
@@ -184,12 +192,13 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
     int n = (int)(q_first / gx.P), r = (int)(q_first % gx.P);
     const float inv_wp = 1.0f / (float)gx.wp;
     const int P = (int)gx.P;
+    const long long ostride = go.PS * 8, rstride = (res_half ? gr.PS : go.PS) * 8;  // elements between chunks
     for (long long t = blockIdx.x + (long long)eg * gridDim.x; t < n_tiles; t += (long long)NG * gridDim.x, it += NG) {
       // flat index q = n * P + r at the input resolution; qo = where the pixel is stored.  sub: the stride-2
       // convolutions are evaluated at full resolution and only the even (y, x) positions are kept.
       bool in_range = n < gx.n;
       bool is_pad = true, res_ok = true;
-      long long qo = (long long)n * P + r, qres = 0;
+      long long qo = (long long)n * P + r, qres = qo;
       if (in_range) {
         int y = __float2int_rz(((float)r + 0.5f) * inv_wp);  // r / wp for r < 2^22 (exact after the fix-up)
         if (y * gx.wp > r) --y;
@@ -206,24 +215,28 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
           in_range = !(y & 1) && !(xo & 1) && yh <= go.h && xh <= go.w;
           is_pad = (yh == go.h) || (xh == go.w);
           qo = (long long)n * go.P + (long long)yh * go.wp + xh;
+          qres = qo;
         }
       }
       n += step_n;
       r += step_r;
       if (r >= P) { r -= P; ++n; }
       const bool live = in_range && !is_pad;
-      const long long o0 = (go.G + qo) * 8, ostride = go.PS * 8;  // element offset of chunk c: o0 + c * ostride
+      __nv_bfloat16* po = out + (go.G + qo) * 8;  // chunk c: po + c * ostride
       // 1. residual / activation loads go out BEFORE we wait for the tensor core
       uint4 rres[MAXCB], ract[MAXCB];
+      if (live) {
+        if (has_res) {
+          const __nv_bfloat16* pr = res + ((res_half ? gr.G : go.G) + qres) * 8;
 #pragma unroll
-      for (int c = 0; c < MAXCB; ++c) {
-        if (c < cbout && live) {
-          const long long o = o0 + c * ostride;
-          if (has_res) {
-            if (!res_half) rres[c] = ld_nc16(res + o);
-            else rres[c] = res_ok ? ld_nc16(res + (gr.G + qres) * 8 + c * (gr.PS * 8)) : make_uint4(0, 0, 0, 0);
-          }
-          if (has_act) ract[c] = ld_nc16(act + o);
+          for (int c = 0; c < MAXCB; ++c)
+            if (c < cbout) rres[c] = res_ok ? ld_nc16(pr + c * rstride) : make_uint4(0, 0, 0, 0);
+        }
+        if (has_act) {
+          const __nv_bfloat16* pa = act + (go.G + qo) * 8;
+#pragma unroll
+          for (int c = 0; c < MAXCB; ++c)
+            if (c < cbout) ract[c] = ld_nc16(pa + c * ostride);
         }
       }
       mbar_wait(&hd->empty[it % n_stages], (uint32_t)((it / n_stages) & 1));
@@ -244,40 +257,44 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
           __syncwarp();
           if (lane == 0) mbar_arrive(&hd->acc_empty[eg]);
         }
-        // 4. arithmetic + stores
+        // 4. arithmetic + stores: one divergent branch per batch, straight-line code inside
+        if (live) {
 #pragma unroll
-        for (int k = 0; k < HALF; ++k) {
-          const int c = half * HALF + k;
-          if (c < cbout && in_range) {
-            float* v = acc[k];
-            if (is_pad) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = 0.f;
-            } else {
+          for (int k = 0; k < HALF; ++k) {
+            const int c = half * HALF + k;
+            if (c < cbout) {
+              float* v = acc[k];
               if (has_res) {
                 float rv[8];
                 unpack8(rres[c], rv);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] += rv[j];
               }
-              if (epi != MIL_EPI_DGRAD) {
+              if (do_bias) {
                 const float4 b0 = *reinterpret_cast<const float4*>(&hd->bias[c * 8]);
                 const float4 b1 = *reinterpret_cast<const float4*>(&hd->bias[c * 8 + 4]);
                 const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] += bv[j];
               }
-              if (epi == MIL_EPI_FWD) {
+              if (do_lrelu) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = mil_lrelu(v[j]);
-              } else if (epi == MIL_EPI_DGRAD) {
+                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], MIL_SLOPE * v[j]);  // == x > 0 ? x : slope * x
+              } else if (has_act) {
                 float av[8];
                 unpack8(ract[c], av);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] *= mil_lrelu_grad(av[j]);
+                for (int j = 0; j < 8; ++j)
+                  if (!(av[j] > 0.f)) v[j] *= MIL_SLOPE;
               }
+              mil_store8(po + c * ostride, v);
             }
-            mil_store8(out + (o0 + c * ostride), v);
+          }
+        } else if (in_range) {  // pad pixel of the output map: keep the zero row / column zero
+#pragma unroll
+          for (int k = 0; k < HALF; ++k) {
+            const int c = half * HALF + k;
+            if (c < cbout) *reinterpret_cast<uint4*>(po + c * ostride) = make_uint4(0, 0, 0, 0);
           }
         }
       }
@@ -409,20 +426,37 @@ int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const vo
   }
   const long long n_tiles = mil_cdiv(gx.Q, TC_M);
   const int grid = (int)std::min<long long>(n_tiles, n_sm);
-#define MIL_TC_LAUNCH(MAXCB, NG)                                                                                  \
+#define MIL_TC_LAUNCH1(MAXCB, NG, MODE)                                                                           \
   do {                                                                                                            \
-    MIL_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<MAXCB, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                        (int)smem));                                                              \
-    conv_tc_kernel<MAXCB, NG><<<grid, 96 + NG * 128, smem, s>>>(                                                  \
+    MIL_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<MAXCB, NG, MODE>,                                          \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+    conv_tc_kernel<MAXCB, NG, MODE><<<grid, 96 + NG * 128, smem, s>>>(                                            \
         (const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)wtc, bias, (const __nv_bfloat16*)res,                  \
         (const __nv_bfloat16*)act, (__nv_bfloat16*)out, go, sh, iss, epi, sub, halo, n_stages,                    \
         gres_half ? *gres_half : go, gres_half ? 1 : 0);                                                          \
+  } while (0)
+  // the network's layers (3 / 5 / 8 / 10 output chunks, five epilogue kinds) run specialised instantiations
+#define MIL_TC_LAUNCH(MAXCB, NG)                                                                                  \
+  do {                                                                                                            \
+    const int mode = sh.cbout != MAXCB ? TCM_GENERIC                                                              \
+                     : (epi == MIL_EPI_PLAIN && bias == nullptr && res == nullptr) ? TCM_PLAIN                    \
+                     : epi == MIL_EPI_FWD ? (res ? TCM_FWD_RES : TCM_FWD)                                          \
+                     : epi == MIL_EPI_DGRAD ? (res ? TCM_DGRAD_RES : TCM_DGRAD) : TCM_GENERIC;                     \
+    switch (mode) {                                                                                               \
+      case TCM_PLAIN: MIL_TC_LAUNCH1(MAXCB, NG, TCM_PLAIN); break;                                                \
+      case TCM_FWD: MIL_TC_LAUNCH1(MAXCB, NG, TCM_FWD); break;                                                    \
+      case TCM_FWD_RES: MIL_TC_LAUNCH1(MAXCB, NG, TCM_FWD_RES); break;                                            \
+      case TCM_DGRAD: MIL_TC_LAUNCH1(MAXCB, NG, TCM_DGRAD); break;                                                \
+      case TCM_DGRAD_RES: MIL_TC_LAUNCH1(MAXCB, NG, TCM_DGRAD_RES); break;                                        \
+      default: MIL_TC_LAUNCH1(MAXCB, NG, TCM_GENERIC); break;                                                     \
+    }                                                                                                             \
   } while (0)
   if (sh.cbout <= 3) MIL_TC_LAUNCH(3, 4);
   else if (sh.cbout <= 5) MIL_TC_LAUNCH(5, 4);
   else if (sh.cbout <= 8) MIL_TC_LAUNCH(8, 2);
   else MIL_TC_LAUNCH(10, 2);
 #undef MIL_TC_LAUNCH
+#undef MIL_TC_LAUNCH1
   MIL_LAUNCH_OK();
   return 0;
 }

@@ -192,6 +192,135 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
   }
 }
 
+// ---- "square" form for the thin layers (3 or 5 chunks on both sides) ----------------------------------------
+// A thin MMA is bound by its operand reads, not by its FLOPs (profiles/r1_mma_cost.txt: M = 128 costs
+// max((128 + N) / 4, N / 2) cycles, M = 64 costs max(28, N / 2)), so the cheapest form has the FEWEST MMAs per K-step:
+// put the three dy shifts on the dz side and the three dx shifts on the x side,
+//   dW[dy][dx][ci][co] = sum_q' x[q' + dx][ci] * dz[q' - dy*wp][co],
+// load every (shift, chunk) plane with its shift applied by the bulk copy's source address (so no plane carries a
+// halo), and ONE M = 128 MMA per K-step produces all nine taps: rows = (dy, co), columns = (dx, ci) + one constant-one
+// plane for the bias gradient.  Layer 1: 52 cycles per 16 pixels instead of 3 x 40, with less shared-memory fill.
+#define WGS_MAX_STAGES 4
+struct WgsSmemHeader {
+  uint64_t full[WGS_MAX_STAGES], empty[WGS_MAX_STAGES], done;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_sq_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat16* __restrict__ dz, MilPF8 gz,
+                float* __restrict__ partial, long long rec_stride, int npad, int n_stages) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  WgsSmemHeader* hd = reinterpret_cast<WgsSmemHeader*>(smem);
+  unsigned char* stage0 = smem + 128;
+  const int na = 3 * gz.cb, nb = 3 * gx.cb;  // A planes (dy, chunk), B planes (dx, chunk); + one all-ones B plane
+  const uint32_t load_bytes = (uint32_t)(na + nb) * WG_A_PLANE;
+  const uint32_t stage_bytes = load_bytes + WG_A_PLANE;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long n_tiles = mil_cdiv(gz.Q, WG_TK);
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < npad) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < n_stages; ++s) { mbar_init(&hd->full[s], 1); mbar_init(&hd->empty[s], 1); }
+    mbar_init(&hd->done, 1);
+    fence_barrier_init();
+  }
+  for (int st = 0; st < n_stages; ++st) {
+    uint32_t* op = reinterpret_cast<uint32_t*>(stage0 + (size_t)st * stage_bytes + load_bytes);
+    for (int i = threadIdx.x; i < WG_A_PLANE / 4; i += blockDim.x) op[i] = 0x3F803F80u;  // two bf16 1.0
+  }
+  fence_proxy_async();
+  if (warp == 1) tmem_alloc(&hd->tmem_base, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = hd->tmem_base;
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      mbar_wait(&hd->empty[stage], phase ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&hd->full[stage], load_bytes);
+        const long long q0 = t * WG_TK;
+        unsigned char* dst = stage0 + (size_t)stage * stage_bytes;
+        for (int e = 0; e < 3; ++e)  // dy = e - 1: the plane holds dz[q - dy * wp]
+          for (int c = 0; c < gz.cb; ++c)
+            bulk_g2s(dst + (size_t)(e * gz.cb + c) * WG_A_PLANE, dz + mil_pf8_off(gz, c, q0 - (long long)(e - 1) * gz.wp),
+                     WG_A_PLANE, &hd->full[stage]);
+        for (int d = 0; d < 3; ++d)  // dx = d - 1: the plane holds x[q + dx]
+          for (int c = 0; c < gx.cb; ++c)
+            bulk_g2s(dst + (size_t)(na + d * gx.cb + c) * WG_A_PLANE, x + mil_pf8_off(gx, c, q0 + d - 1), WG_A_PLANE,
+                     &hd->full[stage]);
+      }
+      __syncwarp();
+      if (++stage == n_stages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    // D = f32, A = B = bf16, both MN-major, M = 128 (the M-groups past 3 * cb read whatever follows in shared
+    // memory: finite bf16 values landing in accumulator rows nobody reads)
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 4) << 24) |
+                           ((uint32_t)(npad >> 3) << 17);
+    int stage = 0;
+    uint32_t phase = 0;
+    bool first = true;
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      mbar_wait(&hd->full[stage], phase);
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(stage0 + (size_t)stage * stage_bytes);
+      const uint64_t ad0 = make_desc(a_base, 128, WG_A_PLANE);
+      const uint64_t bd0 = make_desc(a_base + (uint32_t)na * WG_A_PLANE, 128, WG_A_PLANE);
+      const uint32_t acc0 = first ? 0u : 1u;
+      if (elect_one()) {
+        umma_bf16(tmem_base, ad0, bd0, idesc, acc0);
+#pragma unroll
+        for (int kk = 1; kk < WG_TK / 16; ++kk) umma_bf16(tmem_base, ad0 + kk * 16, bd0 + kk * 16, idesc, 1u);
+        umma_commit(&hd->empty[stage]);
+      }
+      __syncwarp();
+      first = false;
+      if (++stage == n_stages) { stage = 0; phase ^= 1; }
+    }
+    if (elect_one()) umma_commit(&hd->done);
+    __syncwarp();
+  } else {
+    // epilogue: accumulator row (= TMEM lane) (e, c, j) -> tap row dy = e - 1, output channel c * 8 + j;
+    // column block p = (d, cc) -> tap column dx = d - 1, input chunk cc
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int g = row >> 3, e = g / gz.cb, c = g - e * gz.cb;
+    const int co = c * 8 + (row & 7);
+    const int coutp = gz.cb * 8, cinp = gx.cb * 8;
+    mbar_wait(&hd->done, 0);
+    tc_fence_after();
+    if (quarter * 32 < na * 8) {  // warp-uniform
+      float* rec = partial + (size_t)blockIdx.x * rec_stride;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      for (int p = 0; p < nb; ++p) {
+        float v[8];
+        tmem_ld8(taddr + p * 8, v);
+        tmem_ld_wait();
+        const int d = p / gx.cb, cc = p - d * gx.cb;
+        if (g < na) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rec[((size_t)(e * 3 + d) * cinp + cc * 8 + j) * coutp + co] = v[j];
+        }
+      }
+      float v[8];
+      tmem_ld8(taddr + nb * 8, v);
+      tmem_ld_wait();
+      if (g < na && e == 1) rec[(size_t)9 * cinp * coutp + co] = v[0];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------
 static int wg_sm_count() {
   static int n_sm = 0;
@@ -205,12 +334,27 @@ static int wg_sm_count() {
 }
 
 struct WgConfig {
-  int dxcat, fold, npad, groups, tpg, ctas, mma_m, n_stages;
+  int sq, dxcat, fold, npad, groups, tpg, ctas, mma_m, n_stages;
   size_t smem;
 };
 
 static WgConfig wg_config(const MilPF8& gx, const MilPF8& gz, int ks) {
   WgConfig c;
+  const long long n_tiles_sq = mil_cdiv(gz.Q, WG_TK);
+  c.sq = (ks == 3 && 3 * gz.cb <= 16 && ((3 * gx.cb + 1) & 1) == 0 && (3 * gx.cb + 1) * 8 <= 256) ? 1 : 0;
+  if (c.sq) {
+    c.dxcat = c.fold = 0;
+    c.mma_m = 128;
+    c.npad = (3 * gx.cb + 1) * 8;
+    c.groups = 1;
+    c.tpg = 9;
+    c.ctas = (int)std::max<long long>(1, std::min<long long>(n_tiles_sq, wg_sm_count()));
+    const size_t stage = (size_t)(3 * gz.cb + 3 * gx.cb + 1) * WG_A_PLANE;
+    c.n_stages = WGS_MAX_STAGES;
+    while (c.n_stages > 1 && 128 + c.n_stages * stage > 200 * 1024) --c.n_stages;
+    c.smem = 128 + c.n_stages * stage;
+    return c;
+  }
   c.dxcat = ks == 3 ? 1 : 0;
   c.mma_m = gz.cb * 8 <= 64 ? 64 : 128;
   c.fold = (c.dxcat && c.mma_m == 64) ? 1 : 0;
@@ -249,6 +393,17 @@ int mil_launch_wgrad_tc_partials(const void* x, const MilPF8& gx, const void* dz
   MIL_TRY(mil_tc_shape(gx.c, gz.c, ks, &sh));
   const int halo = mil_tc_halo(sh, gx.wp);
   MIL_REQUIRE(halo <= gx.G, "wgrad_tc: the window reaches %d pixels back but the map's guard is %lld", halo, gx.G);
+  const long long rec_sq = (long long)sh.ntaps * gx.cb * 8 * gz.cb * 8 + gz.cb * 8;
+  if (c.sq) {
+    MIL_REQUIRE(halo <= gz.G, "wgrad_tc: the window reaches %d pixels back but the gradient map's guard is %lld", halo, gz.G);
+    MIL_CHECK_CUDA(cudaFuncSetAttribute(wgrad_sq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+    wgrad_sq_kernel<<<c.ctas, WG_THREADS, c.smem, s>>>((const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)dz, gz, partial,
+                                                      rec_sq, c.npad, c.n_stages);
+    MIL_LAUNCH_OK();
+    *ctas_out = c.ctas;
+    *rec_out = rec_sq;
+    return 0;
+  }
   MIL_REQUIRE(c.mma_m == 64 || c.npad % 16 == 0, "wgrad_tc: N = %d is not a multiple of 16 (M = 128)", c.npad);
   MIL_REQUIRE(c.npad <= 256, "wgrad_tc: N = %d too wide", c.npad);
   MIL_REQUIRE(c.smem <= 227 * 1024, "wgrad_tc: tile width %d needs %zu bytes of shared memory", gx.w, c.smem);
