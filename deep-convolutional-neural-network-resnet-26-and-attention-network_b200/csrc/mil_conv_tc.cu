@@ -47,6 +47,35 @@ __global__ void pack_tc_kernel(const float* __restrict__ wp, __nv_bfloat16* __re
   }
 }
 
+// All of a pass's convolutions in ONE launch, straight from the PyTorch layout w[cout][cin][tap] (no fp32 staging):
+// blockIdx.x = table entry.  Forward: K = cin, N = cout;  data gradient (transposed): K = cout, N = cin.
+#define MIL_TC_PACK_MAX 28
+struct TcPackEntry {
+  const float* w;
+  __nv_bfloat16* wtc;
+  short cout, cin;
+  unsigned char taps, transposed, nmma, npad;
+  unsigned char g_tap[2 * MIL_TC_MAX_MMA], g_chunk[2 * MIL_TC_MAX_MMA];
+};
+struct TcPackTable {
+  TcPackEntry e[MIL_TC_PACK_MAX];
+};
+__global__ void pack_tc_table_kernel(const __grid_constant__ TcPackTable t) {
+  const TcPackEntry& p = t.e[blockIdx.x];
+  const int total = p.nmma * 2 * p.npad * 8;
+  const int kin = p.transposed ? p.cout : p.cin, nout = p.transposed ? p.cin : p.cout;
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < total; i += gridDim.y * blockDim.x) {
+    const int e = i & 7, n = (i >> 3) % p.npad, g = (i >> 3) / p.npad;  // g = 2j+h
+    const int tap = p.g_tap[g], k = p.g_chunk[g] * 8 + e;
+    float v = 0.f;
+    if (tap != 0xFF && n < nout && k < kin) {
+      const int co = p.transposed ? k : n, ci = p.transposed ? n : k;
+      v = p.w[((size_t)co * p.cin + ci) * p.taps + tap];
+    }
+    p.wtc[i] = __float2bfloat16_rn(v);
+  }
+}
+
 // ---- the kernel ----------------------------------------------------------------------------------------
 struct TcSmemHeader {
   uint64_t full[TC_MAX_STAGES], empty[TC_MAX_STAGES], acc_empty[TC_MAX_ACC], b_full;
@@ -358,6 +387,28 @@ int mil_launch_pack_tc(const float* wp, void* wtc, const MilTcShape& sh, cudaStr
   const int total = sh.nmma * 2 * sh.npad * 8;
   pack_tc_kernel<<<(int)mil_cdiv(total, 256), 256, 0, s>>>(wp, (__nv_bfloat16*)wtc, sh);
   MIL_LAUNCH_OK();
+  return 0;
+}
+
+int mil_launch_pack_tc_table(const MilTcPackJob* jobs, int count, cudaStream_t s) {
+  for (int base = 0; base < count; base += MIL_TC_PACK_MAX) {
+    TcPackTable t;
+    const int m = std::min(MIL_TC_PACK_MAX, count - base);
+    for (int i = 0; i < m; ++i) {
+      const MilTcPackJob& j = jobs[base + i];
+      MilTcShape sh;
+      MIL_TRY(mil_tc_shape(j.transposed ? j.cout : j.cin, j.transposed ? j.cin : j.cout, j.ks, &sh));
+      TcPackEntry& e = t.e[i];
+      e.w = j.w;
+      e.wtc = (__nv_bfloat16*)j.wtc;
+      e.cout = (short)j.cout; e.cin = (short)j.cin;
+      e.taps = (unsigned char)(j.ks * j.ks); e.transposed = j.transposed ? 1 : 0;
+      e.nmma = (unsigned char)sh.nmma; e.npad = (unsigned char)sh.npad;
+      for (int g = 0; g < 2 * MIL_TC_MAX_MMA; ++g) { e.g_tap[g] = sh.g_tap[g]; e.g_chunk[g] = sh.g_chunk[g]; }
+    }
+    pack_tc_table_kernel<<<dim3(m, 8), 256, 0, s>>>(t);
+    MIL_LAUNCH_OK();
+  }
   return 0;
 }
 

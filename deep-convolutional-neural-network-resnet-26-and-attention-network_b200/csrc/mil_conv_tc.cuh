@@ -36,6 +36,13 @@ int mil_launch_pack_tc(const float* wp, void* wtc, const MilTcShape& sh, cudaStr
 int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const void* wtc, const MilTcShape& sh,
                        const float* bias, const void* res, const void* act, void* out, const MilPF8& go, int epi,
                        int sub, cudaStream_t s, const MilPF8* gres_half = nullptr);
+// every convolution of a pass packed in one launch, straight from the PyTorch weight layout [cout][cin][ks][ks]
+struct MilTcPackJob {
+  const float* w;
+  void* wtc;
+  int cout, cin, ks, transposed;
+};
+int mil_launch_pack_tc_table(const MilTcPackJob* jobs, int count, cudaStream_t s);
 // out (half resolution) = in at the even (y, x) positions (bf16): the input of a stride-2 1x1 projection
 int mil_launch_subsample2(const void* in, const MilPF8& gin, void* out, const MilPF8& gout, cudaStream_t s);
 // out (geometry 2x) = zero-stuffed copy of in: out(n, 2y, 2x) = in(n, y, x), zero elsewhere (bf16)

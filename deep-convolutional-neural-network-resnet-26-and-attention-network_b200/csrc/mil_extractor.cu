@@ -271,23 +271,25 @@ static int pack_weights(const void* const* params, const MilPlan& pl, void* ws, 
   t.count = 0;
   float* area = reinterpret_cast<float*>(wsp(ws, pl.off_wpack));
   for (const auto& c : pl.convs) {
+    if (c.tc) continue;  // the tensor-core convolutions pack straight into their operand blocks below
     const int e = t.count++;
     t.src[e] = reinterpret_cast<const float*>(params[c.p_w]);
     t.dst[e] = area + (transposed ? c.wpt_off : c.wp_off);
     t.cout[e] = (short)c.cout; t.cin[e] = (short)c.cin; t.ks[e] = (unsigned char)c.ks;
     t.transposed[e] = transposed ? 1 : 0;
   }
-  pack_all_kernel<<<dim3(t.count, 8), 256, 0, s>>>(t);
-  MIL_LAUNCH_OK();
+  if (t.count > 0) {
+    pack_all_kernel<<<dim3(t.count, 8), 256, 0, s>>>(t);
+    MIL_LAUNCH_OK();
+  }
   char* tca = wsp(ws, pl.off_wtc);
+  std::vector<MilTcPackJob> jobs;
   for (const auto& c : pl.convs) {
     if (!c.tc) continue;
-    MilTcShape sh;
-    // the kernel's input/output channels: (cin, cout) forward, (cout, cin) for the data gradient
-    MIL_TRY(mil_tc_shape(transposed ? c.cout : c.cin, transposed ? c.cin : c.cout, c.ks, &sh));
-    MIL_TRY(mil_launch_pack_tc(area + (transposed ? c.wpt_off : c.wp_off), tca + (transposed ? c.wtct_off : c.wtc_off),
-                               sh, s));
+    jobs.push_back({reinterpret_cast<const float*>(params[c.p_w]), tca + (transposed ? c.wtct_off : c.wtc_off), c.cout,
+                    c.cin, c.ks, transposed ? 1 : 0});
   }
+  if (!jobs.empty()) MIL_TRY(mil_launch_pack_tc_table(jobs.data(), (int)jobs.size(), s));
   return 0;
 }
 

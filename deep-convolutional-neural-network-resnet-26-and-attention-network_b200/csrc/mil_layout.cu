@@ -106,30 +106,41 @@ int mil_launch_reduce_partials(const float* partial, int nblk, long long stride,
 
 // partial[b][tap][cin_pad][cout_pad] (+ [cout_pad] bias sums at the end of each record) ->
 //   dw[cout][cin][tap] += ... ,  db[cout] += ...      (PyTorch parameter layout)
-__global__ void reduce_conv_w_kernel(const float* __restrict__ partial, int nblk, long long stride,
-                                     float* __restrict__ dw, float* __restrict__ db, int cout, int cin, int ks) {
-  // threads walk the RECORD layout (coalesced reads of every partial record) and scatter into the parameter layout
+#define RCW_PARTS 8
+__global__ void __launch_bounds__(32 * RCW_PARTS)
+reduce_conv_w_kernel(const float* __restrict__ partial, int nblk, long long stride, float* __restrict__ dw,
+                     float* __restrict__ db, int cout, int cin, int ks) {
+  // threadIdx.x walks the RECORD layout (coalesced reads of every partial record), threadIdx.y takes every
+  // RCW_PARTS-th record; the parts are then summed in a fixed order (bit-reproducible) and scattered into the
+  // parameter layout
+  __shared__ float part[RCW_PARTS][32];
   const int cip = (cin + 7) / 8 * 8, cop = (cout + 7) / 8 * 8;
   const int taps = ks * ks;
   const int nrec = taps * cip * cop;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  const int total = nrec + (db != nullptr ? cop : 0);
+  float acc = 0.f;
+  if (i < total)
+    for (int b = threadIdx.y; b < nblk; b += RCW_PARTS) acc += partial[(size_t)b * stride + i];
+  part[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y != 0 || i >= total) return;
+#pragma unroll
+  for (int k = 1; k < RCW_PARTS; ++k) acc += part[k][threadIdx.x];
   if (i < nrec) {
     const int co = i % cop, ci = (i / cop) % cip, t = i / (cop * cip);
-    if (co >= cout || ci >= cin) return;
-    float acc = 0.f;
-    for (int b = 0; b < nblk; ++b) acc += partial[(size_t)b * stride + i];
-    dw[((size_t)co * cin + ci) * taps + t] += acc;
-  } else if (db != nullptr && i < nrec + cout) {
+    if (co < cout && ci < cin) dw[((size_t)co * cin + ci) * taps + t] += acc;
+  } else {
     const int co = i - nrec;
-    float acc = 0.f;
-    for (int b = 0; b < nblk; ++b) acc += partial[(size_t)b * stride + nrec + co];
-    db[co] += acc;
+    if (co < cout) db[co] += acc;
   }
 }
 int mil_launch_reduce_conv_w(const float* partial, int nblk, long long stride, float* dw, float* db, int cout,
                              int cin, int ks, cudaStream_t s) {
-  const int total = ks * ks * ((cin + 7) / 8 * 8) * ((cout + 7) / 8 * 8) + cout;
-  reduce_conv_w_kernel<<<(int)mil_cdiv(total, 128), 128, 0, s>>>(partial, nblk, stride, dw, db, cout, cin, ks);
+  const int cop = (cout + 7) / 8 * 8;
+  const int total = ks * ks * ((cin + 7) / 8 * 8) * cop + cop;
+  reduce_conv_w_kernel<<<(int)mil_cdiv(total, 32), dim3(32, RCW_PARTS), 0, s>>>(partial, nblk, stride, dw, db, cout, cin,
+                                                                               ks);
   MIL_LAUNCH_OK();
   return 0;
 }
