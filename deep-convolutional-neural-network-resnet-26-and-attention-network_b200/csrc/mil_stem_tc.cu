@@ -103,12 +103,34 @@ __device__ __forceinline__ void unpack8h(const uint4& r, float v[8]) {
   }
 }
 
+// one channel of one pooled pixel: the nine window positions in ATen's scan order (first maximum wins).  The
+// arguments are the 32-bit words (two bf16 phases each) of the four neighbouring phase-map pixels, already set to
+// -inf where a neighbour lies outside the conv map:  w?0 = phases (a=0: b=0 | b=1), w?1 = phases (a=1: b=0 | b=1)
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+__device__ __forceinline__ void pool9(uint32_t ul1, uint32_t u1, uint32_t l0, uint32_t l1, uint32_t s0, uint32_t s1,
+                                      float& best, int& am) {
+  best = bf_hi(ul1); am = 0;                 // (py-1, px-1) phase (1,1)  -> window (0,0)
+  float v;
+  v = bf_lo(u1); if (v > best) { best = v; am = 1; }   // (py-1, px) phase (1,0) -> (0,1)
+  v = bf_hi(u1); if (v > best) { best = v; am = 2; }   //            phase (1,1) -> (0,2)
+  v = bf_hi(l0); if (v > best) { best = v; am = 3; }   // (py, px-1) phase (0,1) -> (1,0)
+  v = bf_lo(s0); if (v > best) { best = v; am = 4; }   // (py, px)   phase (0,0) -> (1,1)
+  v = bf_hi(s0); if (v > best) { best = v; am = 5; }   //            phase (0,1) -> (1,2)
+  v = bf_hi(l1); if (v > best) { best = v; am = 6; }   // (py, px-1) phase (1,1) -> (2,0)
+  v = bf_lo(s1); if (v > best) { best = v; am = 7; }   // (py, px)   phase (1,0) -> (2,1)
+  v = bf_hi(s1); if (v > best) { best = v; am = 8; }   //            phase (1,1) -> (2,2)
+}
+
 __global__ void __launch_bounds__(256)
 stem_pool4_kernel(const __nv_bfloat16* __restrict__ cv, MilPF8 gc, int hc, __nv_bfloat16* __restrict__ pooled,
                   MilPF8 gp, uint16_t* __restrict__ argmax) {
   // one thread per (pooled pixel, pooled chunk pc of 3) = four channel pairs cp = 4pc .. 4pc+3 (cp < 10): every
-  // pooled chunk leaves as ONE 16-byte store
+  // pooled chunk leaves as ONE 16-byte store.  The kernel is bound by its instruction stream, not by HBM, so the
+  // common case (even conv size: phases a = 1 / b = 1 always inside the map) is branch-free: neighbours outside the
+  // map (py = 0 / px = 0) are replaced by -inf word-wise.
   const long long total = 3 * gp.Q;
+  const uint32_t NINF2 = 0xFF80FF80u;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int pc = (int)(i / gp.Q);
@@ -120,42 +142,51 @@ stem_pool4_kernel(const __nv_bfloat16* __restrict__ cv, MilPF8 gc, int hc, __nv_
     if (py < gp.h && px < gp.w) {
       const long long qc = (long long)n * gc.P + (long long)py * gc.wp + px;
       const int ncp = pc == 2 ? 2 : 4;  // channel pairs 8, 9 only in the last chunk (channels 20..23 are padding)
-      for (int j = 0; j < ncp; ++j) {
-        const int cp = pc * 4 + j;
+      const bool up_ok = py > 0, left_ok = px > 0;
+      const bool all_phases = 2 * py + 1 < hc && 2 * px + 1 < hc;
+      const uint4* ps = reinterpret_cast<const uint4*>(cv + mil_pf8_off(gc, pc * 4, qc));  // chunk cp: + j * gc.PS
+      uint16_t* pam = argmax + ((size_t)n * 10 + pc * 4) * gp.h * gp.w + (size_t)py * gp.w + px;
+      const size_t am_stride = (size_t)gp.h * gp.w;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j >= ncp) break;
+        const uint4* pj = ps + (size_t)j * gc.PS;
         // the zero halo of PF8 makes (py-1, px-1) readable everywhere; validity is decided on conv coordinates
-        float nb[2][2][8];  // [dy: py-1, py][dx: px-1, px][8 lanes = (co sub-index)*4 + a*2 + b]
+        uint4 S = __ldg(pj), L = __ldg(pj - 1), U = __ldg(pj - gc.wp), UL = __ldg(pj - gc.wp - 1);
+        float best[2];
+        int am[2];
+        if (all_phases) {
+          if (!left_ok) { L.x = L.y = L.z = L.w = NINF2; }
+          if (!up_ok) { U.y = U.w = NINF2; }
+          if (!(up_ok && left_ok)) { UL.y = UL.w = NINF2; }
+          pool9(UL.y, U.y, L.x, L.y, S.x, S.y, best[0], am[0]);
+          pool9(UL.w, U.w, L.z, L.w, S.z, S.w, best[1], am[1]);
+        } else {  // odd conv size, last row / column: test every window position
+          float nb[2][2][8];  // [dy: py-1, py][dx: px-1, px][8 lanes = (co sub-index)*4 + a*2 + b]
+          unpack8h(UL, nb[0][0]); unpack8h(U, nb[0][1]); unpack8h(L, nb[1][0]); unpack8h(S, nb[1][1]);
+          best[0] = best[1] = -INFINITY;
+          am[0] = am[1] = 0;
 #pragma unroll
-        for (int dy = 0; dy < 2; ++dy)
+          for (int wy = 0; wy < 3; ++wy) {
+            const int cy = 2 * py - 1 + wy;
+            const bool oky = cy >= 0 && cy < hc;
+            const int dy = wy == 0 ? 0 : 1, a = wy == 1 ? 0 : 1;
 #pragma unroll
-          for (int dx = 0; dx < 2; ++dx) {
-            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(
-                cv + mil_pf8_off(gc, cp, qc - (1 - dy) * gc.wp - (1 - dx))));
-            unpack8h(raw, nb[dy][dx]);
-          }
-        float best[2] = {-INFINITY, -INFINITY};
-        int am[2] = {0, 0};
-#pragma unroll
-        for (int wy = 0; wy < 3; ++wy) {
-          const int cy = 2 * py - 1 + wy;
-          const bool oky = cy >= 0 && cy < hc;
-          const int dy = wy == 0 ? 0 : 1, a = wy == 1 ? 0 : 1;
-#pragma unroll
-          for (int wx = 0; wx < 3; ++wx) {
-            const int cx = 2 * px - 1 + wx;
-            const int dx = wx == 0 ? 0 : 1, b = wx == 1 ? 0 : 1;
-            if (oky && cx >= 0 && cx < hc) {
-              const float v0 = nb[dy][dx][a * 2 + b], v1 = nb[dy][dx][4 + a * 2 + b];
-              if (v0 > best[0]) { best[0] = v0; am[0] = wy * 3 + wx; }
-              if (v1 > best[1]) { best[1] = v1; am[1] = wy * 3 + wx; }
+            for (int wx = 0; wx < 3; ++wx) {
+              const int cx = 2 * px - 1 + wx;
+              const int dx = wx == 0 ? 0 : 1, b = wx == 1 ? 0 : 1;
+              if (oky && cx >= 0 && cx < hc) {
+                const float v0 = nb[dy][dx][a * 2 + b], v1 = nb[dy][dx][4 + a * 2 + b];
+                if (v0 > best[0]) { best[0] = v0; am[0] = wy * 3 + wx; }
+                if (v1 > best[1]) { best[1] = v1; am[1] = wy * 3 + wx; }
+              }
             }
           }
         }
-        argmax[((size_t)n * 10 + cp) * gp.h * gp.w + (size_t)py * gp.w + px] = (uint16_t)(am[0] | (am[1] << 8));
-        // pooled channel co = 2cp + {0,1} -> chunk co/8 = pc, lane co%8 = 2j + {0,1}
-        if (j == 0) { out[0] = best[0]; out[1] = best[1]; }
-        if (j == 1) { out[2] = best[0]; out[3] = best[1]; }
-        if (j == 2) { out[4] = best[0]; out[5] = best[1]; }
-        if (j == 3) { out[6] = best[0]; out[7] = best[1]; }
+        pam[(size_t)j * am_stride] = (uint16_t)(am[0] | (am[1] << 8));
+        // pooled channel co = 2cp + {0,1} -> chunk co/8 = pc, lane co%8 = 2j + {0,1}   (j is compile-time here)
+        out[2 * j] = best[0];
+        out[2 * j + 1] = best[1];
       }
     }
     mil_store8(pooled + mil_pf8_off(gp, pc, q), out);
@@ -194,25 +225,22 @@ stem_unpool4_kernel(const __nv_bfloat16* __restrict__ g, MilPF8 gp, const uint16
               g + mil_pf8_off(gp, pc, (long long)n * gp.P + (long long)py * gp.wp + px)));
         unpack8h(raw, gv[dyy][dxx]);
       }
-    for (int j = 0; j < ncp; ++j) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j >= ncp) break;
       const int cp = pc * 4 + j;  // chunk of dY4 = channel pair (co = 2cp, 2cp+1) x 4 phases
       float acc[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] = 0.f;
       if (inside) {
         int am0[2][2], am1[2][2];
-        float g0[2][2], g1[2][2];
 #pragma unroll
         for (int dyy = 0; dyy < 2; ++dyy)
 #pragma unroll
           for (int dxx = 0; dxx < 2; ++dxx) {
             am0[dyy][dxx] = am1[dyy][dxx] = 255;
-            // lanes 2j, 2j+1 of the pooled chunk (j is not a compile-time constant: select, do not index)
-            const float* v = gv[dyy][dxx];
-            g0[dyy][dxx] = j == 0 ? v[0] : (j == 1 ? v[2] : (j == 2 ? v[4] : v[6]));
-            g1[dyy][dxx] = j == 0 ? v[1] : (j == 1 ? v[3] : (j == 2 ? v[5] : v[7]));
             if (ok[dyy][dxx]) {
-              const uint16_t amv =
+              const uint32_t amv =
                   argmax[((size_t)n * 10 + cp) * gp.h * gp.w + (size_t)(Y + dyy) * gp.w + (X + dxx)];
               am0[dyy][dxx] = amv & 0xFF;
               am1[dyy][dxx] = amv >> 8;
@@ -220,6 +248,7 @@ stem_unpool4_kernel(const __nv_bfloat16* __restrict__ g, MilPF8 gp, const uint16
           }
         // conv position (2Y+a, 2X+b) seen from pooled window (Y+dyy, X+dxx) is window position
         //   wy = 2Y+a - (2(Y+dyy)-1) = a + 1 - 2 dyy,  wx = b + 1 - 2 dxx   (valid when 0 <= wy,wx <= 2)
+        // pooled gradient lanes 2j, 2j+1 of the chunk (j is compile-time after unrolling)
 #pragma unroll
         for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -231,8 +260,8 @@ stem_unpool4_kernel(const __nv_bfloat16* __restrict__ g, MilPF8 gp, const uint16
                 const int wy = a + 1 - 2 * dyy, wx = b + 1 - 2 * dxx;
                 if (wy < 0 || wx < 0) continue;  // compile-time after unrolling
                 const int want = wy * 3 + wx;
-                if (am0[dyy][dxx] == want) acc[a * 2 + b] += g0[dyy][dxx];
-                if (am1[dyy][dxx] == want) acc[4 + a * 2 + b] += g1[dyy][dxx];
+                if (am0[dyy][dxx] == want) acc[a * 2 + b] += gv[dyy][dxx][2 * j];
+                if (am1[dyy][dxx] == want) acc[4 + a * 2 + b] += gv[dyy][dxx][2 * j + 1];
               }
       }
       mil_store8(dy + mil_pf8_off(gc, cp, q), acc);

@@ -19,6 +19,7 @@
 // [tap][cin_pad][cout_pad] + [cout_pad]; a fixed-order reduction sums the records -> deterministic.  TMEM holds 512
 // columns, so wide layers split the dy taps over two CTA groups (blockIdx.y).
 #include <algorithm>
+#include <cstdlib>
 
 #include "mil_common.cuh"
 #include "mil_conv_tc.cuh"
