@@ -52,10 +52,13 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
   const int back = dxcat ? gx.wp : halo;       // pixels before q0 held by a plane (of the dx = 0 copy)
   const uint32_t b_plane = (uint32_t)span * 16;
   const uint32_t a_bytes = (uint32_t)gz.cb * WG_A_PLANE;
+  // (building the dx = -1 / +1 copies in shared memory instead of fetching them, as wgrad_sq_kernel does, was
+  // measured SLOWER for these wide layers: their MMAs already saturate the shared-memory bandwidth)
+  const uint32_t b_pitch = b_plane;
   const uint32_t load_bytes = a_bytes + (uint32_t)nbp * b_plane;
   // fold = 1: one more B plane per stage, constant 1.0, so the bias gradient is one more N-group of the tap MMAs
   // (a thin M = 64 MMA costs the tensor pipe 28 cycles whatever its N: profiles/r1_mma_cost.txt)
-  const uint32_t stage_bytes = load_bytes + (fold ? b_plane : 0u);
+  const uint32_t stage_bytes = a_bytes + (uint32_t)(nbp + (fold ? 1 : 0)) * b_pitch;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tap_lo = blockIdx.y * taps_per_group;
   const int tap_hi = min(ngrp_taps, tap_lo + taps_per_group);
@@ -72,7 +75,7 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
     reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;  // two bf16 1.0
   if (fold)
     for (int st = 0; st < n_stages; ++st) {
-      uint32_t* op = reinterpret_cast<uint32_t*>(stage0 + (size_t)st * stage_bytes + load_bytes);
+      uint32_t* op = reinterpret_cast<uint32_t*>(stage0 + (size_t)st * stage_bytes + a_bytes + (size_t)nbp * b_pitch);
       for (int i = threadIdx.x; i < (int)(b_plane / 4); i += blockDim.x) op[i] = 0x3F803F80u;
     }
   fence_proxy_async();
@@ -94,10 +97,10 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
         unsigned char* dst = stage0 + (size_t)stage * stage_bytes;
         for (int c = 0; c < gz.cb; ++c)
           bulk_g2s(dst + (size_t)c * WG_A_PLANE, dz + mil_pf8_off(gz, c, q0), WG_A_PLANE, &hd->full[stage]);
-        if (dxcat) {
-          for (int dx = 0; dx < 3; ++dx)
-            for (int c = 0; c < gx.cb; ++c)
-              bulk_g2s(dst + a_bytes + (size_t)(dx * gx.cb + c) * b_plane, x + mil_pf8_off(gx, c, q0 - back + dx - 1),
+        if (dxcat) {  // three shifted fetches of every plane, slots (chunk, dx)
+          for (int c = 0; c < gx.cb; ++c)
+            for (int dx = 0; dx < 3; ++dx)
+              bulk_g2s(dst + a_bytes + (size_t)(c * 3 + dx) * b_plane, x + mil_pf8_off(gx, c, q0 - back + dx - 1),
                        b_plane, &hd->full[stage]);
         } else {
           for (int c = 0; c < gx.cb; ++c)
@@ -131,7 +134,7 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
           const int tap = tap_lo + tl;
           // pixel offset of this tap's window start inside a B plane
           const int s = dxcat ? tap * gx.wp : back + sh.t_dy[tap] * gx.wp + sh.t_dx[tap];
-          const uint64_t bd0 = make_desc(b_base + (uint32_t)s * 16, 128, b_plane);
+          const uint64_t bd0 = make_desc(b_base + (uint32_t)s * 16, 128, b_pitch);
           const uint32_t d = tmem_base + tl * npad;
           umma_bf16(d, ad0, bd0, idesc, acc0);
 #pragma unroll
@@ -169,8 +172,8 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
           tmem_ld8(taddr + tl * npad + p * 8, v);
           tmem_ld_wait();
           // record tap and input chunk of this column block
-          const int rtap = dxcat ? (tap_lo + tl) * 3 + p / gx.cb : tap_lo + tl;
-          const int c = dxcat ? p % gx.cb : p;
+          const int rtap = dxcat ? (tap_lo + tl) * 3 + p % 3 : tap_lo + tl;
+          const int c = dxcat ? p / 3 : p;
           if (co < coutp) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) rec[((size_t)rtap * cinp + c * 8 + j) * coutp + co] = v[j];
@@ -198,12 +201,18 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
 // max((128 + N) / 4, N / 2) cycles, M = 64 costs max(28, N / 2)), so the cheapest form has the FEWEST MMAs per K-step:
 // put the three dy shifts on the dz side and the three dx shifts on the x side,
 //   dW[dy][dx][ci][co] = sum_q' x[q' + dx][ci] * dz[q' - dy*wp][co],
-// load every (shift, chunk) plane with its shift applied by the bulk copy's source address (so no plane carries a
-// halo), and ONE M = 128 MMA per K-step produces all nine taps: rows = (dy, co), columns = (dx, ci) + one constant-one
-// plane for the bias gradient.  Layer 1: 52 cycles per 16 pixels instead of 3 x 40, with less shared-memory fill.
+// and ONE M = 128 MMA per K-step produces all nine taps: rows = (co chunk, dy), columns = (ci chunk, dx) + one
+// constant-one plane for the bias gradient (layer 1: 52 cycles per 16 pixels instead of 3 x 40).
+//
+// What bounds this kernel is the L2 -> shared-memory fill (~24 B/clk/SM measured, profiles/r1_bulk_copy.txt), so the
+// shifted operand planes are NOT fetched three times.  One bulk copy per chunk brings the tile with its halo
+// ([q0 - wp, q0 + TK + wp) of dz, [q0 - 1, q0 + TK + 1) of x), placed so that the UNSHIFTED window already sits in its
+// final plane slot; the four otherwise idle epilogue warps then build the two shifted planes of every chunk with one
+// 16-byte shared-memory copy per thread and plane.  Plane slots are pitch = 2048 + halo bytes apart (the halo of the
+// in-place plane spills into its neighbours' padding), which the MMA descriptor's group stride absorbs.
 #define WGS_MAX_STAGES 4
 struct WgsSmemHeader {
-  uint64_t full[WGS_MAX_STAGES], empty[WGS_MAX_STAGES], done;
+  uint64_t full[WGS_MAX_STAGES], ready[WGS_MAX_STAGES], empty[WGS_MAX_STAGES], done;
   uint32_t tmem_base;
 };
 
@@ -213,21 +222,28 @@ wgrad_sq_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
   extern __shared__ __align__(128) unsigned char smem[];
   WgsSmemHeader* hd = reinterpret_cast<WgsSmemHeader*>(smem);
   unsigned char* stage0 = smem + 128;
-  const int na = 3 * gz.cb, nb = 3 * gx.cb;  // A planes (dy, chunk), B planes (dx, chunk); + one all-ones B plane
-  const uint32_t load_bytes = (uint32_t)(na + nb) * WG_A_PLANE;
-  const uint32_t stage_bytes = load_bytes + WG_A_PLANE;
+  const int na = 3 * gz.cb, nb = 3 * gx.cb;  // A plane slots (co chunk, dy), B plane slots (ci chunk, dx) + ones
+  const uint32_t halo_a = (uint32_t)gz.wp * 16, halo_b = 16;
+  const uint32_t pitch_a = WG_A_PLANE + halo_a, pitch_b = WG_A_PLANE + halo_b;
+  const uint32_t b_bytes = (uint32_t)(nb + 1) * pitch_b;
+  const uint32_t stage_bytes = b_bytes + (uint32_t)na * pitch_a;  // [B slots | ones][A slots]
+  const uint32_t load_bytes = (uint32_t)gz.cb * (WG_A_PLANE + 2 * halo_a) + (uint32_t)gx.cb * (WG_A_PLANE + 2 * halo_b);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long n_tiles = mil_cdiv(gz.Q, WG_TK);
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < npad) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < n_stages; ++s) { mbar_init(&hd->full[s], 1); mbar_init(&hd->empty[s], 1); }
+    for (int s = 0; s < n_stages; ++s) {
+      mbar_init(&hd->full[s], 1);
+      mbar_init(&hd->ready[s], 4);
+      mbar_init(&hd->empty[s], 1);
+    }
     mbar_init(&hd->done, 1);
     fence_barrier_init();
   }
   for (int st = 0; st < n_stages; ++st) {
-    uint32_t* op = reinterpret_cast<uint32_t*>(stage0 + (size_t)st * stage_bytes + load_bytes);
+    uint32_t* op = reinterpret_cast<uint32_t*>(stage0 + (size_t)st * stage_bytes + (size_t)nb * pitch_b);
     for (int i = threadIdx.x; i < WG_A_PLANE / 4; i += blockDim.x) op[i] = 0x3F803F80u;  // two bf16 1.0
   }
   fence_proxy_async();
@@ -245,33 +261,32 @@ wgrad_sq_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
       if (elect_one()) {
         mbar_expect_tx(&hd->full[stage], load_bytes);
         const long long q0 = t * WG_TK;
-        unsigned char* dst = stage0 + (size_t)stage * stage_bytes;
-        for (int e = 0; e < 3; ++e)  // dy = e - 1: the plane holds dz[q - dy * wp]
-          for (int c = 0; c < gz.cb; ++c)
-            bulk_g2s(dst + (size_t)(e * gz.cb + c) * WG_A_PLANE, dz + mil_pf8_off(gz, c, q0 - (long long)(e - 1) * gz.wp),
-                     WG_A_PLANE, &hd->full[stage]);
-        for (int d = 0; d < 3; ++d)  // dx = d - 1: the plane holds x[q + dx]
-          for (int c = 0; c < gx.cb; ++c)
-            bulk_g2s(dst + (size_t)(na + d * gx.cb + c) * WG_A_PLANE, x + mil_pf8_off(gx, c, q0 + d - 1), WG_A_PLANE,
-                     &hd->full[stage]);
+        unsigned char* bdst = stage0 + (size_t)stage * stage_bytes;
+        unsigned char* adst = bdst + b_bytes;
+        for (int c = 0; c < gz.cb; ++c)  // the unshifted window [q0, q0 + TK) lands in slot (c, dy = 0)
+          bulk_g2s(adst + (size_t)(c * 3 + 1) * pitch_a - halo_a, dz + mil_pf8_off(gz, c, q0 - gz.wp),
+                   WG_A_PLANE + 2 * halo_a, &hd->full[stage]);
+        for (int c = 0; c < gx.cb; ++c)
+          bulk_g2s(bdst + (size_t)(c * 3 + 1) * pitch_b - halo_b, x + mil_pf8_off(gx, c, q0 - 1),
+                   WG_A_PLANE + 2 * halo_b, &hd->full[stage]);
       }
       __syncwarp();
       if (++stage == n_stages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
     // D = f32, A = B = bf16, both MN-major, M = 128 (the M-groups past 3 * cb read whatever follows in shared
-    // memory: finite bf16 values landing in accumulator rows nobody reads)
+    // memory -- the next stage or the tail pad: values landing in accumulator rows nobody reads)
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 4) << 24) |
                            ((uint32_t)(npad >> 3) << 17);
     int stage = 0;
     uint32_t phase = 0;
     bool first = true;
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-      mbar_wait(&hd->full[stage], phase);
+      mbar_wait(&hd->ready[stage], phase);
       tc_fence_after();
-      const uint32_t a_base = smem_u32(stage0 + (size_t)stage * stage_bytes);
-      const uint64_t ad0 = make_desc(a_base, 128, WG_A_PLANE);
-      const uint64_t bd0 = make_desc(a_base + (uint32_t)na * WG_A_PLANE, 128, WG_A_PLANE);
+      const uint32_t b_base = smem_u32(stage0 + (size_t)stage * stage_bytes);
+      const uint64_t ad0 = make_desc(b_base + b_bytes, 128, pitch_a);
+      const uint64_t bd0 = make_desc(b_base, 128, pitch_b);
       const uint32_t acc0 = first ? 0u : 1u;
       if (elect_one()) {
         umma_bf16(tmem_base, ad0, bd0, idesc, acc0);
@@ -286,11 +301,40 @@ wgrad_sq_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
     if (elect_one()) umma_commit(&hd->done);
     __syncwarp();
   } else {
-    // epilogue: accumulator row (= TMEM lane) (e, c, j) -> tap row dy = e - 1, output channel c * 8 + j;
-    // column block p = (d, cc) -> tap column dx = d - 1, input chunk cc
+    // ---- main loop: build the shifted planes (thread i of the four warps moves pixel i of every plane) ----
+    {
+      const int tid = threadIdx.x - 64;  // 0..127 = pixel of the K-tile
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        mbar_wait(&hd->full[stage], phase);
+        unsigned char* bdst = stage0 + (size_t)stage * stage_bytes;
+        unsigned char* adst = bdst + b_bytes;
+        for (int c = 0; c < gz.cb; ++c) {
+          unsigned char* mid = adst + (size_t)(c * 3 + 1) * pitch_a + (size_t)tid * 16;  // dz[q0 + tid]
+          const uint4 dn = *reinterpret_cast<const uint4*>(mid + halo_a);                 // dz[q + wp]: dy = -1
+          const uint4 up = *reinterpret_cast<const uint4*>(mid - halo_a);                 // dz[q - wp]: dy = +1
+          *reinterpret_cast<uint4*>(mid - pitch_a) = dn;
+          *reinterpret_cast<uint4*>(mid + pitch_a) = up;
+        }
+        for (int c = 0; c < gx.cb; ++c) {
+          unsigned char* mid = bdst + (size_t)(c * 3 + 1) * pitch_b + (size_t)tid * 16;  // x[q0 + tid]
+          const uint4 lf = *reinterpret_cast<const uint4*>(mid - 16);                     // x[q - 1]: dx = -1
+          const uint4 rt = *reinterpret_cast<const uint4*>(mid + 16);                     // x[q + 1]: dx = +1
+          *reinterpret_cast<uint4*>(mid - pitch_b) = lf;
+          *reinterpret_cast<uint4*>(mid + pitch_b) = rt;
+        }
+        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&hd->ready[stage]);
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
+      }
+    }
+    // ---- epilogue: accumulator row (= TMEM lane) (c, e, j) -> output channel c * 8 + j, tap row dy = e - 1;
+    // column block p = (cc, d) -> input chunk cc, tap column dx = d - 1
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const int g = row >> 3, e = g / gz.cb, c = g - e * gz.cb;
+    const int g = row >> 3, c = g / 3, e = g - c * 3;
     const int co = c * 8 + (row & 7);
     const int coutp = gz.cb * 8, cinp = gx.cb * 8;
     mbar_wait(&hd->done, 0);
@@ -302,7 +346,7 @@ wgrad_sq_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
         float v[8];
         tmem_ld8(taddr + p * 8, v);
         tmem_ld_wait();
-        const int d = p / gx.cb, cc = p - d * gx.cb;
+        const int cc = p / 3, d = p - cc * 3;
         if (g < na) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) rec[((size_t)(e * 3 + d) * cinp + cc * 8 + j) * coutp + co] = v[j];
@@ -350,10 +394,13 @@ static WgConfig wg_config(const MilPF8& gx, const MilPF8& gz, int ks) {
     c.groups = 1;
     c.tpg = 9;
     c.ctas = (int)std::max<long long>(1, std::min<long long>(n_tiles_sq, wg_sm_count()));
-    const size_t stage = (size_t)(3 * gz.cb + 3 * gx.cb + 1) * WG_A_PLANE;
+    // stage = [B slots + ones][A slots]; the M = 128 MMA reads 16 A slots whatever 3 * cb is: tail pad for the last
+    const size_t pitch_a = WG_A_PLANE + (size_t)gz.wp * 16, pitch_b = WG_A_PLANE + 16;
+    const size_t stage = (size_t)(3 * gx.cb + 1) * pitch_b + (size_t)3 * gz.cb * pitch_a;
+    const size_t tail = (size_t)(16 - 3 * gz.cb) * pitch_a + 128;
     c.n_stages = WGS_MAX_STAGES;
-    while (c.n_stages > 1 && 128 + c.n_stages * stage > 200 * 1024) --c.n_stages;
-    c.smem = 128 + c.n_stages * stage;
+    while (c.n_stages > 1 && 128 + c.n_stages * stage + tail > 220 * 1024) --c.n_stages;
+    c.smem = 128 + c.n_stages * stage + tail;
     return c;
   }
   c.dxcat = ks == 3 ? 1 : 0;

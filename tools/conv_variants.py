@@ -61,6 +61,6 @@ for c, h in ((20, 56), (40, 28), (60, 14), (80, 7)):
     ]
     for name, fn, maps in rows:
         us = timed(fn)
-        print(f"c={c:2d} h={h:2d} tiles={n} {name}: {us:8.1f} us   {maps * mapb / us / 1e3:7.2f} TB/s algorithmic "
+        print(f"c={c:2d} h={h:2d} tiles={n} {name}: {us:8.1f} us   {maps * mapb / us:7.2f} TB/s algorithmic "
               f"({maps * mapb / us * 1e3 / HBM * 100:5.1f} % of HBM)   "
               f"{2 * 9 * c * c * h * h * n / us / 1e6:7.1f} TFLOP/s")
