@@ -34,8 +34,8 @@ PKG = "deep-convolutional-neural-network-resnet-26-and-attention-network_b200"
 
 FLOP_FWD_BWD = {224: 1247.7e6, 256: 1629.9e6}      # algorithmic FLOP per tile
 L1_CONV_FLOP_224 = 22.58e6                         # one layer1 3x3 conv, per tile
-# dram__bytes_read.sum + dram__bytes_write.sum of that kernel at 1024 tiles per launch, from the ncu --set full
-# capture summarised in profiles/ (filled in from the capture; None = no capture for this launch size)
+# dram__bytes_read.sum + dram__bytes_write.sum of that kernel per launch size (tiles), from the ncu --set full
+# captures summarised in profiles/ (None = no capture for this launch size)
 L1_CONV_NCU_TRAFFIC = {1024: 316959232 + 132250368}      # profiles/r1_ncu_tc_kernels_final.txt
 METRIC = "tiles/sec fwd+bwd ResNet-26+attention-MIL"
 
@@ -281,7 +281,7 @@ def run_ours(args):
         import ctypes as C
         burst, sustained, hbm, how = peaks()
         h1 = ((side - 1) // 2 + 1 - 1) // 2 + 1
-        nk = min(n, 1024)
+        nk = n                      # the launch the step itself makes: the whole shard in one kernel
         dt = mil.model.DTYPE_CODES[args.precision]
         P = lambda t: C.c_void_p(t.data_ptr())
         nb = int(lib.mil_pf8_bytes(nk, 20, h1, h1, dt))

@@ -129,14 +129,12 @@ stem_pool4_kernel(const __nv_bfloat16* __restrict__ cv, MilPF8 gc, int hc, __nv_
   // pooled chunk leaves as ONE 16-byte store.  The kernel is bound by its instruction stream, not by HBM, so the
   // common case (even conv size: phases a = 1 / b = 1 always inside the map) is branch-free: neighbours outside the
   // map (py = 0 / px = 0) are replaced by -inf word-wise.
-  const long long total = 3 * gp.Q;
+  // grid = (image, pixel block, pooled chunk): no 64-bit index arithmetic per thread
   const uint32_t NINF2 = 0xFF80FF80u;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int pc = (int)(i / gp.Q);
-    const long long q = i - (long long)pc * gp.Q;
-    const int n = (int)(q / gp.P);
-    const int r = (int)(q - (long long)n * gp.P);
+  const int n = blockIdx.x, pc = blockIdx.z;
+  const int r = blockIdx.y * blockDim.x + threadIdx.x;
+  if (r < (int)gp.P) {
+    const long long q = (long long)n * gp.P + r;
     const int py = r / gp.wp, px = r - py * gp.wp;
     float out[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (py < gp.h && px < gp.w) {
@@ -201,13 +199,11 @@ stem_unpool4_kernel(const __nv_bfloat16* __restrict__ g, MilPF8 gp, const uint16
                     __nv_bfloat16* __restrict__ dy, MilPF8 gc, int hc) {
   // one thread per (phase-map pixel, pooled chunk pc of 3): the four neighbouring pooled gradients are loaded as whole
   // 16-byte chunks ONCE and serve the (up to) four channel pairs cp = 4pc .. 4pc+3, each one 16-byte chunk of dY4
-  const long long total = 3 * gc.Q;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int pc = (int)(i / gc.Q);
-    const long long q = i - (long long)pc * gc.Q;
-    const int n = (int)(q / gc.P);
-    const int r = (int)(q - (long long)n * gc.P);
+  // grid = (image, pixel block, pooled chunk): no 64-bit index arithmetic per thread
+  const int n = blockIdx.x, pc = blockIdx.z;
+  const int r = blockIdx.y * blockDim.x + threadIdx.x;
+  if (r < (int)gc.P) {
+    const long long q = (long long)n * gc.P + r;
     const int Y = r / gc.wp, X = r - Y * gc.wp;
     const bool inside = Y < gc.h && X < gc.w;
     const int ncp = pc == 2 ? 2 : 4;
@@ -338,7 +334,7 @@ int mil_launch_stem_tc_fwd(const void* x, int x_u8, const int* idx, int n, int s
   MIL_TRY(mil_tc_shape(STC_CI, STC_CO4, 3, &sh));
   MIL_TRY(mil_launch_pack_tc(wp, wtc, sh, s));
   MIL_TRY(mil_launch_conv_tc(0, xs, gi, wtc, sh, bias4, nullptr, nullptr, convout, gc, MIL_EPI_FWD, 0, s));
-  stem_pool4_kernel<<<grid_for(3 * gp.Q), 256, 0, s>>>((const __nv_bfloat16*)convout, gc, hc, (__nv_bfloat16*)pooled,
+  stem_pool4_kernel<<<dim3(gp.n, (unsigned)mil_cdiv(gp.P, 256), 3), 256, 0, s>>>((const __nv_bfloat16*)convout, gc, hc, (__nv_bfloat16*)pooled,
                                                         gp, argmax);
   MIL_LAUNCH_OK();
   return 0;
@@ -349,7 +345,7 @@ int mil_launch_stem_tc_bwd(const void* xs, int n, int side, const void* g, const
   const uint16_t* argmax = reinterpret_cast<const uint16_t*>(argmax8);
   const MilPF8 gi = mil_stem_tc_geom_in(n, side), gc = mil_stem_tc_geom_conv(n, side);
   const int hc = (side - 1) / 2 + 1;
-  stem_unpool4_kernel<<<grid_for(3 * gc.Q), 256, 0, s>>>((const __nv_bfloat16*)g, gp, argmax, (__nv_bfloat16*)dy, gc,
+  stem_unpool4_kernel<<<dim3(gc.n, (unsigned)mil_cdiv(gc.P, 256), 3), 256, 0, s>>>((const __nv_bfloat16*)g, gp, argmax, (__nv_bfloat16*)dy, gc,
                                                           hc);
   MIL_LAUNCH_OK();
   int ctas;
