@@ -55,6 +55,8 @@ struct TcPackEntry {
   __nv_bfloat16* wtc;
   short cout, cin;
   unsigned char taps, transposed, nmma, npad;
+  unsigned char s2cb;       // != 0: phase-split stride-2 forward, chunk planes = phase * s2cb + chunk
+  unsigned char src_tap[MIL_TC_MAX_TAPS];  // tap of the kernel's window -> tap of the source weight
   unsigned char g_tap[2 * MIL_TC_MAX_MMA], g_chunk[2 * MIL_TC_MAX_MMA];
 };
 struct TcPackTable {
@@ -66,11 +68,18 @@ __global__ void pack_tc_table_kernel(const __grid_constant__ TcPackTable t) {
   const int kin = p.transposed ? p.cout : p.cin, nout = p.transposed ? p.cin : p.cout;
   for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < total; i += gridDim.y * blockDim.x) {
     const int e = i & 7, n = (i >> 3) % p.npad, g = (i >> 3) / p.npad;  // g = 2j+h
-    const int tap = p.g_tap[g], k = p.g_chunk[g] * 8 + e;
+    const int tap = p.g_tap[g];
+    int k = p.g_chunk[g] * 8 + e, stap = tap == 0xFF ? 0 : p.src_tap[tap];
+    if (p.s2cb != 0 && tap != 0xFF) {
+      const int plane = p.g_chunk[g], phase = plane / p.s2cb;
+      k = (plane - phase * p.s2cb) * 8 + e;
+      const int ky = 2 * ((tap >> 1) - 1) + (phase >> 1) + 1, kx = 2 * ((tap & 1) - 1) + (phase & 1) + 1;
+      stap = ky * 3 + kx;
+    }
     float v = 0.f;
     if (tap != 0xFF && n < nout && k < kin) {
       const int co = p.transposed ? k : n, ci = p.transposed ? n : k;
-      v = p.w[((size_t)co * p.cin + ci) * p.taps + tap];
+      v = p.w[((size_t)co * p.cin + ci) * p.taps + stap];
     }
     p.wtc[i] = __float2bfloat16_rn(v);
   }
@@ -381,6 +390,70 @@ int mil_tc_shape(int cin, int cout, int ks, MilTcShape* out) {
   return 0;
 }
 
+int mil_tc_shape_s2(int cin, int cout, MilTcShape* out) {
+  MilTcShape& sh = *out;
+  const int cb = (cin + 7) / 8;
+  sh.ks = 2;
+  sh.ntaps = 4;
+  for (int t = 0; t < 4; ++t) { sh.t_dy[t] = (signed char)((t >> 1) - 1); sh.t_dx[t] = (signed char)((t & 1) - 1); }
+  sh.cbin = 4 * cb;
+  sh.cbout = (cout + 7) / 8;
+  sh.npad = (cout + 15) / 16 * 16;
+  // K-groups sorted by (plane, shift): any two consecutive groups then sit at ascending shared-memory offsets
+  int ng = 0;
+  for (int phase = 0; phase < 4; ++phase)
+    for (int c = 0; c < cb; ++c)
+      for (int t = 0; t < 4; ++t) {
+        const int dy = (t >> 1) - 1, dx = (t & 1) - 1;
+        if ((dy == -1 && !(phase >> 1)) || (dx == -1 && !(phase & 1))) continue;  // that row / column is not read
+        MIL_REQUIRE(ng < 2 * MIL_TC_MAX_MMA, "conv_tc: too many K groups");
+        sh.g_tap[ng] = (unsigned char)t;
+        sh.g_chunk[ng] = (unsigned char)(phase * cb + c);
+        ++ng;
+      }
+  sh.nmma = (ng + 1) / 2;
+  MIL_REQUIRE(sh.nmma <= MIL_TC_MAX_MMA, "conv_tc: too many K groups (%d)", ng);
+  for (int g = ng; g < 2 * MIL_TC_MAX_MMA; ++g) sh.g_tap[g] = sh.g_chunk[g] = 0xFF;
+  return 0;
+}
+
+int mil_tc_shape_s2_dgrad(int cout_conv, int cin_conv, int a, int b, MilTcShape* out, int* src_tap) {
+  // dx[2Y+a][2X+b] = sum over (ky, kx) with ky = a + 1 (mod 2), kx = b + 1 (mod 2) of
+  //   W[ky][kx]^T dz[Y + dY][X + dX],  dY = 1 iff (a == 1 and ky == 0), dX likewise.
+  // The kernel's data-gradient convention is out(q) = sum_t W_t^T in(q - shift_t): t_dy = -dY, t_dx = -dX.
+  MilTcShape& sh = *out;
+  sh.ks = 2;
+  sh.ntaps = 0;
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) {
+      if (((ky + 1) & 1) != a || ((kx + 1) & 1) != b) continue;
+      const int dY = (a == 1 && ky == 0) ? 1 : 0, dX = (b == 1 && kx == 0) ? 1 : 0;
+      sh.t_dy[sh.ntaps] = (signed char)-dY;
+      sh.t_dx[sh.ntaps] = (signed char)-dX;
+      src_tap[sh.ntaps] = ky * 3 + kx;
+      ++sh.ntaps;
+    }
+  // taps in ascending (negated) shift order so that a pair inside one chunk ascends in shared memory
+  for (int i = 0; i < sh.ntaps; ++i)
+    for (int j = i + 1; j < sh.ntaps; ++j) {
+      const int si = -(sh.t_dy[i] * 1024 + sh.t_dx[i]), sj = -(sh.t_dy[j] * 1024 + sh.t_dx[j]);
+      if (sj < si) {
+        std::swap(sh.t_dy[i], sh.t_dy[j]); std::swap(sh.t_dx[i], sh.t_dx[j]); std::swap(src_tap[i], src_tap[j]);
+      }
+    }
+  sh.cbin = (cout_conv + 7) / 8;   // the kernel reads dz (the conv's output channels) ...
+  sh.cbout = (cin_conv + 7) / 8;   // ... and produces the conv's input channels
+  sh.npad = (cin_conv + 15) / 16 * 16;
+  // K-groups sorted by (chunk, tap)
+  int ng = 0;
+  for (int c = 0; c < sh.cbin; ++c)
+    for (int t = 0; t < sh.ntaps; ++t) { sh.g_tap[ng] = (unsigned char)t; sh.g_chunk[ng] = (unsigned char)c; ++ng; }
+  sh.nmma = (ng + 1) / 2;
+  MIL_REQUIRE(sh.nmma <= MIL_TC_MAX_MMA, "conv_tc: too many K groups (%d)", ng);
+  for (int g = ng; g < 2 * MIL_TC_MAX_MMA; ++g) sh.g_tap[g] = sh.g_chunk[g] = 0xFF;
+  return 0;
+}
+
 size_t mil_tc_wpack_bytes(const MilTcShape& sh) { return (size_t)sh.nmma * 2 * sh.npad * 16; }
 
 int mil_launch_pack_tc(const float* wp, void* wtc, const MilTcShape& sh, cudaStream_t s) {
@@ -397,8 +470,14 @@ int mil_launch_pack_tc_table(const MilTcPackJob* jobs, int count, cudaStream_t s
     for (int i = 0; i < m; ++i) {
       const MilTcPackJob& j = jobs[base + i];
       MilTcShape sh;
-      MIL_TRY(mil_tc_shape(j.transposed ? j.cout : j.cin, j.transposed ? j.cin : j.cout, j.ks, &sh));
+      int src_tap[MIL_TC_MAX_TAPS];
+      for (int q = 0; q < MIL_TC_MAX_TAPS; ++q) src_tap[q] = q;
+      if (j.s2 == 1) MIL_TRY(mil_tc_shape_s2(j.cin, j.cout, &sh));
+      else if (j.s2 >= 2) MIL_TRY(mil_tc_shape_s2_dgrad(j.cout, j.cin, (j.s2 - 2) >> 1, (j.s2 - 2) & 1, &sh, src_tap));
+      else MIL_TRY(mil_tc_shape(j.transposed ? j.cout : j.cin, j.transposed ? j.cin : j.cout, j.ks, &sh));
       TcPackEntry& e = t.e[i];
+      e.s2cb = j.s2 == 1 ? (unsigned char)((j.cin + 7) / 8) : 0;
+      for (int q = 0; q < MIL_TC_MAX_TAPS; ++q) e.src_tap[q] = (unsigned char)src_tap[q];
       e.w = j.w;
       e.wtc = (__nv_bfloat16*)j.wtc;
       e.cout = (short)j.cout; e.cin = (short)j.cin;
@@ -417,6 +496,11 @@ static size_t tc_smem_bytes(int halo, const MilTcShape& sh, int n_stages) {
   const size_t b = ((size_t)sh.nmma * 2 * sh.npad * 16 + 127) / 128 * 128;
   const size_t span = TC_M + 2 * (size_t)halo;
   return hdr + b + (size_t)n_stages * span * 16 * (sh.cbin + 1);
+}
+
+bool mil_conv_tc_fits(const MilTcShape& sh, int wp) {
+  const int ng = sh.cbout <= 5 ? 4 : 2;
+  return tc_smem_bytes(mil_tc_halo(sh, wp), sh, ng) <= 227 * 1024;
 }
 
 int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const void* wtc, const MilTcShape& sh,

@@ -30,9 +30,19 @@ static inline int mil_tc_halo(const MilTcShape& sh, int wp) {
 
 bool mil_tc_supported(int dtype, int ks, int stride, int cin, int cout);
 int mil_tc_shape(int cin, int cout, int ks, MilTcShape* out);  // cin/cout = the KERNEL's input/output channels
+// 3x3 / stride-2 convolution on the PHASE-SPLIT input (mil_launch_split2: 4 * cb chunk planes at the output
+// resolution, plane = phase * cb + chunk, phase = (row parity) * 2 + (column parity)): a 2x2 window of taps
+// (-1..0) in which tap (dy, dx) of phase (a, b) carries the weight w[2 dy + a + 1][2 dx + b + 1] -- the same nine
+// K-groups per chunk as a stride-1 3x3 convolution, evaluated at a quarter of the pixels.
+int mil_tc_shape_s2(int cin, int cout, MilTcShape* out);
+// data gradient of that convolution for ONE input phase (a, b): the 1 / 2 / 2 / 4 taps whose weight row / column has
+// the matching parity; src_tap[t] = ky * 3 + kx of tap t in the 3x3 weight
+int mil_tc_shape_s2_dgrad(int cout_conv, int cin_conv, int a, int b, MilTcShape* out, int* src_tap);
 size_t mil_tc_wpack_bytes(const MilTcShape& sh);
 // wp: fp32 packed weights [tap][kin_pad][nout_pad] (mil_launch_pack_conv_w, normal or transposed)
 int mil_launch_pack_tc(const float* wp, void* wtc, const MilTcShape& sh, cudaStream_t s);
+// true when the kernel's shared-memory ring fits for this window on a map of padded row length wp
+bool mil_conv_tc_fits(const MilTcShape& sh, int wp);
 int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const void* wtc, const MilTcShape& sh,
                        const float* bias, const void* res, const void* act, void* out, const MilPF8& go, int epi,
                        int sub, cudaStream_t s, const MilPF8* gres_half = nullptr);
@@ -41,8 +51,11 @@ struct MilTcPackJob {
   const float* w;
   void* wtc;
   int cout, cin, ks, transposed;
+  int s2;  // 0: plain;  1: forward of the stride-2 3x3 on the phase-split input;  2 + phase: its data gradient
 };
 int mil_launch_pack_tc_table(const MilTcPackJob* jobs, int count, cudaStream_t s);
+// out = the four (row parity, column parity) phases of `in` at half resolution, as 4 * cb chunk planes (bf16)
+int mil_launch_split2(const void* in, const MilPF8& gin, void* out, const MilPF8& gout, cudaStream_t s);
 // out (half resolution) = in at the even (y, x) positions (bf16): the input of a stride-2 1x1 projection
 int mil_launch_subsample2(const void* in, const MilPF8& gin, void* out, const MilPF8& gout, cudaStream_t s);
 // out (geometry 2x) = zero-stuffed copy of in: out(n, 2y, 2x) = in(n, y, x), zero elsewhere (bf16)

@@ -71,6 +71,11 @@ int mil_param_index(const char* name) {
 // ---------------------------------------------------------------------------------------------------
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+MilPF8 mil_xs2_geom(const MilPlan& pl, int l) {
+  return pl.s2_split[l] ? mil_split2_geom(pl.n, kMilWidths[l - 1], pl.geo.h[l])
+                        : mil_pf8(pl.n, kMilWidths[l - 1], pl.geo.h[l], pl.geo.h[l]);
+}
+
 int mil_make_plan(int n, int side, int dtype, MilPlan* plan) {
   MIL_REQUIRE(n >= 1, "extractor: need at least one tile (got %d)", n);
   MIL_REQUIRE(side >= 8, "extractor: tile side %d too small", side);
@@ -109,6 +114,14 @@ int mil_make_plan(int n, int side, int dtype, MilPlan* plan) {
           MIL_TRY(mil_tc_shape(c.cout, c.cin, c.ks, &sb));
           c.wtc_off = tcofs; tcofs += align_up(mil_tc_wpack_bytes(sf), 256);
           c.wtct_off = tcofs; tcofs += align_up(mil_tc_wpack_bytes(sb), 256);
+          for (int ph = 0; ph < 4; ++ph) c.wtct_s2_off[ph] = 0;
+          if (c.ks == 3 && c.stride == 2)
+            for (int ph = 0; ph < 4; ++ph) {
+              MilTcShape sp;
+              int src_tap[MIL_TC_MAX_TAPS];
+              MIL_TRY(mil_tc_shape_s2_dgrad(c.cout, c.cin, ph >> 1, ph & 1, &sp, src_tap));
+              c.wtct_s2_off[ph] = tcofs; tcofs += align_up(mil_tc_wpack_bytes(sp), 256);
+            }
         }
         pl.convs.push_back(c);
       }
@@ -138,12 +151,19 @@ int mil_make_plan(int n, int side, int dtype, MilPlan* plan) {
     for (int l = 1; l < 4; ++l)
       pl.up_bytes = std::max(pl.up_bytes, mil_pf8_bytes(mil_pf8(n, kMilWidths[l], pl.geo.h[l - 1], pl.geo.h[l - 1]), dtype));
   for (int i = 0; i < 2; ++i) pl.off_up[i] = take(pl.up_bytes);
-  // inputs of the three stride-2 blocks at their even positions (what the 1x1 / stride-2 projection reads), kept
-  // for the backward pass
-  for (int l = 0; l < 4; ++l) pl.off_xsub[l] = 0;
+  // inputs of the three stride-2 blocks split into their four (row, column) parity phases at the OUTPUT resolution
+  // (what the stride-2 convolutions read; phase (0,0) = the first planes = the 1x1 projection's input), kept for
+  // the backward pass
+  // (a layer whose split form does not fit the convolution kernel's shared memory -- 32 input planes on the way into
+  // layer 4 -- keeps the full-resolution evaluation and stores only the even positions here)
+  for (int l = 0; l < 4; ++l) { pl.off_xs2[l] = 0; pl.s2_split[l] = false; }
   if (dtype == MIL_BF16 && mil_tc_enabled())
-    for (int l = 1; l < 4; ++l)
-      pl.off_xsub[l] = take(mil_pf8_bytes(mil_pf8(n, kMilWidths[l - 1], pl.geo.h[l], pl.geo.h[l]), dtype));
+    for (int l = 1; l < 4; ++l) {
+      MilTcShape sh;
+      MIL_TRY(mil_tc_shape_s2(kMilWidths[l - 1], kMilWidths[l], &sh));
+      pl.s2_split[l] = mil_conv_tc_fits(sh, pl.g[l].wp);
+      pl.off_xs2[l] = take(mil_pf8_bytes(mil_xs2_geom(pl, l), dtype));
+    }
   pl.stem_tc = (dtype == MIL_BF16) && mil_tc_enabled();
   pl.off_xs = pl.off_cv = pl.off_stem_wp = pl.off_stem_wtc = 0;
   if (pl.stem_tc) {
@@ -286,8 +306,16 @@ static int pack_weights(const void* const* params, const MilPlan& pl, void* ws, 
   std::vector<MilTcPackJob> jobs;
   for (const auto& c : pl.convs) {
     if (!c.tc) continue;
-    jobs.push_back({reinterpret_cast<const float*>(params[c.p_w]), tca + (transposed ? c.wtct_off : c.wtc_off), c.cout,
-                    c.cin, c.ks, transposed ? 1 : 0});
+    const float* w = reinterpret_cast<const float*>(params[c.p_w]);
+    if (c.ks == 3 && c.stride == 2 && pl.s2_split[c.layer]) {  // phase-split forms (mil_tc_shape_s2 / mil_tc_shape_s2_dgrad)
+      if (!transposed) jobs.push_back({w, tca + c.wtc_off, c.cout, c.cin, 3, 0, 1});
+      else {
+        for (int ph = 0; ph < 4; ++ph) jobs.push_back({w, tca + c.wtct_s2_off[ph], c.cout, c.cin, 3, 1, 2 + ph});
+        jobs.push_back({w, tca + c.wtct_off, c.cout, c.cin, 3, 1, 0});  // TEMP: full-resolution dgrad still in use
+      }
+      continue;
+    }
+    jobs.push_back({w, tca + (transposed ? c.wtct_off : c.wtc_off), c.cout, c.cin, c.ks, transposed ? 1 : 0, 0});
   }
   if (!jobs.empty()) MIL_TRY(mil_launch_pack_tc_table(jobs.data(), (int)jobs.size(), s));
   return 0;
@@ -314,7 +342,7 @@ int mil_extractor_forward_impl(const void* const* params, const void* bag, int b
       }
     if (pl.dtype == MIL_BF16 && mil_tc_enabled())
       for (int l = 1; l < 4; ++l)
-        guard_add(t, wsp(ws, pl.off_xsub[l]), mil_pf8(pl.n, kMilWidths[l - 1], pl.geo.h[l], pl.geo.h[l]));
+        guard_add(t, wsp(ws, pl.off_xs2[l]), mil_xs2_geom(pl, l));
     MIL_TRY(launch_guards(t, s));
   }
   MIL_TRY(pack_weights(params, pl, ws, false, s));
@@ -342,23 +370,36 @@ int mil_extractor_forward_impl(const void* const* params, const void* bag, int b
       void* y = wsp(ws, pl.off_y[l * 3 + b]);
       const MilConvDesc& c1 = pl.convs[ci++];
       const MilConvDesc& c2 = pl.convs[ci++];
-      if (c1.stride == 2 && c1.tc && ((gx.h & 1) || (gx.w & 1))) {
-        // the subsampled store of the tcgen05 path reaches the zero row / column of the half-resolution map
-        // only when the input size is even: clear the maps first
-        MIL_CHECK_CUDA(cudaMemsetAsync(h, 0, mil_pf8_bytes(go, dt), s));
-        MIL_CHECK_CUDA(cudaMemsetAsync(y, 0, mil_pf8_bytes(go, dt), s));
-      }
-      MIL_TRY(mil_conv_dispatch(dt, 0, X, gx, wpack + c1.wp_off, TCW(c1, false), (const float*)params[c1.p_b], nullptr, nullptr, h,
-                                go, 3, c1.stride, MIL_EPI_FWD, s));
+      if (c1.stride == 2 && c1.tc && !pl.s2_split[l]) {
+        if ((gx.h & 1) || (gx.w & 1)) {
+          // the subsampled store of the full-resolution evaluation reaches the zero row / column of the
+          // half-resolution map only when the input size is even: clear the map first
+          MIL_CHECK_CUDA(cudaMemsetAsync(h, 0, mil_pf8_bytes(go, dt), s));
+        }
+        MIL_TRY(mil_launch_subsample2(X, gx, wsp(ws, pl.off_xs2[l]), mil_xs2_geom(pl, l), s));
+        MIL_TRY(mil_conv_dispatch(dt, 0, X, gx, wpack + c1.wp_off, TCW(c1, false), (const float*)params[c1.p_b], nullptr, nullptr,
+                                  h, go, 3, c1.stride, MIL_EPI_FWD, s));
+      } else if (c1.stride == 2 && c1.tc) {
+        // stride-2 block on the tensor cores: split the input into its four parity phases once; the 3x3 / stride-2
+        // convolution is then a 2x2-window convolution over 4x the channels at the OUTPUT resolution
+        const MilPF8 gs = mil_split2_geom(pl.n, gx.c, go.h);
+        void* xs2 = wsp(ws, pl.off_xs2[l]);
+        MIL_TRY(mil_launch_split2(X, gx, xs2, gs, s));
+        MilTcShape sh;
+        MIL_TRY(mil_tc_shape_s2(c1.cin, c1.cout, &sh));
+        MIL_TRY(mil_launch_conv_tc(0, xs2, gs, TCW(c1, false), sh, (const float*)params[c1.p_b], nullptr, nullptr, h, go,
+                                   MIL_EPI_FWD, 0, s));
+      } else
+        MIL_TRY(mil_conv_dispatch(dt, 0, X, gx, wpack + c1.wp_off, TCW(c1, false), (const float*)params[c1.p_b], nullptr, nullptr,
+                                  h, go, 3, c1.stride, MIL_EPI_FWD, s));
       const void* res = X;
       if (b == 0 && l > 0) {
         const MilConvDesc& cd = pl.convs[ci++];
         // projection shortcut (1x1 / stride 2, no bias) written into y, then consumed in place as the residual
         if (cd.tc) {
-          // tensor-core path: gather the even positions once, then a plain 1x1 conv at the OUTPUT resolution
-          const MilPF8 gxs = mil_pf8(pl.n, gx.c, go.h, go.w);
-          void* xsub = wsp(ws, pl.off_xsub[l]);
-          MIL_TRY(mil_launch_subsample2(X, gx, xsub, gxs, s));
+          // tensor-core path: phase (0,0) of the split input = the even positions; a plain 1x1 conv on it
+          const MilPF8 gxs = mil_split2_phase0(mil_xs2_geom(pl, l), gx.c);
+          void* xsub = wsp(ws, pl.off_xs2[l]);
           MIL_TRY(mil_conv_dispatch(dt, 0, xsub, gxs, wpack + cd.wp_off, TCW(cd, false), nullptr, nullptr, nullptr, y, go, 1,
                                     1, MIL_EPI_PLAIN, s));
         } else
@@ -447,7 +488,8 @@ int mil_extractor_backward_impl(const void* const* params, const float* bag, con
         // gradient into t_sub), and the full-resolution dgrad epilogue adds t_sub at the even positions.
         const MilConvDesc& cd = pl.convs[cb + 2];
         const MilPF8 gu = mil_pf8(pl.n, go.c, gi.h, gi.w);
-        const MilPF8 gxs = mil_pf8(pl.n, gi.c, go.h, go.w);
+        const MilPF8 gxs = mil_split2_phase0(mil_xs2_geom(pl, l), gi.c);
+        const MilPF8 gts = mil_pf8(pl.n, gi.c, go.h, go.w);  // geometry of t_sub (a tensor of its own)
         void* up_pre = wsp(ws, pl.off_up[0]);
         void* t_sub = wsp(ws, pl.off_up[1]);
         {
@@ -455,20 +497,20 @@ int mil_extractor_backward_impl(const void* const* params, const float* bag, con
           t.count = 0;
           t.esize = (int)mil_esize(dt);
           guard_add(t, up_pre, gu);
-          guard_add(t, t_sub, gxs);
+          guard_add(t, t_sub, gts);
           guard_add(t, dnew, gi);
           MIL_TRY(launch_guards(t, s));
         }
         MIL_TRY(mil_launch_upsample2(dpre, go, up_pre, gu, s));
         MIL_TRY(mil_wgrad_dispatch(dt, xin, gi, up_pre, gu, partial, gptr(c1.p_w), gptr(c1.p_b), 3, 1, s));
-        MIL_TRY(mil_wgrad_dispatch(dt, wsp(ws, pl.off_xsub[l]), gxs, dz, go, partial, gptr(cd.p_w), nullptr, 1, 1, s));
-        MIL_TRY(mil_conv_dispatch(dt, 1, dz, go, wpack + cd.wpt_off, TCW(cd, true), nullptr, nullptr, nullptr, t_sub, gxs,
+        MIL_TRY(mil_wgrad_dispatch(dt, wsp(ws, pl.off_xs2[l]), gxs, dz, go, partial, gptr(cd.p_w), nullptr, 1, 1, s));
+        MIL_TRY(mil_conv_dispatch(dt, 1, dz, go, wpack + cd.wpt_off, TCW(cd, true), nullptr, nullptr, nullptr, t_sub, gts,
                                   1, 1, MIL_EPI_PLAIN, s));
         {
           MilTcShape sh;
           MIL_TRY(mil_tc_shape(gu.c, gi.c, 3, &sh));
           MIL_TRY(mil_launch_conv_tc(1, up_pre, gu, TCW(c1, true), sh, nullptr, t_sub, xin, dnew, gi, MIL_EPI_DGRAD, 0, s,
-                                     &gxs));
+                                     &gts));
         }
         {
           GuardTable t;

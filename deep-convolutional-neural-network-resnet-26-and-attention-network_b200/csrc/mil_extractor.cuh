@@ -27,16 +27,30 @@ struct MilConvDesc {
   size_t wp_off, wpt_off;  // float offsets of the packed normal / transposed weights inside the pack area
   bool tc;                 // forward and data gradient run on the tcgen05 kernel (bf16 mode, 3x3 stride 1)
   size_t wtc_off, wtct_off;  // byte offsets of the bf16 UMMA-layout weights (normal / transposed) in the tc area
+  size_t wtct_s2_off[4];     // stride-2 3x3 only: the data-gradient weights of the four input phases
 };
+
+// the phase-split copy of a c-channel map whose stride-2 output is ho x ho: 4 * cb chunk planes at that resolution
+static inline MilPF8 mil_split2_geom(int n, int c, int ho) { return mil_pf8(n, 4 * ((c + 7) / 8) * 8, ho, ho); }
+// view of its phase (0,0) = the first cb planes (same plane stride): the map at its even positions
+static inline MilPF8 mil_split2_phase0(MilPF8 g, int c) {
+  g.c = c;
+  g.cb = (c + 7) / 8;
+  return g;
+}
+
+struct MilPlan;
+MilPF8 mil_xs2_geom(const MilPlan& pl, int l);  // geometry of the saved stride-2 block input of layer l (split or even-only)
 
 struct MilPlan {
   int n, side, dtype;
   MilGeom geo;
   MilPF8 g[4];                  // activation geometry of layer1..4
   std::vector<MilConvDesc> convs;  // 27 entries, forward order
-  size_t off_pooled, off_argmax, off_h[12], off_y[12], off_avg, off_grad[3], off_up[2], off_xsub[4], off_wpack, off_wtc, off_partial;
+  size_t off_pooled, off_argmax, off_h[12], off_y[12], off_avg, off_grad[3], off_up[2], off_xs2[4], off_wpack, off_wtc, off_partial;
   bool stem_tc;                 // stem on the tensor cores (bf16 mode)
   size_t off_xs, off_cv, off_stem_wp, off_stem_wtc;
+  bool s2_split[4];  // stride-2 block of layer l runs on the phase-split input (else: full-resolution evaluation)
   size_t wpack_floats, wtc_bytes, partial_floats, grad_bytes, up_bytes;
   size_t total_bytes;
 };

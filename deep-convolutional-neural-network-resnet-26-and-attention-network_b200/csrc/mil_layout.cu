@@ -163,6 +163,37 @@ __global__ void upsample2_kernel(const uint4* __restrict__ in, MilPF8 gin, uint4
     out[(size_t)cb * gout.PS + gout.G + q] = v;
   }
 }
+// ---- phase split (bf16): out plane (phase * cb + c), pixel (Y, X) = in plane c at (2Y + a, 2X + b), phase = 2a + b ----
+// grid = (image, pixel block of the OUTPUT map, input chunk): a thread reads one 2x2 block, writes four planes
+__global__ void __launch_bounds__(256) split2_kernel(const uint4* __restrict__ in, MilPF8 gin, uint4* __restrict__ out,
+                                                     MilPF8 gout) {
+  const int n = blockIdx.x, c = blockIdx.z;
+  const int r = blockIdx.y * blockDim.x + threadIdx.x;
+  if (r >= (int)gout.P) return;
+  const int Y = r / gout.wp, X = r - Y * gout.wp;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  uint4 v[4] = {zero, zero, zero, zero};
+  if (Y < gout.h && X < gout.w) {
+    const uint4* p = in + (size_t)c * gin.PS + gin.G + (size_t)n * gin.P + (size_t)(2 * Y) * gin.wp + 2 * X;
+    const bool a1 = 2 * Y + 1 < gin.h, b1 = 2 * X + 1 < gin.w;
+    v[0] = p[0];
+    if (b1) v[1] = p[1];
+    if (a1) v[2] = p[gin.wp];
+    if (a1 && b1) v[3] = p[gin.wp + 1];
+  }
+  const size_t o = gout.G + (size_t)n * gout.P + r;
+#pragma unroll
+  for (int ph = 0; ph < 4; ++ph) out[(size_t)(ph * gin.cb + c) * gout.PS + o] = v[ph];
+}
+int mil_launch_split2(const void* in, const MilPF8& gin, void* out, const MilPF8& gout, cudaStream_t s) {
+  MIL_REQUIRE(gin.n == gout.n && gout.cb == 4 * gin.cb && gout.h == (gin.h - 1) / 2 + 1 && gout.w == (gin.w - 1) / 2 + 1,
+              "split2: geometry mismatch");
+  split2_kernel<<<dim3(gin.n, (unsigned)mil_cdiv(gout.P, 256), gin.cb), 256, 0, s>>>((const uint4*)in, gin, (uint4*)out,
+                                                                                    gout);
+  MIL_LAUNCH_OK();
+  return 0;
+}
+
 // ---- even-position subsampling (bf16): out(n, y, x) = in(n, 2y, 2x) -------------------------------------------
 __global__ void subsample2_kernel(const uint4* __restrict__ in, MilPF8 gin, uint4* __restrict__ out, MilPF8 gout) {
   const long long total = (long long)gout.cb * gout.Q;
