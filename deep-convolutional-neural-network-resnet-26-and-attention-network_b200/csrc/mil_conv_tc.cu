@@ -56,7 +56,9 @@ struct TcPackEntry {
   short cout, cin;
   unsigned char taps, transposed, nmma, npad;
   unsigned char s2cb;       // != 0: phase-split stride-2 forward, chunk planes = phase * s2cb + chunk
-  unsigned char src_tap[MIL_TC_MAX_TAPS];  // tap of the kernel's window -> tap of the source weight
+  unsigned char pair_cbh;   // != 0: stride-2 data gradient of row parity pair_a, output rows n = (b, ci)
+  unsigned char pair_a;
+  signed char t_dy[MIL_TC_MAX_TAPS], t_dx[MIL_TC_MAX_TAPS];
   unsigned char g_tap[2 * MIL_TC_MAX_MMA], g_chunk[2 * MIL_TC_MAX_MMA];
 };
 struct TcPackTable {
@@ -69,7 +71,16 @@ __global__ void pack_tc_table_kernel(const __grid_constant__ TcPackTable t) {
   for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < total; i += gridDim.y * blockDim.x) {
     const int e = i & 7, n = (i >> 3) % p.npad, g = (i >> 3) / p.npad;  // g = 2j+h
     const int tap = p.g_tap[g];
-    int k = p.g_chunk[g] * 8 + e, stap = tap == 0xFF ? 0 : p.src_tap[tap];
+    int k = p.g_chunk[g] * 8 + e, stap = tap == 0xFF ? 0 : tap, nn = n;
+    bool ok = true;
+    if (p.pair_cbh != 0 && tap != 0xFF) {
+      const int b = n / (p.pair_cbh * 8), dY = -p.t_dy[tap], dX = -p.t_dx[tap];
+      nn = n - b * p.pair_cbh * 8;
+      const int ky = p.pair_a ? (dY ? 0 : 2) : 1;
+      const int kx = b ? (dX ? 0 : 2) : 1;
+      ok = b < 2 && !(b == 0 && dX != 0);
+      stap = ky * 3 + kx;
+    }
     if (p.s2cb != 0 && tap != 0xFF) {
       const int plane = p.g_chunk[g], phase = plane / p.s2cb;
       k = (plane - phase * p.s2cb) * 8 + e;
@@ -77,8 +88,8 @@ __global__ void pack_tc_table_kernel(const __grid_constant__ TcPackTable t) {
       stap = ky * 3 + kx;
     }
     float v = 0.f;
-    if (tap != 0xFF && n < nout && k < kin) {
-      const int co = p.transposed ? k : n, ci = p.transposed ? n : k;
+    if (tap != 0xFF && ok && nn < nout && k < kin) {
+      const int co = p.transposed ? k : nn, ci = p.transposed ? nn : k;
       v = p.w[((size_t)co * p.cin + ci) * p.taps + stap];
     }
     p.wtc[i] = __float2bfloat16_rn(v);
@@ -122,7 +133,7 @@ __global__ void __launch_bounds__(96 + NG * 128, 1)
 conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat16* __restrict__ wtc,
                const float* __restrict__ bias, const __nv_bfloat16* res, const __nv_bfloat16* act,
                __nv_bfloat16* out, MilPF8 go, MilTcShape sh, const __grid_constant__ TcIssue iss, int epi,
-               int sub, int halo, int n_stages, MilPF8 gr, int res_half) {
+               int sub, int halo, int n_stages, MilPF8 gr, int res_half, int up, int cbh) {
   extern __shared__ __align__(128) unsigned char smem[];
   TcSmemHeader* hd = reinterpret_cast<TcSmemHeader*>(smem);
   const uint32_t hdr_bytes = (uint32_t)((sizeof(TcSmemHeader) + 127) / 128 * 128);
@@ -231,18 +242,31 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
     const float inv_wp = 1.0f / (float)gx.wp;
     const int P = (int)gx.P;
     const long long ostride = go.PS * 8, rstride = (res_half ? gr.PS : go.PS) * 8;  // elements between chunks
+    // element offset of output chunk c: plane c, or in the stride-2 data-gradient mode plane c % cbh, pixel + c / cbh
+#define KOFF(c) (cbh == 0 ? (long long)(c) * ostride : (long long)((c) >= cbh ? (c) - cbh : (c)) * ostride + ((c) >= cbh ? 8 : 0))
     for (long long t = blockIdx.x + (long long)eg * gridDim.x; t < n_tiles; t += (long long)NG * gridDim.x, it += NG) {
       // flat index q = n * P + r at the input resolution; qo = where the pixel is stored.  sub: the stride-2
       // convolutions are evaluated at full resolution and only the even (y, x) positions are kept.
       bool in_range = n < gx.n;
-      bool is_pad = true, res_ok = true;
+      bool is_pad = true, res_ok = true, second_ok = true;
       long long qo = (long long)n * P + r, qres = qo;
       if (in_range) {
         int y = __float2int_rz(((float)r + 0.5f) * inv_wp);  // r / wp for r < 2^22 (exact after the fix-up)
         if (y * gx.wp > r) --y;
         else if ((y + 1) * gx.wp <= r) ++y;
         const int xo = r - y * gx.wp;
-        if (!sub) {
+        if (up) {
+          // data gradient of a stride-2 convolution, input rows of parity a = up - 1: tiles run over the
+          // half-resolution gradient; output chunks [0, cbh) belong at (2y + a, 2x), chunks [cbh, 2 cbh) at
+          // (2y + a, 2x + 1) of the full-resolution map `go` (pads are not touched); the residual (if any) is a
+          // half-resolution map of its own and feeds the first pixel only
+          const int yf = 2 * y + (up - 1), xf = 2 * xo;
+          in_range = y < gx.h && xo < gx.w && yf < go.h && xf < go.w;
+          second_ok = xf + 1 < go.w;
+          is_pad = false;
+          qo = (long long)n * go.P + (long long)yf * go.wp + xf;
+          qres = (long long)n * gr.P + (long long)y * gr.wp + xo;
+        } else if (!sub) {
           is_pad = (y >= gx.h) || (xo >= gx.w);
           if (res_half) {  // the residual lives at HALF resolution and only feeds the even (y, x) positions
             res_ok = !(y & 1) && !(xo & 1);
@@ -268,13 +292,13 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
           const __nv_bfloat16* pr = res + ((res_half ? gr.G : go.G) + qres) * 8;
 #pragma unroll
           for (int c = 0; c < MAXCB; ++c)
-            if (c < cbout) rres[c] = res_ok ? ld_nc16(pr + c * rstride) : make_uint4(0, 0, 0, 0);
+            if (c < cbout) rres[c] = (res_ok && (cbh == 0 || c < cbh)) ? ld_nc16(pr + c * rstride) : make_uint4(0, 0, 0, 0);
         }
         if (has_act) {
           const __nv_bfloat16* pa = act + (go.G + qo) * 8;
 #pragma unroll
           for (int c = 0; c < MAXCB; ++c)
-            if (c < cbout) ract[c] = ld_nc16(pa + c * ostride);
+            if (c < cbout && (c < cbh || cbh == 0 || second_ok)) ract[c] = ld_nc16(pa + KOFF(c));
         }
       }
       mbar_wait(&hd->empty[it % n_stages], (uint32_t)((it / n_stages) & 1));
@@ -325,19 +349,20 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
                 for (int j = 0; j < 8; ++j)
                   if (!(av[j] > 0.f)) v[j] *= MIL_SLOPE;
               }
-              mil_store8(po + c * ostride, v);
+              if (c < cbh || cbh == 0 || second_ok) mil_store8(po + KOFF(c), v);
             }
           }
         } else if (in_range) {  // pad pixel of the output map: keep the zero row / column zero
 #pragma unroll
           for (int k = 0; k < HALF; ++k) {
             const int c = half * HALF + k;
-            if (c < cbout) *reinterpret_cast<uint4*>(po + c * ostride) = make_uint4(0, 0, 0, 0);
+            if (c < cbout) *reinterpret_cast<uint4*>(po + KOFF(c)) = make_uint4(0, 0, 0, 0);
           }
         }
       }
     }
   }
+#undef KOFF
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
@@ -417,39 +442,30 @@ int mil_tc_shape_s2(int cin, int cout, MilTcShape* out) {
   return 0;
 }
 
-int mil_tc_shape_s2_dgrad(int cout_conv, int cin_conv, int a, int b, MilTcShape* out, int* src_tap) {
+int mil_tc_shape_s2_dgrad(int cout_conv, int cin_conv, int a, MilTcShape* out) {
   // dx[2Y+a][2X+b] = sum over (ky, kx) with ky = a + 1 (mod 2), kx = b + 1 (mod 2) of
-  //   W[ky][kx]^T dz[Y + dY][X + dX],  dY = 1 iff (a == 1 and ky == 0), dX likewise.
+  //   W[ky][kx]^T dz[Y + dY][X + dX],  dY = 1 iff (a == 1 and ky == 0), dX = 1 iff (b == 1 and kx == 0).
   // The kernel's data-gradient convention is out(q) = sum_t W_t^T in(q - shift_t): t_dy = -dY, t_dx = -dX.
+  // Taps in ascending (dY, dX) so that the K-group pairs ascend in shared memory.
   MilTcShape& sh = *out;
   sh.ks = 2;
   sh.ntaps = 0;
-  for (int ky = 0; ky < 3; ++ky)
-    for (int kx = 0; kx < 3; ++kx) {
-      if (((ky + 1) & 1) != a || ((kx + 1) & 1) != b) continue;
-      const int dY = (a == 1 && ky == 0) ? 1 : 0, dX = (b == 1 && kx == 0) ? 1 : 0;
+  for (int dY = 0; dY <= a; ++dY)
+    for (int dX = 0; dX <= 1; ++dX) {
       sh.t_dy[sh.ntaps] = (signed char)-dY;
       sh.t_dx[sh.ntaps] = (signed char)-dX;
-      src_tap[sh.ntaps] = ky * 3 + kx;
       ++sh.ntaps;
     }
-  // taps in ascending (negated) shift order so that a pair inside one chunk ascends in shared memory
-  for (int i = 0; i < sh.ntaps; ++i)
-    for (int j = i + 1; j < sh.ntaps; ++j) {
-      const int si = -(sh.t_dy[i] * 1024 + sh.t_dx[i]), sj = -(sh.t_dy[j] * 1024 + sh.t_dx[j]);
-      if (sj < si) {
-        std::swap(sh.t_dy[i], sh.t_dy[j]); std::swap(sh.t_dx[i], sh.t_dx[j]); std::swap(src_tap[i], src_tap[j]);
-      }
-    }
-  sh.cbin = (cout_conv + 7) / 8;   // the kernel reads dz (the conv's output channels) ...
-  sh.cbout = (cin_conv + 7) / 8;   // ... and produces the conv's input channels
-  sh.npad = (cin_conv + 15) / 16 * 16;
-  // K-groups sorted by (chunk, tap)
+  for (int t = sh.ntaps; t < MIL_TC_MAX_TAPS; ++t) sh.t_dy[t] = sh.t_dx[t] = 0;
+  const int cbh = (cin_conv + 7) / 8;
+  sh.cbin = (cout_conv + 7) / 8;  // the kernel reads dz (the conv's output channels) ...
+  sh.cbout = 2 * cbh;             // ... and produces (column parity, the conv's input channels)
+  sh.npad = (2 * cbh * 8 + 15) / 16 * 16;
   int ng = 0;
   for (int c = 0; c < sh.cbin; ++c)
     for (int t = 0; t < sh.ntaps; ++t) { sh.g_tap[ng] = (unsigned char)t; sh.g_chunk[ng] = (unsigned char)c; ++ng; }
   sh.nmma = (ng + 1) / 2;
-  MIL_REQUIRE(sh.nmma <= MIL_TC_MAX_MMA, "conv_tc: too many K groups (%d)", ng);
+  MIL_REQUIRE(sh.nmma <= MIL_TC_MAX_MMA && sh.cbout <= 10, "conv_tc: stride-2 data gradient too wide (%d groups)", ng);
   for (int g = ng; g < 2 * MIL_TC_MAX_MMA; ++g) sh.g_tap[g] = sh.g_chunk[g] = 0xFF;
   return 0;
 }
@@ -470,14 +486,14 @@ int mil_launch_pack_tc_table(const MilTcPackJob* jobs, int count, cudaStream_t s
     for (int i = 0; i < m; ++i) {
       const MilTcPackJob& j = jobs[base + i];
       MilTcShape sh;
-      int src_tap[MIL_TC_MAX_TAPS];
-      for (int q = 0; q < MIL_TC_MAX_TAPS; ++q) src_tap[q] = q;
       if (j.s2 == 1) MIL_TRY(mil_tc_shape_s2(j.cin, j.cout, &sh));
-      else if (j.s2 >= 2) MIL_TRY(mil_tc_shape_s2_dgrad(j.cout, j.cin, (j.s2 - 2) >> 1, (j.s2 - 2) & 1, &sh, src_tap));
+      else if (j.s2 >= 2) MIL_TRY(mil_tc_shape_s2_dgrad(j.cout, j.cin, j.s2 - 2, &sh));
       else MIL_TRY(mil_tc_shape(j.transposed ? j.cout : j.cin, j.transposed ? j.cin : j.cout, j.ks, &sh));
       TcPackEntry& e = t.e[i];
       e.s2cb = j.s2 == 1 ? (unsigned char)((j.cin + 7) / 8) : 0;
-      for (int q = 0; q < MIL_TC_MAX_TAPS; ++q) e.src_tap[q] = (unsigned char)src_tap[q];
+      e.pair_cbh = j.s2 >= 2 ? (unsigned char)((j.cin + 7) / 8) : 0;
+      e.pair_a = j.s2 >= 2 ? (unsigned char)(j.s2 - 2) : 0;
+      for (int q = 0; q < MIL_TC_MAX_TAPS; ++q) { e.t_dy[q] = sh.t_dy[q]; e.t_dx[q] = sh.t_dx[q]; }
       e.w = j.w;
       e.wtc = (__nv_bfloat16*)j.wtc;
       e.cout = (short)j.cout; e.cin = (short)j.cin;
@@ -505,7 +521,11 @@ bool mil_conv_tc_fits(const MilTcShape& sh, int wp) {
 
 int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const void* wtc, const MilTcShape& sh,
                        const float* bias, const void* res, const void* act, void* out, const MilPF8& go, int epi,
-                       int sub, cudaStream_t s, const MilPF8* gres_half) {
+                       int sub, cudaStream_t s, const MilPF8* gres_half, int up_row) {
+  if (up_row >= 0)
+    MIL_REQUIRE(transposed && !sub && gx.n == go.n && gx.h == (go.h - 1) / 2 + 1 && gx.w == (go.w - 1) / 2 + 1 &&
+                    (res == nullptr || gres_half != nullptr) && sh.cbout == 2 * go.cb,
+                "conv_tc: stride-2 data-gradient geometry mismatch");
   if (gres_half != nullptr)
     MIL_REQUIRE(!sub && res != nullptr && gres_half->cb == go.cb && gres_half->h == (go.h - 1) / 2 + 1 &&
                     gres_half->w == (go.w - 1) / 2 + 1,
@@ -513,10 +533,10 @@ int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const vo
   if (sub)
     MIL_REQUIRE(gx.n == go.n && go.h == (gx.h - 1) / 2 + 1 && go.w == (gx.w - 1) / 2 + 1 && !transposed,
                 "conv_tc: stride-2 geometry mismatch");
-  else
+  else if (up_row < 0)
     MIL_REQUIRE(gx.n == go.n && gx.h == go.h && gx.w == go.w && gx.wp == go.wp && gx.hp == go.hp,
                 "conv_tc: geometry mismatch");
-  MIL_REQUIRE(gx.cb == sh.cbin && go.cb == sh.cbout, "conv_tc: channel chunks do not match the packed weights");
+  MIL_REQUIRE(gx.cb == sh.cbin && (up_row >= 0 || go.cb == sh.cbout), "conv_tc: channel chunks do not match the packed weights");
   MIL_REQUIRE(epi != MIL_EPI_DGRAD || act != nullptr, "conv_tc: DGRAD epilogue needs the activation tensor");
   const int halo = mil_tc_halo(sh, gx.wp);
   MIL_REQUIRE(halo <= gx.G, "conv_tc: the window reaches %d pixels back but the map's guard is %lld", halo, gx.G);
@@ -568,7 +588,7 @@ int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const vo
     conv_tc_kernel<MAXCB, NG, MODE><<<grid, 96 + NG * 128, smem, s>>>(                                            \
         (const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)wtc, bias, (const __nv_bfloat16*)res,                  \
         (const __nv_bfloat16*)act, (__nv_bfloat16*)out, go, sh, iss, epi, sub, halo, n_stages,                    \
-        gres_half ? *gres_half : go, gres_half ? 1 : 0);                                                          \
+        gres_half ? *gres_half : go, gres_half ? 1 : 0, up_row + 1, up_row >= 0 ? go.cb : 0);                     \
   } while (0)
   // the network's layers (3 / 5 / 8 / 10 output chunks, five epilogue kinds) run specialised instantiations
 #define MIL_TC_LAUNCH(MAXCB, NG)                                                                                  \
@@ -588,6 +608,7 @@ int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const vo
   } while (0)
   if (sh.cbout <= 3) MIL_TC_LAUNCH(3, 4);
   else if (sh.cbout <= 5) MIL_TC_LAUNCH(5, 4);
+  else if (sh.cbout == 6) MIL_TC_LAUNCH(6, 2);
   else if (sh.cbout <= 8) MIL_TC_LAUNCH(8, 2);
   else MIL_TC_LAUNCH(10, 2);
 #undef MIL_TC_LAUNCH

@@ -35,9 +35,11 @@ int mil_tc_shape(int cin, int cout, int ks, MilTcShape* out);  // cin/cout = the
 // (-1..0) in which tap (dy, dx) of phase (a, b) carries the weight w[2 dy + a + 1][2 dx + b + 1] -- the same nine
 // K-groups per chunk as a stride-1 3x3 convolution, evaluated at a quarter of the pixels.
 int mil_tc_shape_s2(int cin, int cout, MilTcShape* out);
-// data gradient of that convolution for ONE input phase (a, b): the 1 / 2 / 2 / 4 taps whose weight row / column has
-// the matching parity; src_tap[t] = ky * 3 + kx of tap t in the 3x3 weight
-int mil_tc_shape_s2_dgrad(int cout_conv, int cin_conv, int a, int b, MilTcShape* out, int* src_tap);
+// data gradient of that convolution for the input rows of parity a, BOTH column parities at once: the kernel's output
+// chunks are (column parity b, input chunk) = 2 * cb chunks, so that a thread stores the two neighbouring pixels
+// (2Y + a, 2X) and (2Y + a, 2X + 1) together; taps (dY, dX) in {0, a} x {0, 1} of the output gradient, with
+// w[ky][kx] where ky = a ? (dY ? 0 : 2) : 1 and kx = b ? (dX ? 0 : 2) : (dX ? none : 1)
+int mil_tc_shape_s2_dgrad(int cout_conv, int cin_conv, int a, MilTcShape* out);
 size_t mil_tc_wpack_bytes(const MilTcShape& sh);
 // wp: fp32 packed weights [tap][kin_pad][nout_pad] (mil_launch_pack_conv_w, normal or transposed)
 int mil_launch_pack_tc(const float* wp, void* wtc, const MilTcShape& sh, cudaStream_t s);
@@ -45,13 +47,13 @@ int mil_launch_pack_tc(const float* wp, void* wtc, const MilTcShape& sh, cudaStr
 bool mil_conv_tc_fits(const MilTcShape& sh, int wp);
 int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const void* wtc, const MilTcShape& sh,
                        const float* bias, const void* res, const void* act, void* out, const MilPF8& go, int epi,
-                       int sub, cudaStream_t s, const MilPF8* gres_half = nullptr);
+                       int sub, cudaStream_t s, const MilPF8* gres_half = nullptr, int up_row = -1);
 // every convolution of a pass packed in one launch, straight from the PyTorch weight layout [cout][cin][ks][ks]
 struct MilTcPackJob {
   const float* w;
   void* wtc;
   int cout, cin, ks, transposed;
-  int s2;  // 0: plain;  1: forward of the stride-2 3x3 on the phase-split input;  2 + phase: its data gradient
+  int s2;  // 0: plain;  1: forward of the stride-2 3x3 on the phase-split input;  2 + a: its data gradient, rows a
 };
 int mil_launch_pack_tc_table(const MilTcPackJob* jobs, int count, cudaStream_t s);
 // out = the four (row parity, column parity) phases of `in` at half resolution, as 4 * cb chunk planes (bf16)
@@ -68,6 +70,10 @@ int mil_launch_wgrad_tc_partials(const void* x, const MilPF8& gx, const void* dz
                                  int ks, int* ctas_out, long long* rec_out, cudaStream_t s);
 int mil_launch_wgrad_tc(const void* x, const MilPF8& gx, const void* dz, const MilPF8& gz, float* partial, float* dw,
                         float* db, int ks, cudaStream_t s);
+
+// 3x3 / stride-2 convolution: x given as its phase-split copy xs2 (4 * cb planes), dz at the output resolution
+int mil_launch_wgrad_tc_s2(const void* xs2, const MilPF8& gs, const void* dz, const MilPF8& gz, float* partial, float* dw,
+                           float* db, int cin, cudaStream_t s);
 
 // stem on the tensor cores (mil_stem_tc.cu)
 MilPF8 mil_stem_tc_geom_in(int n, int side);    // space-to-depth input: 12 channels, conv-output resolution, pad 2

@@ -114,13 +114,12 @@ int mil_make_plan(int n, int side, int dtype, MilPlan* plan) {
           MIL_TRY(mil_tc_shape(c.cout, c.cin, c.ks, &sb));
           c.wtc_off = tcofs; tcofs += align_up(mil_tc_wpack_bytes(sf), 256);
           c.wtct_off = tcofs; tcofs += align_up(mil_tc_wpack_bytes(sb), 256);
-          for (int ph = 0; ph < 4; ++ph) c.wtct_s2_off[ph] = 0;
-          if (c.ks == 3 && c.stride == 2)
-            for (int ph = 0; ph < 4; ++ph) {
+          for (int a = 0; a < 2; ++a) c.wtct_s2_off[a] = 0;
+          if (c.ks == 3 && c.stride == 2 && 2 * ((c.cin + 7) / 8) <= 10)
+            for (int a = 0; a < 2; ++a) {
               MilTcShape sp;
-              int src_tap[MIL_TC_MAX_TAPS];
-              MIL_TRY(mil_tc_shape_s2_dgrad(c.cout, c.cin, ph >> 1, ph & 1, &sp, src_tap));
-              c.wtct_s2_off[ph] = tcofs; tcofs += align_up(mil_tc_wpack_bytes(sp), 256);
+              MIL_TRY(mil_tc_shape_s2_dgrad(c.cout, c.cin, a, &sp));
+              c.wtct_s2_off[a] = tcofs; tcofs += align_up(mil_tc_wpack_bytes(sp), 256);
             }
         }
         pl.convs.push_back(c);
@@ -161,7 +160,7 @@ int mil_make_plan(int n, int side, int dtype, MilPlan* plan) {
     for (int l = 1; l < 4; ++l) {
       MilTcShape sh;
       MIL_TRY(mil_tc_shape_s2(kMilWidths[l - 1], kMilWidths[l], &sh));
-      pl.s2_split[l] = mil_conv_tc_fits(sh, pl.g[l].wp);
+      pl.s2_split[l] = mil_conv_tc_fits(sh, pl.g[l].wp) && 2 * ((kMilWidths[l - 1] + 7) / 8) <= 10;  // dgrad: 2 * cb output chunks
       pl.off_xs2[l] = take(mil_pf8_bytes(mil_xs2_geom(pl, l), dtype));
     }
   pl.stem_tc = (dtype == MIL_BF16) && mil_tc_enabled();
@@ -310,8 +309,7 @@ static int pack_weights(const void* const* params, const MilPlan& pl, void* ws, 
     if (c.ks == 3 && c.stride == 2 && pl.s2_split[c.layer]) {  // phase-split forms (mil_tc_shape_s2 / mil_tc_shape_s2_dgrad)
       if (!transposed) jobs.push_back({w, tca + c.wtc_off, c.cout, c.cin, 3, 0, 1});
       else {
-        for (int ph = 0; ph < 4; ++ph) jobs.push_back({w, tca + c.wtct_s2_off[ph], c.cout, c.cin, 3, 1, 2 + ph});
-        jobs.push_back({w, tca + c.wtct_off, c.cout, c.cin, 3, 1, 0});  // TEMP: full-resolution dgrad still in use
+        for (int a = 0; a < 2; ++a) jobs.push_back({w, tca + c.wtct_s2_off[a], c.cout, c.cin, 3, 1, 2 + a});
       }
       continue;
     }
@@ -481,7 +479,41 @@ int mil_extractor_backward_impl(const void* const* params, const float* bag, con
         MIL_TRY(mil_launch_from_pf8(dt, dpre, g_dump.dst, go.n, go.c, go.h, go.w, s));
       // conv1: weight gradient (the stride-2 blocks do it inside their own branch below)
       if (!down) MIL_TRY(mil_wgrad_dispatch(dt, xin, gi, dpre, go, partial, gptr(c1.p_w), gptr(c1.p_b), 3, 1, s));
-      if (down && c1.tc) {
+      if (down && c1.tc && pl.s2_split[l]) {
+        // stride-2 block, phase-split form: every gradient of the block is computed at the OUTPUT resolution.
+        //   conv1 wgrad : nine single-tap MMAs over the saved phase-split input
+        //   projection  : 1x1 wgrad against phase (0,0), data gradient into t_sub (half resolution)
+        //   conv1 dgrad : one launch per input ROW parity (2 / 4 taps, both column parities as output chunks), stored
+        //                 straight into the full-resolution map as pixel pairs; the even-even pixels add t_sub; the
+        //                 LeakyReLU' mask is read from the block input
+        const MilConvDesc& cd = pl.convs[cb + 2];
+        const MilPF8 gs = mil_xs2_geom(pl, l);
+        const MilPF8 gxs = mil_split2_phase0(gs, gi.c);
+        const MilPF8 gts = mil_pf8(pl.n, gi.c, go.h, go.w);
+        void* xs2 = wsp(ws, pl.off_xs2[l]);
+        void* t_sub = wsp(ws, pl.off_up[1]);
+        MIL_TRY(mil_zero_guards(dt, t_sub, gts, s));
+        MIL_CHECK_CUDA(cudaMemsetAsync(dnew, 0, mil_pf8_bytes(gi, dt), s));  // pads + guards of the full-resolution map
+        MIL_TRY(mil_launch_wgrad_tc_s2(xs2, gs, dpre, go, partial, gptr(c1.p_w), gptr(c1.p_b), c1.cin, s));
+        MIL_TRY(mil_wgrad_dispatch(dt, xs2, gxs, dz, go, partial, gptr(cd.p_w), nullptr, 1, 1, s));
+        MIL_TRY(mil_conv_dispatch(dt, 1, dz, go, wpack + cd.wpt_off, TCW(cd, true), nullptr, nullptr, nullptr, t_sub, gts,
+                                  1, 1, MIL_EPI_PLAIN, s));
+        for (int a = 0; a < 2; ++a) {
+          MilTcShape sh;
+          MIL_TRY(mil_tc_shape_s2_dgrad(c1.cout, c1.cin, a, &sh));
+          MIL_TRY(mil_launch_conv_tc(1, dpre, go, wsp(ws, pl.off_wtc) + c1.wtct_s2_off[a], sh, nullptr,
+                                     a == 0 ? t_sub : nullptr, xin, dnew, gi, MIL_EPI_DGRAD, 0, s,
+                                     a == 0 ? &gts : nullptr, a));
+        }
+        {
+          GuardTable t;
+          t.count = 0;
+          t.esize = (int)mil_esize(dt);
+          guard_add(t, dz, gi);
+          guard_add(t, dpre, gi);
+          MIL_TRY(launch_guards(t, s));
+        }
+      } else if (down && c1.tc) {
         // stride-2 block on the tensor-core kernels.  The 3x3 conv: zero-stuff its output gradient to the input
         // resolution, after which its gradients are stride-1 problems.  The 1x1 projection: everything stays at
         // the OUTPUT resolution (weight gradient against the even-position input saved by the forward pass, data

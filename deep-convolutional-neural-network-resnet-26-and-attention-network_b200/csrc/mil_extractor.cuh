@@ -27,7 +27,7 @@ struct MilConvDesc {
   size_t wp_off, wpt_off;  // float offsets of the packed normal / transposed weights inside the pack area
   bool tc;                 // forward and data gradient run on the tcgen05 kernel (bf16 mode, 3x3 stride 1)
   size_t wtc_off, wtct_off;  // byte offsets of the bf16 UMMA-layout weights (normal / transposed) in the tc area
-  size_t wtct_s2_off[4];     // stride-2 3x3 only: the data-gradient weights of the four input phases
+  size_t wtct_s2_off[2];     // stride-2 3x3 only: the data-gradient weights of the two input row parities
 };
 
 // the phase-split copy of a c-channel map whose stride-2 output is ho x ho: 4 * cb chunk planes at that resolution

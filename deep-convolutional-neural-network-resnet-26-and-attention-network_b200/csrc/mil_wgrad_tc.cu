@@ -36,17 +36,27 @@ struct WgSmemHeader {
   uint32_t tmem_base;
 };
 
-// dxcat = 1: 3x3 window, taps grouped by dy, N = (dx, chunk) planes;  dxcat = 0: one tap per MMA (1x1 window)
+// Explicit MMA list for the stride-2 3x3 convolution on its phase-split input (mil_tc_shape_s2): MMA i multiplies dz
+// with the `cb` planes starting at plane0[i], read `shift[i]` pixels away, and produces tap rtap[i] = ky * 3 + kx of
+// the 3x3 weight.  n = 0: the taps come from the window description `sh`.
+struct WgCombo {
+  int n, cb;
+  short shift[9];
+  unsigned char plane0[9], rtap[9];
+};
+
+// dxcat = 1: 3x3 window, taps grouped by dy, N = (dx, chunk) planes;  dxcat = 0: one tap per MMA (1x1 window, or the
+// explicit list `cmb`)
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat16* __restrict__ dz, MilPF8 gz,
                 float* __restrict__ partial, long long rec_stride, MilTcShape sh, int halo, int taps_per_group,
-                int npad, int mma_m, int dxcat, int fold, int n_stages) {
+                int npad, int mma_m, int dxcat, int fold, int n_stages, WgCombo cmb) {
   extern __shared__ __align__(128) unsigned char smem[];
   WgSmemHeader* hd = reinterpret_cast<WgSmemHeader*>(smem);
   unsigned char* ones = smem + 128;            // 512 B of bf16 1.0: the B operand of the bias-gradient MMA
   unsigned char* stage0 = smem + 128 + 512;
   const int ntaps = sh.ntaps;                  // taps of the record layout (9 or 1)
-  const int ngrp_taps = dxcat ? 3 : ntaps;     // MMA "taps": dy rows when dxcat
+  const int ngrp_taps = cmb.n ? cmb.n : (dxcat ? 3 : ntaps);  // MMA "taps": dy rows when dxcat
   const int nbp = dxcat ? 3 * gx.cb : gx.cb;   // B planes per stage
   const int span = dxcat ? WG_TK + 2 * gx.wp : WG_TK + 2 * halo;
   const int back = dxcat ? gx.wp : halo;       // pixels before q0 held by a plane (of the dx = 0 copy)
@@ -133,8 +143,9 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
         for (int tl = 0; tl < ntl; ++tl) {
           const int tap = tap_lo + tl;
           // pixel offset of this tap's window start inside a B plane
-          const int s = dxcat ? tap * gx.wp : back + sh.t_dy[tap] * gx.wp + sh.t_dx[tap];
-          const uint64_t bd0 = make_desc(b_base + (uint32_t)s * 16, 128, b_pitch);
+          const int s = cmb.n ? back + cmb.shift[tap] : (dxcat ? tap * gx.wp : back + sh.t_dy[tap] * gx.wp + sh.t_dx[tap]);
+          const uint32_t p0 = cmb.n ? cmb.plane0[tap] * b_pitch : 0u;
+          const uint64_t bd0 = make_desc(b_base + p0 + (uint32_t)s * 16, 128, b_pitch);
           const uint32_t d = tmem_base + tl * npad;
           umma_bf16(d, ad0, bd0, idesc, acc0);
 #pragma unroll
@@ -160,19 +171,20 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
     // accumulator row -> TMEM lane: M = 128: row i in lane i;  M = 64: row i in lane 32*(i/16) + i%16 (each
     // lane quarter holds 16 rows)
     const int co = mma_m == 128 ? quarter * 32 + lane : (lane < 16 ? quarter * 16 + lane : 1 << 20);
-    const int coutp = gz.cb * 8, cinp = gx.cb * 8;
+    const int ncp = cmb.n ? cmb.cb : nbp;  // column blocks (planes) of one tap accumulator
+    const int coutp = gz.cb * 8, cinp = (cmb.n ? cmb.cb : gx.cb) * 8;
     mbar_wait(&hd->done, 0);
     tc_fence_after();
     if ((mma_m == 128 ? quarter * 32 : quarter * 16) < coutp) {  // warp-uniform
       float* rec = partial + (size_t)blockIdx.x * rec_stride;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
       for (int tl = 0; tl < ntl; ++tl) {
-        for (int p = 0; p < nbp; ++p) {
+        for (int p = 0; p < ncp; ++p) {
           float v[8];
           tmem_ld8(taddr + tl * npad + p * 8, v);
           tmem_ld_wait();
           // record tap and input chunk of this column block
-          const int rtap = dxcat ? (tap_lo + tl) * 3 + p % 3 : tap_lo + tl;
+          const int rtap = cmb.n ? cmb.rtap[tap_lo + tl] : (dxcat ? (tap_lo + tl) * 3 + p % 3 : tap_lo + tl);
           const int c = dxcat ? p / 3 : p;
           if (co < coutp) {
 #pragma unroll
@@ -459,11 +471,54 @@ int mil_launch_wgrad_tc_partials(const void* x, const MilPF8& gx, const void* dz
   const long long rec = (long long)sh.ntaps * gx.cb * 8 * gz.cb * 8 + gz.cb * 8;
   wgrad_tc_kernel<<<dim3(c.ctas, c.groups), WG_THREADS, c.smem, s>>>(
       (const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)dz, gz, partial, rec, sh, halo, c.tpg, c.npad, c.mma_m, c.dxcat,
-      c.fold, c.n_stages);
+      c.fold, c.n_stages, WgCombo{});
   MIL_LAUNCH_OK();
   *ctas_out = c.ctas;
   *rec_out = rec;
   return 0;
+}
+
+// weight + bias gradient of a 3x3 / stride-2 convolution from its phase-split input (mil_launch_split2) and the
+// output gradient, both at the OUTPUT resolution: nine single-tap MMAs per K-step over a 2x2 window
+int mil_launch_wgrad_tc_s2(const void* xs2, const MilPF8& gs, const void* dz, const MilPF8& gz, float* partial, float* dw,
+                           float* db, int cin, cudaStream_t s) {
+  const int cb = (cin + 7) / 8;
+  MIL_REQUIRE(gs.n == gz.n && gs.h == gz.h && gs.w == gz.w && gs.wp == gz.wp && gs.cb == 4 * cb,
+              "wgrad_tc_s2: geometry mismatch");
+  WgCombo cmb;
+  cmb.n = 9;
+  cmb.cb = cb;
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) {
+      // w[ky][kx] multiplies phase (a, b) at pixel offset (dy, dx):  ky = 2 dy + a + 1,  kx = 2 dx + b + 1
+      const int a = (ky + 1) & 1, b = (kx + 1) & 1, dy = ky == 0 ? -1 : 0, dx = kx == 0 ? -1 : 0;
+      const int i = ky * 3 + kx;
+      cmb.shift[i] = (short)(dy * gs.wp + dx);
+      cmb.plane0[i] = (unsigned char)((a * 2 + b) * cb);
+      cmb.rtap[i] = (unsigned char)i;
+    }
+  MilTcShape sh;
+  MIL_TRY(mil_tc_shape(cin, gz.c, 3, &sh));  // record layout: nine taps
+  const int halo = gs.wp + 1;
+  MIL_REQUIRE(halo <= gs.G, "wgrad_tc_s2: the window reaches %d pixels back but the map's guard is %lld", halo, gs.G);
+  const int mma_m = gz.cb * 8 <= 64 ? 64 : 128;
+  const int npad = (cb * 8 + 15) / 16 * 16;
+  const int groups = (9 * npad + 16 <= 512) ? 1 : 2;
+  const int tpg = (9 + groups - 1) / groups;
+  const long long n_tiles = mil_cdiv(gz.Q, WG_TK);
+  const int ctas = (int)std::max<long long>(1, std::min<long long>(n_tiles, wg_sm_count() / groups));
+  const size_t span = WG_TK + 2 * (size_t)halo;
+  const size_t stage = (size_t)gz.cb * WG_A_PLANE + (size_t)gs.cb * span * 16;
+  int n_stages = WG_MAX_STAGES;
+  while (n_stages > 1 && 128 + 512 + n_stages * stage + WG_SLACK > 220 * 1024) --n_stages;
+  const size_t smem = 128 + 512 + n_stages * stage + WG_SLACK;
+  MIL_REQUIRE(smem <= 227 * 1024, "wgrad_tc_s2: tile width %d needs %zu bytes of shared memory", gs.w, smem);
+  MIL_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long rec = (long long)9 * cb * 8 * gz.cb * 8 + gz.cb * 8;
+  wgrad_tc_kernel<<<dim3(ctas, groups), WG_THREADS, smem, s>>>((const __nv_bfloat16*)xs2, gs, (const __nv_bfloat16*)dz, gz,
+                                                              partial, rec, sh, halo, tpg, npad, mma_m, 0, 0, n_stages, cmb);
+  MIL_LAUNCH_OK();
+  return mil_launch_reduce_conv_w(partial, ctas, rec, dw, db, gz.c, cin, 3, s);
 }
 
 int mil_launch_wgrad_tc(const void* x, const MilPF8& gx, const void* dz, const MilPF8& gz, float* partial, float* dw,
