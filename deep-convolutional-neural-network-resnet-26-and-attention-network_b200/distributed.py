@@ -67,6 +67,14 @@ class BagGroup:
         lo = sum(sizes[: self.rank])
         perm = torch.randperm(total, generator=self._gen)[: int(total * frac)]
         self._n_global_pending = int(perm.numel())
+        # every rank sees the same permutation, so every rank reaches the same verdict here (nobody is left waiting
+        # in a collective): a shard without a single chosen tile has nothing to launch the kernels on
+        bounds = torch.tensor([0] + sizes).cumsum(0)
+        counts = torch.bucketize(perm, bounds[1:], right=True).bincount(minlength=self.world)
+        if int(counts.min()) == 0 and perm.numel() > 0:
+            raise ValueError(f"train-mode subsample of {int(perm.numel())} tiles leaves rank(s) "
+                             f"{[r for r in range(self.world) if int(counts[r]) == 0]} without a tile; "
+                             f"shard bags this small over fewer ranks")
         mine = perm[(perm >= lo) & (perm < lo + sizes[self.rank])] - lo
         return mine
 
