@@ -15,7 +15,7 @@ from . import _build
 _LOCK = threading.Lock()
 _LIB = None
 
-c_void_p, c_int, c_size_t, c_ll, c_char_p = C.c_void_p, C.c_int, C.c_size_t, C.c_longlong, C.c_char_p
+c_void_p, c_int, c_size_t, c_ll, c_char_p, c_float = C.c_void_p, C.c_int, C.c_size_t, C.c_longlong, C.c_char_p, C.c_float
 
 # name -> (restype, argtypes); mirrors include/mil_b200.h one to one
 PROTOTYPES = {
@@ -59,6 +59,8 @@ PROTOTYPES = {
                              c_size_t, c_void_p]),
     "mil_conv_wgrad_pf8": (c_int, [c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
                                    c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mil_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float,
+                              c_float, c_float, c_void_p]),
 }
 
 

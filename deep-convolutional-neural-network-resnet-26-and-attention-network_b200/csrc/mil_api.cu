@@ -312,6 +312,17 @@ int mil_upsample2_pf8(const void* in, int n, int c, int h, int w, void* out, int
   MIL_API_END
 }
 
+int mil_adam_step(float* params_flat, const float* grads_flat, float* exp_avg, float* exp_avg_sq, long long count,
+                  float step_size, float beta1, float beta2, float bc2_sqrt, float eps, float weight_decay,
+                  void* stream) {
+  MIL_API_BEGIN
+  MIL_TRY(require_device());
+  MIL_REQUIRE(params_flat && grads_flat && exp_avg && exp_avg_sq && count > 0, "mil_adam_step: null pointer argument");
+  return mil_launch_adam_step(params_flat, grads_flat, exp_avg, exp_avg_sq, count, step_size, beta1, beta2, bc2_sqrt,
+                              eps, weight_decay, (cudaStream_t)stream);
+  MIL_API_END
+}
+
 size_t mil_conv_workspace_bytes(int n, int cin, int hi, int wi, int cout, int ho, int wo, int ks) {
   size_t a, b;
   return conv_ws_layout(n, cin, hi, wi, cout, ho, wo, ks, &a, &b);

@@ -145,6 +145,31 @@ int mil_launch_reduce_conv_w(const float* partial, int nblk, long long stride, f
   return 0;
 }
 
+// ---- Adam over the flat parameter buffer (reference: optim.Adam, gbm/classify_combined.py:519) ----
+__global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, long long count, float step_size, float beta1, float beta2,
+                                 float bc2_sqrt, float eps, float weight_decay) {
+  const float w1 = 1.f - beta1, w2 = 1.f - beta2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float pi = p[i];
+    float gi = g[i];
+    if (weight_decay != 0.f) gi += weight_decay * pi;
+    const float mi = m[i] + w1 * (gi - m[i]);
+    const float vi = beta2 * v[i] + w2 * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = pi - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+  }
+}
+int mil_launch_adam_step(float* p, const float* g, float* m, float* v, long long count, float step_size, float beta1,
+                         float beta2, float bc2_sqrt, float eps, float weight_decay, cudaStream_t s) {
+  const int blocks = (int)std::min<long long>(mil_cdiv(count, 256), 148 * 8);
+  adam_step_kernel<<<blocks, 256, 0, s>>>(p, g, m, v, count, step_size, beta1, beta2, bc2_sqrt, eps, weight_decay);
+  MIL_LAUNCH_OK();
+  return 0;
+}
+
 // ---- zero-stuffing (bf16): out(n, 2y, 2x) = in(n, y, x), zero elsewhere ------------------------------------
 // Turns the stride-2 convolutions' data / weight gradients into stride-1 problems the tcgen05 kernels handle:
 // conv_transpose_s2(dz) == conv_transpose_s1(zero_stuff(dz)),  wgrad_s2(x, dz) == wgrad_s1(x, zero_stuff(dz)).

@@ -1,0 +1,87 @@
+"""Training-loop glue for the drop-in.
+
+The reference trains with `optim.Adam(classifier.parameters(), lr=2e-4)` and steps every 5 bags
+(gbm/classify_combined.py:519, :446-454): 65 parameter tensors => ~400 small kernels per step.  `FusedAdam` keeps
+the 640 967 parameters and their gradients in two flat device buffers (state-dict order, the layout the extractor's
+backward already writes) and does the whole step in ONE launch of `mil_adam_step`; gradient accumulation over
+several bags is autograd's ordinary in-place accumulation into the flat gradient views.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+
+
+def flatten_parameters(model):
+    """Re-home every parameter (and its .grad) of an `Attention` module in two flat fp32 buffers, in the library's
+    state-dict order.  Call it after `.cuda()`; `state_dict()` / `load_state_dict()` keep working (same names, the
+    tensors are views).  Returns (flat_params, flat_grads)."""
+    table = model._param_table
+    params = dict(model.named_parameters())
+    dev = next(iter(params.values())).device
+    if dev.type != "cuda":
+        raise RuntimeError("flatten_parameters: move the module to a CUDA device first (no CPU fallback)")
+    total = int(_lib.load().mil_param_total())
+    flat = torch.zeros(total, dtype=torch.float32, device=dev)
+    gflat = torch.zeros(total, dtype=torch.float32, device=dev)
+    with torch.no_grad():
+        for name, shape, off in table:
+            p = params[name]
+            n = p.numel()
+            flat[off:off + n].copy_(p.detach().reshape(-1))
+            if p.grad is not None:
+                gflat[off:off + n].copy_(p.grad.reshape(-1))
+            p.data = flat[off:off + n].view(shape)
+            p.grad = gflat[off:off + n].view(shape)
+    return flat, gflat
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """Adam with torch.optim.Adam's arithmetic (L2 weight decay, no amsgrad) as one kernel over the flat buffers.
+    `param_groups[0]['lr']` is read at every step, so LR schedules written against torch optimizers (the reference's
+    `SetStage`, gbm/classify_combined.py:110-138) keep working."""
+
+    def __init__(self, model, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self._flat, self._gflat = flatten_parameters(model)
+        super().__init__(list(model.parameters()), dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self._m = torch.zeros_like(self._flat)
+        self._v = torch.zeros_like(self._flat)
+        self._t = 0
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        g = self.param_groups[0]
+        b1, b2 = g["betas"]
+        self._t += 1
+        step_size = g["lr"] / (1.0 - b1 ** self._t)
+        bc2_sqrt = math.sqrt(1.0 - b2 ** self._t)
+        P = lambda t: C.c_void_p(t.data_ptr())
+        st = C.c_void_p(torch.cuda.current_stream(self._flat.device).cuda_stream)
+        with torch.cuda.device(self._flat.device):
+            _lib.check(_lib.load().mil_adam_step(P(self._flat), P(self._gflat), P(self._m), P(self._v),
+                                                 self._flat.numel(), step_size, b1, b2, bc2_sqrt, g["eps"],
+                                                 g["weight_decay"], st), "mil_adam_step")
+        return loss
+
+    def zero_grad(self, set_to_none: bool = False):
+        """Keeps the flat gradient views in place (set_to_none would detach them from the flat buffer)."""
+        self._gflat.zero_()
+
+    def state_dict(self):
+        return {"t": self._t, "exp_avg": self._m.clone(), "exp_avg_sq": self._v.clone(),
+                "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
+
+    def load_state_dict(self, sd):
+        self._t = int(sd["t"])
+        self._m.copy_(sd["exp_avg"])
+        self._v.copy_(sd["exp_avg_sq"])
+        for g, s in zip(self.param_groups, sd["param_groups"]):
+            g.update(s)

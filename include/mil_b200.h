@@ -144,6 +144,17 @@ int mil_conv_wgrad_pf8(int dtype, int impl, const void* x, int n, int cin, int h
                        int ho, int wo, int ks, int stride, float* dw, float* db, void* ws, size_t ws_bytes,
                        void* stream);
 
+/* ---- training-loop glue ------------------------------------------------------
+ * One Adam step over the FLAT parameter / gradient buffers (state-dict order, mil_param_offset) in one launch:
+ * what `optim.Adam(classifier.parameters(), lr=2e-4)` + `optimizer.step()` do tensor by tensor in the reference
+ * (gbm/classify_combined.py:519, :450-452).  Same arithmetic as torch.optim.Adam (L2 weight decay, no amsgrad):
+ *   g += weight_decay * p;  m += (1 - beta1) * (g - m);  v = beta2 * v + (1 - beta2) * g * g;
+ *   p -= step_size * m / (sqrt(v) / bc2_sqrt + eps),   step_size = lr / (1 - beta1^t),  bc2_sqrt = sqrt(1 - beta2^t)
+ * (the caller computes step_size and bc2_sqrt in double precision, as torch does).                           */
+int mil_adam_step(float* params_flat, const float* grads_flat, float* exp_avg, float* exp_avg_sq, long long count,
+                  float step_size, float beta1, float beta2, float bc2_sqrt, float eps, float weight_decay,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -359,3 +359,42 @@ def test_full_size_bag_properties():
     net(bag, Y)["loss"].backward()
     for k, p in net.named_parameters():
         assert torch.equal(p.grad, grads[k]), k
+
+
+def test_fused_adam_matches_torch_adam_with_accumulation():
+    """the one-launch Adam over the flat buffers follows torch.optim.Adam (the reference's optimizer,
+    gbm/classify_combined.py:519) through three steps of two accumulated bags each; the state dict keeps the
+    reference's key names and round-trips."""
+    mil = G.pkg()
+    a, b = build_net("fp32").train(), build_net("fp32").train()
+    opt_a = torch.optim.Adam(a.parameters(), lr=2e-4)
+    opt_b = mil.FusedAdam(b, lr=2e-4)
+    assert list(b.state_dict().keys()) == list(a.state_dict().keys())
+    bags = [torch.from_numpy(synth.make_bag(40, 64, seed=s)).cuda() for s in (11, 12)]
+    for step in range(3):
+        opt_a.zero_grad()
+        opt_b.zero_grad()
+        for net in (a, b):
+            for k, bag in enumerate(bags):
+                idx = torch.randperm(40, generator=torch.Generator().manual_seed(100 * step + k))[:8]
+                net.subsample_indices = idx
+                net.drop_mask = (torch.rand((8, 80), generator=torch.Generator().manual_seed(7 * step + k)) > 0.25
+                                 ).float().cuda()
+                net(bag, torch.tensor([k]).cuda())["loss"].backward()
+        for (ka, pa), (kb, pb) in zip(a.named_parameters(), b.named_parameters()):
+            assert torch.equal(pa.grad, pb.grad), ka           # same kernels, same weights, same accumulation order
+        opt_a.step()
+        opt_b.step()
+        for (ka, pa), (kb, pb) in zip(a.named_parameters(), b.named_parameters()):
+            # one Adam step moves a parameter by at most ~lr; the two implementations round m / (sqrt(v) + eps) and
+            # the final subtraction differently: 1e-4 of a step, or a few ulp of the parameter
+            assert torch.allclose(pa.detach(), pb.detach(), rtol=4e-7, atol=1e-4 * 2e-4), \
+                (step, ka, float((pa.detach() - pb.detach()).abs().max()))
+            with torch.no_grad():
+                pb.copy_(pa)    # re-synchronise the ulp differences: the next step compares the optimizers, not chaos
+    sd = {k: v.clone() for k, v in b.state_dict().items()}
+    c = build_net("fp32")
+    mil.flatten_parameters(c)
+    c.load_state_dict(sd)
+    for (kc, pc), (kb, pb) in zip(c.named_parameters(), b.named_parameters()):
+        assert torch.equal(pc, pb), kc
