@@ -11,6 +11,7 @@ from ._build import build, LIB_PATH  # noqa: F401
 from .distributed import BagGroup  # noqa: F401
 from .staging import BagStager  # noqa: F401
 from .optim import FusedAdam, flatten_parameters  # noqa: F401
+from .export import export_attention_maps, minmax_normalize, top_tiles, write_dla  # noqa: F401
 from .model import Attention, BasicResBlock, ContextLayer, CrossEntropyWithProbs, ResNet  # noqa: F401
 from . import _lib, model, synth  # noqa: F401
 

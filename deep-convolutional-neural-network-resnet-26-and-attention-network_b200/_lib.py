@@ -59,6 +59,7 @@ PROTOTYPES = {
                              c_size_t, c_void_p]),
     "mil_conv_wgrad_pf8": (c_int, [c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
                                    c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mil_minmax_normalize": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_void_p]),
     "mil_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float,
                               c_float, c_float, c_void_p]),
 }

@@ -312,6 +312,14 @@ int mil_upsample2_pf8(const void* in, int n, int c, int h, int w, void* out, int
   MIL_API_END
 }
 
+int mil_minmax_normalize(const float* in, float* out, long long count, float* minmax, void* stream) {
+  MIL_API_BEGIN
+  MIL_TRY(require_device());
+  MIL_REQUIRE(in && out && minmax && count > 0, "mil_minmax_normalize: null pointer argument");
+  return mil_launch_minmax_normalize(in, out, count, minmax, (cudaStream_t)stream);
+  MIL_API_END
+}
+
 int mil_adam_step(float* params_flat, const float* grads_flat, float* exp_avg, float* exp_avg_sq, long long count,
                   float step_size, float beta1, float beta2, float bc2_sqrt, float eps, float weight_decay,
                   void* stream) {

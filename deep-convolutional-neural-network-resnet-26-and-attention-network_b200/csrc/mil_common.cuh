@@ -148,6 +148,7 @@ static const int kMilWidths[4] = {20, 40, 60, 80};
 int mil_launch_pack_conv_w(const float* w, float* wp, int cout, int cin, int ks, int transposed, cudaStream_t s);
 int mil_launch_to_pf8(int dtype, const float* nchw, void* pf8, int n, int c, int h, int w, cudaStream_t s);
 int mil_launch_from_pf8(int dtype, const void* pf8, float* nchw, int n, int c, int h, int w, cudaStream_t s);
+int mil_launch_minmax_normalize(const float* in, float* out, long long count, float* minmax, cudaStream_t s);
 int mil_launch_adam_step(float* p, const float* g, float* m, float* v, long long count, float step_size, float beta1,
                          float beta2, float bc2_sqrt, float eps, float weight_decay, cudaStream_t s);
 int mil_launch_reduce_partials(const float* partial, int nblk, long long stride, float* out, long long count,

@@ -170,6 +170,54 @@ int mil_launch_adam_step(float* p, const float* g, float* m, float* v, long long
   return 0;
 }
 
+// ---- min-max scaling of an attention map (reference gbm/classify.py:209) ----------------------
+__device__ __forceinline__ int mm_key(float f) {  // order-preserving float -> int
+  const int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7FFFFFFF;
+}
+__device__ __forceinline__ float mm_val(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7FFFFFFF); }
+__global__ void minmax_init_kernel(int* mm) { mm[0] = 0x7FFFFFFF; mm[1] = (int)0x80000000; }
+__global__ void minmax_reduce_kernel(const float* __restrict__ in, long long count, int* mm) {
+  int lo = 0x7FFFFFFF, hi = (int)0x80000000;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = mm_key(in[i]);
+    lo = min(lo, k);
+    hi = max(hi, k);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMin(&mm[0], lo); atomicMax(&mm[1], hi); }
+}
+__global__ void minmax_scale_kernel(const float* __restrict__ in, float* __restrict__ out, long long count, int* mm) {
+  const float lo = mm_val(mm[0]), hi = mm_val(mm[1]);
+  const float inv = hi > lo ? 1.f / (hi - lo) : 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = (in[i] - lo) * inv;
+}
+// (min, max) handed back as floats once every block of the scaling pass has read the integer keys
+__global__ void minmax_finish_kernel(int* mm) {
+  const float lo = mm_val(mm[0]), hi = mm_val(mm[1]);
+  reinterpret_cast<float*>(mm)[0] = lo;
+  reinterpret_cast<float*>(mm)[1] = hi;
+}
+int mil_launch_minmax_normalize(const float* in, float* out, long long count, float* minmax, cudaStream_t s) {
+  int* mm = reinterpret_cast<int*>(minmax);
+  const int blocks = (int)std::max<long long>(1, std::min<long long>(mil_cdiv(count, 256), 148 * 4));
+  minmax_init_kernel<<<1, 1, 0, s>>>(mm);
+  MIL_LAUNCH_OK();
+  minmax_reduce_kernel<<<blocks, 256, 0, s>>>(in, count, mm);
+  MIL_LAUNCH_OK();
+  minmax_scale_kernel<<<blocks, 256, 0, s>>>(in, out, count, mm);
+  MIL_LAUNCH_OK();
+  minmax_finish_kernel<<<1, 1, 0, s>>>(mm);
+  MIL_LAUNCH_OK();
+  return 0;
+}
+
 // ---- zero-stuffing (bf16): out(n, 2y, 2x) = in(n, y, x), zero elsewhere ------------------------------------
 // Turns the stride-2 convolutions' data / weight gradients into stride-1 problems the tcgen05 kernels handle:
 // conv_transpose_s2(dz) == conv_transpose_s1(zero_stuff(dz)),  wgrad_s2(x, dz) == wgrad_s1(x, zero_stuff(dz)).

@@ -155,6 +155,13 @@ int mil_adam_step(float* params_flat, const float* grads_flat, float* exp_avg, f
                   float step_size, float beta1, float beta2, float bc2_sqrt, float eps, float weight_decay,
                   void* stream);
 
+/* ---- attention-map export -------------------------------------------------------
+ * out = (in - min(in)) / (max(in) - min(in)) over all `count` elements: the `plt.Normalize()(attn)` /
+ * `(A - A.min()) / (A.max() - A.min())` scaling the reference applies to an attention map before writing the per-tile
+ * `x y weight` heat-map files (gbm/classify.py:207-212, gbm/classify_combined.py:163).  minmax: device float[2]
+ * scratch that receives (min, max).  A constant map (max == min) comes back as zeros.                          */
+int mil_minmax_normalize(const float* in, float* out, long long count, float* minmax, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -398,3 +398,27 @@ def test_fused_adam_matches_torch_adam_with_accumulation():
     c.load_state_dict(sd)
     for (kc, pc), (kb, pb) in zip(c.named_parameters(), b.named_parameters()):
         assert torch.equal(pc, pb), kc
+
+
+def test_attention_map_export(tmp_path):
+    """device-side min-max scaling equals the reference's (A - A.min()) / (A.max() - A.min())
+    (gbm/classify_combined.py:163) and the .dla files carry `col row weight` per tile (gbm/classify.py:211)."""
+    mil = G.pkg()
+    net = build_net("bf16", wm=[-1.0, -1.0, -1.0])
+    bag = torch.from_numpy(synth.make_bag(64, 64, seed=6)).cuda()
+    with torch.no_grad():
+        out = net(bag, torch.tensor([1]).cuda())
+    A = out["Aterm"]
+    scaled, mm = mil.minmax_normalize(A)
+    ref = (A - A.min()) / (A.max() - A.min())
+    assert torch.allclose(scaled, ref, rtol=1e-6, atol=1e-7) and float(mm[0]) == float(A.min()) and float(mm[1]) == float(A.max())
+    assert float(scaled.min()) == 0.0 and abs(float(scaled.max()) - 1.0) < 1e-6
+    const, _ = mil.minmax_normalize(torch.full((3, 5), 2.5, device="cuda"))
+    assert float(const.abs().max()) == 0.0
+    raster = np.stack([np.arange(64) // 8, np.arange(64) % 8], 1) * 300
+    paths = mil.export_attention_maps(out, raster, str(tmp_path), "slideX")
+    assert len(paths) == 6
+    rows = np.loadtxt(paths[0])
+    assert rows.shape == (64, 3) and np.array_equal(rows[:, 0], raster[:, 1]) and np.array_equal(rows[:, 1], raster[:, 0])
+    assert np.allclose(rows[:, 2], scaled[0].cpu().numpy(), rtol=1e-6)
+    assert torch.equal(mil.top_tiles(A, 8), torch.topk(A, 8, dim=1).indices)
