@@ -146,6 +146,7 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long n_tiles = mil_cdiv(gx.Q, TC_M);  // tiles run over the INPUT resolution (== output unless sub)
   const uint32_t acc_stride = (uint32_t)((sh.npad + 31) / 32 * 32);
+  const bool pf_rows = !sub && !up && !res_half;  // residual / activation rows share the tile's flat pixel range
   uint32_t tmem_cols = 32;
   while (tmem_cols < acc_stride * NG) tmem_cols <<= 1;
 
@@ -186,6 +187,14 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
         unsigned char* dst = asm0 + (size_t)stage * stage_bytes;
         for (int c = 0; c < sh.cbin; ++c)
           bulk_g2s(dst + (size_t)c * plane, x + mil_pf8_off(gx, c, q0 - halo), plane, &hd->full[stage]);
+        // the epilogue of this tile reads its residual / activation rows with ordinary loads a few tiles from now and
+        // waits out their full latency (only NG tiles are in flight): have L2 fetch those rows already
+        if (pf_rows) {
+          for (int c = 0; c < sh.cbout; ++c) {
+            if (res != nullptr) bulk_prefetch_l2(res + mil_pf8_off(go, c, q0), TC_M * 16);
+            if (epi == MIL_EPI_DGRAD) bulk_prefetch_l2(act + mil_pf8_off(go, c, q0), TC_M * 16);
+          }
+        }
       }
       __syncwarp();
       if (++stage == n_stages) { stage = 0; phase ^= 1; }
@@ -234,7 +243,7 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
     // This thread's pixel as (image n, in-plane offset r), advanced incrementally from tile to tile: the only
     // 64-bit divisions of the kernel happen here, once (the epilogue's instruction stream is what bounds the
     // small-channel layers, not the tensor pipe).
-    constexpr int HALF = MAXCB <= 5 ? MAXCB : 5;           // chunks pulled from TMEM per batch
+    constexpr int HALF = MAXCB;  // chunks pulled from TMEM per batch: all at once, so the accumulator stage is handed back to the MMA warps before any arithmetic
     const long long step_q = (long long)NG * gridDim.x * TC_M;  // this group takes every NG-th tile of the CTA
     const int step_n = (int)(step_q / gx.P), step_r = (int)(step_q % gx.P);
     const long long q_first = ((long long)blockIdx.x + (long long)eg * gridDim.x) * TC_M + row;
@@ -285,7 +294,9 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
       if (r >= P) { r -= P; ++n; }
       const bool live = in_range && !is_pad;
       __nv_bfloat16* po = out + (go.G + qo) * 8;  // chunk c: po + c * ostride
-      // 1. residual / activation loads go out BEFORE we wait for the tensor core
+      // 1. residual / activation loads go out BEFORE we wait for the tensor core (the producer has already asked L2
+      // for these rows).  Issuing them after the accumulator drain instead -- fewer live registers on the wide
+      // layers -- was measured slower, even against a few spilled registers.
       uint4 rres[MAXCB], ract[MAXCB];
       if (live) {
         if (has_res) {

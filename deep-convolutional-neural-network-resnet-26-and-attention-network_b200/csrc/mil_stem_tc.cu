@@ -268,12 +268,16 @@ stem_unpool4_kernel(const __nv_bfloat16* __restrict__ g, MilPF8 gp, const uint16
 
 // ---- 5. reduction of the wgrad_tc partial records + fold back into the PyTorch layout --------------------------
 // record: [tap 9][kin 48][cout 80] + [80] bias sums
-__global__ void stem_reduce4_kernel(const float* __restrict__ partial, int nblk, long long stride,
-                                    float* __restrict__ dw, float* __restrict__ db) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+#define SR4_PARTS 8
+__global__ void __launch_bounds__(32 * SR4_PARTS)
+stem_reduce4_kernel(const float* __restrict__ partial, int nblk, long long stride, float* __restrict__ dw,
+                    float* __restrict__ db) {
+  // threadIdx.x = output element, threadIdx.y takes every SR4_PARTS-th partial record; fixed-order sum of the parts
+  __shared__ float part[SR4_PARTS][32];
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
   if (i < STC_CO * 147) {
     const int kx = i % 7, ky = (i / 7) % 7, c = (i / 49) % 3, co = i / 147;
-    float acc = 0.f;
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
       const int uy = 2 * a + ky - 3;          // = 4 dy + ry
@@ -284,19 +288,23 @@ __global__ void stem_reduce4_kernel(const float* __restrict__ partial, int nblk,
         const int dx = (ux + 4) / 4 - 1, rx = ux - 4 * dx;
         const int t = (dy + 1) * 3 + (dx + 1), cc = (c * 4 + ry) * 4 + rx, co4 = co * 4 + a * 2 + b;
         const size_t src = ((size_t)t * STC_CI + cc) * STC_CO4 + co4;
-        for (int k = 0; k < nblk; ++k) acc += partial[(size_t)k * stride + src];
+        for (int k = threadIdx.y; k < nblk; k += SR4_PARTS) acc += partial[(size_t)k * stride + src];
       }
     }
-    dw[i] += acc;
   } else if (i < STC_CO * 147 + STC_CO) {
     const int co = i - STC_CO * 147;
-    float acc = 0.f;
     for (int ph = 0; ph < 4; ++ph) {
       const size_t src = (size_t)9 * STC_CI * STC_CO4 + co * 4 + ph;
-      for (int k = 0; k < nblk; ++k) acc += partial[(size_t)k * stride + src];
+      for (int k = threadIdx.y; k < nblk; k += SR4_PARTS) acc += partial[(size_t)k * stride + src];
     }
-    db[co] += acc;
   }
+  part[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y != 0) return;
+#pragma unroll
+  for (int k = 1; k < SR4_PARTS; ++k) acc += part[k][threadIdx.x];
+  if (i < STC_CO * 147) dw[i] += acc;
+  else if (i < STC_CO * 147 + STC_CO) db[i - STC_CO * 147] += acc;
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------
@@ -351,7 +359,7 @@ int mil_launch_stem_tc_bwd(const void* xs, int n, int side, const void* g, const
   int ctas;
   long long rec;
   MIL_TRY(mil_launch_wgrad_tc_partials(xs, gi, dy, gc, partial, 3, &ctas, &rec, s));
-  stem_reduce4_kernel<<<(int)mil_cdiv(STC_CO * 147 + STC_CO, 128), 128, 0, s>>>(partial, ctas, rec, dw, db);
+  stem_reduce4_kernel<<<(int)mil_cdiv(STC_CO * 147 + STC_CO, 32), dim3(32, SR4_PARTS), 0, s>>>(partial, ctas, rec, dw, db);
   MIL_LAUNCH_OK();
   return 0;
 }
