@@ -36,7 +36,7 @@ FLOP_FWD_BWD = {224: 1247.7e6, 256: 1629.9e6}      # algorithmic FLOP per tile (
 L1_CONV_FLOP_224 = 22.58e6                         # one layer1 3x3 conv, per tile
 # dram__bytes_read.sum + dram__bytes_write.sum of that kernel per launch size (tiles), from the ncu --set full
 # captures summarised in profiles/ (None = no capture for this launch size)
-L1_CONV_NCU_TRAFFIC = {1024: 316959232 + 132250368}      # profiles/r1_ncu_tc_kernels_final.txt
+L1_CONV_NCU_TRAFFIC = {4096: 1277668000 + 613048064}      # profiles/r1_ncu_tc_kernels_final.txt
 METRIC = "tiles/sec fwd+bwd ResNet-26+attention-MIL"
 
 
