@@ -95,6 +95,25 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(rows), "window": window}
 
 
+def bind_to_gpu_numa_node(index):
+    """N > 1: run this rank on the host cores next to its GPU, so that the pinned staging buffers of the e2e leg are
+    first-touched on that NUMA node (8 ranks pulling their bags through one socket's memory halves the H2D rate)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def cpu_reference_throughput(side, sample_tiles, reps, seed=1):
     """fwd+bwd tiles/s of the CPU oracle port of the reference path on all host threads."""
     import torch
@@ -177,6 +196,7 @@ def run_ours(args):
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     group = mil.BagGroup()
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -341,7 +361,7 @@ def run_ours(args):
             "config": {"workload": f"bag of {n} RGB {side}x{side} tiles per GPU, all tiles through the CNN, fwd+bwd, "
                                    f"3 classes (BASELINE.json configs[1]; N>1: one {n * world}-tile bag sharded "
                                    f"over the ranks, configs[2])",
-                       "tiles_per_gpu": n, "side": side, "parallelism": f"bag-sharded x{world}",
+                       "tiles_per_gpu": n, "side": side, "parallelism": f"bag-sharded x{world}", "host_cores_per_rank": numa,
                        "l2": f"inputs larger than L2 ({n * 3 * side * side * 4 / 1e6:.0f} MB bag per step)",
                        "slides_per_s": value / (n * world), "loss": loss_val},
             "e2e": {"value": e2e_value, "unit": "tiles/s", "h2d_bytes_per_step": n * 3 * side * side * 4,
