@@ -95,9 +95,11 @@ def test_conv_forward_dgrad_wgrad_vs_torch(dtype, impl, cin, cout, ks, stride, H
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_extractor_activations_vs_oracle(precision):
+@pytest.mark.parametrize("n,side", [(3, 64), (2, 256), (2, 129)])
+def test_extractor_activations_vs_oracle(precision, n, side):
+    """Every saved activation of the extractor against the CPU oracle's, layer by layer: 64 (all maps even),
+    256 (BASELINE configs[4] tile size), 129 (odd maps at every level: 33 / 17 / 9 / 5)."""
     tol = 2e-5 if precision == "fp32" else 3e-2
-    n, side = 3, 64
     net = build_net(precision)
     bag = torch.from_numpy(synth.make_bag(n, side, seed=3))
     taps = {}
