@@ -424,3 +424,33 @@ def test_attention_map_export(tmp_path):
     assert rows.shape == (64, 3) and np.array_equal(rows[:, 0], raster[:, 1]) and np.array_equal(rows[:, 1], raster[:, 0])
     assert np.allclose(rows[:, 2], scaled[0].cpu().numpy(), rtol=1e-6)
     assert torch.equal(mil.top_tiles(A, 8), torch.topk(A, 8, dim=1).indices)
+
+
+def test_bag_stager_double_buffering():
+    """Host -> device staging (the e2e path of bench.py): tickets come back in submission order, a third submit
+    without a release is refused, buffers are recycled across dtypes / sizes, and a bag that went through the stager
+    gives bit-identical outputs to the same bag copied with .cuda() (gbm/classify_combined.py:423)."""
+    mil = G.pkg()
+    net = build_net("bf16")
+    stager = mil.BagStager(torch.device("cuda", 0))
+    bags = [torch.from_numpy(synth.make_bag(8, 64, seed=s)).pin_memory() for s in (21, 22, 23)]
+    u8 = ((bags[2] * 0.5 + 0.5) * 255).round().to(torch.uint8).pin_memory()
+    Y = torch.tensor([1]).cuda()
+    t0 = stager.submit(bags[0])
+    t1 = stager.submit(bags[1])
+    with pytest.raises(RuntimeError):
+        stager.submit(bags[2])
+    with torch.no_grad():
+        a = net(stager.get(t0), Y)
+        stager.release(t0)
+        t2 = stager.submit(u8)                       # reuses slot 0 with another dtype and size
+        b = net(stager.get(t1), Y)
+        stager.release(t1)
+        c = net(stager.get(t2), Y)
+        stager.release(t2)
+        ra, rb, rc = net(bags[0].cuda(), Y), net(bags[1].cuda(), Y), net(u8.cuda(), Y)
+    for got, ref in ((a, ra), (b, rb), (c, rc)):
+        for k in ("Aterm", "Mterm", "Fterm", "loss"):
+            assert torch.equal(got[k], ref[k]), k
+    with pytest.raises(ValueError):
+        stager.submit(bags[0].cuda())
