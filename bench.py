@@ -134,6 +134,11 @@ def cpu_reference_throughput(side, sample_tiles, reps, seed=1):
     return sample_tiles / best, cores, times
 
 
+def workload_string(n, side, world):
+    return (f"bag of {n} RGB {side}x{side} tiles per GPU, all tiles through the CNN, fwd+bwd, 3 classes "
+            f"(BASELINE.json configs[1]; N>1: one {n * world}-tile bag sharded over the ranks, configs[2])")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -159,8 +164,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "tiles/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"bag of {args.tiles} RGB {args.side}x{args.side} tiles, all tiles through the CNN, "
-                               f"fwd+bwd, 3 classes (BASELINE.json configs[1])",
+        "config": {"workload": workload_string(args.tiles, args.side, max(1, args.gpus)),
                    "tiles_per_step_timed": sample},
         "cpu_baseline": {"value": v, "unit": "tiles/s", "cores": cores, "kind": "port",
                          "sample": f"{sample} of the {args.tiles} tiles per step, fp32, torch CPU {torch.__version__}"},
@@ -358,9 +362,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "tiles/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": f"bag of {n} RGB {side}x{side} tiles per GPU, all tiles through the CNN, fwd+bwd, "
-                                   f"3 classes (BASELINE.json configs[1]; N>1: one {n * world}-tile bag sharded "
-                                   f"over the ranks, configs[2])",
+            "config": {"workload": workload_string(n, side, world),
                        "tiles_per_gpu": n, "side": side, "parallelism": f"bag-sharded x{world}", "host_cores_per_rank": numa,
                        "l2": f"inputs larger than L2 ({n * 3 * side * side * 4 / 1e6:.0f} MB bag per step)",
                        "slides_per_s": value / (n * world), "loss": loss_val},
@@ -385,7 +387,7 @@ def main():
     ap.add_argument("--tiles", type=int, default=4096, help="tiles per GPU per step")
     ap.add_argument("--side", type=int, default=224)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--ref-tiles", type=int, default=64, help="tiles per step of the CPU arm (bounded sample)")
+    ap.add_argument("--ref-tiles", type=int, default=256, help="tiles per step of the CPU arm (bounded sample)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
