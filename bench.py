@@ -387,7 +387,7 @@ def main():
     ap.add_argument("--tiles", type=int, default=4096, help="tiles per GPU per step")
     ap.add_argument("--side", type=int, default=224)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--ref-tiles", type=int, default=256, help="tiles per step of the CPU arm (bounded sample)")
+    ap.add_argument("--ref-tiles", type=int, default=64, help="tiles per step of the CPU arm (bounded sample)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
