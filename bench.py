@@ -261,15 +261,31 @@ def run_ours(args):
     del bag
     stager = mil.BagStager(dev)
 
+    loss_host = torch.empty(2, dtype=torch.float32).pin_memory()
+
     def e2e_run(k_steps):
+        """Every step: bag host -> device (submitted one step ahead), forward + backward, loss device -> host.  The
+        loss of step k is READ on the host while step k+1 is already enqueued (a training loop that logs one step
+        late): blocking on it right away would idle the GPU for the ~1.9 ms it takes the host to enqueue a step."""
         ticket = stager.submit(host)
+        pending, losses = None, []
         for k in range(k_steps):
             nxt = stager.submit(host) if k + 1 < k_steps else None
             o = step(stager.get(ticket))
-            loss = float(o["loss"].detach())            # device -> host read of the step's result
+            slot = k & 1
+            loss_host[slot:slot + 1].copy_(o["loss"].detach().reshape(1), non_blocking=True)   # D2H of this step's result
+            ev = torch.cuda.Event()
+            ev.record()
             stager.release(ticket)
+            if pending is not None:
+                pending[1].synchronize()
+                losses.append(float(loss_host[pending[0]]))
+            pending = (slot, ev)
             ticket = nxt
-        return loss
+        pending[1].synchronize()
+        losses.append(float(loss_host[pending[0]]))
+        assert len(losses) == k_steps and all(v == v for v in losses)
+        return losses[-1]
 
     e2e_run(max(1, min(args.warmup, 2)))
     barrier()

@@ -148,6 +148,11 @@ static const int kMilWidths[4] = {20, 40, 60, 80};
 int mil_launch_pack_conv_w(const float* w, float* wp, int cout, int cin, int ks, int transposed, cudaStream_t s);
 int mil_launch_to_pf8(int dtype, const float* nchw, void* pf8, int n, int c, int h, int w, cudaStream_t s);
 int mil_launch_from_pf8(int dtype, const void* pf8, float* nchw, int n, int c, int h, int w, cudaStream_t s);
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a high-water mark: raise it only when a launch needs more than any
+// earlier one did (the call costs microseconds, and a training step makes ~140 launches).  Keyed by (kernel, device).
+int mil_raise_max_dynamic_smem(const void* func, int bytes);
+#define MIL_SET_SMEM(kernel, bytes) MIL_TRY(mil_raise_max_dynamic_smem(reinterpret_cast<const void*>(kernel), (int)(bytes)))
+
 int mil_launch_minmax_normalize(const float* in, float* out, long long count, float* minmax, cudaStream_t s);
 int mil_launch_adam_step(float* p, const float* g, float* m, float* v, long long count, float step_size, float beta1,
                          float beta2, float bc2_sqrt, float eps, float weight_decay, cudaStream_t s);

@@ -594,8 +594,7 @@ int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const vo
   const int grid = (int)std::min<long long>(n_tiles, n_sm);
 #define MIL_TC_LAUNCH1(MAXCB, NG, MODE)                                                                           \
   do {                                                                                                            \
-    MIL_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<MAXCB, NG, MODE>,                                          \
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+    MIL_SET_SMEM((conv_tc_kernel<MAXCB, NG, MODE>), smem);                                                        \
     conv_tc_kernel<MAXCB, NG, MODE><<<grid, 96 + NG * 128, smem, s>>>(                                            \
         (const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)wtc, bias, (const __nv_bfloat16*)res,                  \
         (const __nv_bfloat16*)act, (__nv_bfloat16*)out, go, sh, iss, epi, sub, halo, n_stages,                    \

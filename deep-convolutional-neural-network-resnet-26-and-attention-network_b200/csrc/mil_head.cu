@@ -218,8 +218,7 @@ int mil_launch_head_scores(const MilHeadParams& P, const float* H, const float* 
                            const double* stats, float* raw, float* g, float* b, double* part_ws, double* sums,
                            cudaStream_t s) {
   const int nblk = (int)mil_cdiv(n, HT);
-  MIL_CHECK_CUDA(cudaFuncSetAttribute(head_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)sizeof(HeadSmem)));
+  MIL_SET_SMEM((head_scores_kernel), (int)sizeof(HeadSmem));
   head_scores_kernel<<<nblk, HT, sizeof(HeadSmem), s>>>(P, H, drop, n, n_global, stats, raw, g, b, part_ws);
   MIL_LAUNCH_OK();
   reduce_double_kernel<<<1, 32, 0, s>>>(part_ws, nblk, MIL_HEAD_NSUMS, sums);
@@ -498,7 +497,7 @@ int mil_launch_head_bwd_a(const MilHeadParams& P, const MilHeadGrads& G, const f
                           double* bnsums, cudaStream_t s) {
   const int nblk = (int)mil_cdiv(n, HT);
   const size_t smem = sizeof(HeadSmem) + (size_t)4 * HT * (HD + 1) * sizeof(float) + (size_t)HT * 8 * sizeof(float);
-  MIL_CHECK_CUDA(cudaFuncSetAttribute(head_bwd_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MIL_SET_SMEM((head_bwd_a_kernel), (int)smem);
   head_bwd_a_kernel<<<nblk, HT, smem, s>>>(P, H, drop, n, n_global, stats, raw, g, b, scal, gloss, dHz, dHi, part_ws);
   MIL_LAUNCH_OK();
   head_bwd_reduce_kernel<<<(int)mil_cdiv(HB_REC, 128), 128, 0, s>>>(part_ws, nblk, G, bnsums);

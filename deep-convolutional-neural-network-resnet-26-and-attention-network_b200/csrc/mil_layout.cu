@@ -5,6 +5,24 @@
 #include "mil_common.cuh"
 #include "mil_conv_tc.cuh"
 
+#include <map>
+#include <mutex>
+#include <utility>
+
+int mil_raise_max_dynamic_smem(const void* func, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, int> high;
+  int dev = 0;
+  MIL_CHECK_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  int& h = high[{func, dev}];
+  if (bytes > h) {
+    MIL_CHECK_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    h = bytes;
+  }
+  return 0;
+}
+
 // ---- conv weight packing ---------------------------------------------------------------------------
 // PyTorch layout w[cout][cin][ks][ks] (reference nnBlocks.py:160-168 nn.Conv2d) ->
 //   normal     : wp[tap][cin_pad ][cout_pad]   (forward conv: contraction over cin)

@@ -117,12 +117,10 @@ int mil_launch_stem_fwd(int dtype, const float* x, const int* idx, int n, int si
   dim3 grid((unsigned)mil_cdiv(gp.wp, STEM_TP), (unsigned)mil_cdiv(gp.hp, STEM_TP), (unsigned)n);
   MIL_REQUIRE(n <= 65535, "stem_fwd: at most 65535 tiles per launch (got %d)", n);
   if (dtype == MIL_BF16) {
-    MIL_CHECK_CUDA(cudaFuncSetAttribute(stem_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
+    MIL_SET_SMEM((stem_fwd_kernel<__nv_bfloat16>), (int)smem);
     stem_fwd_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(x, idx, side, g.hc, w, b, (__nv_bfloat16*)pooled, gp, argmax);
   } else {
-    MIL_CHECK_CUDA(cudaFuncSetAttribute(stem_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
+    MIL_SET_SMEM((stem_fwd_kernel<float>), (int)smem);
     stem_fwd_kernel<float><<<grid, 256, smem, s>>>(x, idx, side, g.hc, w, b, (float*)pooled, gp, argmax);
   }
   MIL_LAUNCH_OK();

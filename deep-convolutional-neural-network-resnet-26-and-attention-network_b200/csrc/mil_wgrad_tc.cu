@@ -456,7 +456,7 @@ int mil_launch_wgrad_tc_partials(const void* x, const MilPF8& gx, const void* dz
   const long long rec_sq = (long long)sh.ntaps * gx.cb * 8 * gz.cb * 8 + gz.cb * 8;
   if (c.sq) {
     MIL_REQUIRE(halo <= gz.G, "wgrad_tc: the window reaches %d pixels back but the gradient map's guard is %lld", halo, gz.G);
-    MIL_CHECK_CUDA(cudaFuncSetAttribute(wgrad_sq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+    MIL_SET_SMEM((wgrad_sq_kernel), (int)c.smem);
     wgrad_sq_kernel<<<c.ctas, WG_THREADS, c.smem, s>>>((const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)dz, gz, partial,
                                                       rec_sq, c.npad, c.n_stages);
     MIL_LAUNCH_OK();
@@ -467,7 +467,7 @@ int mil_launch_wgrad_tc_partials(const void* x, const MilPF8& gx, const void* dz
   MIL_REQUIRE(c.mma_m == 64 || c.npad % 16 == 0, "wgrad_tc: N = %d is not a multiple of 16 (M = 128)", c.npad);
   MIL_REQUIRE(c.npad <= 256, "wgrad_tc: N = %d too wide", c.npad);
   MIL_REQUIRE(c.smem <= 227 * 1024, "wgrad_tc: tile width %d needs %zu bytes of shared memory", gx.w, c.smem);
-  MIL_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+  MIL_SET_SMEM((wgrad_tc_kernel), (int)c.smem);
   const long long rec = (long long)sh.ntaps * gx.cb * 8 * gz.cb * 8 + gz.cb * 8;
   wgrad_tc_kernel<<<dim3(c.ctas, c.groups), WG_THREADS, c.smem, s>>>(
       (const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)dz, gz, partial, rec, sh, halo, c.tpg, c.npad, c.mma_m, c.dxcat,
@@ -513,7 +513,7 @@ int mil_launch_wgrad_tc_s2(const void* xs2, const MilPF8& gs, const void* dz, co
   while (n_stages > 1 && 128 + 512 + n_stages * stage + WG_SLACK > 220 * 1024) --n_stages;
   const size_t smem = 128 + 512 + n_stages * stage + WG_SLACK;
   MIL_REQUIRE(smem <= 227 * 1024, "wgrad_tc_s2: tile width %d needs %zu bytes of shared memory", gs.w, smem);
-  MIL_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MIL_SET_SMEM((wgrad_tc_kernel), (int)smem);
   const long long rec = (long long)9 * cb * 8 * gz.cb * 8 + gz.cb * 8;
   wgrad_tc_kernel<<<dim3(ctas, groups), WG_THREADS, smem, s>>>((const __nv_bfloat16*)xs2, gs, (const __nv_bfloat16*)dz, gz,
                                                               partial, rec, sh, halo, tpg, npad, mma_m, 0, 0, n_stages, cmb);

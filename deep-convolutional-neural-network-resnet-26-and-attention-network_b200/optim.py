@@ -37,6 +37,7 @@ def flatten_parameters(model):
                 gflat[off:off + n].copy_(p.grad.reshape(-1))
             p.data = flat[off:off + n].view(shape)
             p.grad = gflat[off:off + n].view(shape)
+    model._gflat = gflat      # the backward pass accumulates straight into it (model._MilFunction.backward)
     return flat, gflat
 
 
