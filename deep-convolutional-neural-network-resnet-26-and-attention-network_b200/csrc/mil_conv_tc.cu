@@ -1,7 +1,8 @@
-// tcgen05 implicit-GEMM convolution on the PF8 layout -- forward AND data gradient of the 3x3 / 1x1 layers
-// (stride 1; stride 2 forward = full-resolution evaluation + subsampled store) and the stem's 7x7 / stride-2
-// convolution in space-to-depth form (4x4 window over 12 channels).  bf16 operands, fp32 accumulation in TMEM,
-// fused epilogue (bias, residual, LeakyReLU / LeakyReLU').
+// tcgen05 implicit-GEMM convolution on the PF8 layout -- forward AND data gradient of the 3x3 / 1x1 layers, the
+// stride-2 3x3 convolutions in their phase-split forms (mil_tc_shape_s2 / mil_tc_shape_s2_dgrad; the block into
+// layer 4 still uses full-resolution evaluation + subsampled store) and the stem's 7x7 / stride-2 convolution in
+// space-to-depth form.  bf16 operands, fp32 accumulation in TMEM, fused epilogue (bias, residual, LeakyReLU /
+// LeakyReLU').
 // Reference semantics: nnBlocks.py:178-187 (conv3x3 + bias -> [+identity] -> LeakyReLU(0.1)), gbm/model.py:24-25,51-52
 // (conv1 + LeakyReLU) and their autograd.
 //
@@ -15,14 +16,17 @@
 // memory for the whole kernel in the matching core-matrix layout.
 //
 // Warp roles (one persistent CTA per SM, tiles strided over CTAs):
-//   warp 0      : producer -- bulk-TMA (cp.async.bulk) of the span planes into a 3-stage ring, mbarrier tx
-//   warp 1      : MMA issuer -- one elected lane issues the tcgen05.mma chain of a tile (descriptors are
-//                 precomputed templates + the stage base) into one of two TMEM accumulator stages;
-//                 tcgen05.commit releases the smem stage / publishes the accumulator
-//   warps 2..9  : epilogue, two groups of 4 warps (one per accumulator stage).  Per tile a thread (= pixel)
-//                 first issues its residual / activation loads, THEN waits for the accumulator, pulls its
-//                 row out of TMEM, hands the accumulator stage back, and only then does the arithmetic and the
-//                 16-byte coalesced stores; pad pixels are written as zeros (PF8 invariant).
+//   warp 0      : producer -- bulk-TMA (cp.async.bulk) of the span planes into a ring of up to 8 stages (mbarrier tx),
+//                 plus an L2 prefetch of the residual / activation rows the tile's epilogue will read
+//   warps 1..2  : MMA issuers, alternate tiles -- whole warp in uniform control flow, one elected lane issues the
+//                 tcgen05.mma chain of a tile (descriptor templates from kernel parameters + the stage base) into one
+//                 of NG TMEM accumulator stages; ONE tcgen05.commit per tile releases the smem stage and publishes
+//                 the accumulator
+//   warps 3..   : epilogue, NG groups of 4 warps (NG = 4 up to 5 output chunks, 2 above).  Per tile a thread (=
+//                 pixel) first issues its residual / activation loads, THEN waits for the accumulator, pulls its
+//                 WHOLE row out of TMEM, hands the accumulator stage back, and only then does the arithmetic and the
+//                 16-byte coalesced stores; pad pixels are written as zeros (PF8 invariant).  The epilogue is
+//                 compiled per (chunk count, kind): conv_tc_kernel<MAXCB, NG, MODE>.
 #include <algorithm>
 
 #include "mil_common.cuh"

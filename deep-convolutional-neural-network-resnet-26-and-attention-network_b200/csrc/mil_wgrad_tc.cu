@@ -8,11 +8,15 @@
 // -- [pixel][8 channels], i.e. "MN-major" core matrices of 8 pixels x 16 B -- so a 128-pixel K-tile needs only
 // bulk-TMA copies and NO transposition: A = the dz planes, B = x planes read from a shifted start address.
 //
-// A thin MMA costs the tensor pipe as much as a wide one (~0.35*M cycles up to N = 64, profiles/r1_mma_cost.txt),
-// so for the 3x3 layers the three dx taps are CONCATENATED along N: the producer loads three copies of every x
-// plane, shifted by -1 / 0 / +1 pixel, as consecutive shared-memory planes; N-group (dx, chunk) then sits at a
-// uniform stride and ONE MMA per (dy, K-step) covers N = 3*Cin columns (72 .. 240) -- 24 + 8 MMAs per K-tile
-// instead of 72 + 8.  The price is 3x the L2 -> shared-memory traffic of x.
+// Three kernels share this file:
+//   wgrad_sq_kernel  layers 1-2 (3 or 5 chunks on both sides): ONE M = 128 MMA per K-step yields all nine taps and
+//                    the bias gradient; shifted operand planes are built in shared memory (see its own header)
+//   wgrad_tc_kernel  everything else.  A thin MMA is bound by its operand reads (profiles/r1_mma_cost2.txt), so for
+//                    the 3x3 layers the three dx taps are CONCATENATED along N: the producer loads three copies of
+//                    every x plane, shifted by -1 / 0 / +1 pixel, as consecutive shared-memory planes; N-group
+//                    (chunk, dx) then sits at a uniform stride and ONE MMA per (dy, K-step) covers N = 3*Cin columns
+//                    (+8 for the bias gradient when M = 64).  1x1 windows and the stride-2 3x3 convolution on its
+//                    phase-split input (explicit MMA list, WgCombo) use one MMA per tap.
 //
 // The tap accumulators (and the bias block, B = a constant all-ones block) stay in TMEM for the whole kernel: every
 // CTA accumulates its share of the pixel tiles (split-K over CTAs), then writes ONE partial record
