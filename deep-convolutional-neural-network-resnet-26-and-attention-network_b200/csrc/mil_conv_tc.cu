@@ -137,7 +137,8 @@ __global__ void __launch_bounds__(96 + NG * 128, 1)
 conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat16* __restrict__ wtc,
                const float* __restrict__ bias, const __nv_bfloat16* res, const __nv_bfloat16* act,
                __nv_bfloat16* out, MilPF8 go, MilTcShape sh, const __grid_constant__ TcIssue iss, int epi,
-               int sub, int halo, int n_stages, MilPF8 gr, int res_half, int up, int cbh) {
+               int sub, int halo, int n_stages, MilPF8 gr, int res_half, int up, int cbh,
+               const uint32_t* __restrict__ mask_in, uint32_t* __restrict__ mask_out) {
   extern __shared__ __align__(128) unsigned char smem[];
   TcSmemHeader* hd = reinterpret_cast<TcSmemHeader*>(smem);
   const uint32_t hdr_bytes = (uint32_t)((sizeof(TcSmemHeader) + 127) / 128 * 128);
@@ -196,7 +197,7 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
         if (pf_rows) {
           for (int c = 0; c < sh.cbout; ++c) {
             if (res != nullptr) bulk_prefetch_l2(res + mil_pf8_off(go, c, q0), TC_M * 16);
-            if (epi == MIL_EPI_DGRAD) bulk_prefetch_l2(act + mil_pf8_off(go, c, q0), TC_M * 16);
+            if (epi == MIL_EPI_DGRAD && mask_in == nullptr) bulk_prefetch_l2(act + mil_pf8_off(go, c, q0), TC_M * 16);
           }
         }
       }
@@ -301,7 +302,11 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
       // 1. residual / activation loads go out BEFORE we wait for the tensor core (the producer has already asked L2
       // for these rows).  Issuing them after the accumulator drain instead -- fewer live registers on the wide
       // layers -- was measured slower, even against a few spilled registers.
+      constexpr int MW = (MAXCB + 3) / 4;  // 32-bit sign-mask words per pixel
       uint4 rres[MAXCB], ract[MAXCB];
+      uint32_t rmask[MW], wmask[MW];
+#pragma unroll
+      for (int w = 0; w < MW; ++w) rmask[w] = wmask[w] = 0;
       if (live) {
         if (has_res) {
           const __nv_bfloat16* pr = res + ((res_half ? gr.G : go.G) + qres) * 8;
@@ -309,11 +314,37 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
           for (int c = 0; c < MAXCB; ++c)
             if (c < cbout) rres[c] = (res_ok && (cbh == 0 || c < cbh)) ? ld_nc16(pr + c * rstride) : make_uint4(0, 0, 0, 0);
         }
-        if (has_act) {
+        if (has_act && mask_in == nullptr) {
           const __nv_bfloat16* pa = act + (go.G + qo) * 8;
 #pragma unroll
           for (int c = 0; c < MAXCB; ++c)
             if (c < cbout && (c < cbh || cbh == 0 || second_ok)) ract[c] = ld_nc16(pa + KOFF(c));
+        }
+        if (has_act && mask_in != nullptr) {
+          // sign bits of the activation (written by the forward epilogue): 4 bytes per pixel and 4 chunks instead of
+          // 16 bytes per pixel and chunk.  Stride-2 data gradient: chunks [cbh, 2 cbh) belong to the next pixel.
+          const uint32_t* pm = mask_in + go.G + qo;
+#pragma unroll
+          for (int w = 0; w < MW; ++w) {
+            if (cbh == 0) {
+              if (w * 4 < cbout) rmask[w] = __ldg(pm + (long long)w * go.PS);
+            } else {
+              // word w covers kernel chunks 4w .. 4w+3 = (pixel b, map chunk c) pairs; gather their bytes
+              uint32_t v = 0;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int k = w * 4 + e;
+                if (k < cbout) {
+                  const int b = k >= cbh ? 1 : 0, c = k - b * cbh;
+                  if (b == 0 || second_ok) {
+                    const uint32_t mwrd = __ldg(pm + b + (long long)(c >> 2) * go.PS);
+                    v |= ((mwrd >> ((c & 3) * 8)) & 0xFFu) << (e * 8);
+                  }
+                }
+              }
+              rmask[w] = v;
+            }
+          }
         }
       }
       mbar_wait(&hd->empty[it % n_stages], (uint32_t)((it / n_stages) & 1));
@@ -357,6 +388,11 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
               if (do_lrelu) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], MIL_SLOPE * v[j]);  // == x > 0 ? x : slope * x
+              } else if (has_act && mask_in != nullptr) {
+                const uint32_t bits = rmask[c >> 2] >> ((c & 3) * 8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (!((bits >> j) & 1u)) v[j] *= MIL_SLOPE;
               } else if (has_act) {
                 float av[8];
                 unpack8(ract[c], av);
@@ -364,8 +400,29 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
                 for (int j = 0; j < 8; ++j)
                   if (!(av[j] > 0.f)) v[j] *= MIL_SLOPE;
               }
-              if (c < cbh || cbh == 0 || second_ok) mil_store8(po + KOFF(c), v);
+              if (do_lrelu && mask_out != nullptr) {
+                // pack here (not in mil_store8) and lift the eight sign bits out of the packed words: the top bytes
+                // of values 0..3 / 4..7 gathered by one PRMT each, "sign clear" flags compressed by one multiply.
+                // (+0 counts as positive; the reference's LeakyReLU'(0) = slope differs on a set of measure zero)
+                uint4 pk;
+                __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) hp[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                const uint32_t t0 = ~__byte_perm(pk.x, pk.y, 0x7531) & 0x80808080u;
+                const uint32_t t1 = ~__byte_perm(pk.z, pk.w, 0x7531) & 0x80808080u;
+                const uint32_t bits = ((t0 * 0x00204081u) >> 28) | (((t1 * 0x00204081u) >> 28) << 4);
+                wmask[c >> 2] |= bits << ((c & 3) * 8);
+                *reinterpret_cast<uint4*>(po + KOFF(c)) = pk;
+              } else if (c < cbh || cbh == 0 || second_ok) {
+                mil_store8(po + KOFF(c), v);
+              }
             }
+          }
+          if (do_lrelu && mask_out != nullptr) {
+            uint32_t* pm = mask_out + go.G + qo;
+#pragma unroll
+            for (int w = 0; w < MW; ++w)
+              if (w * 4 < cbout) pm[(long long)w * go.PS] = wmask[w];
           }
         } else if (in_range) {  // pad pixel of the output map: keep the zero row / column zero
 #pragma unroll
@@ -536,7 +593,8 @@ bool mil_conv_tc_fits(const MilTcShape& sh, int wp) {
 
 int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const void* wtc, const MilTcShape& sh,
                        const float* bias, const void* res, const void* act, void* out, const MilPF8& go, int epi,
-                       int sub, cudaStream_t s, const MilPF8* gres_half, int up_row) {
+                       int sub, cudaStream_t s, const MilPF8* gres_half, int up_row, const void* mask_in,
+                       void* mask_out) {
   if (up_row >= 0)
     MIL_REQUIRE(transposed && !sub && gx.n == go.n && gx.h == (go.h - 1) / 2 + 1 && gx.w == (go.w - 1) / 2 + 1 &&
                     (res == nullptr || gres_half != nullptr) && sh.cbout == 2 * go.cb,
@@ -602,7 +660,8 @@ int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const vo
     conv_tc_kernel<MAXCB, NG, MODE><<<grid, 96 + NG * 128, smem, s>>>(                                            \
         (const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)wtc, bias, (const __nv_bfloat16*)res,                  \
         (const __nv_bfloat16*)act, (__nv_bfloat16*)out, go, sh, iss, epi, sub, halo, n_stages,                    \
-        gres_half ? *gres_half : go, gres_half ? 1 : 0, up_row + 1, up_row >= 0 ? go.cb : 0);                     \
+        gres_half ? *gres_half : go, gres_half ? 1 : 0, up_row + 1, up_row >= 0 ? go.cb : 0,                      \
+        (const uint32_t*)mask_in, (uint32_t*)mask_out);                                                           \
   } while (0)
   // the network's layers (3 / 5 / 8 / 10 output chunks, five epilogue kinds) run specialised instantiations
 #define MIL_TC_LAUNCH(MAXCB, NG)                                                                                  \

@@ -47,7 +47,12 @@ int mil_launch_pack_tc(const float* wp, void* wtc, const MilTcShape& sh, cudaStr
 bool mil_conv_tc_fits(const MilTcShape& sh, int wp);
 int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const void* wtc, const MilTcShape& sh,
                        const float* bias, const void* res, const void* act, void* out, const MilPF8& go, int epi,
-                       int sub, cudaStream_t s, const MilPF8* gres_half = nullptr, int up_row = -1);
+                       int sub, cudaStream_t s, const MilPF8* gres_half = nullptr, int up_row = -1,
+                       const void* mask_in = nullptr, void* mask_out = nullptr);
+// Sign mask of an activation map (1 bit per element: value > 0), written by the forward epilogues (mask_out) and read
+// by the data-gradient epilogues (mask_in) in place of the 16-bit activations: word w of a pixel holds chunks 4w..4w+3
+// (byte = chunk, bit = channel), words are planes of PS pixels like the chunk planes of the map itself.
+static inline size_t mil_sign_mask_bytes(const MilPF8& g) { return (size_t)((g.cb + 3) / 4) * g.PS * 4; }
 // every convolution of a pass packed in one launch, straight from the PyTorch weight layout [cout][cin][ks][ks]
 struct MilTcPackJob {
   const float* w;

@@ -139,6 +139,15 @@ int mil_make_plan(int n, int side, int dtype, MilPlan* plan) {
       pl.off_h[l * 3 + b] = take(mil_pf8_bytes(pl.g[l], dtype));
       pl.off_y[l * 3 + b] = take(mil_pf8_bytes(pl.g[l], dtype));
     }
+  // 1-bit sign masks of every saved activation map: what the data-gradient epilogues read in place of the map
+  pl.masks = dtype == MIL_BF16 && mil_tc_enabled();
+  for (int i = 0; i < 12; ++i) pl.off_mh[i] = pl.off_my[i] = 0;
+  if (pl.masks)
+    for (int l = 0; l < 4; ++l)
+      for (int b = 0; b < 3; ++b) {
+        pl.off_mh[l * 3 + b] = take(mil_sign_mask_bytes(pl.g[l]));
+        pl.off_my[l * 3 + b] = take(mil_sign_mask_bytes(pl.g[l]));
+      }
   pl.off_avg = take((size_t)n * 80 * sizeof(float));
   pl.grad_bytes = 0;
   for (int l = 0; l < 4; ++l) pl.grad_bytes = std::max(pl.grad_bytes, mil_pf8_bytes(pl.g[l], dtype));
@@ -271,11 +280,12 @@ bool mil_tc_enabled() {
 
 int mil_conv_dispatch(int dtype, int transposed, const void* x, const MilPF8& gi, const float* wp, const void* wtc,
                       const float* bias, const void* res, const void* act, void* out, const MilPF8& go, int ks,
-                      int stride, int epi, cudaStream_t s) {
+                      int stride, int epi, cudaStream_t s, const void* mask_in, void* mask_out) {
   if (wtc != nullptr && mil_tc_supported(dtype, ks, stride, gi.c, go.c) && !(stride == 2 && transposed)) {
     MilTcShape sh;
     MIL_TRY(mil_tc_shape(gi.c, go.c, ks, &sh));
-    return mil_launch_conv_tc(transposed, x, gi, wtc, sh, bias, res, act, out, go, epi, stride == 2, s);
+    return mil_launch_conv_tc(transposed, x, gi, wtc, sh, bias, res, act, out, go, epi, stride == 2, s, nullptr, -1,
+                              mask_in, mask_out);
   }
   return mil_launch_conv_direct(dtype, transposed, x, gi, wp, bias, res, act, out, go, ks, stride, epi, s);
 }
@@ -366,6 +376,8 @@ int mil_extractor_forward_impl(const void* const* params, const void* bag, int b
       const MilPF8& go = pl.g[l];
       void* h = wsp(ws, pl.off_h[l * 3 + b]);
       void* y = wsp(ws, pl.off_y[l * 3 + b]);
+      void* mh = pl.masks ? wsp(ws, pl.off_mh[l * 3 + b]) : nullptr;  // sign masks of h and y for the backward pass
+      void* my = pl.masks ? wsp(ws, pl.off_my[l * 3 + b]) : nullptr;
       const MilConvDesc& c1 = pl.convs[ci++];
       const MilConvDesc& c2 = pl.convs[ci++];
       if (c1.stride == 2 && c1.tc && !pl.s2_split[l]) {
@@ -376,7 +388,7 @@ int mil_extractor_forward_impl(const void* const* params, const void* bag, int b
         }
         MIL_TRY(mil_launch_subsample2(X, gx, wsp(ws, pl.off_xs2[l]), mil_xs2_geom(pl, l), s));
         MIL_TRY(mil_conv_dispatch(dt, 0, X, gx, wpack + c1.wp_off, TCW(c1, false), (const float*)params[c1.p_b], nullptr, nullptr,
-                                  h, go, 3, c1.stride, MIL_EPI_FWD, s));
+                                  h, go, 3, c1.stride, MIL_EPI_FWD, s, nullptr, mh));
       } else if (c1.stride == 2 && c1.tc) {
         // stride-2 block on the tensor cores: split the input into its four parity phases once; the 3x3 / stride-2
         // convolution is then a 2x2-window convolution over 4x the channels at the OUTPUT resolution
@@ -386,10 +398,10 @@ int mil_extractor_forward_impl(const void* const* params, const void* bag, int b
         MilTcShape sh;
         MIL_TRY(mil_tc_shape_s2(c1.cin, c1.cout, &sh));
         MIL_TRY(mil_launch_conv_tc(0, xs2, gs, TCW(c1, false), sh, (const float*)params[c1.p_b], nullptr, nullptr, h, go,
-                                   MIL_EPI_FWD, 0, s));
+                                   MIL_EPI_FWD, 0, s, nullptr, -1, nullptr, mh));
       } else
         MIL_TRY(mil_conv_dispatch(dt, 0, X, gx, wpack + c1.wp_off, TCW(c1, false), (const float*)params[c1.p_b], nullptr, nullptr,
-                                  h, go, 3, c1.stride, MIL_EPI_FWD, s));
+                                  h, go, 3, c1.stride, MIL_EPI_FWD, s, nullptr, c1.tc ? mh : nullptr));
       const void* res = X;
       if (b == 0 && l > 0) {
         const MilConvDesc& cd = pl.convs[ci++];
@@ -406,7 +418,7 @@ int mil_extractor_forward_impl(const void* const* params, const void* bag, int b
         res = y;
       }
       MIL_TRY(mil_conv_dispatch(dt, 0, h, go, wpack + c2.wp_off, TCW(c2, false), (const float*)params[c2.p_b], res, nullptr, y, go,
-                                3, 1, MIL_EPI_FWD, s));
+                                3, 1, MIL_EPI_FWD, s, nullptr, c2.tc ? my : nullptr));
       X = y;
       gx = go;
     }
@@ -467,13 +479,18 @@ int mil_extractor_backward_impl(const void* const* params, const float* bag, con
                                 : (l > 0 ? wsp(ws, pl.off_y[(l - 1) * 3 + 2]) : wsp(ws, pl.off_pooled));
       const MilPF8& gi = down ? pl.g[l - 1] : pl.g[l];
       const void* h = wsp(ws, pl.off_h[l * 3 + b]);
+      // sign masks: of h (this block's first activation) and of the block input (the previous block's output; the
+      // pooled stem output has none -> the activation itself is read)
+      const void* mh = pl.masks ? wsp(ws, pl.off_mh[l * 3 + b]) : nullptr;
+      const void* mx = !pl.masks ? nullptr
+                       : (b > 0 ? wsp(ws, pl.off_my[l * 3 + b - 1]) : (l > 0 ? wsp(ws, pl.off_my[(l - 1) * 3 + 2]) : nullptr));
       const size_t cb = conv_base(l, b);
       const MilConvDesc& c1 = pl.convs[cb];
       const MilConvDesc& c2 = pl.convs[cb + 1];
       // conv2: weight gradient, then data gradient through conv2 and the first LeakyReLU
       MIL_TRY(mil_wgrad_dispatch(dt, h, go, dz, go, partial, gptr(c2.p_w), gptr(c2.p_b), 3, 1, s));
       MIL_TRY(mil_conv_dispatch(dt, 1, dz, go, wpack + c2.wpt_off, TCW(c2, true), nullptr, nullptr, h, dpre, go, 3, 1,
-                                MIL_EPI_DGRAD, s));
+                                MIL_EPI_DGRAD, s, c2.tc ? mh : nullptr));
       // which 1: gradient w.r.t. the pre-activation of this block's first conv (geometry go)
       if (g_dump.dst != nullptr && g_dump.layer == l && g_dump.block == b && g_dump.which == 1)
         MIL_TRY(mil_launch_from_pf8(dt, dpre, g_dump.dst, go.n, go.c, go.h, go.w, s));
@@ -503,7 +520,7 @@ int mil_extractor_backward_impl(const void* const* params, const float* bag, con
           MIL_TRY(mil_tc_shape_s2_dgrad(c1.cout, c1.cin, a, &sh));
           MIL_TRY(mil_launch_conv_tc(1, dpre, go, wsp(ws, pl.off_wtc) + c1.wtct_s2_off[a], sh, nullptr,
                                      a == 0 ? t_sub : nullptr, xin, dnew, gi, MIL_EPI_DGRAD, 0, s,
-                                     a == 0 ? &gts : nullptr, a));
+                                     a == 0 ? &gts : nullptr, a, mx));
         }
         {
           GuardTable t;
@@ -542,7 +559,7 @@ int mil_extractor_backward_impl(const void* const* params, const float* bag, con
           MilTcShape sh;
           MIL_TRY(mil_tc_shape(gu.c, gi.c, 3, &sh));
           MIL_TRY(mil_launch_conv_tc(1, up_pre, gu, TCW(c1, true), sh, nullptr, t_sub, xin, dnew, gi, MIL_EPI_DGRAD, 0, s,
-                                     &gts));
+                                     &gts, -1, mx));
         }
         {
           GuardTable t;
@@ -578,7 +595,7 @@ int mil_extractor_backward_impl(const void* const* params, const float* bag, con
         }
       } else {
         MIL_TRY(mil_conv_dispatch(dt, 1, dpre, go, wpack + c1.wpt_off, TCW(c1, true), nullptr, dz, xin, dnew, gi, 3, 1,
-                                  MIL_EPI_DGRAD, s));
+                                  MIL_EPI_DGRAD, s, c1.tc ? mx : nullptr));
       }
       // which 0: gradient w.r.t. the pre-activation feeding this block's input (geometry gi)
       if (g_dump.dst != nullptr && g_dump.layer == l && g_dump.block == b && g_dump.which == 0)
