@@ -103,23 +103,34 @@ __device__ __forceinline__ void unpack8h(const uint4& r, float v[8]) {
   }
 }
 
-// one channel of one pooled pixel: the nine window positions in ATen's scan order (first maximum wins).  The
-// arguments are the 32-bit words (two bf16 phases each) of the four neighbouring phase-map pixels, already set to
-// -inf where a neighbour lies outside the conv map:  w?0 = phases (a=0: b=0 | b=1), w?1 = phases (a=1: b=0 | b=1)
-__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
-__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
-__device__ __forceinline__ void pool9(uint32_t ul1, uint32_t u1, uint32_t l0, uint32_t l1, uint32_t s0, uint32_t s1,
-                                      float& best, int& am) {
-  best = bf_hi(ul1); am = 0;                 // (py-1, px-1) phase (1,1)  -> window (0,0)
-  float v;
-  v = bf_lo(u1); if (v > best) { best = v; am = 1; }   // (py-1, px) phase (1,0) -> (0,1)
-  v = bf_hi(u1); if (v > best) { best = v; am = 2; }   //            phase (1,1) -> (0,2)
-  v = bf_hi(l0); if (v > best) { best = v; am = 3; }   // (py, px-1) phase (0,1) -> (1,0)
-  v = bf_lo(s0); if (v > best) { best = v; am = 4; }   // (py, px)   phase (0,0) -> (1,1)
-  v = bf_hi(s0); if (v > best) { best = v; am = 5; }   //            phase (0,1) -> (1,2)
-  v = bf_hi(l1); if (v > best) { best = v; am = 6; }   // (py, px-1) phase (1,1) -> (2,0)
-  v = bf_lo(s1); if (v > best) { best = v; am = 7; }   // (py, px)   phase (1,0) -> (2,1)
-  v = bf_hi(s1); if (v > best) { best = v; am = 8; }   //            phase (1,1) -> (2,2)
+// One pooled pixel, the nine window positions in ATen's scan order (first maximum wins).  The arguments are the
+// 16-byte chunks of the four neighbouring phase-map pixels, already set to -inf where a neighbour lies outside the conv
+// map; per channel the words are  w0 = phases (a=0: b=0 | b=1), w1 = phases (a=1: b=0 | b=1).
+// Both channels of a pair at once on packed bf16x2 words (comparisons of bf16 values are exact, so this is the same
+// arithmetic as pool9, at half the instructions): lane 0 = channel 2cp, lane 1 = channel 2cp+1.  Returns the pooled
+// pair (already in output layout) and the two window positions as (am0 | am1 << 8).
+__device__ __forceinline__ uint32_t pool9_pair(const uint4& UL, const uint4& U, const uint4& L, const uint4& S,
+                                               uint32_t& am_pair) {
+  auto lo = [](uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x5410); };  // (a.lo, b.lo)
+  auto hi = [](uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x7632); };  // (a.hi, b.hi)
+  auto as2 = [](uint32_t w) { return *reinterpret_cast<const __nv_bfloat162*>(&w); };
+  uint32_t best = hi(UL.y, UL.w), idx = 0;  // window (0,0)
+  auto step = [&](uint32_t cand, uint32_t pos) {
+    const uint32_t m = __hgt2_mask(as2(cand), as2(best));  // 0xFFFF per lane where cand > best (first maximum wins)
+    const __nv_bfloat162 mx = __hmax2(as2(cand), as2(best));
+    best = *reinterpret_cast<const uint32_t*>(&mx);
+    idx = (idx & ~m) | ((pos | (pos << 16)) & m);
+  };
+  step(lo(U.y, U.w), 1);   // (py-1, px) phase (1,0) -> (0,1)
+  step(hi(U.y, U.w), 2);   //            phase (1,1) -> (0,2)
+  step(hi(L.x, L.z), 3);   // (py, px-1) phase (0,1) -> (1,0)
+  step(lo(S.x, S.z), 4);   // (py, px)   phase (0,0) -> (1,1)
+  step(hi(S.x, S.z), 5);   //            phase (0,1) -> (1,2)
+  step(hi(L.y, L.w), 6);   // (py, px-1) phase (1,1) -> (2,0)
+  step(lo(S.y, S.w), 7);   // (py, px)   phase (1,0) -> (2,1)
+  step(hi(S.y, S.w), 8);   //            phase (1,1) -> (2,2)
+  am_pair = (idx | (idx >> 8)) & 0xFFFFu;
+  return best;
 }
 
 __global__ void __launch_bounds__(256)
@@ -137,6 +148,8 @@ stem_pool4_kernel(const __nv_bfloat16* __restrict__ cv, MilPF8 gc, int hc, __nv_
     const long long q = (long long)n * gp.P + r;
     const int py = r / gp.wp, px = r - py * gp.wp;
     float out[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    uint32_t outw[4] = {0u, 0u, 0u, 0u};  // the same chunk as packed bf16x2 words (fast path)
+    bool packed = false;
     if (py < gp.h && px < gp.w) {
       const long long qc = (long long)n * gc.P + (long long)py * gc.wp + px;
       const int ncp = pc == 2 ? 2 : 4;  // channel pairs 8, 9 only in the last chunk (channels 20..23 are padding)
@@ -157,8 +170,11 @@ stem_pool4_kernel(const __nv_bfloat16* __restrict__ cv, MilPF8 gc, int hc, __nv_
           if (!left_ok) { L.x = L.y = L.z = L.w = NINF2; }
           if (!up_ok) { U.y = U.w = NINF2; }
           if (!(up_ok && left_ok)) { UL.y = UL.w = NINF2; }
-          pool9(UL.y, U.y, L.x, L.y, S.x, S.y, best[0], am[0]);
-          pool9(UL.w, U.w, L.z, L.w, S.z, S.w, best[1], am[1]);
+          uint32_t amp;
+          outw[j] = pool9_pair(UL, U, L, S, amp);
+          pam[(size_t)j * am_stride] = (uint16_t)amp;
+          packed = true;
+          continue;
         } else {  // odd conv size, last row / column: test every window position
           float nb[2][2][8];  // [dy: py-1, py][dx: px-1, px][8 lanes = (co sub-index)*4 + a*2 + b]
           unpack8h(UL, nb[0][0]); unpack8h(U, nb[0][1]); unpack8h(L, nb[1][0]); unpack8h(S, nb[1][1]);
@@ -187,7 +203,8 @@ stem_pool4_kernel(const __nv_bfloat16* __restrict__ cv, MilPF8 gc, int hc, __nv_
         out[2 * j + 1] = best[1];
       }
     }
-    mil_store8(pooled + mil_pf8_off(gp, pc, q), out);
+    if (packed) *reinterpret_cast<uint4*>(pooled + mil_pf8_off(gp, pc, q)) = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+    else mil_store8(pooled + mil_pf8_off(gp, pc, q), out);
   }
 }
 
