@@ -54,7 +54,7 @@ struct WgCombo {
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat16* __restrict__ dz, MilPF8 gz,
                 float* __restrict__ partial, long long rec_stride, MilTcShape sh, int halo, int taps_per_group,
-                int npad, int mma_m, int dxcat, int fold, int n_stages, WgCombo cmb) {
+                int npad, int mma_m, int dxcat, int fold, int n_stages, WgCombo cmb, int lane_split) {
   extern __shared__ __align__(128) unsigned char smem[];
   WgSmemHeader* hd = reinterpret_cast<WgSmemHeader*>(smem);
   unsigned char* ones = smem + 128;            // 512 B of bf16 1.0: the B operand of the bias-gradient MMA
@@ -150,7 +150,10 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
           const int s = cmb.n ? back + cmb.shift[tap] : (dxcat ? tap * gx.wp : back + sh.t_dy[tap] * gx.wp + sh.t_dx[tap]);
           const uint32_t p0 = cmb.n ? cmb.plane0[tap] * b_pitch : 0u;
           const uint64_t bd0 = make_desc(b_base + p0 + (uint32_t)s * 16, 128, b_pitch);
-          const uint32_t d = tmem_base + tl * npad;
+          // M = 64 accumulators occupy lanes 0-15 of every lane quarter only: lane_split = h > 0 parks the taps from
+          // h on in lanes 16-31 of the same columns (TMEM holds twice as many M = 64 accumulators that way)
+          const uint32_t d = (lane_split && tl >= lane_split) ? tmem_base + (16u << 16) + (tl - lane_split) * npad
+                                                              : tmem_base + tl * npad;
           umma_bf16(d, ad0, bd0, idesc, acc0);
 #pragma unroll
           for (int kk = 1; kk < WG_TK / 16; ++kk) umma_bf16(d, ad0 + kk * 16, bd0 + kk * 16, idesc, 1u);
@@ -174,7 +177,9 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
     const int quarter = warp & 3;
     // accumulator row -> TMEM lane: M = 128: row i in lane i;  M = 64: row i in lane 32*(i/16) + i%16 (each
     // lane quarter holds 16 rows)
-    const int co = mma_m == 128 ? quarter * 32 + lane : (lane < 16 ? quarter * 16 + lane : 1 << 20);
+    const bool upper = lane >= 16;  // M = 64: second accumulator set (lane_split) or unused lanes
+    const int co = mma_m == 128 ? quarter * 32 + lane
+                                : ((!upper || lane_split) ? quarter * 16 + (lane & 15) : 1 << 20);
     const int ncp = cmb.n ? cmb.cb : nbp;  // column blocks (planes) of one tap accumulator
     const int coutp = gz.cb * 8, cinp = (cmb.n ? cmb.cb : gx.cb) * 8;
     mbar_wait(&hd->done, 0);
@@ -182,15 +187,18 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
     if ((mma_m == 128 ? quarter * 32 : quarter * 16) < coutp) {  // warp-uniform
       float* rec = partial + (size_t)blockIdx.x * rec_stride;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-      for (int tl = 0; tl < ntl; ++tl) {
+      const int ncol_taps = lane_split ? lane_split : ntl;  // accumulator column blocks to walk
+      for (int tc = 0; tc < ncol_taps; ++tc) {
+        // the tap this LANE finds in column block tc
+        const int tl = (lane_split && upper) ? lane_split + tc : tc;
         for (int p = 0; p < ncp; ++p) {
           float v[8];
-          tmem_ld8(taddr + tl * npad + p * 8, v);
+          tmem_ld8(taddr + tc * npad + p * 8, v);
           tmem_ld_wait();
           // record tap and input chunk of this column block
           const int rtap = cmb.n ? cmb.rtap[tap_lo + tl] : (dxcat ? (tap_lo + tl) * 3 + p % 3 : tap_lo + tl);
           const int c = dxcat ? p / 3 : p;
-          if (co < coutp) {
+          if (co < coutp && tl < ntl) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) rec[((size_t)rtap * cinp + c * 8 + j) * coutp + co] = v[j];
           }
@@ -200,7 +208,7 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
         float v[8];
         tmem_ld8(taddr + (fold ? nbp * 8 : ntl * npad), v);
         tmem_ld_wait();
-        if (co < coutp) rec[(size_t)ntaps * cinp * coutp + co] = v[0];
+        if (co < coutp && !(lane_split && upper)) rec[(size_t)ntaps * cinp * coutp + co] = v[0];
       }
     }
   }
@@ -395,7 +403,7 @@ static int wg_sm_count() {
 }
 
 struct WgConfig {
-  int sq, dxcat, fold, npad, groups, tpg, ctas, mma_m, n_stages;
+  int sq, dxcat, fold, npad, groups, tpg, ctas, mma_m, n_stages, lane_split;
   size_t smem;
 };
 
@@ -404,7 +412,7 @@ static WgConfig wg_config(const MilPF8& gx, const MilPF8& gz, int ks) {
   const long long n_tiles_sq = mil_cdiv(gz.Q, WG_TK);
   c.sq = (ks == 3 && 3 * gz.cb <= 16 && ((3 * gx.cb + 1) & 1) == 0 && (3 * gx.cb + 1) * 8 <= 256) ? 1 : 0;
   if (c.sq) {
-    c.dxcat = c.fold = 0;
+    c.dxcat = c.fold = c.lane_split = 0;
     c.mma_m = 128;
     c.npad = (3 * gx.cb + 1) * 8;
     c.groups = 1;
@@ -425,6 +433,13 @@ static WgConfig wg_config(const MilPF8& gx, const MilPF8& gz, int ks) {
   c.npad = c.dxcat ? (3 * gx.cb + c.fold) * 8 : (gx.c + 15) / 16 * 16;
   const int gtaps = c.dxcat ? 3 : ks * ks;
   c.groups = (gtaps * c.npad + (c.fold ? 0 : 16) <= 512) ? 1 : 2;
+  c.lane_split = 0;
+  if (c.groups == 2 && c.mma_m == 64 && c.fold && ((gtaps + 1) / 2) * c.npad <= 512) {
+    // M = 64 accumulators use half of the TMEM lanes: the second half of the taps goes to lanes 16-31 of the same
+    // columns, and ONE CTA group covers all taps (no second group re-fetching every tile)
+    c.groups = 1;
+    c.lane_split = (gtaps + 1) / 2;
+  }
   c.tpg = (gtaps + c.groups - 1) / c.groups;
   const long long n_tiles = mil_cdiv(gz.Q, WG_TK);
   c.ctas = (int)std::max<long long>(1, std::min<long long>(n_tiles, wg_sm_count() / c.groups));
@@ -475,7 +490,7 @@ int mil_launch_wgrad_tc_partials(const void* x, const MilPF8& gx, const void* dz
   const long long rec = (long long)sh.ntaps * gx.cb * 8 * gz.cb * 8 + gz.cb * 8;
   wgrad_tc_kernel<<<dim3(c.ctas, c.groups), WG_THREADS, c.smem, s>>>(
       (const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)dz, gz, partial, rec, sh, halo, c.tpg, c.npad, c.mma_m, c.dxcat,
-      c.fold, c.n_stages, WgCombo{});
+      c.fold, c.n_stages, WgCombo{}, c.lane_split);
   MIL_LAUNCH_OK();
   *ctas_out = c.ctas;
   *rec_out = rec;
@@ -520,7 +535,7 @@ int mil_launch_wgrad_tc_s2(const void* xs2, const MilPF8& gs, const void* dz, co
   MIL_SET_SMEM((wgrad_tc_kernel), (int)smem);
   const long long rec = (long long)9 * cb * 8 * gz.cb * 8 + gz.cb * 8;
   wgrad_tc_kernel<<<dim3(ctas, groups), WG_THREADS, smem, s>>>((const __nv_bfloat16*)xs2, gs, (const __nv_bfloat16*)dz, gz,
-                                                              partial, rec, sh, halo, tpg, npad, mma_m, 0, 0, n_stages, cmb);
+                                                              partial, rec, sh, halo, tpg, npad, mma_m, 0, 0, n_stages, cmb, 0);
   MIL_LAUNCH_OK();
   return mil_launch_reduce_conv_w(partial, ctas, rec, dw, db, gz.c, cin, 3, s);
 }
