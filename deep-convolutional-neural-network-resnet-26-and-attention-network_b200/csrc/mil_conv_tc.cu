@@ -107,13 +107,6 @@ struct TcSmemHeader {
   alignas(16) float bias[96];
 };
 
-// per-MMA descriptor templates, precomputed on the host and passed as kernel parameters so that the issuing
-// warp reads them through the uniform datapath (constant bank): A relative to the start of an A stage, B
-// relative to the start of the weight block
-struct TcIssue {
-  uint64_t a_desc[MIL_TC_MAX_MMA];
-  uint64_t b_desc[MIL_TC_MAX_MMA];
-};
 
 __device__ __forceinline__ uint4 ld_nc16(const __nv_bfloat16* p) {
   return __ldg(reinterpret_cast<const uint4*>(p));
@@ -591,6 +584,30 @@ bool mil_conv_tc_fits(const MilTcShape& sh, int wp) {
   return tc_smem_bytes(mil_tc_halo(sh, wp), sh, ng) <= 227 * 1024;
 }
 
+int mil_tc_build_issue(const MilTcShape& sh, int wp, int halo, int transposed, TcIssue* out) {
+  TcIssue& iss = *out;
+  const int plane = (TC_M + 2 * halo) * 16;
+  for (int j = 0; j < sh.nmma; ++j) {
+    int off[2];
+    for (int h = 0; h < 2; ++h) {
+      const int tap = sh.g_tap[2 * j + h], chunk = sh.g_chunk[2 * j + h];
+      if (tap == 0xFF) {
+        off[h] = -1;
+      } else {
+        int sft = sh.t_dy[tap] * wp + sh.t_dx[tap];  // forward reads x(q + s); the data gradient reads dz(q - s)
+        if (transposed) sft = -sft;
+        off[h] = chunk * plane + (halo + sft) * 16;
+      }
+    }
+    if (off[1] < 0) off[1] = sh.cbin * plane + halo * 16;  // dummy half -> the all-zero plane
+    MIL_REQUIRE(off[1] > off[0], "conv_tc: internal error, K-halves out of order");
+    iss.a_desc[j] = make_desc_bits((uint32_t)off[0], (uint32_t)(off[1] - off[0]), 128);
+    iss.b_desc[j] = make_desc_bits((uint32_t)j * 2 * sh.npad * 16, (uint32_t)sh.npad * 16, 128);
+  }
+  for (int j = sh.nmma; j < MIL_TC_MAX_MMA; ++j) iss.a_desc[j] = iss.b_desc[j] = 0;
+  return 0;
+}
+
 int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const void* wtc, const MilTcShape& sh,
                        const float* bias, const void* res, const void* act, void* out, const MilPF8& go, int epi,
                        int sub, cudaStream_t s, const MilPF8* gres_half, int up_row, const void* mask_in,
@@ -631,27 +648,7 @@ int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const vo
     MIL_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   }
   TcIssue iss;
-  {
-    const int plane = (TC_M + 2 * halo) * 16;
-    for (int j = 0; j < sh.nmma; ++j) {
-      int off[2];
-      for (int h = 0; h < 2; ++h) {
-        const int tap = sh.g_tap[2 * j + h], chunk = sh.g_chunk[2 * j + h];
-        if (tap == 0xFF) {
-          off[h] = -1;
-        } else {
-          int sft = sh.t_dy[tap] * gx.wp + sh.t_dx[tap];  // forward reads x(q + s); the data gradient reads dz(q - s)
-          if (transposed) sft = -sft;
-          off[h] = chunk * plane + (halo + sft) * 16;
-        }
-      }
-      if (off[1] < 0) off[1] = sh.cbin * plane + halo * 16;  // dummy half -> the all-zero plane
-      MIL_REQUIRE(off[1] > off[0], "conv_tc: internal error, K-halves out of order");
-      iss.a_desc[j] = make_desc_bits((uint32_t)off[0], (uint32_t)(off[1] - off[0]), 128);
-      iss.b_desc[j] = make_desc_bits((uint32_t)j * 2 * sh.npad * 16, (uint32_t)sh.npad * 16, 128);
-    }
-    for (int j = sh.nmma; j < MIL_TC_MAX_MMA; ++j) iss.a_desc[j] = iss.b_desc[j] = 0;
-  }
+  MIL_TRY(mil_tc_build_issue(sh, gx.wp, halo, transposed, &iss));
   const long long n_tiles = mil_cdiv(gx.Q, TC_M);
   const int grid = (int)std::min<long long>(n_tiles, n_sm);
 #define MIL_TC_LAUNCH1(MAXCB, NG, MODE)                                                                           \

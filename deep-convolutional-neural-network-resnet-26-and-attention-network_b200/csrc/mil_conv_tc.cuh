@@ -28,6 +28,15 @@ static inline int mil_tc_halo(const MilTcShape& sh, int wp) {
   return m;
 }
 
+// per-MMA descriptor templates, precomputed on the host and passed as kernel parameters so that the issuing
+// warp reads them through the uniform datapath (constant bank): A relative to the start of an A stage, B
+// relative to the start of the weight block (M-tile = 128 pixels, planes of 128 + 2 * halo pixels)
+struct TcIssue {
+  uint64_t a_desc[MIL_TC_MAX_MMA];
+  uint64_t b_desc[MIL_TC_MAX_MMA];
+};
+int mil_tc_build_issue(const MilTcShape& sh, int wp, int halo, int transposed, TcIssue* out);
+
 bool mil_tc_supported(int dtype, int ks, int stride, int cin, int cout);
 int mil_tc_shape(int cin, int cout, int ks, MilTcShape* out);  // cin/cout = the KERNEL's input/output channels
 // 3x3 / stride-2 convolution on the PHASE-SPLIT input (mil_launch_split2: 4 * cb chunk planes at the output
@@ -80,14 +89,21 @@ int mil_launch_wgrad_tc(const void* x, const MilPF8& gx, const void* dz, const M
 int mil_launch_wgrad_tc_s2(const void* xs2, const MilPF8& gs, const void* dz, const MilPF8& gz, float* partial, float* dw,
                            float* db, int cin, cudaStream_t s);
 
+// stem convolution with the max-pool fused into its epilogue (mil_stem_pool.cu): xs -> pooled map + arg-max (+ sign
+// mask); supported for even conv-map sizes and padded rows of at most 127 pixels
+bool mil_stem_conv_pool_supported(const MilPF8& gp, int hc);
+int mil_launch_stem_conv_pool(const void* xs, const MilPF8& gi, const void* wtc, const float* bias4, void* pooled,
+                              const MilPF8& gp, uint16_t* argmax, void* mask_out, int hc, cudaStream_t s);
+
 // stem on the tensor cores (mil_stem_tc.cu)
 MilPF8 mil_stem_tc_geom_in(int n, int side);    // space-to-depth input: 12 channels, conv-output resolution, pad 2
 MilPF8 mil_stem_tc_geom_conv(int n, int side);  // conv1 output: 20 channels, pad 2
 size_t mil_stem_tc_wpack_floats();
 size_t mil_stem_tc_wtc_bytes();
 size_t mil_stem_tc_partial_floats(int n, int side);
+bool mil_stem_tc_fused_pool(const MilPF8& gp, int side);
 int mil_launch_stem_tc_fwd(const void* x, int x_u8, const int* idx, int n, int side, const float* w, const float* b, void* xs,
                            void* convout, float* wp, void* wtc, void* pooled, const MilPF8& gp, uint8_t* argmax,
-                           cudaStream_t s);
+                           cudaStream_t s, void* pooled_mask = nullptr);
 int mil_launch_stem_tc_bwd(const void* xs, int n, int side, const void* g, const MilPF8& gp, const uint8_t* argmax,
                            void* dy, float* partial, float* dw, float* db, cudaStream_t s);

@@ -148,6 +148,9 @@ int mil_make_plan(int n, int side, int dtype, MilPlan* plan) {
         pl.off_mh[l * 3 + b] = take(mil_sign_mask_bytes(pl.g[l]));
         pl.off_my[l * 3 + b] = take(mil_sign_mask_bytes(pl.g[l]));
       }
+  pl.off_mpool = 0;
+  pl.pool_mask = pl.masks && mil_stem_tc_fused_pool(pl.g[0], side);
+  if (pl.pool_mask) pl.off_mpool = take(mil_sign_mask_bytes(pl.g[0]));
   pl.off_avg = take((size_t)n * 80 * sizeof(float));
   pl.grad_bytes = 0;
   for (int l = 0; l < 4; ++l) pl.grad_bytes = std::max(pl.grad_bytes, mil_pf8_bytes(pl.g[l], dtype));
@@ -363,7 +366,7 @@ int mil_extractor_forward_impl(const void* const* params, const void* bag, int b
     MIL_TRY(mil_launch_stem_tc_fwd(bag, bag_u8, idx, pl.n, pl.side, (const float*)params[p_c1w], (const float*)params[p_c1b],
                                    wsp(ws, pl.off_xs), wsp(ws, pl.off_cv), (float*)wsp(ws, pl.off_stem_wp),
                                    wsp(ws, pl.off_stem_wtc), wsp(ws, pl.off_pooled), pl.g[0],
-                                   (uint8_t*)wsp(ws, pl.off_argmax), s));
+                                   (uint8_t*)wsp(ws, pl.off_argmax), s, pl.pool_mask ? wsp(ws, pl.off_mpool) : nullptr));
   else
     MIL_TRY(mil_launch_stem_fwd(dt, (const float*)bag, idx, pl.n, pl.side, (const float*)params[p_c1w],
                                 (const float*)params[p_c1b], wsp(ws, pl.off_pooled), pl.g[0],
@@ -483,7 +486,9 @@ int mil_extractor_backward_impl(const void* const* params, const float* bag, con
       // pooled stem output has none -> the activation itself is read)
       const void* mh = pl.masks ? wsp(ws, pl.off_mh[l * 3 + b]) : nullptr;
       const void* mx = !pl.masks ? nullptr
-                       : (b > 0 ? wsp(ws, pl.off_my[l * 3 + b - 1]) : (l > 0 ? wsp(ws, pl.off_my[(l - 1) * 3 + 2]) : nullptr));
+                       : (b > 0 ? wsp(ws, pl.off_my[l * 3 + b - 1])
+                                : (l > 0 ? wsp(ws, pl.off_my[(l - 1) * 3 + 2])
+                                         : (pl.pool_mask ? wsp(ws, pl.off_mpool) : nullptr)));
       const size_t cb = conv_base(l, b);
       const MilConvDesc& c1 = pl.convs[cb];
       const MilConvDesc& c2 = pl.convs[cb + 1];

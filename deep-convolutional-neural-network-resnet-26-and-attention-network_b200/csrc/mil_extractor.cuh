@@ -47,9 +47,10 @@ struct MilPlan {
   MilGeom geo;
   MilPF8 g[4];                  // activation geometry of layer1..4
   std::vector<MilConvDesc> convs;  // 27 entries, forward order
-  size_t off_pooled, off_argmax, off_h[12], off_y[12], off_avg, off_grad[3], off_up[2], off_xs2[4], off_mh[12], off_my[12], off_wpack, off_wtc, off_partial;
+  size_t off_pooled, off_argmax, off_h[12], off_y[12], off_avg, off_grad[3], off_up[2], off_xs2[4], off_mh[12], off_my[12], off_mpool, off_wpack, off_wtc, off_partial;
   bool stem_tc;                 // stem on the tensor cores (bf16 mode)
   size_t off_xs, off_cv, off_stem_wp, off_stem_wtc;
+  bool pool_mask;    // the fused stem kernel also writes the sign mask of the pooled map (off_mpool)
   bool masks;        // sign masks of the saved activations exist (bf16 tensor-core path): off_mh / off_my
   bool s2_split[4];  // stride-2 block of layer l runs on the phase-split input (else: full-resolution evaluation)
   size_t wpack_floats, wtc_bytes, partial_floats, grad_bytes, up_bytes;

@@ -16,6 +16,7 @@
 //   backward: unpool (pooled gradient -> the 4-phase conv gradient through the arg-max, as a gather => deterministic)
 //             ->  wgrad_tc (9 taps, 48 x 80)  ->  fixed-order reduction + fold back into the [20][3][7][7] layout
 #include <algorithm>
+#include <cstdlib>
 
 #include "mil_common.cuh"
 #include "mil_conv_tc.cuh"
@@ -340,9 +341,19 @@ size_t mil_stem_tc_partial_floats(int n, int side) {
 
 static int grid_for(long long work) { return (int)std::max<long long>(1, std::min<long long>(mil_cdiv(work, 256), 148 * 16)); }
 
+// true when the forward pass runs the fused conv + pool kernel (which also writes the pooled map's sign mask);
+// MIL_B200_STEM_UNFUSED=1 forces the two-kernel path
+bool mil_stem_tc_fused_pool(const MilPF8& gp, int side) {
+  static const bool unfused = [] {
+    const char* e = getenv("MIL_B200_STEM_UNFUSED");
+    return e != nullptr && e[0] == '1';
+  }();
+  return !unfused && mil_stem_conv_pool_supported(gp, (side - 1) / 2 + 1);
+}
+
 int mil_launch_stem_tc_fwd(const void* x, int x_u8, const int* idx, int n, int side, const float* w, const float* b, void* xs,
                            void* convout, float* wp, void* wtc, void* pooled, const MilPF8& gp, uint8_t* argmax8,
-                           cudaStream_t s) {
+                           cudaStream_t s, void* pooled_mask) {
   uint16_t* argmax = reinterpret_cast<uint16_t*>(argmax8);  // [tile][10 channel pairs][h0*w0] (same 20 B per pixel)
   const MilPF8 gi = mil_stem_tc_geom_in(n, side), gc = mil_stem_tc_geom_conv(n, side);
   const int hc = (side - 1) / 2 + 1;
@@ -358,6 +369,8 @@ int mil_launch_stem_tc_fwd(const void* x, int x_u8, const int* idx, int n, int s
   MilTcShape sh;
   MIL_TRY(mil_tc_shape(STC_CI, STC_CO4, 3, &sh));
   MIL_TRY(mil_launch_pack_tc(wp, wtc, sh, s));
+  if (mil_stem_tc_fused_pool(gp, side))  // conv + pool in one kernel: the conv map never reaches HBM
+    return mil_launch_stem_conv_pool(xs, gi, wtc, bias4, pooled, gp, argmax, pooled_mask, hc, s);
   MIL_TRY(mil_launch_conv_tc(0, xs, gi, wtc, sh, bias4, nullptr, nullptr, convout, gc, MIL_EPI_FWD, 0, s));
   stem_pool4_kernel<<<dim3(gp.n, (unsigned)mil_cdiv(gp.P, 256), 3), 256, 0, s>>>((const __nv_bfloat16*)convout, gc, hc, (__nv_bfloat16*)pooled,
                                                         gp, argmax);
