@@ -85,6 +85,9 @@ int mil_launch_wgrad_tc_partials(const void* x, const MilPF8& gx, const void* dz
 int mil_launch_wgrad_tc(const void* x, const MilPF8& gx, const void* dz, const MilPF8& gz, float* partial, float* dw,
                         float* db, int ks, cudaStream_t s);
 
+// stem backward with the unpool fused into the A-operand construction (see mil_wgrad_tc.cu)
+int mil_launch_wgrad_tc_unpool(const void* x, const MilPF8& gx, const MilPF8& gz, const void* g, const MilPF8& gp,
+                               const uint16_t* argmax, float* partial, int* ctas_out, long long* rec_out, cudaStream_t s);
 // 3x3 / stride-2 convolution: x given as its phase-split copy xs2 (4 * cb planes), dz at the output resolution
 int mil_launch_wgrad_tc_s2(const void* xs2, const MilPF8& gs, const void* dz, const MilPF8& gz, float* partial, float* dw,
                            float* db, int cin, cudaStream_t s);

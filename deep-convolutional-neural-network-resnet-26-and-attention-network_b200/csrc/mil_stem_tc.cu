@@ -383,12 +383,22 @@ int mil_launch_stem_tc_bwd(const void* xs, int n, int side, const void* g, const
   const uint16_t* argmax = reinterpret_cast<const uint16_t*>(argmax8);
   const MilPF8 gi = mil_stem_tc_geom_in(n, side), gc = mil_stem_tc_geom_conv(n, side);
   const int hc = (side - 1) / 2 + 1;
-  stem_unpool4_kernel<<<dim3(gc.n, (unsigned)mil_cdiv(gc.P, 256), 3), 256, 0, s>>>((const __nv_bfloat16*)g, gp, argmax, (__nv_bfloat16*)dy, gc,
-                                                          hc);
-  MIL_LAUNCH_OK();
   int ctas;
   long long rec;
-  MIL_TRY(mil_launch_wgrad_tc_partials(xs, gi, dy, gc, partial, 3, &ctas, &rec, s));
+  static const bool unfused = [] {
+    const char* e = getenv("MIL_B200_STEM_UNFUSED");
+    return e != nullptr && e[0] == '1';
+  }();
+  if (!unfused) {
+    // the un-pooled gradient (80 channels at the phase-map resolution, the largest tensor of the backward pass) is
+    // built inside the weight-gradient kernel, tile by tile, straight into its A-operand planes
+    MIL_TRY(mil_launch_wgrad_tc_unpool(xs, gi, gc, g, gp, argmax, partial, &ctas, &rec, s));
+  } else {
+    stem_unpool4_kernel<<<dim3(gc.n, (unsigned)mil_cdiv(gc.P, 256), 3), 256, 0, s>>>((const __nv_bfloat16*)g, gp, argmax,
+                                                                                   (__nv_bfloat16*)dy, gc, hc);
+    MIL_LAUNCH_OK();
+    MIL_TRY(mil_launch_wgrad_tc_partials(xs, gi, dy, gc, partial, 3, &ctas, &rec, s));
+  }
   stem_reduce4_kernel<<<(int)mil_cdiv(STC_CO * 147 + STC_CO, 32), dim3(32, SR4_PARTS), 0, s>>>(partial, ctas, rec, dw, db);
   MIL_LAUNCH_OK();
   return 0;
