@@ -179,7 +179,8 @@ int mil_make_plan(int n, int side, int dtype, MilPlan* plan) {
   pl.off_xs = pl.off_cv = pl.off_stem_wp = pl.off_stem_wtc = 0;
   if (pl.stem_tc) {
     pl.off_xs = take(mil_pf8_bytes(mil_stem_tc_geom_in(n, side), dtype));
-    pl.off_cv = take(mil_pf8_bytes(mil_stem_tc_geom_conv(n, side), dtype));
+    // the 80-channel conv map exists in HBM only on the un-fused stem path (odd conv size, MIL_B200_STEM_UNFUSED=1)
+    if (!mil_stem_tc_fused_pool(pl.g[0], side)) pl.off_cv = take(mil_pf8_bytes(mil_stem_tc_geom_conv(n, side), dtype));
     pl.off_stem_wp = take(mil_stem_tc_wpack_floats() * sizeof(float));
     pl.off_stem_wtc = take(mil_stem_tc_wtc_bytes());
   }
@@ -344,7 +345,7 @@ int mil_extractor_forward_impl(const void* const* params, const void* bag, int b
     guard_add(t, wsp(ws, pl.off_pooled), pl.g[0]);
     if (pl.stem_tc) {
       guard_add(t, wsp(ws, pl.off_xs), mil_stem_tc_geom_in(pl.n, pl.side));
-      guard_add(t, wsp(ws, pl.off_cv), mil_stem_tc_geom_conv(pl.n, pl.side));
+      if (!mil_stem_tc_fused_pool(pl.g[0], pl.side)) guard_add(t, wsp(ws, pl.off_cv), mil_stem_tc_geom_conv(pl.n, pl.side));
     }
     for (int l = 0; l < 4; ++l)
       for (int b = 0; b < 3; ++b) {
