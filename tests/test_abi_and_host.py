@@ -176,3 +176,52 @@ def test_bag_group_over_gloo_world_size_2(tmp_path, mil):
         if all(f"rank {r} ok" in o for r, o in enumerate(outs)):
             return
     raise AssertionError("\n".join(outs))
+
+
+def test_dla_writer_and_export_refuse_cpu(tmp_path, mil):
+    """SURVEY 8f N3 host side: `col row weight` lines like the reference's write_map (gbm/classify.py:211), and the
+    device-side scaling has no CPU fallback."""
+    raster = np.array([[0, 300], [300, 0], [600, 900]])
+    path = str(tmp_path / "m.dla")
+    mil.write_dla(path, raster, [0.25, 0.5, 1.0])
+    rows = np.loadtxt(path)
+    assert rows.tolist() == [[300.0, 0.0, 0.25], [0.0, 300.0, 0.5], [900.0, 600.0, 1.0]]
+    with pytest.raises(ValueError):
+        mil.write_dla(path, raster, [1.0, 2.0])
+    with pytest.raises(RuntimeError):
+        mil.minmax_normalize(torch.rand(3, 5))
+    with pytest.raises(RuntimeError):
+        mil.flatten_parameters(mil.Attention(n_classes=3))      # CPU module: no CPU fallback for the fused optimizer
+
+
+def test_sharded_subsample_bookkeeping(mil):
+    """BagGroup.subsample over a 3-rank bag without a process group (the shard sizes are injected): every rank
+    draws the same permutation, keeps the indices of its shard, and ALL ranks raise when some shard gets none."""
+    sizes = [30, 50, 20]
+    picks = []
+    for rank in range(3):
+        g = mil.BagGroup()
+        g.world, g.rank = 3, rank
+        g._gen = torch.Generator().manual_seed(5)
+        g._sizes = {sizes[rank]: sizes}
+        idx = g.subsample(sizes[rank], 0.2)
+        assert g.total(int(idx.numel())) == 20
+        assert int(idx.min()) >= 0 and int(idx.max()) < sizes[rank]
+        picks.append(idx + sum(sizes[:rank]))
+    allp = torch.cat(picks)
+    assert allp.numel() == 20 and allp.unique().numel() == 20
+    ref = torch.randperm(100, generator=torch.Generator().manual_seed(5))[:20]
+    assert sorted(allp.tolist()) == sorted(ref.tolist())
+    sizes = [3, 3, 3]
+    errs = 0
+    for rank in range(3):
+        g = mil.BagGroup()
+        g.world, g.rank = 3, rank
+        g._gen = torch.Generator().manual_seed(1)
+        g._sizes = {3: sizes}
+        try:
+            g.subsample(3, 0.2)                                   # one tile for three ranks
+        except ValueError as e:
+            errs += 1
+            assert "without a tile" in str(e)
+    assert errs == 3
