@@ -27,6 +27,8 @@ PROTOTYPES = {
     "mil_param_shape": (c_int, [c_int, C.POINTER(c_int), C.POINTER(c_ll)]),
     "mil_param_offset": (c_ll, [c_int]),
     "mil_param_total": (c_ll, []),
+    "mil_set_option": (c_int, [c_char_p, c_int]),
+    "mil_get_option": (c_int, [c_char_p, C.POINTER(c_int)]),
     "mil_extractor_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "mil_extractor_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t,
                                       c_void_p, c_void_p]),
@@ -115,3 +117,14 @@ def param_table():
         out.append((lib.mil_param_name(i).decode(), tuple(int(shp[k]) for k in range(nd.value)),
                     int(lib.mil_param_offset(i))))
     return out
+
+
+def set_option(name: str, value: int) -> None:
+    """Runtime switch of the library (include/mil_b200.h: "disable_tc", "stem_unfused", ...)."""
+    check(load().mil_set_option(name.encode(), int(value)), "mil_set_option")
+
+
+def get_option(name: str) -> int:
+    v = c_int(0)
+    check(load().mil_get_option(name.encode(), C.byref(v)), "mil_get_option")
+    return int(v.value)

@@ -110,6 +110,12 @@ long long mil_param_total(void) {
   return t.back().offset + t.back().numel;
 }
 
+int mil_set_option(const char* name, int value) { return mil_opt_set(name, value); }
+int mil_get_option(const char* name, int* value) {
+  MIL_REQUIRE(value != nullptr, "mil_get_option: null pointer argument");
+  return mil_opt_get(name, value);
+}
+
 // ---- extractor ---------------------------------------------------------------------------------------
 size_t mil_extractor_workspace_bytes(int n_tiles, int side, int dtype) {
   try {

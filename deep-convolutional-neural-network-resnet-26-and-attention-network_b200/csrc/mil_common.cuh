@@ -58,6 +58,17 @@ void mil_count_launch();
     if (_rc != 0) return _rc; \
   } while (0)
 
+// ---- runtime switches (mil_set_option / mil_get_option of the C ABI; the environment variables of the same
+// meaning -- MIL_B200_DISABLE_TC, MIL_B200_STEM_UNFUSED, ... -- only give the initial values) -------------------
+enum MilOpt {
+  MIL_OPT_DISABLE_TC = 0,    // 1: CUDA-core kernels only (cross-check of the tcgen05 path, same rounding points)
+  MIL_OPT_STEM_UNFUSED = 1,  // 1: stem as separate conv / pool / unpool / wgrad kernels (cross-check of the fused ones)
+  MIL_OPT_COUNT
+};
+int mil_opt(int id);
+int mil_opt_set(const char* name, int value);  // 0 = ok
+int mil_opt_get(const char* name, int* value);
+
 __host__ __device__ static inline long long mil_cdiv(long long a, long long b) { return (a + b - 1) / b; }
 __host__ __device__ static inline long long mil_rup(long long a, long long b) { return mil_cdiv(a, b) * b; }
 static inline size_t mil_esize(int dtype) { return dtype == MIL_BF16 ? 2 : 4; }
@@ -121,6 +132,16 @@ __device__ __forceinline__ void mil_store8(__nv_bfloat16* p, const float v[8]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
   *reinterpret_cast<uint4*>(p) = r;
+}
+// bit j = (bf16 value j of the chunk > 0): the sign-mask byte of one 8-channel chunk
+__device__ __forceinline__ uint32_t mil_positive_bits(const uint4& pk) {
+  const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+  const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&pk);
+  const uint32_t m0 = __hgt2_mask(hp[0], z), m1 = __hgt2_mask(hp[1], z), m2 = __hgt2_mask(hp[2], z),
+                 m3 = __hgt2_mask(hp[3], z);
+  const uint32_t t0 = __byte_perm(m0, m1, 0x7531) & 0x80808080u;
+  const uint32_t t1 = __byte_perm(m2, m3, 0x7531) & 0x80808080u;
+  return ((t0 * 0x00204081u) >> 28) | (((t1 * 0x00204081u) >> 28) << 4);
 }
 __device__ __forceinline__ float mil_to_float(float v) { return v; }
 __device__ __forceinline__ float mil_to_float(__nv_bfloat16 v) { return __bfloat162float(v); }

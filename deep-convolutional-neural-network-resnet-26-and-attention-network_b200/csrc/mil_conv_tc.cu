@@ -394,16 +394,15 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
                   if (!(av[j] > 0.f)) v[j] *= MIL_SLOPE;
               }
               if (do_lrelu && mask_out != nullptr) {
-                // pack here (not in mil_store8) and lift the eight sign bits out of the packed words: the top bytes
-                // of values 0..3 / 4..7 gathered by one PRMT each, "sign clear" flags compressed by one multiply.
-                // (+0 counts as positive; the reference's LeakyReLU'(0) = slope differs on a set of measure zero)
+                // pack here (not in mil_store8) and derive the eight "value > 0" bits from the packed words: one packed
+                // compare per word (0xFFFF per positive half; an activation of exactly 0 -- every pixel of an all-zero
+                // tile at zero bias, RoiBuilder.py:234-236 -- is NOT positive, LeakyReLU'(0) = slope as in ATen), the
+                // top bytes of the four masks gathered by one PRMT per pair, compressed by one multiply.
                 uint4 pk;
                 __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) hp[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-                const uint32_t t0 = ~__byte_perm(pk.x, pk.y, 0x7531) & 0x80808080u;
-                const uint32_t t1 = ~__byte_perm(pk.z, pk.w, 0x7531) & 0x80808080u;
-                const uint32_t bits = ((t0 * 0x00204081u) >> 28) | (((t1 * 0x00204081u) >> 28) << 4);
+                const uint32_t bits = mil_positive_bits(pk);
                 wmask[c >> 2] |= bits << ((c & 3) * 8);
                 *reinterpret_cast<uint4*>(po + KOFF(c)) = pk;
               } else if (c < cbh || cbh == 0 || second_ok) {

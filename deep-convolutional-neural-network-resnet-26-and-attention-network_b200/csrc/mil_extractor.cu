@@ -2,6 +2,7 @@
 // nnBlocks.py:157-189): parameter table, workspace plan, forward and backward launch sequences.
 // Everything is enqueued on the caller's stream; nothing is allocated here (the caller owns the workspace).
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 
@@ -211,6 +212,7 @@ struct PackTable {
   short cout[MIL_MAX_PACK], cin[MIL_MAX_PACK];
   unsigned char ks[MIL_MAX_PACK], transposed[MIL_MAX_PACK];
   int count;
+  int round_bf16;  // bf16 mode: the CUDA-core kernels multiply with bf16-rounded weights, like the tensor-core path
 };
 __global__ void pack_all_kernel(PackTable t) {
   const int e = blockIdx.x;
@@ -223,7 +225,9 @@ __global__ void pack_all_kernel(PackTable t) {
   for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < total; i += gridDim.y * blockDim.x) {
     const int b = i % B, a = (i / B) % A, tp = i / (A * B);
     const int co = tr ? a : b, ci = tr ? b : a;
-    wp[i] = (co < cout && ci < cin) ? w[((size_t)co * cin + ci) * taps + tp] : 0.f;
+    float v = (co < cout && ci < cin) ? w[((size_t)co * cin + ci) * taps + tp] : 0.f;
+    if (t.round_bf16) v = __bfloat162float(__float2bfloat16_rn(v));
+    wp[i] = v;
   }
 }
 
@@ -274,13 +278,43 @@ int mil_wgrad_dispatch(int dtype, const void* x, const MilPF8& gi, const void* d
   return mil_launch_wgrad_direct(dtype, x, gi, dz, go, partial, dw, db, ks, stride, s);
 }
 
-bool mil_tc_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("MIL_B200_DISABLE_TC");
-    return !(e != nullptr && e[0] == '1');
+// runtime switches: initial value from the environment, changed through mil_set_option (tests flip them to run the
+// same bag through the tcgen05 and the CUDA-core kernels, the fused and the un-fused stem)
+static const char* const kOptNames[MIL_OPT_COUNT] = {"disable_tc", "stem_unfused"};
+static const char* const kOptEnv[MIL_OPT_COUNT] = {"MIL_B200_DISABLE_TC", "MIL_B200_STEM_UNFUSED"};
+static std::atomic<int>* opt_slots() {
+  static std::atomic<int> v[MIL_OPT_COUNT];
+  static const bool init = [] {
+    for (int i = 0; i < MIL_OPT_COUNT; ++i) {
+      const char* e = getenv(kOptEnv[i]);
+      v[i].store(e != nullptr ? atoi(e) : 0);
+    }
+    return true;
   }();
-  return on;
+  (void)init;
+  return v;
 }
+int mil_opt(int id) { return opt_slots()[id].load(std::memory_order_relaxed); }
+int mil_opt_set(const char* name, int value) {
+  for (int i = 0; i < MIL_OPT_COUNT; ++i)
+    if (name != nullptr && strcmp(name, kOptNames[i]) == 0) {
+      opt_slots()[i].store(value);
+      return 0;
+    }
+  mil_set_error("mil_set_option: unknown option '%s'", name ? name : "(null)");
+  return 2;
+}
+int mil_opt_get(const char* name, int* value) {
+  for (int i = 0; i < MIL_OPT_COUNT; ++i)
+    if (name != nullptr && strcmp(name, kOptNames[i]) == 0) {
+      *value = mil_opt(i);
+      return 0;
+    }
+  mil_set_error("mil_get_option: unknown option '%s'", name ? name : "(null)");
+  return 2;
+}
+
+bool mil_tc_enabled() { return mil_opt(MIL_OPT_DISABLE_TC) == 0; }
 
 int mil_conv_dispatch(int dtype, int transposed, const void* x, const MilPF8& gi, const float* wp, const void* wtc,
                       const float* bias, const void* res, const void* act, void* out, const MilPF8& go, int ks,
@@ -302,6 +336,7 @@ static inline char* wsp(void* ws, size_t off) { return reinterpret_cast<char*>(w
 static int pack_weights(const void* const* params, const MilPlan& pl, void* ws, bool transposed, cudaStream_t s) {
   PackTable t;
   t.count = 0;
+  t.round_bf16 = pl.dtype == MIL_BF16 ? 1 : 0;
   float* area = reinterpret_cast<float*>(wsp(ws, pl.off_wpack));
   for (const auto& c : pl.convs) {
     if (c.tc) continue;  // the tensor-core convolutions pack straight into their operand blocks below

@@ -18,6 +18,13 @@
 #define STEM_TI 39   // input tile side = 2*(TC-1)+7
 #define STEM_TIW 40  // padded row length in shared memory
 
+// bf16 mode: these kernels are the cross-check of the tensor-core stem (mil_stem_tc.cu), so they round where it rounds
+// -- the input tile, the weights and the conv map go through bf16 -- and differ from it by summation order only
+template <typename T> __device__ __forceinline__ float stem_round(float v) { return v; }
+template <> __device__ __forceinline__ float stem_round<__nv_bfloat16>(float v) {
+  return __bfloat162float(__float2bfloat16_rn(v));
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 stem_fwd_kernel(const float* __restrict__ x, const int* __restrict__ idx, int side, int hc, const float* __restrict__ w,
@@ -37,12 +44,12 @@ stem_fwd_kernel(const float* __restrict__ x, const int* __restrict__ idx, int si
     const int gy = iy0 + yy, gx = ix0 + xx;
     float v = 0.f;
     if (xx < STEM_TI && gy >= 0 && gy < side && gx >= 0 && gx < side) v = xin[((size_t)c * side + gy) * side + gx];
-    s_in[i] = v;
+    s_in[i] = stem_round<T>(v);
   }
   // weights: PyTorch [20][3][7][7] -> s_w[k][co]
   for (int i = threadIdx.x; i < STEM_K * STEM_CO; i += blockDim.x) {
     const int co = i % STEM_CO, k = i / STEM_CO;
-    s_w[i] = w[co * STEM_K + k];
+    s_w[i] = stem_round<T>(w[co * STEM_K + k]);
   }
   __syncthreads();
   // conv tile: item = (channel group of 4, conv pixel); lanes of a warp share the channel group
@@ -68,7 +75,8 @@ stem_fwd_kernel(const float* __restrict__ x, const int* __restrict__ idx, int si
           }
         }
       }
-      a0 = mil_lrelu(a0); a1 = mil_lrelu(a1); a2 = mil_lrelu(a2); a3 = mil_lrelu(a3);
+      a0 = stem_round<T>(mil_lrelu(a0)); a1 = stem_round<T>(mil_lrelu(a1));
+      a2 = stem_round<T>(mil_lrelu(a2)); a3 = stem_round<T>(mil_lrelu(a3));
     }
     float* o = s_cv + p * 21 + cg * 4;
     o[0] = a0; o[1] = a1; o[2] = a2; o[3] = a3;
@@ -183,9 +191,9 @@ stem_bwd_kernel(const float* __restrict__ x, const int* __restrict__ idx, int n_
         const int iy = 2 * yc + it_ky[k] - 3, ix = 2 * xc + it_kx[k] - 3;
         if (iy >= 0 && iy < side && ix >= 0 && ix < side) {
           const float* p = xin + (size_t)iy * side + ix;
-          acc[k][0] = fmaf(gv, p[0], acc[k][0]);
-          acc[k][1] = fmaf(gv, p[(size_t)side * side], acc[k][1]);
-          acc[k][2] = fmaf(gv, p[(size_t)2 * side * side], acc[k][2]);
+          acc[k][0] = fmaf(gv, stem_round<T>(p[0]), acc[k][0]);
+          acc[k][1] = fmaf(gv, stem_round<T>(p[(size_t)side * side]), acc[k][1]);
+          acc[k][2] = fmaf(gv, stem_round<T>(p[(size_t)2 * side * side]), acc[k][2]);
         }
       }
     }

@@ -227,9 +227,7 @@ stem_conv_pool_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv
           uint32_t m = 0;
 #pragma unroll
           for (int pc = 0; pc < 3; ++pc) {
-            const uint32_t t0 = ~__byte_perm(outw[4 * pc], outw[4 * pc + 1], 0x7531) & 0x80808080u;
-            const uint32_t t1 = ~__byte_perm(outw[4 * pc + 2], outw[4 * pc + 3], 0x7531) & 0x80808080u;
-            m |= (((t0 * 0x00204081u) >> 28) | (((t1 * 0x00204081u) >> 28) << 4)) << (8 * pc);
+            m |= mil_positive_bits(make_uint4(outw[4 * pc], outw[4 * pc + 1], outw[4 * pc + 2], outw[4 * pc + 3])) << (8 * pc);
           }
           mask_out[gp.G + qo] = m;
         }

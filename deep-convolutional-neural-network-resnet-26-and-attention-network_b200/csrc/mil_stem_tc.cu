@@ -344,11 +344,7 @@ static int grid_for(long long work) { return (int)std::max<long long>(1, std::mi
 // true when the forward pass runs the fused conv + pool kernel (which also writes the pooled map's sign mask);
 // MIL_B200_STEM_UNFUSED=1 forces the two-kernel path
 bool mil_stem_tc_fused_pool(const MilPF8& gp, int side) {
-  static const bool unfused = [] {
-    const char* e = getenv("MIL_B200_STEM_UNFUSED");
-    return e != nullptr && e[0] == '1';
-  }();
-  return !unfused && mil_stem_conv_pool_supported(gp, (side - 1) / 2 + 1);
+  return mil_opt(MIL_OPT_STEM_UNFUSED) == 0 && mil_stem_conv_pool_supported(gp, (side - 1) / 2 + 1);
 }
 
 int mil_launch_stem_tc_fwd(const void* x, int x_u8, const int* idx, int n, int side, const float* w, const float* b, void* xs,
@@ -385,11 +381,7 @@ int mil_launch_stem_tc_bwd(const void* xs, int n, int side, const void* g, const
   const int hc = (side - 1) / 2 + 1;
   int ctas;
   long long rec;
-  static const bool unfused = [] {
-    const char* e = getenv("MIL_B200_STEM_UNFUSED");
-    return e != nullptr && e[0] == '1';
-  }();
-  if (!unfused) {
+  if (mil_opt(MIL_OPT_STEM_UNFUSED) == 0) {
     // the un-pooled gradient (80 channels at the phase-map resolution, the largest tensor of the backward pass) is
     // built inside the weight-gradient kernel, tile by tile, straight into its A-operand planes
     MIL_TRY(mil_launch_wgrad_tc_unpool(xs, gi, gc, g, gp, argmax, partial, &ctas, &rec, s));

@@ -14,7 +14,7 @@ GPU would, up to fp64 summation order.  `BagGroup()` without a process group is 
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional
+from typing import List, Optional
 
 import torch
 
@@ -33,40 +33,41 @@ class BagGroup:
             self.rank = dist.get_rank(group)
         self.grad_buckets = max(1, int(grad_buckets))
         self._gen = torch.Generator().manual_seed(int(seed)) if self.world > 1 else None
-        self._sizes: Dict[int, List[int]] = {}
-        self._n_global_pending: Optional[int] = None
         self._comm_stream = None
+
+    # True: the ranks hold shards of ONE bag (AR-1..3 couple them).  SlideGroup overrides this.
+    shares_bag = True
 
     # ---- shard bookkeeping -------------------------------------------------------------------------
     def shard_sizes(self, n_local_bag: int, device=None) -> List[int]:
-        """Bag sizes of every rank (one all-gather per distinct local size, then cached)."""
+        """Bag sizes of every rank: ONE all-gather of 8 bytes per call, entered by every rank unconditionally.
+        (Nothing is cached: real slides differ in size from bag to bag, and a rank that skipped the collective
+        because ITS shard happened to keep its size would leave the others waiting in it.)"""
         if self.world == 1:
-            return [n_local_bag]
-        if n_local_bag not in self._sizes:
-            import torch.distributed as dist
-            backend = dist.get_backend(self.group)
-            if backend == "nccl":
-                dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-            else:
-                dev = torch.device("cpu")
-            mine = torch.tensor([n_local_bag], dtype=torch.int64, device=dev)
-            out = [torch.zeros_like(mine) for _ in range(self.world)]
-            dist.all_gather(out, mine, group=self.group)
-            self._sizes[n_local_bag] = [int(t.item()) for t in out]
-        return self._sizes[n_local_bag]
+            return [int(n_local_bag)]
+        import torch.distributed as dist
+        backend = dist.get_backend(self.group)
+        if backend == "nccl":
+            dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        else:
+            dev = torch.device("cpu")
+        mine = torch.tensor([n_local_bag], dtype=torch.int64, device=dev)
+        out = torch.zeros(self.world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(out, mine, group=self.group)
+        return [int(v) for v in out.tolist()]
 
-    def subsample(self, n_local_bag: int, frac: float, device=None) -> torch.Tensor:
-        """Train-mode tile subset (gbm/model.py:193): `randperm(N)[:int(N*frac)]` over the WHOLE bag; returns
-        the local indices of the chosen tiles that live in this rank's shard (order of the permutation kept)."""
+    def subsample(self, n_local_bag: int, frac: float, device=None, sizes: Optional[List[int]] = None):
+        """Train-mode tile subset (gbm/model.py:193): `randperm(N)[:int(N*frac)]` over the WHOLE bag.  Returns
+        (local indices of the chosen tiles that live in this rank's shard, in permutation order; number of tiles
+        chosen over the whole bag).  `sizes` injects the per-rank shard sizes (tests)."""
         if self.world == 1:
             idx = torch.randperm(n_local_bag)[: int(n_local_bag * frac)]
-            self._n_global_pending = int(idx.numel())
-            return idx
-        sizes = self.shard_sizes(n_local_bag, device)
+            return idx, int(idx.numel())
+        if sizes is None:
+            sizes = self.shard_sizes(n_local_bag, device)
         total = sum(sizes)
         lo = sum(sizes[: self.rank])
         perm = torch.randperm(total, generator=self._gen)[: int(total * frac)]
-        self._n_global_pending = int(perm.numel())
         # every rank sees the same permutation, so every rank reaches the same verdict here (nobody is left waiting
         # in a collective): a shard without a single chosen tile has nothing to launch the kernels on
         bounds = torch.tensor([0] + sizes).cumsum(0)
@@ -76,17 +77,16 @@ class BagGroup:
                              f"{[r for r in range(self.world) if int(counts[r]) == 0]} without a tile; "
                              f"shard bags this small over fewer ranks")
         mine = perm[(perm >= lo) & (perm < lo + sizes[self.rank])] - lo
-        return mine
+        return mine, int(perm.numel())
 
-    def total(self, n_local: int, n_local_bag: Optional[int] = None) -> int:
-        """Number of tiles the head sees over the whole bag."""
-        if self._n_global_pending is not None:      # set by subsample() for this forward
-            n = self._n_global_pending
-            self._n_global_pending = None
-            return n
+    def total(self, n_local: int, hint: Optional[int] = None, device=None) -> int:
+        """Number of tiles the head sees over the whole bag.  `hint`: the caller already knows it (a loader that
+        shards a slide does) -- saves the all-gather and its host synchronisation."""
         if self.world == 1:
-            return n_local
-        return sum(self.shard_sizes(n_local))
+            return int(n_local)
+        if hint is not None:
+            return int(hint)
+        return sum(self.shard_sizes(n_local, device))
 
     # ---- collectives ------------------------------------------------------------------------------
     def all_reduce_sum(self, t: torch.Tensor) -> None:
@@ -128,3 +128,25 @@ class BagGroup:
         for w in works:
             w.wait()                      # makes the current stream wait for the collective
         cur.wait_stream(self._comm_stream)
+
+
+class SlideGroup(BagGroup):
+    """Multi-slide data parallelism (BASELINE configs[4]; the reference accumulates five slides' gradients before an
+    optimizer step, gbm/classify_combined.py:446-454): every rank holds its OWN bag.  The bag-wide sums AR-1..3 stay
+    local -- mixing BatchNorm1d / pooling statistics of different slides would be wrong -- and only AR-4, the bucketed
+    all-reduce (sum over the slides) of the parameter gradients overlapped with backward, remains."""
+
+    shares_bag = False
+
+    def shard_sizes(self, n_local_bag: int, device=None) -> List[int]:
+        return [int(n_local_bag)]
+
+    def subsample(self, n_local_bag: int, frac: float, device=None, sizes=None):
+        idx = torch.randperm(n_local_bag)[: int(n_local_bag * frac)]      # the reference's own draw, per slide
+        return idx, int(idx.numel())
+
+    def total(self, n_local: int, hint: Optional[int] = None, device=None) -> int:
+        return int(n_local)
+
+    def all_reduce_sum(self, t: torch.Tensor) -> None:
+        return None

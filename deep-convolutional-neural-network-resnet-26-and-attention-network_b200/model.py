@@ -136,9 +136,10 @@ class _WorkspacePool:
     def acquire(self, key, nbytes, device) -> _Workspace:
         lst = self._items.setdefault(key, [])
         for ws in lst:
-            if not ws.busy:
+            if not ws.busy and ws.buf.numel() >= nbytes:     # the size also depends on the library's runtime switches
                 ws.busy = True
                 return ws
+        lst[:] = [w for w in lst if w.busy]
         # drop idle workspaces of other shapes before growing (they can be several GB)
         for k in list(self._items):
             if k != key:
@@ -168,8 +169,8 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def _check_param(name, p):
@@ -184,29 +185,35 @@ def _check_param(name, p):
 # ------------------------------------------------------------------------------------------------------
 class _MilFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, owner, bag, Y, idx, drop, *params):
+    def forward(ctx, owner, bag, Y, idx, drop, n_global, *params):
+        with torch.cuda.device(bag.device):      # the library launches on the CURRENT device: make it the bag's
+            return _MilFunction._forward(ctx, owner, bag, Y, idx, drop, n_global, *params)
+
+    @staticmethod
+    def _forward(ctx, owner, bag, Y, idx, drop, n_global, *params):
         lib = _lib.load()
         dev = bag.device
         names = owner._param_names
         for nm, p in zip(names, params):
             _check_param(nm, p)
+            if p.device != dev:
+                raise RuntimeError(f"parameter {nm} is on {p.device} but the bag is on {dev}")
         pp = (C.c_void_p * len(params))(*[p.data_ptr() for p in params])
         n = int(idx.numel()) if idx is not None else int(bag.shape[0])
         side = int(bag.shape[2])
         dt = DTYPE_CODES[owner.precision]
         group: BagGroup = owner.bag_group
-        n_global = group.total(n)
         if n_global < 2:
             # nn.BatchNorm1d refuses a single row, in train and eval mode alike (reference behaviour)
             raise ValueError(f"Expected more than 1 value per channel when training, got input size "
                              f"torch.Size([{n_global}, 80])")
-        need_grad = any(ctx.needs_input_grad[5:])
+        need_grad = any(ctx.needs_input_grad[6:])
         nbytes = int(lib.mil_extractor_workspace_bytes(n, side, dt))
         if nbytes == 0:
             _lib.check(1, "mil_extractor_workspace_bytes")
         ws = owner._pool.acquire((n, side, dt, dev.index), nbytes, dev)
         lease = _Lease(ws)
-        st = _stream()
+        st = _stream(dev)
         f32 = dict(dtype=torch.float32, device=dev)
         H = torch.empty((n, 80), **f32)
         fwd = lib.mil_extractor_forward_u8 if bag.dtype == torch.uint8 else lib.mil_extractor_forward
@@ -249,6 +256,11 @@ class _MilFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gloss, *_):
+        with torch.cuda.device(ctx.saved_tensors[0].device):
+            return _MilFunction._backward(ctx, gloss)
+
+    @staticmethod
+    def _backward(ctx, gloss):
         lib = _lib.load()
         H, raw, g, b, scal, small = ctx.saved_tensors
         stats, bnsums = small[:160], small[176:]
@@ -258,13 +270,13 @@ class _MilFunction(torch.autograd.Function):
         dev = H.device
         group: BagGroup = owner.bag_group
         pp = (C.c_void_p * len(params))(*[p.data_ptr() for p in params])
-        st = _stream()
+        st = _stream(dev)
         total = int(lib.mil_param_total())
         # flattened module (optim.flatten_parameters / FusedAdam): the library accumulates straight into the flat
         # gradient buffer the parameters' .grad are views of -- no per-tensor AccumulateGrad work (65 small kernels
         # and ~1 ms of host time per step otherwise).  Sharded bags reduce this step's gradients first.
         gflat = getattr(owner, "_gflat", None)
-        direct = gflat is not None and gflat.device == dev and all(ctx.needs_input_grad[5:])
+        direct = gflat is not None and gflat.device == dev and all(ctx.needs_input_grad[6:])
         if direct and group.world == 1:
             grads = gflat
         else:
@@ -302,14 +314,14 @@ class _MilFunction(torch.autograd.Function):
         if direct:
             if grads is not gflat:
                 gflat.add_(grads)
-            return (None,) * (5 + len(params))
+            return (None,) * (6 + len(params))
         out = []
-        for (nm, shape, off), need in zip(owner._param_table, ctx.needs_input_grad[5:]):
+        for (nm, shape, off), need in zip(owner._param_table, ctx.needs_input_grad[6:]):
             numel = 1
             for s in shape:
                 numel *= s
             out.append(grads[off:off + numel].view(shape) if need else None)
-        return (None, None, None, None, None, *out)
+        return (None, None, None, None, None, None, *out)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -423,7 +435,7 @@ class Attention(nn.Module):
             return None
         return torch.as_tensor(w, dtype=torch.float32).to(device).contiguous()
 
-    def _prepare(self, full_input, Y):
+    def _prepare(self, full_input, Y, bag_tiles=None):
         if not full_input.is_cuda:
             raise RuntimeError("Attention.forward needs a CUDA tensor: the B200 path has no CPU fallback")
         if full_input.dim() != 4 or full_input.shape[1] != 3 or full_input.shape[2] != full_input.shape[3]:
@@ -445,12 +457,14 @@ class Attention(nn.Module):
         Yl = Y.to(dev).long().reshape(-1)[:1].contiguous()                            # gbm/model.py:239
         idx = None
         drop = None
+        group = self.bag_group
         if self.training:
             n_bag = bag.shape[0]
             if self.subsample_indices is not None:
                 indices = torch.as_tensor(self.subsample_indices).long().cpu()
+                n_global = group.total(int(indices.numel()), device=dev)
             else:
-                indices = self.bag_group.subsample(n_bag, SUBSAMPLE)                  # gbm/model.py:193
+                indices, n_global = group.subsample(n_bag, SUBSAMPLE, device=dev)     # gbm/model.py:193
             idx = indices.to(torch.int32).to(dev, non_blocking=True)
             n = int(indices.numel())
             if self.drop_mask is not None:
@@ -459,7 +473,9 @@ class Attention(nn.Module):
                     raise ValueError(f"drop_mask must be [{n},80], got {tuple(drop.shape)}")
             else:
                 drop = (torch.rand((n, 80), device=dev) >= DROP_P).float()           # Dropout(0.25), gbm/model.py:107
-        return bag, Yl, idx, drop
+        else:
+            n_global = group.total(int(bag.shape[0]), hint=bag_tiles, device=dev)
+        return bag, Yl, idx, drop, n_global
 
     # ---- the reference surface ----
     def _params(self):
@@ -471,11 +487,14 @@ class Attention(nn.Module):
             c = self._param_list_cache = [p for _, p in self.named_parameters()]
         return c
 
-    def forward(self, full_input: torch.Tensor, Y: Optional[torch.Tensor] = None):
-        bag, Yl, idx, drop = self._prepare(full_input, Y)
+    def forward(self, full_input: torch.Tensor, Y: Optional[torch.Tensor] = None, bag_tiles: Optional[int] = None):
+        """The reference's `forward(full_input, Y) -> dict` (gbm/model.py:189-264).  `bag_tiles` (extra, optional):
+        total tiles of the whole bag when it is sharded over a BagGroup and the caller knows the number -- saves the
+        all-gather of the shard sizes in eval mode."""
+        bag, Yl, idx, drop, n_global = self._prepare(full_input, Y, bag_tiles)
         params = self._params()
         (loss, A, wroi, b, M, H, amu, avar, kld, ypred, yhat, err) = _MilFunction.apply(
-            self, bag, Yl, idx, drop, *params)
+            self, bag, Yl, idx, drop, n_global, *params)
         # Classifier penalty (gbm/model.py:246): two tiny norms, kept in autograd like the reference
         l2 = (self.buffer.lin1.weight.norm() + self.buffer.classifier.weight.norm()) * 0.5
         return {
@@ -503,9 +522,10 @@ class Attention(nn.Module):
         nbytes = int(lib.mil_extractor_workspace_bytes(n, side, dt))
         ws = self._pool.acquire((n, side, dt, bag.device.index), nbytes, bag.device)
         try:
-            H = torch.empty((n, 80), dtype=torch.float32, device=bag.device)
-            _lib.check(lib.mil_extractor_forward(pp, _ptr(bag), None, n, side, dt, _ptr(ws.buf), nbytes, _ptr(H),
-                                                 _stream()), "mil_extractor_forward")
+            with torch.cuda.device(bag.device):
+                H = torch.empty((n, 80), dtype=torch.float32, device=bag.device)
+                _lib.check(lib.mil_extractor_forward(pp, _ptr(bag), None, n, side, dt, _ptr(ws.buf), nbytes, _ptr(H),
+                                                     _stream(bag.device)), "mil_extractor_forward")
         finally:
             _WorkspacePool.release(ws)
         return H

@@ -45,10 +45,13 @@ class BagStager:
         else:
             raise RuntimeError("all staging buffers are in flight: release() a ticket first")
         s.busy = True
-        if s.buf is None or s.buf.numel() < host_bag.numel() or s.buf.dtype != host_bag.dtype:
-            s.buf = torch.empty(host_bag.numel(), dtype=host_bag.dtype, device=self.device)
-        s.view = s.buf[: host_bag.numel()].view(host_bag.shape)
         with torch.cuda.stream(self.stream):
+            if s.buf is None or s.buf.numel() < host_bag.numel() or s.buf.dtype != host_bag.dtype:
+                # allocated ON the side stream: the caching allocator then never hands out a block whose last use is
+                # still queued on another stream (a block just freed on the main stream could otherwise be
+                # overwritten by this copy underneath kernels that have not run yet)
+                s.buf = torch.empty(host_bag.numel(), dtype=host_bag.dtype, device=self.device)
+            s.view = s.buf[: host_bag.numel()].view(host_bag.shape)
             if s.consumed is not None:
                 self.stream.wait_event(s.consumed)      # previous user of this buffer has finished reading it
             s.view.copy_(host_bag, non_blocking=True)
@@ -58,7 +61,9 @@ class BagStager:
     def get(self, ticket: int) -> torch.Tensor:
         """The staged bag; work queued on the current stream after this call sees the finished copy."""
         s = self.slots[ticket]
-        torch.cuda.current_stream(self.device).wait_event(s.copied)
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(s.copied)
+        s.view.record_stream(cur)       # the buffer lives on the side stream's pool: tell the allocator who reads it
         return s.view
 
     def release(self, ticket: int) -> None:

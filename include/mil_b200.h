@@ -56,6 +56,13 @@ int mil_param_shape(int i, int* ndim, long long shape4[4]);
 long long mil_param_offset(int i);                /* float offset inside the flat gradient buffer */
 long long mil_param_total(void);                  /* 640967 */
 
+/* Runtime switches (cross-checks; the environment variables MIL_B200_<NAME> give the initial values):
+ *   "disable_tc"   1 = CUDA-core (FFMA) kernels only, with the tensor-core path's bf16 rounding points
+ *   "stem_unfused" 1 = stem as separate conv / pool / unpool / weight-gradient kernels
+ * A forward pass and its backward pass must run under the same settings (they size the workspace). */
+int mil_set_option(const char* name, int value);
+int mil_get_option(const char* name, int* value);
+
 /* ---- feature extractor: ResNet.forward (gbm/model.py:50-61) + BasicResBlock (nnBlocks.py:175-189) ----
  * bag   : fp32 NCHW [n_bag,3,side,side], the caller's tensor as handed to Attention.forward (gbm/model.py:189)
  * idx   : optional int32[n_tiles] gather list = the train-mode 20 % subsample (gbm/model.py:193-194);

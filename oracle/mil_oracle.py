@@ -106,7 +106,34 @@ def init_params(seed: int = 0, dtype=torch.float32) -> "OrderedDict[str, torch.T
 # feature extractor (gbm/model.py:50-61, nnBlocks.py:175-189)
 # --------------------------------------------------------------------------------------------
 def _bf16(t: torch.Tensor) -> torch.Tensor:
-    return t.to(torch.bfloat16).to(t.dtype)
+    return t.detach().to(torch.bfloat16).to(t.dtype)
+
+
+class _RoundOperand(torch.autograd.Function):
+    """bf16 rounding of a tensor-core OPERAND that has an fp32 master (conv weights, the input tiles, the conv map
+    the pool compares): rounded in the forward pass, gradient passed through unchanged (the CUDA path accumulates
+    weight gradients in fp32)."""
+
+    @staticmethod
+    def forward(ctx, t):
+        return _bf16(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _RoundStored(torch.autograd.Function):
+    """bf16 rounding of a STORED activation map: the CUDA bf16 mode also stores the gradient maps that flow back
+    through these points in bf16, so the gradient is rounded on the way back as well."""
+
+    @staticmethod
+    def forward(ctx, t):
+        return _bf16(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _bf16(g)
 
 
 def resnet26_forward(p: Dict[str, torch.Tensor], x: torch.Tensor, prefix: str = "cnn.module.",
@@ -119,8 +146,8 @@ def resnet26_forward(p: Dict[str, torch.Tensor], x: torch.Tensor, prefix: str = 
     tests to separate kernel defects (must match the emulation tightly) from the conditioning of the
     head with respect to bf16 features (the distance between the emulation and the fp32 reference)."""
     lr = lambda t: F.leaky_relu(t, SLOPE)
-    ra = _bf16 if emulate_bf16 else (lambda t: t)
-    rw = _bf16 if emulate_bf16 == "act+w" else (lambda t: t)
+    ra = _RoundStored.apply if emulate_bf16 else (lambda t: t)
+    rw = _RoundOperand.apply if emulate_bf16 == "act+w" else (lambda t: t)
     # "act+w": the stem runs on the tensor cores too -> bf16 input and conv1 weights, bf16 conv map before the pool
     y = F.conv2d(rw(x), rw(p[prefix + "conv1.weight"]), p[prefix + "conv1.bias"], stride=2, padding=3)
     y = ra(F.max_pool2d(rw(lr(y)), kernel_size=3, stride=2, padding=1))
@@ -212,7 +239,7 @@ def subsample_indices(n_bag: int, generator: Optional[torch.Generator] = None) -
 def attention_forward(p: Dict[str, torch.Tensor], bag: torch.Tensor, Y: torch.Tensor,
                       class_weights: Optional[torch.Tensor] = None, training: bool = False,
                       indices: Optional[torch.Tensor] = None,
-                      drop_mask: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+                      drop_mask: Optional[torch.Tensor] = None, emulate_bf16: str = "") -> Dict[str, torch.Tensor]:
     """Whole Attention.forward (gbm/model.py:189-264).  In training mode pass `indices`
     (the subsample) and `drop_mask` explicitly so the run is reproducible."""
     x = bag.detach()
@@ -220,17 +247,19 @@ def attention_forward(p: Dict[str, torch.Tensor], bag: torch.Tensor, Y: torch.Te
         if indices is None:
             indices = subsample_indices(bag.shape[0])
         x = x[indices]
-    H = resnet26_forward(p, x)
+    H = resnet26_forward(p, x, emulate_bf16=emulate_bf16)
     return head_forward(p, H, Y, class_weights, drop_mask if training else None)
 
 
 def forward_backward(p: Dict[str, torch.Tensor], bag: torch.Tensor, Y: torch.Tensor,
                      class_weights: Optional[torch.Tensor] = None, training: bool = False,
                      indices: Optional[torch.Tensor] = None,
-                     drop_mask: Optional[torch.Tensor] = None):
-    """Returns (outputs dict, grads dict of d loss / d param) using autograd on the restatement."""
+                     drop_mask: Optional[torch.Tensor] = None, emulate_bf16: str = ""):
+    """Returns (outputs dict, grads dict of d loss / d param) using autograd on the restatement.
+    emulate_bf16="act+w": forward AND backward with the CUDA bf16 mode's rounding points (see resnet26_forward,
+    _RoundOperand, _RoundStored) -- the tight gate for the bf16 gradients."""
     q = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in p.items())
-    out = attention_forward(q, bag, Y, class_weights, training, indices, drop_mask)
+    out = attention_forward(q, bag, Y, class_weights, training, indices, drop_mask, emulate_bf16)
     out["loss"].backward()
     grads = OrderedDict((k, (v.grad if v.grad is not None else torch.zeros_like(v))) for k, v in q.items())
     return {k: (v.detach() if torch.is_tensor(v) else v) for k, v in out.items()}, grads

@@ -118,11 +118,15 @@ grp = mil.BagGroup(dist.group.WORLD, seed=7)
 n_local = 5 if rank == 0 else 3
 assert grp.shard_sizes(n_local) == [5, 3]
 assert grp.total(n_local) == 8
+# two consecutive bags where only ONE rank's shard size changes (50/50 then 50/49): nothing is cached, every rank
+# enters the all-gather every time, both see the new total (a stale cache on rank 0 used to desynchronise the ranks)
+assert grp.total(50) == 100
+assert grp.total(50 if rank == 0 else 49) == 99
+assert grp.total(50 if rank == 0 else 49, hint=99) == 99
 # train-mode subsample: the union over ranks is one global randperm prefix, disjoint, in shard range
 grp2 = mil.BagGroup(dist.group.WORLD, seed=7)
 n_bag = 40 if rank == 0 else 24
-idx = grp2.subsample(n_bag, 0.2)
-k = grp2.total(int(idx.numel()))
+idx, k = grp2.subsample(n_bag, 0.2)
 assert k == int(64 * 0.2)
 cnt = torch.tensor([idx.numel()]); dist.all_reduce(cnt); assert int(cnt) == k
 assert idx.numel() == 0 or (int(idx.min()) >= 0 and int(idx.max()) < n_bag)
@@ -155,6 +159,22 @@ assert torch.allclose(A_local, A_full, rtol=1e-10, atol=1e-14)
 flat = torch.arange(1000, dtype=torch.float32) * (rank + 1)
 mil.BagGroup(dist.group.WORLD, grad_buckets=3).all_reduce_grads(flat)
 assert torch.equal(flat, torch.arange(1000, dtype=torch.float32) * 3)
+# multi-slide data parallelism (BASELINE configs[4]): every rank its own bag -- bag-wide sums stay local, sizes are
+# local, only the gradient all-reduce crosses ranks and yields the SUM of the per-slide gradients
+sg = mil.SlideGroup(dist.group.WORLD, grad_buckets=2)
+assert sg.world == 2 and not sg.shares_bag and grp.shares_bag
+assert sg.total(5 if rank == 0 else 3) == (5 if rank == 0 else 3)
+loc = torch.full((4,), float(rank + 1), dtype=torch.float64)
+sg.all_reduce_sum(loc)
+assert torch.equal(loc, torch.full((4,), float(rank + 1), dtype=torch.float64))
+torch.manual_seed(11 + rank)
+want = torch.randperm(30)[:6]
+torch.manual_seed(11 + rank)
+got, kk = sg.subsample(30, 0.2)
+assert kk == 6 and torch.equal(got, want)
+gslide = torch.arange(500, dtype=torch.float32) * (10 ** rank)
+sg.all_reduce_grads(gslide)
+assert torch.equal(gslide, torch.arange(500, dtype=torch.float32) * 11)
 dist.barrier()
 print("rank", rank, "ok", flush=True)
 dist.destroy_process_group()
@@ -203,9 +223,8 @@ def test_sharded_subsample_bookkeeping(mil):
         g = mil.BagGroup()
         g.world, g.rank = 3, rank
         g._gen = torch.Generator().manual_seed(5)
-        g._sizes = {sizes[rank]: sizes}
-        idx = g.subsample(sizes[rank], 0.2)
-        assert g.total(int(idx.numel())) == 20
+        idx, k = g.subsample(sizes[rank], 0.2, sizes=sizes)
+        assert k == 20
         assert int(idx.min()) >= 0 and int(idx.max()) < sizes[rank]
         picks.append(idx + sum(sizes[:rank]))
     allp = torch.cat(picks)
@@ -218,9 +237,8 @@ def test_sharded_subsample_bookkeeping(mil):
         g = mil.BagGroup()
         g.world, g.rank = 3, rank
         g._gen = torch.Generator().manual_seed(1)
-        g._sizes = {3: sizes}
         try:
-            g.subsample(3, 0.2)                                   # one tile for three ranks
+            g.subsample(3, 0.2, sizes=sizes)                      # one tile for three ranks
         except ValueError as e:
             errs += 1
             assert "without a tile" in str(e)
