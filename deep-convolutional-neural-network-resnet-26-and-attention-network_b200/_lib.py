@@ -61,6 +61,11 @@ PROTOTYPES = {
                              c_size_t, c_void_p]),
     "mil_conv_wgrad_pf8": (c_int, [c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
                                    c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mil_stem_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "mil_stem_forward": (c_int, [c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                 c_void_p]),
+    "mil_stem_backward": (c_int, [c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                  c_void_p]),
     "mil_minmax_normalize": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_void_p]),
     "mil_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float,
                               c_float, c_float, c_void_p]),

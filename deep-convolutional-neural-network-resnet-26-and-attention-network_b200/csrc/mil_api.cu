@@ -293,21 +293,46 @@ int mil_from_pf8(int dtype, const void* pf8, float* nchw, int n, int c, int h, i
   MIL_API_END
 }
 
-static size_t conv_ws_layout(int n, int cin, int hi, int wi, int cout, int ho, int wo, int ks, size_t* off_tc,
-                             size_t* off_partial) {
+// true when the 3x3 / stride-2 convolution cin -> cout with output rows of `wo` pixels runs in its phase-split
+// tensor-core forms (the extractor plan takes the same decision, mil_extractor.cu)
+static bool s2_split_ok(int cin, int cout, int wo) {
+  MilTcShape sh;
+  if (cin < 9 || mil_tc_shape_s2(cin, cout, &sh) != 0) return false;
+  return mil_conv_tc_fits(sh, wo + 1) && 2 * ((cin + 7) / 8) <= 10;
+}
+
+struct ConvWs {
+  size_t off_tc, off_tc2, off_aux, off_partial, total;
+};
+// layer-level workspace: [fp32 packed weights][tc weights][tc weights 2][aux map][partial records]
+static ConvWs conv_ws_layout(int n, int cin, int hi, int wi, int cout, int ho, int wo, int ks) {
   const MilPF8 gi = mil_pf8(n, cin, hi, wi), go = mil_pf8(n, cout, ho, wo);
   const size_t wp = ((size_t)ks * ks * gi.cb * 8 * go.cb * 8 * sizeof(float) + 255) / 256 * 256;
   size_t tc = 0;
   if (cin >= 9 && cout >= 9) {
     MilTcShape a, b;
     if (mil_tc_shape(cin, cout, ks, &a) == 0 && mil_tc_shape(cout, cin, ks, &b) == 0)
-      tc = (std::max(mil_tc_wpack_bytes(a), mil_tc_wpack_bytes(b)) + 255) / 256 * 256;
+      tc = std::max(mil_tc_wpack_bytes(a), mil_tc_wpack_bytes(b));
+    if (ks == 3 && mil_tc_shape_s2(cin, cout, &a) == 0) tc = std::max(tc, mil_tc_wpack_bytes(a));
+    for (int r = 0; r < 2; ++r)
+      if (ks == 3 && 2 * gi.cb <= 10 && mil_tc_shape_s2_dgrad(cout, cin, r, &a) == 0) tc = std::max(tc, mil_tc_wpack_bytes(a));
+    tc = (tc + 255) / 256 * 256;
   }
-  *off_tc = wp;
-  *off_partial = wp + tc;
+  ConvWs w;
+  w.off_tc = wp;
+  w.off_tc2 = wp + tc;
+  w.off_aux = wp + 2 * tc;
+  // aux: the phase-split / even-position copy of the input of a stride-2 convolution (at most 4 * cb planes at the
+  // output resolution), or the zero-stuffed half-resolution residual of its data gradient (cin channels, input size)
+  size_t aux = 0;
+  if (hi != ho || wi != wo)
+    aux = std::max(mil_pf8_bytes(mil_split2_geom(n, cin, ho), MIL_F32), mil_pf8_bytes(gi, MIL_F32));
+  aux = (aux + 255) / 256 * 256;
+  w.off_partial = w.off_aux + aux;
   size_t pf = mil_wgrad_direct_partial_floats(gi, go, ks);
-  if (hi == ho && wi == wo) pf = std::max(pf, mil_wgrad_tc_partial_floats(gi, go, ks));
-  return wp + tc + pf * sizeof(float) + 1024;
+  pf = std::max(pf, mil_wgrad_tc_partial_floats(mil_pf8(n, cin, ho, wo), go, ks));
+  w.total = w.off_partial + pf * sizeof(float) + 1024;
+  return w;
 }
 
 int mil_upsample2_pf8(const void* in, int n, int c, int h, int w, void* out, int ho, int wo, void* stream) {
@@ -338,8 +363,7 @@ int mil_adam_step(float* params_flat, const float* grads_flat, float* exp_avg, f
 }
 
 size_t mil_conv_workspace_bytes(int n, int cin, int hi, int wi, int cout, int ho, int wo, int ks) {
-  size_t a, b;
-  return conv_ws_layout(n, cin, hi, wi, cout, ho, wo, ks, &a, &b);
+  return conv_ws_layout(n, cin, hi, wi, cout, ho, wo, ks).total;
 }
 
 int mil_conv_pf8(int dtype, int impl, int transposed, const void* x, int n, int cx, int hx, int wx, const float* w,
@@ -352,21 +376,60 @@ int mil_conv_pf8(int dtype, int impl, int transposed, const void* x, int n, int 
               transposed ? cout : cin);
   const MilPF8 gx = mil_pf8(n, cx, hx, wx);
   const MilPF8 go = mil_pf8(n, transposed ? cin : cout, ho, wo);
-  size_t off_tc, off_partial;
-  const size_t need = transposed ? conv_ws_layout(n, cin, ho, wo, cout, hx, wx, ks, &off_tc, &off_partial)
-                                 : conv_ws_layout(n, cin, hx, wx, cout, ho, wo, ks, &off_tc, &off_partial);
-  MIL_REQUIRE(ws_bytes >= need, "mil_conv_pf8: workspace too small (%zu < %zu)", ws_bytes, need);
+  const ConvWs L = transposed ? conv_ws_layout(n, cin, ho, wo, cout, hx, wx, ks) : conv_ws_layout(n, cin, hx, wx, cout, ho, wo, ks);
+  MIL_REQUIRE(ws_bytes >= L.total, "mil_conv_pf8: workspace too small (%zu < %zu)", ws_bytes, L.total);
   cudaStream_t s = (cudaStream_t)stream;
+  char* wsb = reinterpret_cast<char*>(ws);
   MIL_TRY(mil_launch_pack_conv_w(w, (float*)ws, cout, cin, ks, transposed, s));
   const bool tc_ok = mil_tc_supported(dtype, ks, stride, gx.c, go.c) && !(stride == 2 && transposed);
-  MIL_REQUIRE(impl != 2 || tc_ok, "mil_conv_pf8: impl=2 (tcgen05) does not support dtype=%d ks=%d stride=%d", dtype, ks,
-              stride);
-  if (impl == 1 || !tc_ok || (impl == 0 && !mil_tc_enabled()))
+  // the stride-2 3x3 convolution in the forms the extractor runs: forward on the phase-split input, data gradient
+  // per input row parity (res: the HALF-resolution gradient of the projection branch, added at the even positions)
+  const bool split = dtype == MIL_BF16 && ks == 3 && stride == 2 &&
+                     (transposed ? s2_split_ok(cin, cout, wx) : s2_split_ok(cin, cout, wo));
+  MIL_REQUIRE(impl != 2 || tc_ok || split, "mil_conv_pf8: impl=2 (tcgen05) does not support dtype=%d ks=%d stride=%d",
+              dtype, ks, stride);
+  const bool use_tc = impl != 1 && (tc_ok || split) && (impl == 2 || mil_tc_enabled());
+  if (stride == 2 && transposed && res != nullptr && !(use_tc && split)) {
+    // CUDA-core / zero-stuffed path: the half-resolution residual becomes a full-resolution map first
+    const MilPF8 gh = mil_pf8(n, cin, hx, wx);
+    void* up = wsb + L.off_aux;
+    MIL_CHECK_CUDA(cudaMemsetAsync(up, 0, mil_pf8_bytes(go, dtype), s));
+    if (dtype == MIL_BF16) MIL_TRY(mil_launch_upsample2(res, gh, up, go, s));
+    else MIL_REQUIRE(false, "mil_conv_pf8: stride-2 data gradient with a residual needs dtype bf16");
+    res = up;
+  }
+  if (!use_tc)
     return mil_launch_conv_direct(dtype, transposed, x, gx, (const float*)ws, bias, res, act, out, go, ks, stride,
                                   epi, s);
+  if (split && !transposed) {
+    const MilPF8 gs = mil_split2_geom(n, cin, ho);
+    void* xs2 = wsb + L.off_aux;
+    MIL_TRY(mil_zero_guards(dtype, xs2, gs, s));
+    MIL_TRY(mil_launch_split2(x, gx, xs2, gs, s));
+    MilTcPackJob job = {w, wsb + L.off_tc, cout, cin, 3, 0, 1};
+    MIL_TRY(mil_launch_pack_tc_table(&job, 1, s));
+    MilTcShape sh;
+    MIL_TRY(mil_tc_shape_s2(cin, cout, &sh));
+    return mil_launch_conv_tc(0, xs2, gs, wsb + L.off_tc, sh, bias, res, act, out, go, epi, 0, s);
+  }
+  if (split && transposed) {
+    MIL_REQUIRE(epi == MIL_EPI_DGRAD && bias == nullptr, "mil_conv_pf8: the stride-2 data gradient has the DGRAD epilogue");
+    const MilPF8 gh = mil_pf8(n, cin, hx, wx);  // geometry of the half-resolution residual
+    MIL_CHECK_CUDA(cudaMemsetAsync(out, 0, mil_pf8_bytes(go, dtype), s));  // pads + guards of the full-resolution map
+    for (int a = 0; a < 2; ++a) {
+      char* wtc = wsb + (a ? L.off_tc2 : L.off_tc);
+      MilTcPackJob job = {w, wtc, cout, cin, 3, 1, 2 + a};
+      MIL_TRY(mil_launch_pack_tc_table(&job, 1, s));
+      MilTcShape sh;
+      MIL_TRY(mil_tc_shape_s2_dgrad(cout, cin, a, &sh));
+      MIL_TRY(mil_launch_conv_tc(1, x, gx, wtc, sh, nullptr, (a == 0) ? res : nullptr, act, out, go, MIL_EPI_DGRAD, 0, s,
+                                 (a == 0 && res != nullptr) ? &gh : nullptr, a, nullptr));
+    }
+    return 0;
+  }
   MilTcShape sh;
   MIL_TRY(mil_tc_shape(gx.c, go.c, ks, &sh));
-  void* wtc = reinterpret_cast<char*>(ws) + off_tc;
+  void* wtc = wsb + L.off_tc;
   MIL_TRY(mil_launch_pack_tc((const float*)ws, wtc, sh, s));
   return mil_launch_conv_tc(transposed, x, gx, wtc, sh, bias, res, act, out, go, epi, stride == 2, s);
   MIL_API_END
@@ -379,16 +442,104 @@ int mil_conv_wgrad_pf8(int dtype, int impl, const void* x, int n, int cin, int h
   MIL_TRY(require_device());
   MIL_REQUIRE(x && dz && dw && ws, "mil_conv_wgrad_pf8: null pointer argument");
   const MilPF8 gi = mil_pf8(n, cin, hi, wi), go = mil_pf8(n, cout, ho, wo);
-  size_t off_tc, off_partial;
-  const size_t need = conv_ws_layout(n, cin, hi, wi, cout, ho, wo, ks, &off_tc, &off_partial);
-  MIL_REQUIRE(ws_bytes >= need, "mil_conv_wgrad_pf8: workspace too small (%zu < %zu)", ws_bytes, need);
-  float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + off_partial);
+  const ConvWs L = conv_ws_layout(n, cin, hi, wi, cout, ho, wo, ks);
+  MIL_REQUIRE(ws_bytes >= L.total, "mil_conv_wgrad_pf8: workspace too small (%zu < %zu)", ws_bytes, L.total);
+  char* wsb = reinterpret_cast<char*>(ws);
+  float* partial = reinterpret_cast<float*>(wsb + L.off_partial);
+  cudaStream_t s = (cudaStream_t)stream;
   const bool tc_ok = mil_wgrad_tc_supported(dtype, ks, stride, cin, cout);
-  MIL_REQUIRE(impl != 2 || tc_ok, "mil_conv_wgrad_pf8: impl=2 (tcgen05) does not support dtype=%d ks=%d stride=%d",
-              dtype, ks, stride);
-  if (impl == 1 || !tc_ok || (impl == 0 && !mil_tc_enabled()))
-    return mil_launch_wgrad_direct(dtype, x, gi, dz, go, partial, dw, db, ks, stride, (cudaStream_t)stream);
-  return mil_launch_wgrad_tc(x, gi, dz, go, partial, dw, db, ks, (cudaStream_t)stream);
+  // stride 2 in the forms the extractor runs: 3x3 on the phase-split input (nine single-tap MMAs), 1x1 on the
+  // even-position copy -- everything at the OUTPUT resolution
+  const bool s2_3 = dtype == MIL_BF16 && ks == 3 && stride == 2 && s2_split_ok(cin, cout, wo);
+  const bool s2_1 = dtype == MIL_BF16 && ks == 1 && stride == 2 && mil_wgrad_tc_supported(dtype, 1, 1, cin, cout);
+  MIL_REQUIRE(impl != 2 || tc_ok || s2_3 || s2_1,
+              "mil_conv_wgrad_pf8: impl=2 (tcgen05) does not support dtype=%d ks=%d stride=%d", dtype, ks, stride);
+  if (impl == 1 || !(tc_ok || s2_3 || s2_1) || (impl == 0 && !mil_tc_enabled()))
+    return mil_launch_wgrad_direct(dtype, x, gi, dz, go, partial, dw, db, ks, stride, s);
+  if (s2_3) {
+    const MilPF8 gs = mil_split2_geom(n, cin, ho);
+    void* xs2 = wsb + L.off_aux;
+    MIL_TRY(mil_zero_guards(dtype, xs2, gs, s));
+    MIL_TRY(mil_launch_split2(x, gi, xs2, gs, s));
+    return mil_launch_wgrad_tc_s2(xs2, gs, dz, go, partial, dw, db, cin, s);
+  }
+  if (s2_1) {
+    const MilPF8 gsub = mil_pf8(n, cin, ho, wo);
+    void* xsub = wsb + L.off_aux;
+    MIL_TRY(mil_zero_guards(dtype, xsub, gsub, s));
+    MIL_TRY(mil_launch_subsample2(x, gi, xsub, gsub, s));
+    return mil_launch_wgrad_tc(xsub, gsub, dz, go, partial, dw, db, 1, s);
+  }
+  return mil_launch_wgrad_tc(x, gi, dz, go, partial, dw, db, ks, s);
+  MIL_API_END
+}
+
+// ---- stem at layer level ----------------------------------------------------------------------------------
+struct StemWs {
+  size_t off_argmax, off_xs, off_cv, off_wp, off_wtc, off_partial, total;
+};
+static StemWs stem_ws_layout(int n, int side, int dtype) {
+  const MilGeom geo = mil_geom(side);
+  const MilPF8 gp = mil_pf8(n, 20, geo.h[0], geo.h[0]);
+  StemWs L;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) / 256 * 256; return o; };
+  L.off_argmax = take(std::max((size_t)n * geo.h[0] * geo.h[0] * 20, mil_stem_tc_argmax_bytes(gp)));
+  L.off_xs = take(mil_pf8_bytes(mil_stem_tc_geom_in(n, side), MIL_BF16));
+  L.off_cv = take(mil_pf8_bytes(mil_stem_tc_geom_conv(n, side), MIL_BF16));
+  L.off_wp = take(mil_stem_tc_wpack_floats() * sizeof(float));
+  L.off_wtc = take(mil_stem_tc_wtc_bytes());
+  L.off_partial = take(std::max(mil_stem_bwd_partial_floats(), mil_stem_tc_partial_floats(n, side)) * sizeof(float));
+  L.total = off;
+  (void)dtype;
+  return L;
+}
+static bool stem_use_tc(int dtype, int impl) { return dtype == MIL_BF16 && impl != 1 && (impl == 2 || mil_tc_enabled()); }
+
+size_t mil_stem_workspace_bytes(int n, int side, int dtype) {
+  if (n < 1 || side < 8) return 0;
+  return stem_ws_layout(n, side, dtype).total;
+}
+
+int mil_stem_forward(int dtype, int impl, const float* bag, int n, int side, const float* w, const float* b, void* pooled,
+                     void* ws, size_t ws_bytes, void* stream) {
+  MIL_API_BEGIN
+  MIL_TRY(require_device());
+  MIL_REQUIRE(bag && w && b && pooled && ws, "mil_stem_forward: null pointer argument");
+  MIL_REQUIRE(n >= 1 && side >= 8, "mil_stem_forward: bad shape n=%d side=%d", n, side);
+  MIL_REQUIRE(impl != 2 || dtype == MIL_BF16, "mil_stem_forward: impl=2 (tcgen05) needs dtype bf16");
+  const StemWs L = stem_ws_layout(n, side, dtype);
+  MIL_REQUIRE(ws_bytes >= L.total, "mil_stem_forward: workspace too small (%zu < %zu)", ws_bytes, L.total);
+  const MilGeom geo = mil_geom(side);
+  const MilPF8 gp = mil_pf8(n, 20, geo.h[0], geo.h[0]);
+  char* wsb = reinterpret_cast<char*>(ws);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!stem_use_tc(dtype, impl))
+    return mil_launch_stem_fwd(dtype, bag, nullptr, n, side, w, b, pooled, gp, (uint8_t*)(wsb + L.off_argmax), s);
+  MIL_TRY(mil_zero_guards(MIL_BF16, wsb + L.off_xs, mil_stem_tc_geom_in(n, side), s));
+  MIL_TRY(mil_zero_guards(MIL_BF16, wsb + L.off_cv, mil_stem_tc_geom_conv(n, side), s));
+  return mil_launch_stem_tc_fwd(bag, 0, nullptr, n, side, w, b, wsb + L.off_xs, wsb + L.off_cv, (float*)(wsb + L.off_wp),
+                                wsb + L.off_wtc, pooled, gp, (uint8_t*)(wsb + L.off_argmax), s, nullptr);
+  MIL_API_END
+}
+
+int mil_stem_backward(int dtype, int impl, const float* bag, int n, int side, const void* g, float* dw, float* db, void* ws,
+                      size_t ws_bytes, void* stream) {
+  MIL_API_BEGIN
+  MIL_TRY(require_device());
+  MIL_REQUIRE(bag && g && dw && db && ws, "mil_stem_backward: null pointer argument");
+  MIL_REQUIRE(n >= 1 && side >= 8, "mil_stem_backward: bad shape n=%d side=%d", n, side);
+  const StemWs L = stem_ws_layout(n, side, dtype);
+  MIL_REQUIRE(ws_bytes >= L.total, "mil_stem_backward: workspace too small (%zu < %zu)", ws_bytes, L.total);
+  const MilGeom geo = mil_geom(side);
+  const MilPF8 gp = mil_pf8(n, 20, geo.h[0], geo.h[0]);
+  char* wsb = reinterpret_cast<char*>(ws);
+  cudaStream_t s = (cudaStream_t)stream;
+  float* partial = reinterpret_cast<float*>(wsb + L.off_partial);
+  if (!stem_use_tc(dtype, impl))
+    return mil_launch_stem_bwd(dtype, bag, nullptr, n, side, g, gp, (const uint8_t*)(wsb + L.off_argmax), partial, dw, db, s);
+  return mil_launch_stem_tc_bwd(wsb + L.off_xs, n, side, g, gp, (const uint8_t*)(wsb + L.off_argmax), wsb + L.off_cv, partial,
+                                dw, db, s);
   MIL_API_END
 }
 

@@ -85,9 +85,12 @@ int mil_launch_wgrad_tc_partials(const void* x, const MilPF8& gx, const void* dz
 int mil_launch_wgrad_tc(const void* x, const MilPF8& gx, const void* dz, const MilPF8& gz, float* partial, float* dw,
                         float* db, int ks, cudaStream_t s);
 
-// stem backward with the unpool fused into the A-operand construction (see mil_wgrad_tc.cu)
-int mil_launch_wgrad_tc_unpool(const void* x, const MilPF8& gx, const MilPF8& gz, const void* g, const MilPF8& gp,
-                               const uint16_t* argmax, float* partial, int* ctas_out, long long* rec_out, cudaStream_t s);
+// stem backward with the un-pool fused into the A-operand construction (mil_stem_wgrad.cu): partial records of the
+// space-to-depth weight gradient from xs, the POOLED gradient g and the arg-max records am (mil_stem_unpool.cuh)
+bool mil_stem_wgrad_supported(const MilPF8& gp);
+size_t mil_stem_wgrad_partial_floats();
+int mil_launch_stem_wgrad(const void* xs, const MilPF8& gx, const void* g, const MilPF8& gp, const void* am, float* partial,
+                          int* ctas_out, long long* rec_out, cudaStream_t s);
 // 3x3 / stride-2 convolution: x given as its phase-split copy xs2 (4 * cb planes), dz at the output resolution
 int mil_launch_wgrad_tc_s2(const void* xs2, const MilPF8& gs, const void* dz, const MilPF8& gz, float* partial, float* dw,
                            float* db, int cin, cudaStream_t s);
@@ -96,7 +99,7 @@ int mil_launch_wgrad_tc_s2(const void* xs2, const MilPF8& gs, const void* dz, co
 // mask); supported for even conv-map sizes and padded rows of at most 127 pixels
 bool mil_stem_conv_pool_supported(const MilPF8& gp, int hc);
 int mil_launch_stem_conv_pool(const void* xs, const MilPF8& gi, const void* wtc, const float* bias4, void* pooled,
-                              const MilPF8& gp, uint16_t* argmax, void* mask_out, int hc, cudaStream_t s);
+                              const MilPF8& gp, void* argmax, void* mask_out, int hc, cudaStream_t s);
 
 // stem on the tensor cores (mil_stem_tc.cu)
 MilPF8 mil_stem_tc_geom_in(int n, int side);    // space-to-depth input: 12 channels, conv-output resolution, pad 2
@@ -104,6 +107,7 @@ MilPF8 mil_stem_tc_geom_conv(int n, int side);  // conv1 output: 20 channels, pa
 size_t mil_stem_tc_wpack_floats();
 size_t mil_stem_tc_wtc_bytes();
 size_t mil_stem_tc_partial_floats(int n, int side);
+size_t mil_stem_tc_argmax_bytes(const MilPF8& gp);  // arg-max records of the pooled map (mil_stem_unpool.cuh)
 bool mil_stem_tc_fused_pool(const MilPF8& gp, int side);
 int mil_launch_stem_tc_fwd(const void* x, int x_u8, const int* idx, int n, int side, const float* w, const float* b, void* xs,
                            void* convout, float* wp, void* wtc, void* pooled, const MilPF8& gp, uint8_t* argmax,

@@ -134,7 +134,8 @@ int mil_make_plan(int n, int side, int dtype, MilPlan* plan) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   pl.off_pooled = take(mil_pf8_bytes(pl.g[0], dtype));
-  pl.off_argmax = take((size_t)n * pl.geo.h[0] * pl.geo.h[0] * 20);
+  // max-pool arg-max: 1 byte per pooled element (CUDA-core stem) or the records of mil_stem_unpool.cuh (tensor-core stem)
+  pl.off_argmax = take(std::max((size_t)n * pl.geo.h[0] * pl.geo.h[0] * 20, mil_stem_tc_argmax_bytes(pl.g[0])));
   for (int l = 0; l < 4; ++l)
     for (int b = 0; b < 3; ++b) {
       pl.off_h[l * 3 + b] = take(mil_pf8_bytes(pl.g[l], dtype));

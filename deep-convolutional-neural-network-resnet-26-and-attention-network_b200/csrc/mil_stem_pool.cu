@@ -19,6 +19,7 @@
 
 #include "mil_common.cuh"
 #include "mil_conv_tc.cuh"
+#include "mil_stem_unpool.cuh"
 #include "mil_tc_ptx.cuh"
 
 #define SP_M 128
@@ -62,7 +63,7 @@ __device__ __forceinline__ uint32_t sp_pool9_pair(const uint4& UL, const uint4& 
 __global__ void __launch_bounds__(96 + SP_NG * 128, 1)
 stem_conv_pool_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat16* __restrict__ wtc,
                       const float* __restrict__ bias4, __nv_bfloat16* __restrict__ pooled, MilPF8 gp,
-                      uint16_t* __restrict__ argmax, uint32_t* __restrict__ mask_out, MilTcShape sh,
+                      uint2* __restrict__ argmax, uint32_t* __restrict__ mask_out, MilTcShape sh,
                       const __grid_constant__ TcIssue iss, int halo, int n_stages, long long chunk) {
   extern __shared__ __align__(128) unsigned char smem[];
   SpSmemHeader* hd = reinterpret_cast<SpSmemHeader*>(smem);
@@ -149,7 +150,6 @@ stem_conv_pool_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv
     const int row = quarter * 32 + lane;  // pixel of the tile = TMEM lane
     const int wp = (int)gp.wp;
     const uint32_t NINF2 = 0xFF80FF80u;
-    const size_t am_stride = (size_t)gp.h * gp.w;
     for (long long it = eg; it < nloc; it += SP_NG) {
       const long long q = (t_begin + it) * SP_M + row;
       const int n = (int)(q / gp.P);
@@ -205,7 +205,9 @@ stem_conv_pool_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv
         uint32_t outw[12];
 #pragma unroll
         for (int i = 0; i < 12; ++i) outw[i] = 0u;
-        uint16_t* pam = argmax + (size_t)n * 10 * am_stride + (size_t)y * gp.w + xo;
+        uint32_t amw[12];  // arg-max codes of the channel pairs (mil_stem_unpool.cuh)
+#pragma unroll
+        for (int i = 0; i < 12; ++i) amw[i] = MIL_AM_CODE;
 #pragma unroll
         for (int cp = 0; cp < SP_CB; ++cp) {
           uint4 L = pl[cp * SP_M], U = pu[cp * SP_M], UL = pul[cp * SP_M];
@@ -214,10 +216,14 @@ stem_conv_pool_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv
           if (!(up_ok && left_ok)) { UL.y = UL.w = NINF2; }
           uint32_t amp;
           outw[cp] = sp_pool9_pair(UL, U, L, pk[cp], amp);
-          pam[(size_t)cp * am_stride] = (uint16_t)amp;
+          amw[cp] = amp | MIL_AM_CODE;
         }
         // pooled channel 2cp + {0,1} -> chunk cp / 4, word cp % 4 (channels 20..23 stay zero)
         const long long qo = (long long)n * gp.P + r;
+#pragma unroll
+        for (int pc = 0; pc < 3; ++pc)
+          argmax[(long long)pc * gp.PS + gp.G + qo] =
+              make_uint2(amw[4 * pc] | (amw[4 * pc + 1] << 16), amw[4 * pc + 2] | (amw[4 * pc + 3] << 16));
 #pragma unroll
         for (int pc = 0; pc < 3; ++pc)
           *reinterpret_cast<uint4*>(pooled + mil_pf8_off(gp, pc, qo)) =
@@ -261,7 +267,7 @@ bool mil_stem_conv_pool_supported(const MilPF8& gp, int hc) {
 }
 
 int mil_launch_stem_conv_pool(const void* xs, const MilPF8& gi, const void* wtc, const float* bias4, void* pooled,
-                              const MilPF8& gp, uint16_t* argmax, void* mask_out, int hc, cudaStream_t s) {
+                              const MilPF8& gp, void* argmax, void* mask_out, int hc, cudaStream_t s) {
   MIL_REQUIRE(mil_stem_conv_pool_supported(gp, hc), "stem_conv_pool: unsupported geometry (conv size %d, row %lld)", hc, gp.wp);
   MIL_REQUIRE(gi.n == gp.n && gi.h == gp.h && gi.w == gp.w && gi.wp == gp.wp && gi.cb == 6 && gp.cb == 3,
               "stem_conv_pool: geometry mismatch");
@@ -285,7 +291,7 @@ int mil_launch_stem_conv_pool(const void* xs, const MilPF8& gi, const void* wtc,
   const long long chunk = mil_cdiv(n_tiles, grid);
   MIL_SET_SMEM(stem_conv_pool_kernel, smem);
   stem_conv_pool_kernel<<<grid, 96 + SP_NG * 128, smem, s>>>((const __nv_bfloat16*)xs, gi, (const __nv_bfloat16*)wtc, bias4,
-                                                          (__nv_bfloat16*)pooled, gp, argmax, (uint32_t*)mask_out, sh, iss,
+                                                          (__nv_bfloat16*)pooled, gp, (uint2*)argmax, (uint32_t*)mask_out, sh, iss,
                                                           halo, n_stages, chunk);
   MIL_LAUNCH_OK();
   return 0;

@@ -20,6 +20,7 @@
 
 #include "mil_common.cuh"
 #include "mil_conv_tc.cuh"
+#include "mil_stem_unpool.cuh"
 
 #define STC_CO 20
 #define STC_CI 48   // 3 * 4 * 4
@@ -94,7 +95,7 @@ __global__ void stem_pack_w4_kernel(const float* __restrict__ w, const float* __
 // pooled (py,px) covers conv rows 2py-1, 2py, 2py+1 = (py-1, a=1), (py, a=0), (py, a=1); same for columns: the
 // nine window positions live in FOUR neighbouring pixels of the phase map.  cv channel = co*4 + a*2 + b -> chunk
 // co/2; thread = (pooled pixel, pair of output channels) loads those four 16-byte chunks once.
-// arg-max layout: [tile][channel pair cp][py*w + px] as uint16 = (am of co 2cp) | (am of co 2cp+1) << 8.
+// arg-max records: mil_stem_unpool.cuh (uint2 per pooled chunk and flat pixel).
 __device__ __forceinline__ void unpack8h(const uint4& r, float v[8]) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
 #pragma unroll
@@ -136,7 +137,7 @@ __device__ __forceinline__ uint32_t pool9_pair(const uint4& UL, const uint4& U, 
 
 __global__ void __launch_bounds__(256)
 stem_pool4_kernel(const __nv_bfloat16* __restrict__ cv, MilPF8 gc, int hc, __nv_bfloat16* __restrict__ pooled,
-                  MilPF8 gp, uint16_t* __restrict__ argmax) {
+                  MilPF8 gp, uint2* __restrict__ argmax) {
   // one thread per (pooled pixel, pooled chunk pc of 3) = four channel pairs cp = 4pc .. 4pc+3 (cp < 10): every
   // pooled chunk leaves as ONE 16-byte store.  The kernel is bound by its instruction stream, not by HBM, so the
   // common case (even conv size: phases a = 1 / b = 1 always inside the map) is branch-free: neighbours outside the
@@ -157,8 +158,7 @@ stem_pool4_kernel(const __nv_bfloat16* __restrict__ cv, MilPF8 gc, int hc, __nv_
       const bool up_ok = py > 0, left_ok = px > 0;
       const bool all_phases = 2 * py + 1 < hc && 2 * px + 1 < hc;
       const uint4* ps = reinterpret_cast<const uint4*>(cv + mil_pf8_off(gc, pc * 4, qc));  // chunk cp: + j * gc.PS
-      uint16_t* pam = argmax + ((size_t)n * 10 + pc * 4) * gp.h * gp.w + (size_t)py * gp.w + px;
-      const size_t am_stride = (size_t)gp.h * gp.w;
+      uint32_t amw[4] = {MIL_AM_CODE, MIL_AM_CODE, MIL_AM_CODE, MIL_AM_CODE};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (j >= ncp) break;
@@ -173,7 +173,7 @@ stem_pool4_kernel(const __nv_bfloat16* __restrict__ cv, MilPF8 gc, int hc, __nv_
           if (!(up_ok && left_ok)) { UL.y = UL.w = NINF2; }
           uint32_t amp;
           outw[j] = pool9_pair(UL, U, L, S, amp);
-          pam[(size_t)j * am_stride] = (uint16_t)amp;
+          amw[j] = amp | MIL_AM_CODE;
           packed = true;
           continue;
         } else {  // odd conv size, last row / column: test every window position
@@ -198,11 +198,12 @@ stem_pool4_kernel(const __nv_bfloat16* __restrict__ cv, MilPF8 gc, int hc, __nv_
             }
           }
         }
-        pam[(size_t)j * am_stride] = (uint16_t)(am[0] | (am[1] << 8));
+        amw[j] = (uint32_t)(am[0] | (am[1] << 8)) | MIL_AM_CODE;
         // pooled channel co = 2cp + {0,1} -> chunk co/8 = pc, lane co%8 = 2j + {0,1}   (j is compile-time here)
         out[2 * j] = best[0];
         out[2 * j + 1] = best[1];
       }
+      argmax[(long long)pc * gp.PS + gp.G + q] = make_uint2(amw[0] | (amw[1] << 16), amw[2] | (amw[3] << 16));
     }
     if (packed) *reinterpret_cast<uint4*>(pooled + mil_pf8_off(gp, pc, q)) = make_uint4(outw[0], outw[1], outw[2], outw[3]);
     else mil_store8(pooled + mil_pf8_off(gp, pc, q), out);
@@ -210,14 +211,14 @@ stem_pool4_kernel(const __nv_bfloat16* __restrict__ cv, MilPF8 gc, int hc, __nv_
 }
 
 // ---- 4. backward: dY4(Y,X)[(co,a,b)] = sum of g(py,px)[co] over the pooled windows whose arg-max is conv (2Y+a, 2X+b)
-// The windows that can point into pixel (Y,X) of the phase map are the pooled pixels (Y,X), (Y,X+1), (Y+1,X),
-// (Y+1,X+1): load their arg-max pairs and gradient pairs once, then test the nine (window, position) combinations.
+// Un-fused form (cross-check of mil_stem_wgrad.cu, which builds the same chunks in shared memory): the windows that
+// can point into pixel (Y,X) of the phase map are the pooled pixels (Y,X), (Y,X+1), (Y+1,X), (Y+1,X+1); the routing
+// arithmetic is mil_unpool_pair, shared with the fused kernel.
 __global__ void __launch_bounds__(256)
-stem_unpool4_kernel(const __nv_bfloat16* __restrict__ g, MilPF8 gp, const uint16_t* __restrict__ argmax,
-                    __nv_bfloat16* __restrict__ dy, MilPF8 gc, int hc) {
-  // one thread per (phase-map pixel, pooled chunk pc of 3): the four neighbouring pooled gradients are loaded as whole
-  // 16-byte chunks ONCE and serve the (up to) four channel pairs cp = 4pc .. 4pc+3, each one 16-byte chunk of dY4
-  // grid = (image, pixel block, pooled chunk): no 64-bit index arithmetic per thread
+stem_unpool4_kernel(const __nv_bfloat16* __restrict__ g, MilPF8 gp, const uint2* __restrict__ argmax,
+                    __nv_bfloat16* __restrict__ dy, MilPF8 gc) {
+  // one thread per (phase-map pixel, pooled chunk pc of 3): the (up to) four channel pairs cp = 4pc .. 4pc+3, each one
+  // 16-byte chunk of dY4.  grid = (image, pixel block, pooled chunk): no 64-bit index arithmetic per thread
   const int n = blockIdx.x, pc = blockIdx.z;
   const int r = blockIdx.y * blockDim.x + threadIdx.x;
   if (r < (int)gc.P) {
@@ -225,62 +226,24 @@ stem_unpool4_kernel(const __nv_bfloat16* __restrict__ g, MilPF8 gp, const uint16
     const int Y = r / gc.wp, X = r - Y * gc.wp;
     const bool inside = Y < gc.h && X < gc.w;
     const int ncp = pc == 2 ? 2 : 4;
-    float gv[2][2][8];
-    bool ok[2][2];
+    const int wp = gp.wp;
+    uint4 out[4];
 #pragma unroll
-    for (int dyy = 0; dyy < 2; ++dyy)
+    for (int k = 0; k < 4; ++k) out[k] = make_uint4(0, 0, 0, 0);
+    if (inside) {
+      const uint4* gpl = reinterpret_cast<const uint4*>(g) + (long long)pc * gp.PS + gp.G;
+      const uint2* apl = argmax + (long long)pc * gp.PS + gp.G;
+      const uint4 G00 = __ldg(gpl + q), G01 = __ldg(gpl + q + 1), G10 = __ldg(gpl + q + wp), G11 = __ldg(gpl + q + wp + 1);
+      const uint2 A00 = __ldg(apl + q), A01 = __ldg(apl + q + 1), A10 = __ldg(apl + q + wp), A11 = __ldg(apl + q + wp + 1);
 #pragma unroll
-      for (int dxx = 0; dxx < 2; ++dxx) {
-        const int py = Y + dyy, px = X + dxx;
-        ok[dyy][dxx] = inside && py < gp.h && px < gp.w;
-        uint4 raw = make_uint4(0, 0, 0, 0);
-        if (ok[dyy][dxx])
-          raw = __ldg(reinterpret_cast<const uint4*>(
-              g + mil_pf8_off(gp, pc, (long long)n * gp.P + (long long)py * gp.wp + px)));
-        unpack8h(raw, gv[dyy][dxx]);
-      }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (j >= ncp) break;
-      const int cp = pc * 4 + j;  // chunk of dY4 = channel pair (co = 2cp, 2cp+1) x 4 phases
-      float acc[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-      if (inside) {
-        int am0[2][2], am1[2][2];
-#pragma unroll
-        for (int dyy = 0; dyy < 2; ++dyy)
-#pragma unroll
-          for (int dxx = 0; dxx < 2; ++dxx) {
-            am0[dyy][dxx] = am1[dyy][dxx] = 255;
-            if (ok[dyy][dxx]) {
-              const uint32_t amv =
-                  argmax[((size_t)n * 10 + cp) * gp.h * gp.w + (size_t)(Y + dyy) * gp.w + (X + dxx)];
-              am0[dyy][dxx] = amv & 0xFF;
-              am1[dyy][dxx] = amv >> 8;
-            }
-          }
-        // conv position (2Y+a, 2X+b) seen from pooled window (Y+dyy, X+dxx) is window position
-        //   wy = 2Y+a - (2(Y+dyy)-1) = a + 1 - 2 dyy,  wx = b + 1 - 2 dxx   (valid when 0 <= wy,wx <= 2)
-        // pooled gradient lanes 2j, 2j+1 of the chunk (j is compile-time after unrolling)
-#pragma unroll
-        for (int a = 0; a < 2; ++a)
-#pragma unroll
-          for (int b = 0; b < 2; ++b)
-#pragma unroll
-            for (int dyy = 0; dyy < 2; ++dyy)
-#pragma unroll
-              for (int dxx = 0; dxx < 2; ++dxx) {
-                const int wy = a + 1 - 2 * dyy, wx = b + 1 - 2 * dxx;
-                if (wy < 0 || wx < 0) continue;  // compile-time after unrolling
-                const int want = wy * 3 + wx;
-                if (am0[dyy][dxx] == want) acc[a * 2 + b] += gv[dyy][dxx][2 * j];
-                if (am1[dyy][dxx] == want) acc[4 + a * 2 + b] += gv[dyy][dxx][2 * j + 1];
-              }
-      }
-      mil_store8(dy + mil_pf8_off(gc, cp, q), acc);
+      for (int k = 0; k < 4; ++k)
+        if (k < ncp)
+          out[k] = mil_unpool_pair(mil_word(G00, k), mil_word(G01, k), mil_word(G10, k), mil_word(G11, k),
+                                   mil_am_lanes(A00, k), mil_am_lanes(A01, k), mil_am_lanes(A10, k), mil_am_lanes(A11, k));
     }
-    (void)hc;  // positions beyond the conv map can never be an arg-max: nothing to mask here
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < ncp) *reinterpret_cast<uint4*>(dy + mil_pf8_off(gc, pc * 4 + k, q)) = out[k];
   }
 }
 
@@ -336,8 +299,10 @@ size_t mil_stem_tc_wtc_bytes() {
   return mil_tc_wpack_bytes(sh);
 }
 size_t mil_stem_tc_partial_floats(int n, int side) {
-  return mil_wgrad_tc_partial_floats(mil_stem_tc_geom_in(n, side), mil_stem_tc_geom_conv(n, side), 3);
+  return std::max(mil_wgrad_tc_partial_floats(mil_stem_tc_geom_in(n, side), mil_stem_tc_geom_conv(n, side), 3),
+                  mil_stem_wgrad_partial_floats());
 }
+size_t mil_stem_tc_argmax_bytes(const MilPF8& gp) { return (size_t)3 * gp.PS * sizeof(uint2); }
 
 static int grid_for(long long work) { return (int)std::max<long long>(1, std::min<long long>(mil_cdiv(work, 256), 148 * 16)); }
 
@@ -350,7 +315,7 @@ bool mil_stem_tc_fused_pool(const MilPF8& gp, int side) {
 int mil_launch_stem_tc_fwd(const void* x, int x_u8, const int* idx, int n, int side, const float* w, const float* b, void* xs,
                            void* convout, float* wp, void* wtc, void* pooled, const MilPF8& gp, uint8_t* argmax8,
                            cudaStream_t s, void* pooled_mask) {
-  uint16_t* argmax = reinterpret_cast<uint16_t*>(argmax8);  // [tile][10 channel pairs][h0*w0] (same 20 B per pixel)
+  uint2* argmax = reinterpret_cast<uint2*>(argmax8);  // arg-max records [3][gp.PS] (mil_stem_unpool.cuh)
   const MilPF8 gi = mil_stem_tc_geom_in(n, side), gc = mil_stem_tc_geom_conv(n, side);
   const int hc = (side - 1) / 2 + 1;
   MIL_REQUIRE(gp.h == gi.h && gp.w == gi.w && gp.c == STC_CO && gp.n == n, "stem_tc_fwd: geometry mismatch");
@@ -376,18 +341,17 @@ int mil_launch_stem_tc_fwd(const void* x, int x_u8, const int* idx, int n, int s
 
 int mil_launch_stem_tc_bwd(const void* xs, int n, int side, const void* g, const MilPF8& gp, const uint8_t* argmax8,
                            void* dy, float* partial, float* dw, float* db, cudaStream_t s) {
-  const uint16_t* argmax = reinterpret_cast<const uint16_t*>(argmax8);
+  const uint2* argmax = reinterpret_cast<const uint2*>(argmax8);
   const MilPF8 gi = mil_stem_tc_geom_in(n, side), gc = mil_stem_tc_geom_conv(n, side);
-  const int hc = (side - 1) / 2 + 1;
   int ctas;
   long long rec;
-  if (mil_opt(MIL_OPT_STEM_UNFUSED) == 0) {
+  if (mil_opt(MIL_OPT_STEM_UNFUSED) == 0 && mil_stem_wgrad_supported(gp)) {
     // the un-pooled gradient (80 channels at the phase-map resolution, the largest tensor of the backward pass) is
     // built inside the weight-gradient kernel, tile by tile, straight into its A-operand planes
-    MIL_TRY(mil_launch_wgrad_tc_unpool(xs, gi, gc, g, gp, argmax, partial, &ctas, &rec, s));
+    MIL_TRY(mil_launch_stem_wgrad(xs, gi, g, gp, argmax, partial, &ctas, &rec, s));
   } else {
     stem_unpool4_kernel<<<dim3(gc.n, (unsigned)mil_cdiv(gc.P, 256), 3), 256, 0, s>>>((const __nv_bfloat16*)g, gp, argmax,
-                                                                                   (__nv_bfloat16*)dy, gc, hc);
+                                                                                   (__nv_bfloat16*)dy, gc);
     MIL_LAUNCH_OK();
     MIL_TRY(mil_launch_wgrad_tc_partials(xs, gi, dy, gc, partial, 3, &ctas, &rec, s));
   }

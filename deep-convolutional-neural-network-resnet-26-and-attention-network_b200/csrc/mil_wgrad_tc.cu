@@ -11,7 +11,7 @@
 // Three kernels share this file:
 //   wgrad_sq_kernel  layers 1-2 (3 or 5 chunks on both sides): ONE M = 128 MMA per K-step yields all nine taps and
 //                    the bias gradient; shifted operand planes are built in shared memory (see its own header)
-//   wgrad_tc_kernel  everything else.  A thin MMA is bound by its operand reads (profiles/r1_mma_cost2.txt), so for
+//   wgrad_tc_kernel  everything else (the stem's own weight gradient lives in mil_stem_wgrad.cu).  A thin MMA is bound by its operand reads (profiles/r1_mma_cost2.txt), so for
 //                    the 3x3 layers the three dx taps are CONCATENATED along N: the producer loads three copies of
 //                    every x plane, shifted by -1 / 0 / +1 pixel, as consecutive shared-memory planes; N-group
 //                    (chunk, dx) then sits at a uniform stride and ONE MMA per (dy, K-step) covers N = 3*Cin columns
@@ -36,92 +36,9 @@
 #define WG_SLACK (8 * 1024)
 
 struct WgSmemHeader {
-  uint64_t full[WG_MAX_STAGES], empty[WG_MAX_STAGES], a_ready[WG_MAX_STAGES], done;
+  uint64_t full[WG_MAX_STAGES], empty[WG_MAX_STAGES], done;
   uint32_t tmem_base;
 };
-#define WG_BUILD_WARPS 20  // stem backward only: warps 6..25 compute the A operand (un-pooled gradient) in place;
-                           // ~170 instructions per (pixel, chunk): the work needs most of the SM's issue slots
-
-// The stem's output gradient at the phase-map resolution, built ON THE FLY from the pooled gradient and the arg-max
-// (what stem_unpool4_kernel writes to HBM in the un-fused path): chunk cp = channel pair (2cp, 2cp+1) x 4 phases of
-// phase-map pixel (n, Y, X).  The pooled windows that can point into it are (Y,X), (Y,X+1), (Y+1,X), (Y+1,X+1).
-struct WgUnpool {
-  const __nv_bfloat16* g;   // pooled gradient (PF8, geometry gp); nullptr = the A operand comes from memory
-  const uint16_t* argmax;   // [tile][10][h*w], (am of channel 2cp) | (am of 2cp+1) << 8
-  MilPF8 gp;
-};
-// Per-thread state of one phase-map pixel: validity, pooled-gradient pointers and arg-max pointers of the four
-// windows, computed once per tile; wg_unpool_chunk then costs ~65 instructions per chunk.
-struct WgUnpoolPix {
-  bool ok[2][2];
-  const uint4* g[2][2];         // chunk 0 of the pooled gradient at the window's pixel
-  const uint16_t* am[2][2];     // channel pair 0 of the arg-max at the window's pixel
-  long long g_plane;            // uint4 between pooled-gradient chunks
-  size_t am_plane;              // elements between arg-max channel pairs
-};
-__device__ __forceinline__ WgUnpoolPix wg_unpool_pixel(const WgUnpool& u, int n, int Y, int X, bool inside) {
-  WgUnpoolPix px;
-  px.g_plane = u.gp.PS;
-  px.am_plane = (size_t)u.gp.h * u.gp.w;
-  const uint4* gbase = reinterpret_cast<const uint4*>(u.g) + u.gp.G + (long long)n * u.gp.P;
-  const uint16_t* abase = u.argmax + (size_t)n * 10 * px.am_plane;
-#pragma unroll
-  for (int dyy = 0; dyy < 2; ++dyy)
-#pragma unroll
-    for (int dxx = 0; dxx < 2; ++dxx) {
-      const int py = Y + dyy, pxx = X + dxx;
-      px.ok[dyy][dxx] = inside && py < u.gp.h && pxx < u.gp.w;
-      px.g[dyy][dxx] = gbase + (long long)py * u.gp.wp + pxx;
-      px.am[dyy][dxx] = abase + (size_t)py * u.gp.w + pxx;
-    }
-  return px;
-}
-// gq[dyy][dxx] = pooled-gradient chunk (cp / 4) of the four windows, loaded once per pooled chunk by the caller
-__device__ __forceinline__ uint4 wg_unpool_chunk(const WgUnpoolPix& px, const uint4 gq[2][2], int cp) {
-  float acc[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-  const int j = cp & 3;
-  int am0[2][2], am1[2][2];
-  float g0[2][2], g1[2][2];
-#pragma unroll
-  for (int dyy = 0; dyy < 2; ++dyy)
-#pragma unroll
-    for (int dxx = 0; dxx < 2; ++dxx) {
-      am0[dyy][dxx] = am1[dyy][dxx] = 255;
-      const uint4& v = gq[dyy][dxx];
-      const uint32_t gw = j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w));  // channels 2cp, 2cp+1
-      g0[dyy][dxx] = __uint_as_float(gw << 16);
-      g1[dyy][dxx] = __uint_as_float(gw & 0xFFFF0000u);
-      if (px.ok[dyy][dxx]) {
-        const uint32_t amv = px.am[dyy][dxx][(size_t)cp * px.am_plane];
-        am0[dyy][dxx] = amv & 0xFF;
-        am1[dyy][dxx] = amv >> 8;
-      }
-    }
-  // conv position (2Y+a, 2X+b) seen from pooled window (Y+dyy, X+dxx) is window position
-  //   wy = a + 1 - 2 dyy,  wx = b + 1 - 2 dxx   (valid when 0 <= wy, wx <= 2)
-#pragma unroll
-  for (int a = 0; a < 2; ++a)
-#pragma unroll
-    for (int b = 0; b < 2; ++b)
-#pragma unroll
-      for (int dyy = 0; dyy < 2; ++dyy)
-#pragma unroll
-        for (int dxx = 0; dxx < 2; ++dxx) {
-          const int wy = a + 1 - 2 * dyy, wx = b + 1 - 2 * dxx;
-          if (wy < 0 || wx < 0) continue;  // compile-time after unrolling
-          const int want = wy * 3 + wx;
-          if (am0[dyy][dxx] == want) acc[a * 2 + b] += g0[dyy][dxx];
-          if (am1[dyy][dxx] == want) acc[4 + a * 2 + b] += g1[dyy][dxx];
-        }
-  uint4 r;
-  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(acc[2 * i], acc[2 * i + 1]);
-  return r;
-}
-
 // Explicit MMA list for the stride-2 3x3 convolution on its phase-split input (mil_tc_shape_s2): MMA i multiplies dz
 // with the `cb` planes starting at plane0[i], read `shift[i]` pixels away, and produces tap rtap[i] = ky * 3 + kx of
 // the 3x3 weight.  n = 0: the taps come from the window description `sh`.
@@ -133,10 +50,10 @@ struct WgCombo {
 
 // dxcat = 1: 3x3 window, taps grouped by dy, N = (dx, chunk) planes;  dxcat = 0: one tap per MMA (1x1 window, or the
 // explicit list `cmb`)
-__global__ void __launch_bounds__(WG_THREADS + 32 * WG_BUILD_WARPS, 1)
+__global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat16* __restrict__ dz, MilPF8 gz,
                 float* __restrict__ partial, long long rec_stride, MilTcShape sh, int halo, int taps_per_group,
-                int npad, int mma_m, int dxcat, int fold, int n_stages, WgCombo cmb, int lane_split, WgUnpool unp) {
+                int npad, int mma_m, int dxcat, int fold, int n_stages, WgCombo cmb, int lane_split) {
   extern __shared__ __align__(128) unsigned char smem[];
   WgSmemHeader* hd = reinterpret_cast<WgSmemHeader*>(smem);
   unsigned char* ones = smem + 128;            // 512 B of bf16 1.0: the B operand of the bias-gradient MMA
@@ -151,8 +68,7 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
   // (building the dx = -1 / +1 copies in shared memory instead of fetching them, as wgrad_sq_kernel does, was
   // measured SLOWER for these wide layers: their MMAs already saturate the shared-memory bandwidth)
   const uint32_t b_pitch = b_plane;
-  const bool build_a = unp.g != nullptr;  // A planes computed by the builder warps instead of fetched
-  const uint32_t load_bytes = (build_a ? 0u : a_bytes) + (uint32_t)nbp * b_plane;
+  const uint32_t load_bytes = a_bytes + (uint32_t)nbp * b_plane;
   // fold = 1: one more B plane per stage, constant 1.0, so the bias gradient is one more N-group of the tap MMAs
   // (a thin M = 64 MMA costs the tensor pipe 28 cycles whatever its N: profiles/r1_mma_cost.txt)
   const uint32_t stage_bytes = a_bytes + (uint32_t)(nbp + (fold ? 1 : 0)) * b_pitch;
@@ -167,7 +83,6 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
     for (int s = 0; s < n_stages; ++s) {
       mbar_init(&hd->full[s], 1);
       mbar_init(&hd->empty[s], 1);
-      mbar_init(&hd->a_ready[s], WG_BUILD_WARPS);
     }
     mbar_init(&hd->done, 1);
     fence_barrier_init();
@@ -196,9 +111,8 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
         mbar_expect_tx(&hd->full[stage], load_bytes);
         const long long q0 = t * WG_TK;
         unsigned char* dst = stage0 + (size_t)stage * stage_bytes;
-        if (!build_a)
-          for (int c = 0; c < gz.cb; ++c)
-            bulk_g2s(dst + (size_t)c * WG_A_PLANE, dz + mil_pf8_off(gz, c, q0), WG_A_PLANE, &hd->full[stage]);
+        for (int c = 0; c < gz.cb; ++c)
+          bulk_g2s(dst + (size_t)c * WG_A_PLANE, dz + mil_pf8_off(gz, c, q0), WG_A_PLANE, &hd->full[stage]);
         if (dxcat) {  // three shifted fetches of every plane, slots (chunk, dx)
           for (int c = 0; c < gx.cb; ++c)
             for (int dx = 0; dx < 3; ++dx)
@@ -225,7 +139,6 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
     bool first = true;
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       mbar_wait(&hd->full[stage], phase);
-      if (build_a) mbar_wait(&hd->a_ready[stage], phase);
       tc_fence_after();
       const uint32_t a_base = smem_u32(stage0 + (size_t)stage * stage_bytes);
       const uint32_t b_base = a_base + a_bytes;
@@ -261,43 +174,6 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
     }
     if (elect_one()) umma_commit(&hd->done);
     __syncwarp();
-  } else if (warp >= WG_THREADS / 32) {
-    // A builders (stem backward): thread = (pixel of the K-tile, half of the chunks); the stage's A planes are free
-    // when the MMAs of its previous use have completed (same barrier the producer waits on)
-    if (build_a) {
-      // thread = (pixel, k): chunks k, k + 5 (10 chunks over 5 thread sets)
-      const int tid = threadIdx.x - WG_THREADS, p = tid & (WG_TK - 1), kset = tid >> 7;
-      int stage = 0;
-      uint32_t phase = 0;
-      for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const long long q = t * WG_TK + p;
-        const int n = (int)(q / gz.P);
-        const int r = (int)(q - (long long)n * gz.P);
-        const int Y = r / gz.wp, X = r - Y * gz.wp;
-        const bool inside = n < gz.n && Y < gz.h && X < gz.w;
-        const WgUnpoolPix px = wg_unpool_pixel(unp, n, Y, X, inside);
-        mbar_wait(&hd->empty[stage], phase ^ 1);
-        uint4* ap = reinterpret_cast<uint4*>(stage0 + (size_t)stage * stage_bytes);
-        int pc_loaded = -1;
-        uint4 gq[2][2];
-        for (int cp = kset; cp < gz.cb; cp += WG_BUILD_WARPS / 4) {
-          if ((cp >> 2) != pc_loaded) {  // next pooled chunk: its four window pixels, once
-            pc_loaded = cp >> 2;
-#pragma unroll
-            for (int dyy = 0; dyy < 2; ++dyy)
-#pragma unroll
-              for (int dxx = 0; dxx < 2; ++dxx)
-                gq[dyy][dxx] = px.ok[dyy][dxx] ? __ldg(px.g[dyy][dxx] + (long long)pc_loaded * px.g_plane)
-                                               : make_uint4(0, 0, 0, 0);
-          }
-          ap[cp * WG_TK + p] = wg_unpool_chunk(px, gq, cp);
-        }
-        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&hd->a_ready[stage]);
-        if (++stage == n_stages) { stage = 0; phase ^= 1; }
-      }
-    }
   } else {
     // epilogue: TMEM lane = output channel co, columns = (local tap, B plane, 8 ci)
     const int quarter = warp & 3;
@@ -616,7 +492,7 @@ int mil_launch_wgrad_tc_partials(const void* x, const MilPF8& gx, const void* dz
   const long long rec = (long long)sh.ntaps * gx.cb * 8 * gz.cb * 8 + gz.cb * 8;
   wgrad_tc_kernel<<<dim3(c.ctas, c.groups), WG_THREADS, c.smem, s>>>(
       (const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)dz, gz, partial, rec, sh, halo, c.tpg, c.npad, c.mma_m, c.dxcat,
-      c.fold, c.n_stages, WgCombo{}, c.lane_split, WgUnpool{});
+      c.fold, c.n_stages, WgCombo{}, c.lane_split);
   MIL_LAUNCH_OK();
   *ctas_out = c.ctas;
   *rec_out = rec;
@@ -661,38 +537,9 @@ int mil_launch_wgrad_tc_s2(const void* xs2, const MilPF8& gs, const void* dz, co
   MIL_SET_SMEM((wgrad_tc_kernel), (int)smem);
   const long long rec = (long long)9 * cb * 8 * gz.cb * 8 + gz.cb * 8;
   wgrad_tc_kernel<<<dim3(ctas, groups), WG_THREADS, smem, s>>>((const __nv_bfloat16*)xs2, gs, (const __nv_bfloat16*)dz, gz,
-                                                              partial, rec, sh, halo, tpg, npad, mma_m, 0, 0, n_stages, cmb, 0, WgUnpool{});
+                                                              partial, rec, sh, halo, tpg, npad, mma_m, 0, 0, n_stages, cmb, 0);
   MIL_LAUNCH_OK();
   return mil_launch_reduce_conv_w(partial, ctas, rec, dw, db, gz.c, cin, 3, s);
-}
-
-// Stem backward: partial records of the 3x3 weight gradient of (xs, dY4) where dY4 = unpool(g, argmax) is computed
-// inside the kernel (gz = geometry of the phase map, 80 channels; g / argmax at the pooled geometry gp)
-int mil_launch_wgrad_tc_unpool(const void* x, const MilPF8& gx, const MilPF8& gz, const void* g, const MilPF8& gp,
-                               const uint16_t* argmax, float* partial, int* ctas_out, long long* rec_out, cudaStream_t s) {
-  MIL_REQUIRE(gx.n == gz.n && gx.h == gz.h && gx.w == gz.w && gx.wp == gz.wp && gp.h == gz.h && gp.w == gz.w &&
-                  gp.wp == gz.wp && gz.cb == 10 && gp.cb == 3,
-              "wgrad_tc_unpool: geometry mismatch");
-  const WgConfig c = wg_config(gx, gz, 3);
-  MIL_REQUIRE(!c.sq && c.dxcat && c.groups == 1 && !c.fold, "wgrad_tc_unpool: unexpected kernel configuration");
-  MilTcShape sh;
-  MIL_TRY(mil_tc_shape(gx.c, gz.c, 3, &sh));
-  const int halo = mil_tc_halo(sh, gx.wp);
-  MIL_REQUIRE(halo <= gx.G, "wgrad_tc_unpool: the window reaches %d pixels back but the map's guard is %lld", halo, gx.G);
-  MIL_REQUIRE(c.smem <= 227 * 1024, "wgrad_tc_unpool: tile width %d needs %zu bytes of shared memory", gx.w, c.smem);
-  MIL_SET_SMEM((wgrad_tc_kernel), (int)c.smem);
-  const long long rec = (long long)sh.ntaps * gx.cb * 8 * gz.cb * 8 + gz.cb * 8;
-  WgUnpool u;
-  u.g = (const __nv_bfloat16*)g;
-  u.argmax = argmax;
-  u.gp = gp;
-  wgrad_tc_kernel<<<dim3(c.ctas, 1), WG_THREADS + 32 * WG_BUILD_WARPS, c.smem, s>>>(
-      (const __nv_bfloat16*)x, gx, nullptr, gz, partial, rec, sh, halo, c.tpg, c.npad, c.mma_m, c.dxcat, c.fold, c.n_stages,
-      WgCombo{}, 0, u);
-  MIL_LAUNCH_OK();
-  *ctas_out = c.ctas;
-  *rec_out = rec;
-  return 0;
 }
 
 int mil_launch_wgrad_tc(const void* x, const MilPF8& gx, const void* dz, const MilPF8& gz, float* partial, float* dw,

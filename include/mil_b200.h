@@ -142,7 +142,11 @@ int mil_upsample2_pf8(const void* in, int n, int c, int h, int w, void* out, int
 size_t mil_conv_workspace_bytes(int n, int cin, int hi, int wi, int cout, int ho, int wo, int ks);
 /* out = epilogue(conv(x, w)):  epi 0: lrelu(acc+bias+res), 1: (acc+res)*lrelu'(act), 2: acc+bias+res.
  * transposed=1 computes the data gradient (x has the conv's OUTPUT geometry, out its INPUT geometry).
- * w is the PyTorch [cout,cin,ks,ks] fp32 weight.                                                            */
+ * w is the PyTorch [cout,cin,ks,ks] fp32 weight.  res has out's geometry, EXCEPT for the stride-2 data gradient
+ * (transposed=1, stride=2), where it is the half-resolution gradient of the block's 1x1 projection branch
+ * ([n,cin] at x's spatial size) and is added at the even positions -- how nnBlocks.py:183-187's two branches meet in
+ * backward.  In bf16 mode the stride-2 3x3 convolution runs in the extractor's own tensor-core forms (forward on the
+ * phase-split input, data gradient per input row parity) whenever they fit.                                  */
 int mil_conv_pf8(int dtype, int impl, int transposed, const void* x, int n, int cx, int hx, int wx, const float* w,
                  int cout, int cin, int ks, int stride, const float* bias, const void* res, const void* act,
                  void* out, int ho, int wo, int epi, void* ws, size_t ws_bytes, void* stream);
@@ -150,6 +154,18 @@ int mil_conv_pf8(int dtype, int impl, int transposed, const void* x, int n, int 
 int mil_conv_wgrad_pf8(int dtype, int impl, const void* x, int n, int cin, int hi, int wi, const void* dz, int cout,
                        int ho, int wo, int ks, int stride, float* dw, float* db, void* ws, size_t ws_bytes,
                        void* stream);
+
+/* Stem at layer level (gbm/model.py:24-26,51-53: conv 7x7 / stride 2 / pad 3 + bias, LeakyReLU(0.1), max-pool 3x3 /
+ * stride 2 / pad 1) and its backward pass (weight + bias gradient; the bag is detached, gbm/model.py:194,196).
+ * bag: fp32 NCHW [n,3,side,side]; pooled / g: PF8 [n,20,h0,h0] (the pooled map / the gradient w.r.t. its
+ * PRE-activation, i.e. already multiplied by LeakyReLU'); dw [20,3,7,7], db [20] are ACCUMULATED.  impl: 0 = what the
+ * extractor runs, 1 = CUDA-core kernels, 2 = tcgen05 (bf16).  mil_stem_backward needs the workspace of the
+ * mil_stem_forward call on the same bag (space-to-depth input, arg-max records).                                 */
+size_t mil_stem_workspace_bytes(int n, int side, int dtype);
+int mil_stem_forward(int dtype, int impl, const float* bag, int n, int side, const float* w, const float* b, void* pooled,
+                     void* ws, size_t ws_bytes, void* stream);
+int mil_stem_backward(int dtype, int impl, const float* bag, int n, int side, const void* g, float* dw, float* db, void* ws,
+                      size_t ws_bytes, void* stream);
 
 /* ---- training-loop glue ------------------------------------------------------
  * One Adam step over the FLAT parameter / gradient buffers (state-dict order, mil_param_offset) in one launch:

@@ -127,3 +127,67 @@ def relerr(a, b, atol=1e-7):
         return 0.0
     den = float(b.abs().max())
     return diff / (den if den > 0 else 1.0)
+
+
+def extractor_forward_backward(params, bag, dH, precision, idx=None):
+    """mil_extractor_forward + mil_extractor_backward through the C ABI with a CALLER-CHOSEN upstream gradient dH
+    [n,80]: the extractor's kernels without the head in front of them (whose bag-wide BatchNorm1d backward makes the
+    whole-path gradients of small bags an ill-conditioned difference of large numbers).
+    params: dict name -> tensor (state-dict order is taken from the library).  Returns (H, {name: gradient})."""
+    import ctypes
+    mil = pkg()
+    L = lib()
+    table = mil._lib.param_table()
+    dev = torch.device("cuda")
+    ps = [params[nm].detach().float().contiguous().to(dev) for nm, _, _ in table]
+    pp = (ctypes.c_void_p * len(ps))(*[p.data_ptr() for p in ps])
+    dt = DT[precision]
+    bag = bag.contiguous().to(dev)
+    n = int(bag.shape[0]) if idx is None else int(idx.numel())
+    side = int(bag.shape[2])
+    nbytes = int(L.mil_extractor_workspace_bytes(n, side, dt))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    H = torch.empty((n, 80), dtype=torch.float32, device=dev)
+    ix = None if idx is None else idx.to(torch.int32).to(dev)
+    fwd = L.mil_extractor_forward_u8 if bag.dtype == torch.uint8 else L.mil_extractor_forward
+    check(fwd(pp, _p(bag), _p(ix), n, side, dt, _p(ws), nbytes, _p(H), _s()), "mil_extractor_forward")
+    grads = torch.zeros(int(L.mil_param_total()), dtype=torch.float32, device=dev)
+    dH = dH.float().contiguous().to(dev)
+    check(L.mil_extractor_backward(pp, _p(bag), _p(ix), n, side, dt, _p(ws), nbytes, _p(dH), _p(grads), _s()),
+          "mil_extractor_backward")
+    torch.cuda.synchronize()
+    out = {}
+    for nm, shape, off in table:
+        if nm.startswith("cnn."):
+            numel = 1
+            for d in shape:
+                numel *= d
+            out[nm] = grads[off:off + numel].view(shape).clone()
+    return H, out
+
+
+class Stem:
+    """Layer-level stem (mil_stem_forward / mil_stem_backward): keeps the workspace between the two calls."""
+
+    def __init__(self, bag, w, b, dtype, impl=0):
+        self.bag = bag.float().contiguous().cuda()
+        self.w, self.b = w.float().contiguous().cuda(), b.float().contiguous().cuda()
+        self.dtype, self.impl = dtype, impl
+        self.n, self.side = int(bag.shape[0]), int(bag.shape[2])
+        nbytes = int(lib().mil_stem_workspace_bytes(self.n, self.side, DT[dtype]))
+        self.ws = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+        hc = (self.side - 1) // 2 + 1
+        self.h0 = (hc - 1) // 2 + 1
+
+    def forward(self) -> PF8:
+        out = PF8(self.n, 20, self.h0, self.h0, self.dtype)
+        check(lib().mil_stem_forward(DT[self.dtype], self.impl, _p(self.bag), self.n, self.side, _p(self.w), _p(self.b),
+                                     _p(out.buf), _p(self.ws), self.ws.numel(), _s()), "mil_stem_forward")
+        return out
+
+    def backward(self, g: PF8):
+        dw = torch.zeros((20, 3, 7, 7), dtype=torch.float32, device="cuda")
+        db = torch.zeros(20, dtype=torch.float32, device="cuda")
+        check(lib().mil_stem_backward(DT[self.dtype], self.impl, _p(self.bag), self.n, self.side, _p(g.buf), _p(dw), _p(db),
+                                      _p(self.ws), self.ws.numel(), _s()), "mil_stem_backward")
+        return dw, db

@@ -58,8 +58,15 @@ def test_pf8_layout_round_trip_and_zero_halo(dtype):
     assert abs(float(raw.abs().sum()) - float(q(x, dtype).abs().sum())) < 1e-4 * float(x.abs().sum())
 
 
+# (cin, cout, ks, stride, H, n).  In bf16 mode impl=0 runs what the extractor runs: tcgen05 kernels, the stride-2 3x3
+# convolutions in their phase-split forms (forward on the split input, weight gradient as nine single-tap MMAs, data
+# gradient per input row parity with the half-resolution residual), 1x1 / stride-2 on the even-position copy; 60 -> 80
+# does not fit the split form and takes the full-resolution evaluation / zero-stuffed gradients.  48 -> 80 is the
+# stem's space-to-depth shape (the un-fused stem backward runs this weight gradient).
 CONV_CASES = [(20, 20, 3, 1, 14, 3), (20, 40, 3, 2, 14, 2), (20, 40, 1, 2, 14, 2), (40, 60, 3, 2, 13, 3),
-              (40, 60, 1, 2, 13, 3), (60, 80, 3, 2, 10, 2), (80, 80, 3, 1, 5, 37), (20, 20, 3, 1, 56, 2)]
+              (40, 60, 1, 2, 13, 3), (60, 80, 3, 2, 10, 2), (80, 80, 3, 1, 5, 37), (20, 20, 3, 1, 56, 2),
+              (20, 40, 3, 2, 56, 2), (40, 60, 3, 2, 28, 3), (40, 60, 3, 2, 27, 2), (60, 80, 3, 2, 14, 5),
+              (48, 80, 3, 1, 16, 3), (40, 40, 3, 1, 28, 2), (60, 60, 3, 1, 14, 4)]
 
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
@@ -82,16 +89,63 @@ def test_conv_forward_dgrad_wgrad_vs_torch(dtype, impl, cin, cout, ks, stride, H
     assert abs(float(raw.abs().sum()) - float(out.to_nchw().abs().sum())) <= 1e-5 * float(raw.abs().sum())
     dz = q(torch.randn(n, cout, Ho, Ho, device="cuda", generator=gen), dtype)
     act = q(torch.randn(n, cin, H, H, device="cuda", generator=gen), dtype)
-    rs = q(torch.randn(n, cin, H, H, device="cuda", generator=gen), dtype)
-    DZ, ACT, RS = (G.PF8.from_nchw(t, dtype) for t in (dz, act, rs))
-    out = G.conv(DZ, w, res=RS, act=ACT, stride=stride, epi=1, transposed=True, out_hw=(H, H), impl=impl)
     gi = torch.nn.grad.conv2d_input(x.shape, w, dz, stride=stride, padding=pad)
-    assert G.relerr(out.to_nchw(), (gi + rs) * lgrad(act)) < tol
+    if stride == 1:
+        rs = q(torch.randn(n, cin, H, H, device="cuda", generator=gen), dtype)
+    elif dtype == "bf16" and ks == 3:
+        # stride-2 data gradient: the residual is the HALF-resolution gradient of the block's projection branch, added
+        # at the even positions (include/mil_b200.h)
+        rs_half = q(torch.randn(n, cin, Ho, Ho, device="cuda", generator=gen), dtype)
+        rs = torch.zeros(n, cin, H, H, device="cuda")
+        rs[:, :, ::2, ::2] = rs_half
+    else:
+        rs = None
+    DZ, ACT = (G.PF8.from_nchw(t, dtype) for t in (dz, act))
+    RS = None if rs is None else G.PF8.from_nchw(rs if stride == 1 else rs_half, dtype)
+    out = G.conv(DZ, w, res=RS, act=ACT, stride=stride, epi=1, transposed=True, out_hw=(H, H), impl=impl)
+    assert G.relerr(out.to_nchw(), (gi + (0 if rs is None else rs)) * lgrad(act)) < tol
+    raw = out.raw().float()   # the full-resolution gradient map keeps its zero pad row / column and guards
+    assert abs(float(raw.abs().sum()) - float(out.to_nchw().abs().sum())) <= 1e-5 * float(raw.abs().sum())
     dw, db = G.wgrad(X, DZ, ks, stride, impl=impl)
     gw = torch.nn.grad.conv2d_weight(x, w.shape, dz, stride=stride, padding=pad)
     wtol = 2e-5 if dtype == "fp32" else 2e-3
     assert G.relerr(dw, gw) < wtol
     assert G.relerr(db, dz.sum(dim=(0, 2, 3))) < wtol
+
+
+@pytest.mark.parametrize("dtype,impl", [("fp32", 1), ("bf16", 1), ("bf16", 2)])
+@pytest.mark.parametrize("n,side", [(3, 224), (5, 64), (2, 129), (2, 256), (3, 100)])
+def test_stem_forward_backward_vs_torch(dtype, impl, n, side):
+    """The stem alone (conv 7x7 / stride 2 + bias, LeakyReLU, max-pool 3x3 / stride 2; backward = weight + bias
+    gradient, gbm/model.py:24-26,51-53,194) against torch fp32.  impl 2 = the tensor-core kernels the bench times:
+    space-to-depth conv with the pool fused into its epilogue (even conv maps) or conv + pool kernels (odd: 129 and
+    100), and the weight-gradient kernel that un-pools inside (mil_stem_wgrad.cu).  In bf16 mode both sides see
+    bf16-representable tiles and weights, and torch pools the bf16-rounded conv map (where the kernels round); what is
+    left for the gradient is summation order plus the rare window whose two largest values differ by less than the
+    fp32 summation noise BEFORE rounding (the arg-max then routes the gradient to the other one): 3e-2 normwise --
+    a wrong tap or phase would be off by > 0.1."""
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    x = q(torch.randn(n, 3, side, side, device="cuda", generator=gen), dtype)
+    w = q(torch.randn(20, 3, 7, 7, device="cuda", generator=gen) / 147 ** 0.5, dtype)
+    b = torch.randn(20, device="cuda", generator=gen) * 0.1
+    st = G.Stem(x, w, b, dtype, impl)
+    pooled = st.forward()
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    cv = F.leaky_relu(F.conv2d(x, wr, br, stride=2, padding=3), 0.1)
+    if dtype == "bf16":
+        cv = cv + (cv.detach().bfloat16().float() - cv.detach())       # rounded values, straight-through gradient
+    ref = F.max_pool2d(cv, 3, 2, 1)
+    assert G.relerr(pooled.to_nchw(), ref) < (1e-5 if dtype == "fp32" else 8e-3)
+    raw = pooled.raw().float()
+    assert abs(float(raw.abs().sum()) - float(pooled.to_nchw().abs().sum())) <= 1e-5 * float(raw.abs().sum())
+    g = q(torch.randn(ref.shape, device="cuda", generator=gen), dtype)
+    # the kernels take the gradient w.r.t. the conv PRE-activation at the arg-max (the producer multiplies by LeakyReLU')
+    gpre = q(g * lgrad(ref.detach()), dtype)
+    dw, db = st.backward(G.PF8.from_nchw(gpre, dtype))
+    ref.backward(gpre / lgrad(ref.detach()))
+    gtol = 2e-4 if dtype == "fp32" else 3e-2
+    assert l2rel(dw, wr.grad.cpu()) < gtol, l2rel(dw, wr.grad.cpu())
+    assert l2rel(db, br.grad.cpu()) < gtol, l2rel(db, br.grad.cpu())
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
