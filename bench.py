@@ -1,23 +1,30 @@
 #!/usr/bin/env python
 """Benchmark of the ResNet-26 + attention-MIL hot path (BASELINE.json metric: tiles/sec fwd+bwd).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--tiles T] [--side S]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode M] [--tiles T] [--side S]
 
-A step = one forward + backward of `Attention` over one bag (BASELINE.json configs[1]: 4,096 RGB 224x224 tiles,
-bf16, all tiles through the CNN).  With N > 1 (torchrun, one rank per GPU) the bag is N x 4,096 tiles sharded
-over the ranks (configs[2]-style; weak scaling), the head's bag-wide sums and the weight gradients are
-all-reduced over NCCL.  Prints ONE JSON line (rank 0).
+--mode train (default): a step = one forward + backward of `Attention` over one bag (BASELINE.json configs[1]: 4,096
+    RGB 224x224 tiles, bf16, all tiles through the CNN).  With N > 1 (torchrun, one rank per GPU) the bag is N x 4,096
+    tiles sharded over the ranks (configs[2]; weak scaling): the head's bag-wide sums and the weight gradients are
+    all-reduced over NCCL.
+--mode multi-slide: configs[4] -- every rank its OWN bag (SlideGroup: bag statistics stay local, only the bucketed
+    gradient all-reduce overlapped with backward crosses ranks); use --tiles 8192 --side 256.
+--mode inference: configs[3] -- forward only under torch.no_grad() (forward-only extractor + head), every rank works
+    through its own slides (no collective); use --tiles 10000; slides/s is reported next to tiles/s.
+Prints ONE JSON line (rank 0).
 
   value  : tiles/s, bag resident in HBM, CUDA-event timed, max over ranks
   e2e    : same metric through the public API with the bag in pinned HOST memory: the fp32 NCHW bag is copied
-           host->device every step and the loss is read back, inside the timed region
+           host->device every step and the result (loss / attention weights) is read back, inside the timed region
   roofline: the dominant kernel (the 3x3 convolution of layer1, 31 % of the FLOPs) timed alone with CUDA events;
            it is HBM-bound (48 FLOP/B): achieved = algorithmic bytes per launch / duration against
-           MEASURED_PEAKS.json's copy bandwidth; the tensor-pipe fraction of the same launch is reported next to it
-  cpu_baseline: the CPU oracle port of the reference path (torch CPU, all host threads) on a bounded sample
+           MEASURED_PEAKS.json's copy bandwidth; `kernels` lists the other heavy kernels (layer-1 weight gradient,
+           stem weight gradient) the same way, so the line shows the worst ones and not only a representative one
+  cpu_baseline: the UNMODIFIED reference (oracle/_ref: gbm/model.py + nnBlocks.py under the three-piece shim) on all
+           host threads, fwd+bwd of a bounded 256-tile sample, 1 warm-up + 5 timed iterations, best and median
 
---impl reference times that CPU path alone (the reference is pure Python + torch and cannot travel to the GPU
-box, so the oracle port -- pinned to the reference's golden vectors -- stands in: kind "port").
+--impl reference times that CPU path alone with --steps / --warmup (kind "reference"; "port" = the oracle
+restatement, only when oracle/_ref is missing).
 """
 import argparse
 import importlib
@@ -114,27 +121,72 @@ def bind_to_gpu_numa_node(index):
     return None
 
 
-def cpu_reference_throughput(side, sample_tiles, reps, seed=1):
-    """fwd+bwd tiles/s of the CPU oracle port of the reference path on all host threads."""
+def cpu_arm(side, forward_only=False):
+    """fwd+bwd (or forward only, under no_grad) of the reference path on the CPU.  Returns (step(bag, Y), kind, description): the UNMODIFIED reference
+    source under the import shim when it is available (build container: /root/reference; GPU box: the copies
+    oracle/make_ref.py left under oracle/_ref), else the oracle restatement."""
     import torch
-    from oracle import mil_oracle
-    mil = importlib.import_module(PKG)
+    from oracle import mil_oracle, ref_shim
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
+    if ref_shim.reference_available():
+        net = ref_shim.build_reference(seed=0).eval()      # eval: every tile goes through the CNN (gbm/model.py:196)
+
+        def step(bag, Y):
+            if forward_only:
+                with torch.no_grad():
+                    return float(net(bag, Y)["loss"])
+            net.zero_grad(set_to_none=True)
+            out = net(bag, Y)
+            out["loss"].backward()
+            return float(out["loss"].detach())
+        return step, "reference", f"unmodified gbm/model.py + nnBlocks.py under oracle/ref_shim.py ({ref_shim.REFERENCE_ROOT})", cores
     p = mil_oracle.init_params(seed=0)
+
+    def step(bag, Y):
+        if forward_only:
+            with torch.no_grad():
+                return float(mil_oracle.attention_forward(p, bag, Y)["loss"])
+        out, _ = mil_oracle.forward_backward(p, bag, Y)
+        return float(out["loss"])
+    return step, "port", "oracle/mil_oracle.py restatement (oracle/_ref missing)", cores
+
+
+def cpu_model_name():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown CPU"
+
+
+def cpu_reference_throughput(side, sample_tiles, reps, warmup=1, seed=1, forward_only=False):
+    """(best tiles/s, median tiles/s, cores, kind, description, times) of the CPU arm on a bounded sample."""
+    import torch
+    mil = importlib.import_module(PKG)
+    step, kind, what, cores = cpu_arm(side, forward_only)
     bag = torch.from_numpy(mil.synth.make_bag(sample_tiles, side, seed=seed))
     Y = torch.tensor([1])
-    mil_oracle.forward_backward(p, bag[: max(2, sample_tiles // 8)], Y)      # warm-up
+    for _ in range(warmup):
+        step(bag, Y)
     times = []
     for _ in range(reps):
         t0 = time.perf_counter()
-        mil_oracle.forward_backward(p, bag, Y)
+        step(bag, Y)
         times.append(time.perf_counter() - t0)
-    best = min(times)
-    return sample_tiles / best, cores, times
+    srt = sorted(times)
+    return sample_tiles / srt[0], sample_tiles / srt[len(srt) // 2], cores, kind, what, times
 
 
-def workload_string(n, side, world):
+def workload_string(n, side, world, mode="train"):
+    if mode == "multi-slide":
+        return (f"{world} bag(s) of {n} RGB {side}x{side} tiles per step, one per GPU, all tiles through the CNN, fwd+bwd, "
+                f"gradients summed over the bags (BASELINE.json configs[4])")
+    if mode == "inference":
+        return (f"slides of {n} RGB {side}x{side} tiles, forward only (features + attention weights + logits), one slide "
+                f"per GPU per step (BASELINE.json configs[3])")
     return (f"bag of {n} RGB {side}x{side} tiles per GPU, all tiles through the CNN, fwd+bwd, 3 classes "
             f"(BASELINE.json configs[1]; N>1: one {n * world}-tile bag sharded over the ranks, configs[2])")
 
@@ -146,28 +198,32 @@ def run_reference(args):
     sample = args.ref_tiles
     t_all0 = time.perf_counter()
     import torch
-    from oracle import mil_oracle
     mil = importlib.import_module(PKG)
-    cores = len(os.sched_getaffinity(0))
-    torch.set_num_threads(cores)
-    p = mil_oracle.init_params(seed=0)
+    step, kind, what, cores = cpu_arm(args.side, forward_only=args.mode == "inference")
     bag = torch.from_numpy(mil.synth.make_bag(sample, args.side, seed=1))
     Y = torch.tensor([1])
     for _ in range(args.warmup):
-        mil_oracle.forward_backward(p, bag, Y)
-    t0 = time.perf_counter()
+        step(bag, Y)
+    times = []
     for _ in range(args.steps):
-        mil_oracle.forward_backward(p, bag, Y)
-    dt = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        step(bag, Y)
+        times.append(time.perf_counter() - t0)
+    dt = sum(times)
     v = sample * args.steps / dt
+    srt = sorted(times)
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": "tiles/s", "n_gpus": args.gpus,
+        "impl": "reference",
+        "metric": METRIC if args.mode != "inference" else "tiles/sec forward-only ResNet-26+attention-MIL (attention-map extraction)",
+        "value": v, "unit": "tiles/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_string(args.tiles, args.side, max(1, args.gpus)),
-                   "tiles_per_step_timed": sample},
-        "cpu_baseline": {"value": v, "unit": "tiles/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} of the {args.tiles} tiles per step, fp32, torch CPU {torch.__version__}"},
+        "config": {"workload": workload_string(args.tiles, args.side, max(1, args.gpus), args.mode),
+                   "tiles_per_step_timed": sample, "mode": args.mode},
+        "cpu_baseline": {"value": v, "unit": "tiles/s", "cores": cores, "kind": kind, "cpu": cpu_model_name(),
+                         "best": sample / srt[0], "median": sample / srt[len(srt) // 2],
+                         "sample": f"{sample} of the {args.tiles} tiles per step (throughput per tile, extrapolated "
+                                   f"linearly), {'forward only' if args.mode == 'inference' else 'fwd+bwd'}, fp32, torch CPU {torch.__version__}; {what}"},
         "e2e": {"value": v, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t_all0,
     }
@@ -190,6 +246,114 @@ def make_device_bag(mil, n, side, device, seed=1):
     return bag
 
 
+def time_calls(fn, reps, warm=3):
+    """Average duration (ms) of fn() over `reps` back-to-back calls, CUDA events on the current stream."""
+    import torch
+    for _ in range(warm):
+        fn()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    k0.record()
+    for _ in range(reps):
+        fn()
+    k1.record()
+    torch.cuda.synchronize()
+    return k0.elapsed_time(k1) / reps
+
+
+def kernel_rooflines(mil, lib, dev, n, side, precision, value_per_gpu):
+    """The heavy kernels of the step timed alone at the step's launch size, against the HBM roofline (all of them sit
+    left of the 253 FLOP/B ridge).  Algorithmic bytes = un-padded bf16 maps read + written once."""
+    import ctypes as C
+    import torch
+    burst, sustained, hbm, how = peaks()
+    h1 = ((side - 1) // 2 + 1 - 1) // 2 + 1
+    dt = mil.model.DTYPE_CODES[precision]
+    elem = 2 if precision == "bf16" else 4
+    P = lambda t: C.c_void_p(t.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ck = mil._lib.check
+    nb = int(lib.mil_pf8_bytes(n, 20, h1, h1, dt))
+    xin = torch.randn(n, 20, h1, h1, device=dev)
+    X = torch.zeros(nb, dtype=torch.uint8, device=dev)
+    R = torch.zeros(nb, dtype=torch.uint8, device=dev)     # residual / output gradient: a separate map, as in the network
+    O = torch.zeros(nb, dtype=torch.uint8, device=dev)
+    ck(lib.mil_to_pf8(dt, P(xin), P(X), n, 20, h1, h1, None), "mil_to_pf8")
+    ck(lib.mil_to_pf8(dt, P(torch.randn_like(xin)), P(R), n, 20, h1, h1, None), "mil_to_pf8")
+    del xin
+    w = torch.randn(20, 20, 3, 3, device=dev) * 0.1
+    bias = torch.zeros(20, device=dev)
+    wsb = int(lib.mil_conv_workspace_bytes(n, 20, h1, h1, 20, h1, h1, 3))
+    wsk = torch.zeros(wsb, dtype=torch.uint8, device=dev)
+
+    def conv_once():      # one weight-pack launch (~2 us) + the convolution kernel
+        ck(lib.mil_conv_pf8(dt, 0, 0, P(X), n, 20, h1, h1, P(w), 20, 20, 3, 1, P(bias), P(R), None, P(O), h1, h1, 0, P(wsk),
+                            wsb, st), "mil_conv_pf8")
+    kms = time_calls(conv_once, 10)
+    flop = 2.0 * 20 * 20 * 9 * h1 * h1 * n
+    ach = flop / (kms * 1e-3) / 1e12
+    abytes = 3.0 * 20 * h1 * h1 * elem * n      # input map + residual map + output map
+    gbs = abytes / (kms * 1e-3) / 1e9
+    src = f"MEASURED_PEAKS.json hbm_gbs ({how}, burst copy)"
+    roof = {"bound": "hbm", "kernel": "conv3x3 20->20 (layer1), fused bias+residual+LeakyReLU",
+            "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+            "traffic": L1_CONV_NCU_TRAFFIC.get(n), "peak_source": src,
+            "algorithmic_bytes_per_launch": abytes, "tiles_per_launch": n, "ms_per_launch": kms,
+            "tensor": {"achieved": ach, "peak": burst, "unit": "TFLOP/s", "frac": ach / burst},
+            "whole_step_tensor_frac_of_sustained": value_per_gpu * FLOP_FWD_BWD.get(side, 0) / 1e12 / sustained}
+    others = []
+    # layer-1 weight + bias gradient (wgrad_sq_kernel + its 10-us record reduction): reads x and dz
+    dw = torch.zeros(20, 20, 3, 3, device=dev)
+    db = torch.zeros(20, device=dev)
+
+    def wgrad_once():
+        ck(lib.mil_conv_wgrad_pf8(dt, 0, P(X), n, 20, h1, h1, P(R), 20, h1, h1, 3, 1, P(dw), P(db), P(wsk), wsb, st),
+           "mil_conv_wgrad_pf8")
+    wms = time_calls(wgrad_once, 10)
+    wbytes = 2.0 * 20 * h1 * h1 * elem * n
+    others.append({"kernel": "weight gradient 3x3 20->20 (layer1, 6 launches per step)", "bound": "hbm",
+                   "achieved": wbytes / (wms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                   "frac": wbytes / (wms * 1e-3) / 1e9 / hbm, "ms_per_launch": wms,
+                   "algorithmic_bytes_per_launch": wbytes,
+                   "tensor_tflops": flop / (wms * 1e-3) / 1e12})
+    del X, R, O, wsk
+    # stem: forward (space-to-depth + conv + bias + LeakyReLU + pool) and weight gradient with the un-pool inside
+    if precision == "bf16":
+        bag = torch.rand(n, 3, side, side, device=dev) * 2 - 1
+        w1 = torch.randn(20, 3, 7, 7, device=dev) * 0.08
+        b1 = torch.zeros(20, device=dev)
+        sws = int(lib.mil_stem_workspace_bytes(n, side, dt))
+        swk = torch.zeros(sws, dtype=torch.uint8, device=dev)
+        pooled = torch.zeros(nb, dtype=torch.uint8, device=dev)
+        gmap = torch.zeros(nb, dtype=torch.uint8, device=dev)
+        ck(lib.mil_to_pf8(dt, P(torch.randn(n, 20, h1, h1, device=dev)), P(gmap), n, 20, h1, h1, None), "mil_to_pf8")
+        dw1 = torch.zeros(20, 3, 7, 7, device=dev)
+
+        def stem_fwd():
+            ck(lib.mil_stem_forward(dt, 0, P(bag), n, side, P(w1), P(b1), P(pooled), P(swk), sws, st), "mil_stem_forward")
+
+        def stem_bwd():
+            ck(lib.mil_stem_backward(dt, 0, P(bag), n, side, P(gmap), P(dw1), P(b1), P(swk), sws, st), "mil_stem_backward")
+        fms = time_calls(stem_fwd, 5)
+        bms = time_calls(stem_bwd, 5)
+        px = h1 * h1
+        # forward: fp32 tiles in, bf16 space-to-depth copy out and back in, pooled map + arg-max records out
+        fbytes = (3.0 * side * side * 4 + 2 * 48 * px * 2 + 20 * px * 2 + 24 * px) * n
+        # backward: space-to-depth input + pooled gradient + arg-max records in
+        bbytes = (48.0 * px * 2 + 20 * px * 2 + 24 * px) * n
+        sflop = 2.0 * 20 * 147 * (2 * h1) * (2 * h1) * n
+        others.append({"kernel": "stem forward (3 launches: space-to-depth, conv7x7/s2+bias+LeakyReLU+max-pool)",
+                       "bound": "hbm", "achieved": fbytes / (fms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                       "frac": fbytes / (fms * 1e-3) / 1e9 / hbm, "ms_per_launch": fms,
+                       "algorithmic_bytes_per_launch": fbytes, "tensor_tflops": sflop / (fms * 1e-3) / 1e12})
+        others.append({"kernel": "stem weight gradient with the un-pool inside (stem_wgrad_kernel + reduction)",
+                       "bound": "hbm", "achieved": bbytes / (bms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                       "frac": bbytes / (bms * 1e-3) / 1e9 / hbm, "ms_per_launch": bms,
+                       "algorithmic_bytes_per_launch": bbytes, "tensor_tflops": sflop / (bms * 1e-3) / 1e12})
+    roof["kernels"] = others
+    return roof
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -198,13 +362,17 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    mode = args.mode
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     numa = bind_to_gpu_numa_node(local) if world > 1 else None
     group = mil.BagGroup()
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-        group = mil.BagGroup(dist.group.WORLD, seed=0, grad_buckets=1)
+        if mode == "train":
+            group = mil.BagGroup(dist.group.WORLD, seed=0, grad_buckets=1)       # ONE bag sharded over the ranks
+        elif mode == "multi-slide":
+            group = mil.SlideGroup(dist.group.WORLD)                             # one bag per rank, gradients summed
     lib = mil._lib.load()
 
     torch.manual_seed(0)
@@ -214,17 +382,37 @@ def run_ours(args):
     n, side = args.tiles, args.side
     bag = make_device_bag(mil, n, side, dev, seed=1 + rank)
     Y = torch.tensor([1], device=dev)
+    bag_tiles = n * world if (mode == "train" and world > 1) else None   # the loader knows the slide's size
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(x):
-        net.zero_grad(set_to_none=True)
-        out = net(x, Y)
-        out["loss"].backward()
-        return out
+    if mode == "inference":
+        def step(x):
+            with torch.no_grad():
+                return net(x, Y)
+        result_of = lambda out: out["Aterm"]            # the deliverable of the interface loop: attention weights
+    else:
+        def step(x):
+            net.zero_grad(set_to_none=True)
+            out = net(x, Y, bag_tiles=bag_tiles)
+            out["loss"].backward()
+            return out
+        result_of = lambda out: out["loss"].detach().reshape(1)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn(steps)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps, r
 
     # ---------------- device-resident ----------------
     sampler = ClockSampler(local)
@@ -237,158 +425,122 @@ def run_ours(args):
     barrier()
     t_begin = time.perf_counter()
     l0 = lib.mil_kernel_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        out = step(bag)
-    ev1.record()
-    barrier()
+
+    def resident(k):
+        out = None
+        for _ in range(k):
+            out = step(bag)
+        return out
+    ms_step, out = timed(resident, args.steps)
     launches = lib.mil_kernel_launch_count() - l0
     clocks = sampler.stop(t_begin, time.perf_counter()) if rank == 0 else None
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_step = float(ms) / args.steps
     value = n * world / (ms_step * 1e-3)
     loss_val = float(out["loss"].detach())
 
+    # ---------------- reference-faithful train mode: 20 % subsample + dropout (gbm/model.py:193, :107) ----------------
+    train_mode = None
+    if mode == "train" and world == 1:
+        net.train()
+        torch.manual_seed(1)
+
+        def train_steps(k):
+            for _ in range(k):
+                step(bag)
+        train_steps(2)
+        tms, _ = timed(train_steps, args.steps)
+        net.eval()
+        n_cnn = int(n * 0.2)
+        train_mode = {"bag_tiles_per_s": n / (tms * 1e-3), "cnn_tiles_per_s": n_cnn / (tms * 1e-3), "ms_per_step": tms,
+                      "tiles_through_cnn": n_cnn,
+                      "note": "module in train(): randperm 20 % subsample gathered inside the stem load + Dropout(0.25)"}
+
     # ---------------- end to end from pinned host memory ----------------
-    # Every step's bag starts in pinned HOST memory and is copied to the device inside the timed region; the loss
+    # Every step's bag starts in pinned HOST memory and is copied to the device inside the timed region; the result
     # is read back every step.  The copy of step k+1 is submitted (BagStager: side stream, double buffer) before
     # step k is processed, the way a prefetching input pipeline feeds a training loop.
     host = torch.empty((n, 3, side, side), dtype=torch.float32).pin_memory()
     host.copy_(bag)
     del bag
     stager = mil.BagStager(dev)
-
-    loss_host = torch.empty(2, dtype=torch.float32).pin_memory()
+    res_elems = 3 * n if mode == "inference" else 1
+    res_host = torch.empty((2, res_elems), dtype=torch.float32).pin_memory()
 
     def e2e_run(k_steps):
-        """Every step: bag host -> device (submitted one step ahead), forward + backward, loss device -> host.  The
-        loss of step k is READ on the host while step k+1 is already enqueued (a training loop that logs one step
-        late): blocking on it right away would idle the GPU for the ~1.9 ms it takes the host to enqueue a step."""
+        """Every step: bag host -> device (submitted one step ahead), the step, result device -> host.  The result of
+        step k is READ on the host while step k+1 is already enqueued (a loop that logs one step late): blocking on it
+        right away would idle the GPU for the ~1.5 ms it takes the host to enqueue a step."""
         ticket = stager.submit(host)
-        pending, losses = None, []
+        pending, seen = None, []
         for k in range(k_steps):
             nxt = stager.submit(host) if k + 1 < k_steps else None
             o = step(stager.get(ticket))
             slot = k & 1
-            loss_host[slot:slot + 1].copy_(o["loss"].detach().reshape(1), non_blocking=True)   # D2H of this step's result
+            res_host[slot].copy_(result_of(o).reshape(-1), non_blocking=True)      # D2H of this step's result
             ev = torch.cuda.Event()
             ev.record()
             stager.release(ticket)
             if pending is not None:
                 pending[1].synchronize()
-                losses.append(float(loss_host[pending[0]]))
+                seen.append(float(res_host[pending[0]][0]))
             pending = (slot, ev)
             ticket = nxt
         pending[1].synchronize()
-        losses.append(float(loss_host[pending[0]]))
-        assert len(losses) == k_steps and all(v == v for v in losses)
-        return losses[-1]
+        seen.append(float(res_host[pending[0]][0]))
+        assert len(seen) == k_steps and all(v == v for v in seen)
+        return seen[-1]
 
     e2e_run(max(1, min(args.warmup, 2)))
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    e2e_run(args.steps)
-    e1.record()
-    barrier()
-    ems = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-    e2e_value = n * world / (float(ems) / args.steps * 1e-3)
+    ems, _ = timed(e2e_run, args.steps)
+    e2e_value = n * world / (ems * 1e-3)
     # the same loop fed with raw 8-bit tiles (the reference's loader normalises uint8 pixels on the CPU; here the
     # normalisation is fused into the stem): a quarter of the PCIe bytes.  Reported as an extra key, `e2e` stays fp32.
     host_u8 = ((host + 1.0) * 127.5).round_().clamp_(0, 255).to(torch.uint8).pin_memory()
     host = host_u8
     e2e_run(2)
-    barrier()
-    u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    u0.record()
-    e2e_run(args.steps)
-    u1.record()
-    barrier()
-    ums = torch.tensor([u0.elapsed_time(u1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ums, op=dist.ReduceOp.MAX)
-    e2e_u8_value = n * world / (float(ums) / args.steps * 1e-3)
+    ums, _ = timed(e2e_run, args.steps)
+    e2e_u8_value = n * world / (ums * 1e-3)
     del host, host_u8, stager
 
-    # ---------------- dominant kernel alone: layer1 3x3 conv (rank 0) ----------------
+    # ---------------- heavy kernels alone (rank 0) ----------------
     roofline = None
     if rank == 0:
-        import ctypes as C
-        burst, sustained, hbm, how = peaks()
-        h1 = ((side - 1) // 2 + 1 - 1) // 2 + 1
-        nk = n                      # the launch the step itself makes: the whole shard in one kernel
-        dt = mil.model.DTYPE_CODES[args.precision]
-        P = lambda t: C.c_void_p(t.data_ptr())
-        nb = int(lib.mil_pf8_bytes(nk, 20, h1, h1, dt))
-        xin = torch.randn(nk, 20, h1, h1, device=dev)
-        X = torch.zeros(nb, dtype=torch.uint8, device=dev)
-        R = torch.zeros(nb, dtype=torch.uint8, device=dev)     # residual: a separate map, as inside the network
-        O = torch.zeros(nb, dtype=torch.uint8, device=dev)
-        mil._lib.check(lib.mil_to_pf8(dt, P(xin), P(X), nk, 20, h1, h1, None), "mil_to_pf8")
-        mil._lib.check(lib.mil_to_pf8(dt, P(torch.randn_like(xin)), P(R), nk, 20, h1, h1, None), "mil_to_pf8")
-        w = torch.randn(20, 20, 3, 3, device=dev) * 0.1
-        bias = torch.zeros(20, device=dev)
-        wsb = int(lib.mil_conv_workspace_bytes(nk, 20, h1, h1, 20, h1, h1, 3))
-        wsk = torch.zeros(wsb, dtype=torch.uint8, device=dev)
-        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        roofline = kernel_rooflines(mil, lib, dev, n, side, args.precision, value / world)
 
-        def conv_once():      # one weight-pack launch (~2 us) + the convolution kernel
-            mil._lib.check(lib.mil_conv_pf8(dt, 0, 0, P(X), nk, 20, h1, h1, P(w), 20, 20, 3, 1, P(bias), P(R), None,
-                                            P(O), h1, h1, 0, P(wsk), wsb, st), "mil_conv_pf8")
-        for _ in range(3):
-            conv_once()
-        reps = 10
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        k0.record()
-        for _ in range(reps):
-            conv_once()
-        k1.record()
-        torch.cuda.synchronize()
-        kms = k0.elapsed_time(k1) / reps
-        flop = 2.0 * 20 * 20 * 9 * h1 * h1 * nk
-        ach = flop / (kms * 1e-3) / 1e12
-        # algorithmic bytes: input map + residual map + output map, 20 channels bf16, un-padded (DESIGN.md section 4);
-        # at 48 FLOP/B this kernel sits far left of the 253 FLOP/B ridge: HBM is the roofline that binds it
-        elem = 2 if args.precision == "bf16" else 4
-        abytes = 3.0 * 20 * h1 * h1 * elem * nk
-        gbs = abytes / (kms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "conv3x3 20->20 (layer1), fused bias+residual+LeakyReLU",
-                    "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
-                    "traffic": L1_CONV_NCU_TRAFFIC.get(nk),
-                    "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({how}, burst copy)",
-                    "algorithmic_bytes_per_launch": abytes, "tiles_per_launch": nk, "ms_per_launch": kms,
-                    "tensor": {"achieved": ach, "peak": burst, "unit": "TFLOP/s", "frac": ach / burst},
-                    "whole_step_tensor_frac_of_sustained": value * FLOP_FWD_BWD.get(side, 0) / 1e12 / sustained}
-
-    # ---------------- CPU baseline (rank 0, N=1 only) ----------------
+    # ---------------- CPU baseline (rank 0, N=1 only): the unmodified reference, BASELINE.md section 4 protocol ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, cores, times = cpu_reference_throughput(side, args.ref_tiles, reps=2)
-        cpu = {"value": v, "unit": "tiles/s", "cores": cores, "kind": "port",
-               "sample": f"{args.ref_tiles} tiles of the same synthetic workload, fwd+bwd, fp32, best of {len(times)}"}
+        best, med, cores, kind, what, times = cpu_reference_throughput(side, args.ref_tiles, reps=5, warmup=1,
+                                                                       forward_only=mode == "inference")
+        cpu = {"value": best, "unit": "tiles/s", "cores": cores, "kind": kind, "cpu": cpu_model_name(), "best": best,
+               "median": med,
+               "sample": f"{args.ref_tiles} tiles of the same synthetic workload (per-tile throughput, extrapolated linearly "
+                         f"to the {n}-tile bag), {'forward only' if mode == 'inference' else 'fwd+bwd'}, fp32, 1 warm-up + "
+                         f"{len(times)} timed iterations; {what}"}
 
     if rank == 0:
+        bag_bytes = n * 3 * side * side
+        par = {"train": f"bag-sharded x{world}", "multi-slide": f"slide-parallel x{world} (gradient all-reduce only)",
+               "inference": f"slide-parallel x{world} (no collective)"}[mode]
         line = {
-            "metric": METRIC, "value": value, "unit": "tiles/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC if mode != "inference" else "tiles/sec forward-only ResNet-26+attention-MIL (attention-map extraction)",
+            "value": value, "unit": "tiles/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": workload_string(n, side, world),
-                       "tiles_per_gpu": n, "side": side, "parallelism": f"bag-sharded x{world}", "host_cores_per_rank": numa,
-                       "l2": f"inputs larger than L2 ({n * 3 * side * side * 4 / 1e6:.0f} MB bag per step)",
-                       "slides_per_s": value / (n * world), "loss": loss_val},
-            "e2e": {"value": e2e_value, "unit": "tiles/s", "h2d_bytes_per_step": n * 3 * side * side * 4,
-                    "d2h_bytes_per_step": 4},
-            "e2e_uint8_tiles": {"value": e2e_u8_value, "unit": "tiles/s", "h2d_bytes_per_step": n * 3 * side * side,
-                                "d2h_bytes_per_step": 4,
-                                "note": "same loop, 8-bit tiles, normalisation fused into the stem load"},
+            "config": {"workload": workload_string(n, side, world, mode), "mode": mode,
+                       "tiles_per_gpu": n, "side": side, "parallelism": par, "host_cores_per_rank": numa,
+                       "l2": f"inputs larger than L2 ({bag_bytes * 4 / 1e6:.0f} MB bag per GPU per step)",
+                       "slides_per_s": value / n if mode != "train" else value / (n * world), "loss": loss_val},
+            # bytes per STEP of the whole job (all ranks)
+            "e2e": {"value": e2e_value, "unit": "tiles/s", "h2d_bytes_per_step": bag_bytes * 4 * world,
+                    "d2h_bytes_per_step": 4 * res_elems * world},
+            "e2e_uint8_tiles": {"value": e2e_u8_value, "unit": "tiles/s", "h2d_bytes_per_step": bag_bytes * world,
+                                "d2h_bytes_per_step": 4 * res_elems * world,
+                                "note": "same loop, 8-bit tiles (what the reference's loader holds before ToTensor): "
+                                        "normalisation fused into the stem load -- the documented fast ingest path"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }
+        if train_mode is not None:
+            line["train_mode"] = train_mode
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -403,7 +555,8 @@ def main():
     ap.add_argument("--tiles", type=int, default=4096, help="tiles per GPU per step")
     ap.add_argument("--side", type=int, default=224)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--ref-tiles", type=int, default=64, help="tiles per step of the CPU arm (bounded sample)")
+    ap.add_argument("--mode", default="train", choices=["train", "multi-slide", "inference"])
+    ap.add_argument("--ref-tiles", type=int, default=256, help="tiles per step of the CPU arm (bounded sample)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -34,6 +34,9 @@ PROTOTYPES = {
                                       c_void_p, c_void_p]),
     "mil_extractor_forward_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t,
                                          c_void_p, c_void_p]),
+    "mil_extractor_infer_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "mil_extractor_infer": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t,
+                                    c_void_p, c_void_p]),
     "mil_extractor_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t,
                                        c_void_p, c_void_p, c_void_p]),
     "mil_extractor_backward_staged": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t,

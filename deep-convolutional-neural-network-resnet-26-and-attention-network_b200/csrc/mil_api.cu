@@ -128,6 +128,30 @@ size_t mil_extractor_workspace_bytes(int n_tiles, int side, int dtype) {
   }
 }
 
+size_t mil_extractor_infer_workspace_bytes(int n_tiles, int side, int dtype) {
+  try {
+    MilPlan pl;
+    if (mil_make_plan(n_tiles, side, dtype, &pl, true) != 0) return 0;
+    return pl.total_bytes;
+  } catch (...) {
+    mil_set_error("internal C++ exception");
+    return 0;
+  }
+}
+
+int mil_extractor_infer(const void* const* params, const void* bag, int bag_is_u8, const int32_t* idx, int n_tiles,
+                        int side, int dtype, void* ws, size_t ws_bytes, float* H, void* stream) {
+  MIL_API_BEGIN
+  MIL_TRY(require_device());
+  MIL_REQUIRE(params && bag && ws && H, "mil_extractor_infer: null pointer argument");
+  MilPlan pl;
+  MIL_TRY(mil_make_plan(n_tiles, side, dtype, &pl, true));
+  MIL_REQUIRE(ws_bytes >= pl.total_bytes, "mil_extractor_infer: workspace too small (%zu < %zu)", ws_bytes,
+              pl.total_bytes);
+  return mil_extractor_forward_impl(params, bag, bag_is_u8 ? 1 : 0, idx, pl, ws, H, (cudaStream_t)stream);
+  MIL_API_END
+}
+
 int mil_extractor_read_activation(int n_tiles, int side, int dtype, const void* ws, int which, float* nchw,
                                   void* stream) {
   MIL_API_BEGIN

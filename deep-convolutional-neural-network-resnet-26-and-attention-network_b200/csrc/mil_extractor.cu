@@ -77,12 +77,12 @@ MilPF8 mil_xs2_geom(const MilPlan& pl, int l) {
                         : mil_pf8(pl.n, kMilWidths[l - 1], pl.geo.h[l], pl.geo.h[l]);
 }
 
-int mil_make_plan(int n, int side, int dtype, MilPlan* plan) {
+int mil_make_plan(int n, int side, int dtype, MilPlan* plan, bool infer) {
   MIL_REQUIRE(n >= 1, "extractor: need at least one tile (got %d)", n);
   MIL_REQUIRE(side >= 8, "extractor: tile side %d too small", side);
   MIL_REQUIRE(dtype == MIL_F32 || dtype == MIL_BF16, "extractor: unknown dtype %d", dtype);
   MilPlan& pl = *plan;
-  pl.n = n; pl.side = side; pl.dtype = dtype;
+  pl.n = n; pl.side = side; pl.dtype = dtype; pl.infer = infer;
   pl.geo = mil_geom(side);
   for (int l = 0; l < 4; ++l) pl.g[l] = mil_pf8(n, kMilWidths[l], pl.geo.h[l], pl.geo.h[l]);
   pl.convs.clear();
@@ -135,14 +135,30 @@ int mil_make_plan(int n, int side, int dtype, MilPlan* plan) {
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   pl.off_pooled = take(mil_pf8_bytes(pl.g[0], dtype));
   // max-pool arg-max: 1 byte per pooled element (CUDA-core stem) or the records of mil_stem_unpool.cuh (tensor-core stem)
-  pl.off_argmax = take(std::max((size_t)n * pl.geo.h[0] * pl.geo.h[0] * 20, mil_stem_tc_argmax_bytes(pl.g[0])));
-  for (int l = 0; l < 4; ++l)
-    for (int b = 0; b < 3; ++b) {
-      pl.off_h[l * 3 + b] = take(mil_pf8_bytes(pl.g[l], dtype));
-      pl.off_y[l * 3 + b] = take(mil_pf8_bytes(pl.g[l], dtype));
-    }
+  pl.off_argmax = take(infer && dtype == MIL_BF16 && mil_tc_enabled()
+                           ? 256
+                           : std::max((size_t)n * pl.geo.h[0] * pl.geo.h[0] * 20, mil_stem_tc_argmax_bytes(pl.g[0])));
+  if (!infer) {
+    for (int l = 0; l < 4; ++l)
+      for (int b = 0; b < 3; ++b) {
+        pl.off_h[l * 3 + b] = take(mil_pf8_bytes(pl.g[l], dtype));
+        pl.off_y[l * 3 + b] = take(mil_pf8_bytes(pl.g[l], dtype));
+      }
+  } else {
+    // forward only (attention-map extraction, gbm/classify_combined.py:221-298): nothing is kept for a backward pass.
+    // The pooled map and two more buffers of the largest (layer-1) size rotate: block input -> h -> y -> next input
+    const size_t big = mil_pf8_bytes(pl.g[0], dtype);
+    const size_t rot[3] = {pl.off_pooled, take(big), take(big)};
+    int cur = 0;  // buffer holding the block input
+    for (int l = 0; l < 4; ++l)
+      for (int b = 0; b < 3; ++b) {
+        pl.off_h[l * 3 + b] = rot[(cur + 1) % 3];
+        pl.off_y[l * 3 + b] = rot[(cur + 2) % 3];
+        cur = (cur + 2) % 3;
+      }
+  }
   // 1-bit sign masks of every saved activation map: what the data-gradient epilogues read in place of the map
-  pl.masks = dtype == MIL_BF16 && mil_tc_enabled();
+  pl.masks = dtype == MIL_BF16 && mil_tc_enabled() && !infer;
   for (int i = 0; i < 12; ++i) pl.off_mh[i] = pl.off_my[i] = 0;
   if (pl.masks)
     for (int l = 0; l < 4; ++l)
@@ -156,11 +172,12 @@ int mil_make_plan(int n, int side, int dtype, MilPlan* plan) {
   pl.off_avg = take((size_t)n * 80 * sizeof(float));
   pl.grad_bytes = 0;
   for (int l = 0; l < 4; ++l) pl.grad_bytes = std::max(pl.grad_bytes, mil_pf8_bytes(pl.g[l], dtype));
+  if (infer) pl.grad_bytes = 0;
   for (int i = 0; i < 3; ++i) pl.off_grad[i] = take(pl.grad_bytes);
   // zero-stuffed output gradients of the three stride-2 blocks (tcgen05 path only): Cout channels at the
   // block's INPUT resolution
   pl.up_bytes = 0;
-  if (dtype == MIL_BF16 && mil_tc_enabled())
+  if (dtype == MIL_BF16 && mil_tc_enabled() && !infer)
     for (int l = 1; l < 4; ++l)
       pl.up_bytes = std::max(pl.up_bytes, mil_pf8_bytes(mil_pf8(n, kMilWidths[l], pl.geo.h[l - 1], pl.geo.h[l - 1]), dtype));
   for (int i = 0; i < 2; ++i) pl.off_up[i] = take(pl.up_bytes);
@@ -175,7 +192,7 @@ int mil_make_plan(int n, int side, int dtype, MilPlan* plan) {
       MilTcShape sh;
       MIL_TRY(mil_tc_shape_s2(kMilWidths[l - 1], kMilWidths[l], &sh));
       pl.s2_split[l] = mil_conv_tc_fits(sh, pl.g[l].wp) && 2 * ((kMilWidths[l - 1] + 7) / 8) <= 10;  // dgrad: 2 * cb output chunks
-      pl.off_xs2[l] = take(mil_pf8_bytes(mil_xs2_geom(pl, l), dtype));
+      pl.off_xs2[l] = (infer && l > 1) ? pl.off_xs2[1] : take(mil_pf8_bytes(mil_xs2_geom(pl, l), dtype));  // layer 2's is the largest
     }
   pl.stem_tc = (dtype == MIL_BF16) && mil_tc_enabled();
   pl.off_xs = pl.off_cv = pl.off_stem_wp = pl.off_stem_wtc = 0;
@@ -197,6 +214,7 @@ int mil_make_plan(int n, int side, int dtype, MilPlan* plan) {
       pf = std::max(pf, mil_wgrad_tc_partial_floats(gi, mil_pf8(n, c.cout, gi.h, gi.w), c.ks));
   }
   if (pl.stem_tc) pf = std::max(pf, mil_stem_tc_partial_floats(n, side));
+  if (infer) pf = 64;
   pl.partial_floats = pf;
   pl.off_partial = take(pf * sizeof(float));
   pl.total_bytes = off;
@@ -383,14 +401,19 @@ int mil_extractor_forward_impl(const void* const* params, const void* bag, int b
       guard_add(t, wsp(ws, pl.off_xs), mil_stem_tc_geom_in(pl.n, pl.side));
       if (!mil_stem_tc_fused_pool(pl.g[0], pl.side)) guard_add(t, wsp(ws, pl.off_cv), mil_stem_tc_geom_conv(pl.n, pl.side));
     }
-    for (int l = 0; l < 4; ++l)
-      for (int b = 0; b < 3; ++b) {
-        guard_add(t, wsp(ws, pl.off_h[l * 3 + b]), pl.g[l]);
-        guard_add(t, wsp(ws, pl.off_y[l * 3 + b]), pl.g[l]);
-      }
-    if (pl.dtype == MIL_BF16 && mil_tc_enabled())
-      for (int l = 1; l < 4; ++l)
-        guard_add(t, wsp(ws, pl.off_xs2[l]), mil_xs2_geom(pl, l));
+    if (!pl.infer) {
+      for (int l = 0; l < 4; ++l)
+        for (int b = 0; b < 3; ++b) {
+          guard_add(t, wsp(ws, pl.off_h[l * 3 + b]), pl.g[l]);
+          guard_add(t, wsp(ws, pl.off_y[l * 3 + b]), pl.g[l]);
+        }
+      if (pl.dtype == MIL_BF16 && mil_tc_enabled())
+        for (int l = 1; l < 4; ++l)
+          guard_add(t, wsp(ws, pl.off_xs2[l]), mil_xs2_geom(pl, l));
+    } else {  // rotating buffers: layer 1's geometry now, re-done at every layer boundary below
+      guard_add(t, wsp(ws, pl.off_h[0]), pl.g[0]);
+      guard_add(t, wsp(ws, pl.off_y[0]), pl.g[0]);
+    }
     MIL_TRY(launch_guards(t, s));
   }
   MIL_TRY(pack_weights(params, pl, ws, false, s));
@@ -403,7 +426,8 @@ int mil_extractor_forward_impl(const void* const* params, const void* bag, int b
     MIL_TRY(mil_launch_stem_tc_fwd(bag, bag_u8, idx, pl.n, pl.side, (const float*)params[p_c1w], (const float*)params[p_c1b],
                                    wsp(ws, pl.off_xs), wsp(ws, pl.off_cv), (float*)wsp(ws, pl.off_stem_wp),
                                    wsp(ws, pl.off_stem_wtc), wsp(ws, pl.off_pooled), pl.g[0],
-                                   (uint8_t*)wsp(ws, pl.off_argmax), s, pl.pool_mask ? wsp(ws, pl.off_mpool) : nullptr));
+                                   pl.infer ? nullptr : (uint8_t*)wsp(ws, pl.off_argmax), s,
+                                   pl.pool_mask ? wsp(ws, pl.off_mpool) : nullptr));
   else
     MIL_TRY(mil_launch_stem_fwd(dt, (const float*)bag, idx, pl.n, pl.side, (const float*)params[p_c1w],
                                 (const float*)params[p_c1b], wsp(ws, pl.off_pooled), pl.g[0],
@@ -412,7 +436,21 @@ int mil_extractor_forward_impl(const void* const* params, const void* bag, int b
   MilPF8 gx = pl.g[0];
   size_t ci = 0;
   for (int l = 0; l < 4; ++l) {
+    if (pl.infer && l > 0) {
+      // forward-only plan: the block's outputs land in buffers that held maps of the previous layer's geometry
+      GuardTable t;
+      t.count = 0;
+      t.esize = (int)mil_esize(dt);
+      guard_add(t, wsp(ws, pl.off_h[l * 3]), pl.g[l]);
+      guard_add(t, wsp(ws, pl.off_y[l * 3]), pl.g[l]);
+      if (pl.dtype == MIL_BF16 && mil_tc_enabled()) guard_add(t, wsp(ws, pl.off_xs2[l]), mil_xs2_geom(pl, l));
+      MIL_TRY(launch_guards(t, s));
+    }
     for (int b = 0; b < 3; ++b) {
+      if (pl.infer && l > 0 && b == 1) {
+        // the third rotating buffer still has the previous layer's geometry (it held this layer's block-0 input)
+        MIL_TRY(mil_zero_guards(dt, wsp(ws, pl.off_h[l * 3 + 1]), pl.g[l], s));
+      }
       const MilPF8& go = pl.g[l];
       void* h = wsp(ws, pl.off_h[l * 3 + b]);
       void* y = wsp(ws, pl.off_y[l * 3 + b]);

@@ -44,6 +44,7 @@ MilPF8 mil_xs2_geom(const MilPlan& pl, int l);  // geometry of the saved stride-
 
 struct MilPlan {
   int n, side, dtype;
+  bool infer;                   // forward-only plan: three rotating map buffers, no sign masks, no arg-max records
   MilGeom geo;
   MilPF8 g[4];                  // activation geometry of layer1..4
   std::vector<MilConvDesc> convs;  // 27 entries, forward order
@@ -56,7 +57,7 @@ struct MilPlan {
   size_t wpack_floats, wtc_bytes, partial_floats, grad_bytes, up_bytes;
   size_t total_bytes;
 };
-int mil_make_plan(int n, int side, int dtype, MilPlan* plan);
+int mil_make_plan(int n, int side, int dtype, MilPlan* plan, bool infer = false);
 
 int mil_extractor_forward_impl(const void* const* params, const void* bag, int bag_u8, const int* idx,
                                const MilPlan& pl, void* ws, float* H, cudaStream_t s);

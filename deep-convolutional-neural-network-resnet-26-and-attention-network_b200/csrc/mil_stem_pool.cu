@@ -220,10 +220,11 @@ stem_conv_pool_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv
         }
         // pooled channel 2cp + {0,1} -> chunk cp / 4, word cp % 4 (channels 20..23 stay zero)
         const long long qo = (long long)n * gp.P + r;
+        if (argmax != nullptr)  // (forward-only runs keep no arg-max records)
 #pragma unroll
-        for (int pc = 0; pc < 3; ++pc)
-          argmax[(long long)pc * gp.PS + gp.G + qo] =
-              make_uint2(amw[4 * pc] | (amw[4 * pc + 1] << 16), amw[4 * pc + 2] | (amw[4 * pc + 3] << 16));
+          for (int pc = 0; pc < 3; ++pc)
+            argmax[(long long)pc * gp.PS + gp.G + qo] =
+                make_uint2(amw[4 * pc] | (amw[4 * pc + 1] << 16), amw[4 * pc + 2] | (amw[4 * pc + 3] << 16));
 #pragma unroll
         for (int pc = 0; pc < 3; ++pc)
           *reinterpret_cast<uint4*>(pooled + mil_pf8_off(gp, pc, qo)) =

@@ -203,7 +203,8 @@ stem_pool4_kernel(const __nv_bfloat16* __restrict__ cv, MilPF8 gc, int hc, __nv_
         out[2 * j] = best[0];
         out[2 * j + 1] = best[1];
       }
-      argmax[(long long)pc * gp.PS + gp.G + q] = make_uint2(amw[0] | (amw[1] << 16), amw[2] | (amw[3] << 16));
+      if (argmax != nullptr)
+        argmax[(long long)pc * gp.PS + gp.G + q] = make_uint2(amw[0] | (amw[1] << 16), amw[2] | (amw[3] << 16));
     }
     if (packed) *reinterpret_cast<uint4*>(pooled + mil_pf8_off(gp, pc, q)) = make_uint4(outw[0], outw[1], outw[2], outw[3]);
     else mil_store8(pooled + mil_pf8_off(gp, pc, q), out);

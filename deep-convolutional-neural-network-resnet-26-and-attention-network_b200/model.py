@@ -208,17 +208,24 @@ class _MilFunction(torch.autograd.Function):
             raise ValueError(f"Expected more than 1 value per channel when training, got input size "
                              f"torch.Size([{n_global}, 80])")
         need_grad = any(ctx.needs_input_grad[6:])
-        nbytes = int(lib.mil_extractor_workspace_bytes(n, side, dt))
+        # no gradient wanted (validation / attention-map extraction under torch.no_grad(),
+        # gbm/classify_combined.py:221-357): the forward-only extractor keeps nothing for a backward pass
+        wsb = lib.mil_extractor_workspace_bytes if need_grad else lib.mil_extractor_infer_workspace_bytes
+        nbytes = int(wsb(n, side, dt))
         if nbytes == 0:
             _lib.check(1, "mil_extractor_workspace_bytes")
-        ws = owner._pool.acquire((n, side, dt, dev.index), nbytes, dev)
+        ws = owner._pool.acquire((n, side, dt, dev.index, need_grad), nbytes, dev)
         lease = _Lease(ws)
         st = _stream(dev)
         f32 = dict(dtype=torch.float32, device=dev)
         H = torch.empty((n, 80), **f32)
-        fwd = lib.mil_extractor_forward_u8 if bag.dtype == torch.uint8 else lib.mil_extractor_forward
-        _lib.check(fwd(pp, _ptr(bag), _ptr(idx), n, side, dt, _ptr(ws.buf), nbytes, _ptr(H), st),
-                   "mil_extractor_forward")
+        if need_grad:
+            fwd = lib.mil_extractor_forward_u8 if bag.dtype == torch.uint8 else lib.mil_extractor_forward
+            _lib.check(fwd(pp, _ptr(bag), _ptr(idx), n, side, dt, _ptr(ws.buf), nbytes, _ptr(H), st),
+                       "mil_extractor_forward")
+        else:
+            _lib.check(lib.mil_extractor_infer(pp, _ptr(bag), int(bag.dtype == torch.uint8), _ptr(idx), n, side, dt,
+                                               _ptr(ws.buf), nbytes, _ptr(H), st), "mil_extractor_infer")
         # ---- head (gbm/model.py:200-246) with the three bag-wide sums reduced across the bag group ----
         hws_bytes = int(lib.mil_head_workspace_bytes(n))
         hws = torch.empty(hws_bytes, dtype=torch.uint8, device=dev)
@@ -511,21 +518,28 @@ class Attention(nn.Module):
     def features(self, full_input: torch.Tensor) -> torch.Tensor:
         """Extractor only: bag [N,3,S,S] -> Fterm [N,80] (no subsample, no head)."""
         lib = _lib.load()
-        bag = full_input.detach().float().contiguous()
-        if not bag.is_cuda:
+        if not full_input.is_cuda:
             raise RuntimeError("features() needs a CUDA tensor: the B200 path has no CPU fallback")
+        bag = full_input.detach()
+        if bag.dtype == torch.uint8 and self.precision == "bf16":
+            bag = bag.contiguous()          # raw 8-bit tiles: normalised inside the stem's load
+        elif bag.dtype == torch.uint8:
+            bag = ((bag.float() / 255.0 - 0.5) / 0.5).contiguous()
+        else:
+            bag = bag.float().contiguous()
         params = self._params()
         for nm, p in zip(self._param_names, params):
             _check_param(nm, p)
         pp = (C.c_void_p * len(params))(*[p.data_ptr() for p in params])
         n, side, dt = int(bag.shape[0]), int(bag.shape[2]), DTYPE_CODES[self.precision]
-        nbytes = int(lib.mil_extractor_workspace_bytes(n, side, dt))
-        ws = self._pool.acquire((n, side, dt, bag.device.index), nbytes, bag.device)
+        nbytes = int(lib.mil_extractor_infer_workspace_bytes(n, side, dt))
+        ws = self._pool.acquire((n, side, dt, bag.device.index, False), nbytes, bag.device)
         try:
             with torch.cuda.device(bag.device):
                 H = torch.empty((n, 80), dtype=torch.float32, device=bag.device)
-                _lib.check(lib.mil_extractor_forward(pp, _ptr(bag), None, n, side, dt, _ptr(ws.buf), nbytes, _ptr(H),
-                                                     _stream(bag.device)), "mil_extractor_forward")
+                _lib.check(lib.mil_extractor_infer(pp, _ptr(bag), int(bag.dtype == torch.uint8), None, n, side, dt,
+                                                   _ptr(ws.buf), nbytes, _ptr(H), _stream(bag.device)),
+                           "mil_extractor_infer")
         finally:
             _WorkspacePool.release(ws)
         return H

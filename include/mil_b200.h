@@ -78,6 +78,13 @@ int mil_extractor_forward(const void* const* params_host, const float* bag, cons
  * bf16 mode only.  The backward entry points never read the bag in bf16 mode (pass the same pointer).            */
 int mil_extractor_forward_u8(const void* const* params_host, const uint8_t* bag, const int32_t* idx, int n_tiles,
                              int side, int dtype, void* ws, size_t ws_bytes, float* H, void* stream);
+/* Forward only -- attention-map extraction / validation under torch.no_grad() (gbm/classify_combined.py:221-298,
+ * :302-357): same kernels, but nothing is kept for a backward pass: three rotating map buffers instead of 25 saved
+ * maps, no sign masks, no arg-max records (workspace ~0.5 MB per 224x224 tile instead of ~3.5 MB).  bag_is_u8 selects
+ * raw 8-bit tiles (bf16 mode).  The workspace cannot be handed to mil_extractor_backward.                        */
+size_t mil_extractor_infer_workspace_bytes(int n_tiles, int side, int dtype);
+int mil_extractor_infer(const void* const* params_host, const void* bag, int bag_is_u8, const int32_t* idx, int n_tiles,
+                        int side, int dtype, void* ws, size_t ws_bytes, float* H, void* stream);
 /* autograd of the above (gbm/classify_combined.py:447): dH fp32 [n_tiles,80] -> grads_flat += d/d(params).
  * No gradient flows to `bag` (it is detached, gbm/model.py:194,196).                                         */
 int mil_extractor_backward(const void* const* params_host, const float* bag, const int32_t* idx, int n_tiles, int side,

@@ -1,8 +1,10 @@
 """Import the UNMODIFIED reference `gbm/model.py` on a CPU-only box.  TEST INFRASTRUCTURE ONLY.
 
-Works only where the reference checkout exists (the build container: /root/reference).  It is used
-by tests/golden/make_golden.py to generate the committed golden vectors, by the (skipped when the
-checkout is absent) live oracle-vs-reference test, and never by anything that runs on the GPU box.
+Needs the reference's two source files: the checkout of the build container (/root/reference) or the
+byte-for-byte copies oracle/make_ref.py puts under oracle/_ref/ (git-ignored; they travel to the GPU box).
+Used by tests/golden/make_golden.py to generate the committed golden vectors, by the live
+oracle-vs-reference test, and by bench.py's CPU legs (--impl reference, cpu_baseline) -- never by the
+product path.
 
 The shim is harness code, not a restatement:
   1. `PyTorchHelpers` (gbm/model.py:7) is not shipped with the reference -> empty stub module;
@@ -19,7 +21,19 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("MIL_REFERENCE_ROOT", "/root/reference")
+_VENDORED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")   # oracle/make_ref.py (git-ignored copies)
+
+
+def _find_root() -> str:
+    env = os.environ.get("MIL_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isfile("/root/reference/gbm/model.py"):
+        return "/root/reference"
+    return _VENDORED
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available() -> bool:

@@ -101,7 +101,7 @@ def read_activation(net, n, side, which):
     """Saved activation `which` of the most recent forward of `net` (see mil_extractor_read_activation)."""
     mil = pkg()
     dt = mil.model.DTYPE_CODES[net.precision]
-    key = (n, side, dt, torch.cuda.current_device())
+    key = (n, side, dt, torch.cuda.current_device(), True)      # the workspace of a forward that kept its activations
     ws = net._pool._items[key][0]
     # geometry
     hc = (side - 1) // 2 + 1

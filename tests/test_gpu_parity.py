@@ -158,7 +158,8 @@ def test_extractor_activations_vs_oracle(precision, n, side):
     bag = torch.from_numpy(synth.make_bag(n, side, seed=3))
     taps = {}
     Href = mil_oracle.resnet26_forward(golden_weights(), bag, taps=taps)
-    H = net.features(bag.cuda())
+    out = net(bag.cuda(), torch.tensor([1]).cuda())      # a forward that keeps its activations for backward
+    H = out["Fterm"]
     assert G.relerr(G.read_activation(net, n, side, -1), taps["stem"]) < tol
     for l in range(4):
         for b in range(3):
@@ -323,6 +324,32 @@ def test_uint8_tiles_equal_reference_normalisation(precision):
     else:                       # fp32 mode normalises with torch on the device (division rounding may differ by 1 ulp)
         for k in ("Fterm", "Aterm", "Mterm", "loss"):
             assert G.relerr(oa[k], ob[k]) < 1e-5, k
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+@pytest.mark.parametrize("n,side", [(20, 224), (7, 129), (9, 64), (4, 256)])
+def test_forward_only_extractor_equals_training_forward(precision, n, side):
+    """Validation / attention-map extraction runs under torch.no_grad() (gbm/classify_combined.py:221-357): the
+    forward-only extractor (three rotating map buffers, no sign masks, no arg-max records) must give the bits of the
+    forward pass that keeps everything for backward -- for fp32 and 8-bit bags, through forward() and features()."""
+    net = build_net(precision)
+    bag = torch.from_numpy(synth.make_bag(n, side, seed=13)).cuda()
+    Y = torch.tensor([1]).cuda()
+    full = net(bag, Y)
+    with torch.no_grad():
+        lean = net(bag, Y)
+    for k in ("Fterm", "Aterm", "wROIs", "Bterm", "Mterm", "y_pred", "loss", "KLD", "Aterm_mu", "Aterm_var"):
+        assert torch.equal(full[k], lean[k]), k
+    assert torch.equal(net.features(bag), full["Fterm"])
+    lib = G.lib()
+    dt = G.DT[precision]
+    assert lib.mil_extractor_infer_workspace_bytes(n, side, dt) < 0.4 * lib.mil_extractor_workspace_bytes(n, side, dt)
+    u8 = ((bag * 0.5 + 0.5) * 255).round().to(torch.uint8)
+    with torch.no_grad():
+        a = net(u8, Y)
+    b = net(u8, Y)
+    assert torch.equal(a["Fterm"], b["Fterm"]) and torch.equal(a["Aterm"], b["Aterm"])
+    assert torch.equal(net.features(u8), a["Fterm"])
 
 
 def test_single_tile_bag_raises_value_error_like_reference():

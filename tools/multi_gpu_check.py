@@ -5,6 +5,8 @@
 
 A bag is sharded over the ranks (uneven shards on purpose); every rank must obtain the SAME logits / loss /
 gradients as a single GPU processing the whole bag (the bag-wide sums are exact), and its shard of Aterm / Fterm.
+Then the multi-slide mode (SlideGroup, BASELINE configs[4]): every rank its own slide; its outputs must be the
+single-GPU outputs of that slide and the reduced gradients the sum of the slides' single-GPU gradients.
 """
 import importlib
 import os
@@ -78,6 +80,35 @@ def main():
         print(f"rank {rank} {precision} train: local tiles {outt['Aterm'].shape[1]} total {int(cnt)} (expect {int(n * 0.2)}) "
               f"ranks agree: {agree} finite: {bool(torch.isfinite(v).all())}", flush=True)
         ok = ok and agree and int(cnt) == int(n * 0.2) and bool(torch.isfinite(v).all())
+    # ---- multi-slide data parallelism (BASELINE configs[4]): every rank its own bag; only the gradients cross ranks ----
+    for precision, tol in (("fp32", 2e-5), ("bf16", 2e-5)):
+        side = 64
+        sizes = [40 + 8 * r for r in range(world)]                      # slides differ in size
+        bags = [torch.from_numpy(mil.synth.make_bag(sizes[r], side, seed=20 + r)).to(dev) for r in range(world)]
+        labels = [torch.tensor([r % 3], device=dev) for r in range(world)]
+        torch.manual_seed(0)
+        ref = mil.Attention(n_classes=3).to(dev).eval()
+        ref.precision = precision
+        outs = []
+        for r in range(world):                                          # the reference's loop: one slide after the other,
+            o = ref(bags[r], labels[r])                                 # gradients accumulate (gbm/classify_combined.py:446-454)
+            o["loss"].backward()
+            outs.append(o)
+        g1 = torch.cat([p.grad.flatten() for p in ref.parameters()])
+        torch.manual_seed(0)
+        net = mil.Attention(n_classes=3).to(dev).eval()
+        net.precision = precision
+        net.bag_group = mil.SlideGroup(dist.group.WORLD)
+        out = net(bags[rank], labels[rank])
+        out["loss"].backward()
+        g = torch.cat([p.grad.flatten() for p in net.parameters()])
+        errs = {"loss(own slide)": rel(out["loss"].detach(), outs[rank]["loss"].detach()),
+                "Aterm(own slide)": rel(out["Aterm"], outs[rank]["Aterm"]), "grads(sum over slides)": rel(g, g1)}
+        same = torch.equal(out["Aterm"], outs[rank]["Aterm"]) and torch.equal(out["Fterm"], outs[rank]["Fterm"])
+        bad = {k: v for k, v in errs.items() if not v < tol}
+        print(f"rank {rank} {precision} multi-slide: " + " ".join(f"{k}={v:.1e}" for k, v in errs.items())
+              + f" own-slide outputs bit-identical: {same}" + ("  FAIL " + str(bad) if bad else "  ok"), flush=True)
+        ok = ok and not bad and same
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
