@@ -175,26 +175,44 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
       bulk_g2s(bsm, wtc, b_bytes, &hd->b_full);
     }
     __syncwarp();
+    // The producer's instruction stream is on the kernel's critical path: ONE warp issues every tile's copies, and with
+    // the addresses recomputed per copy (64-bit multiplies, generic -> shared conversions, one bulk prefetch per
+    // residual row) it needed ~1000 cycles per tile on layer 1 -- more than the tensor pipe (620) or HBM
+    // (profiles/r2_ncu_conv_wgrad_stalls.txt: the producer never waited for a free stage).  So: every address is a
+    // running pointer advanced by a constant, and the L2 prefetch of the epilogue's residual / activation rows is one
+    // 128-byte line per LANE (a 2 KB row = 16 lanes) instead of a bulk prefetch per row issued by the elected lane.
     int stage = 0;
     uint32_t phase = 0;
+    const uint32_t cbin = (uint32_t)sh.cbin, tx_bytes = plane * cbin;
+    const uint32_t a0 = smem_u32(asm0), full0 = smem_u32(&hd->full[0]);
+    const char* src = reinterpret_cast<const char*>(x) + (gx.G - halo + (long long)blockIdx.x * TC_M) * 16;  // chunk 0
+    const long long cstride = gx.PS * 16, tstride = (long long)gridDim.x * TC_M * 16;
+    // prefetch: lane -> (row of pass k = chunk 2k + lane / 16, line lane % 16)
+    const bool pf_res = pf_rows && res != nullptr, pf_act = pf_rows && epi == MIL_EPI_DGRAD && mask_in == nullptr;
+    const int npass = (pf_res || pf_act) ? (sh.cbout + 1) / 2 : 0;
+    const long long pf_lane = ((long long)(lane >> 4) * go.PS + go.G + (long long)blockIdx.x * TC_M) * 16 + (lane & 15) * 128;
+    const long long pf_pass = 2 * go.PS * 16;
+    const char* pres = reinterpret_cast<const char*>(res) + pf_lane;
+    const char* pact = reinterpret_cast<const char*>(act) + pf_lane;
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       mbar_wait(&hd->empty[stage], phase ^ 1);
       if (elect_one()) {
-        mbar_expect_tx(&hd->full[stage], plane * sh.cbin);
-        const long long q0 = t * TC_M;
-        unsigned char* dst = asm0 + (size_t)stage * stage_bytes;
-        for (int c = 0; c < sh.cbin; ++c)
-          bulk_g2s(dst + (size_t)c * plane, x + mil_pf8_off(gx, c, q0 - halo), plane, &hd->full[stage]);
-        // the epilogue of this tile reads its residual / activation rows with ordinary loads a few tiles from now and
-        // waits out their full latency (only NG tiles are in flight): have L2 fetch those rows already
-        if (pf_rows) {
-          for (int c = 0; c < sh.cbout; ++c) {
-            if (res != nullptr) bulk_prefetch_l2(res + mil_pf8_off(go, c, q0), TC_M * 16);
-            if (epi == MIL_EPI_DGRAD && mask_in == nullptr) bulk_prefetch_l2(act + mil_pf8_off(go, c, q0), TC_M * 16);
-          }
-        }
+        const uint32_t bar = full0 + (uint32_t)stage * 8;
+        mbar_expect_tx_u32(bar, tx_bytes);
+        uint32_t dst = a0 + (uint32_t)stage * stage_bytes;
+        const char* sp = src;
+        for (uint32_t c = 0; c < cbin; ++c, dst += plane, sp += cstride) bulk_g2s_u32(dst, sp, plane, bar);
       }
       __syncwarp();
+      // the epilogue of this tile reads its residual / activation rows with ordinary loads a few tiles from now and
+      // waits out their full latency (only NG tiles are in flight): have L2 fetch those rows already
+      for (int k = 0; k < npass; ++k) {
+        if (2 * k + (lane >> 4) < sh.cbout) {
+          if (pf_res) prefetch_l2_line(pres + k * pf_pass);
+          if (pf_act) prefetch_l2_line(pact + k * pf_pass);
+        }
+      }
+      src += tstride; pres += tstride; pact += tstride;
       if (++stage == n_stages) { stage = 0; phase ^= 1; }
     }
   } else if (warp <= 2) {
@@ -208,14 +226,18 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
     mbar_wait(&hd->b_full, 0);
     const int nmma = sh.nmma;
     const uint64_t b_add = (uint64_t)(smem_u32(bsm) >> 4);
-    long long it = warp - 1;  // CTA-local tile counter
-    for (long long t = blockIdx.x + it * gridDim.x; t < n_tiles; t += 2LL * gridDim.x, it += 2) {
-      const int stage = (int)(it % n_stages), acc = (int)(it % NG);
-      mbar_wait(&hd->acc_empty[acc], (uint32_t)((it / NG) & 1) ^ 1);
-      mbar_wait(&hd->full[stage], (uint32_t)((it / n_stages) & 1));
+    // CTA-local tile counter it = warp - 1, +2 per iteration, kept as ring positions + phase bits: the issuing warps'
+    // per-tile bookkeeping is on the kernel's critical path (profiles/r2_ncu_conv_wgrad_stalls.txt: with 64-bit
+    // divisions here the two warps needed ~1700 cycles per tile each while the tensor pipe needs 620)
+    int stage = warp - 1, acc = warp - 1;        // n_stages and NG are even: a step of 2 wraps at most once
+    uint32_t full_par = 0, acc_par = 1;
+    const uint32_t a_base = smem_u32(asm0) >> 4, a_step = stage_bytes >> 4;
+    for (long long t = blockIdx.x + (long long)(warp - 1) * gridDim.x; t < n_tiles; t += 2LL * gridDim.x) {
+      mbar_wait(&hd->acc_empty[acc], acc_par);
+      mbar_wait(&hd->full[stage], full_par);
       tc_fence_after();
       // the start-address field sits in the low 14 bits of the descriptor: adding a base cannot carry
-      const uint64_t a_add = (uint64_t)(smem_u32(asm0 + (size_t)stage * stage_bytes) >> 4);
+      const uint64_t a_add = (uint64_t)(a_base + (uint32_t)stage * a_step);
       const uint32_t d = tmem_base + acc * acc_stride;
       if (elect_one()) {
 #pragma unroll 4
@@ -223,6 +245,10 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
         umma_commit(&hd->empty[stage]);
       }
       __syncwarp();
+      stage += 2;
+      if (stage >= n_stages) { stage -= n_stages; full_par ^= 1; }
+      acc += 2;
+      if (acc >= NG) { acc -= NG; acc_par ^= 1; }
     }
   } else {
     // ===================== epilogue: group eg serves accumulator stage eg =====================
@@ -237,7 +263,8 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
     const bool has_act = SPEC ? (MODE == TCM_DGRAD || MODE == TCM_DGRAD_RES) : epi == MIL_EPI_DGRAD;
     const bool do_bias = SPEC ? (MODE == TCM_FWD || MODE == TCM_FWD_RES) : epi != MIL_EPI_DGRAD;
     const bool do_lrelu = SPEC ? (MODE == TCM_FWD || MODE == TCM_FWD_RES) : epi == MIL_EPI_FWD;
-    long long it = eg;  // CTA-local tile counter of this group
+    int estage = eg;        // ring position + phase bit of this group's tiles (CTA-local tile counter eg, +NG per
+    uint32_t epar = 0;      // iteration; n_stages is a multiple of NG)
     // This thread's pixel as (image n, in-plane offset r), advanced incrementally from tile to tile: the only
     // 64-bit divisions of the kernel happen here, once (the epilogue's instruction stream is what bounds the
     // small-channel layers, not the tensor pipe).
@@ -251,7 +278,7 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
     const long long ostride = go.PS * 8, rstride = (res_half ? gr.PS : go.PS) * 8;  // elements between chunks
     // element offset of output chunk c: plane c, or in the stride-2 data-gradient mode plane c % cbh, pixel + c / cbh
 #define KOFF(c) (cbh == 0 ? (long long)(c) * ostride : (long long)((c) >= cbh ? (c) - cbh : (c)) * ostride + ((c) >= cbh ? 8 : 0))
-    for (long long t = blockIdx.x + (long long)eg * gridDim.x; t < n_tiles; t += (long long)NG * gridDim.x, it += NG) {
+    for (long long t = blockIdx.x + (long long)eg * gridDim.x; t < n_tiles; t += (long long)NG * gridDim.x) {
       // flat index q = n * P + r at the input resolution; qo = where the pixel is stored.  sub: the stride-2
       // convolutions are evaluated at full resolution and only the even (y, x) positions are kept.
       bool in_range = n < gx.n;
@@ -340,8 +367,10 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
           }
         }
       }
-      mbar_wait(&hd->empty[it % n_stages], (uint32_t)((it / n_stages) & 1));
+      mbar_wait(&hd->empty[estage], epar);
       tc_fence_after();
+      estage += NG;
+      if (estage >= n_stages) { estage -= n_stages; epar ^= 1; }
       const uint32_t taddr = tmem_base + eg * acc_stride + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll
       for (int half = 0; half < (MAXCB + HALF - 1) / HALF; ++half) {

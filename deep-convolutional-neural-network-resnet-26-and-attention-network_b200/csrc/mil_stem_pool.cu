@@ -109,18 +109,24 @@ stem_conv_pool_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv
       bulk_g2s(bsm, wtc, b_bytes, &hd->b_full);
     }
     __syncwarp();
+    // running pointers advanced by constants: the producer's instruction stream is on the critical path (conv_tc_kernel)
     int stage = 0;
     uint32_t phase = 0;
+    const uint32_t cbin = (uint32_t)sh.cbin, tx_bytes = plane * cbin;
+    const uint32_t a0 = smem_u32(asm0), full0 = smem_u32(&hd->full[0]);
+    const char* src = reinterpret_cast<const char*>(x) + (gx.G - halo + t_begin * SP_M) * 16;  // chunk 0
+    const long long cstride = gx.PS * 16;
     for (long long it = 0; it < nloc; ++it) {
       mbar_wait(&hd->empty[stage], phase ^ 1);
       if (elect_one()) {
-        mbar_expect_tx(&hd->full[stage], plane * sh.cbin);
-        const long long q0 = (t_begin + it) * SP_M;
-        unsigned char* dst = asm0 + (size_t)stage * stage_bytes;
-        for (int c = 0; c < sh.cbin; ++c)
-          bulk_g2s(dst + (size_t)c * plane, x + mil_pf8_off(gx, c, q0 - halo), plane, &hd->full[stage]);
+        const uint32_t bar = full0 + (uint32_t)stage * 8;
+        mbar_expect_tx_u32(bar, tx_bytes);
+        uint32_t dst = a0 + (uint32_t)stage * stage_bytes;
+        const char* sp = src;
+        for (uint32_t c = 0; c < cbin; ++c, dst += plane, sp += cstride) bulk_g2s_u32(dst, sp, plane, bar);
       }
       __syncwarp();
+      src += SP_M * 16;
       if (++stage == n_stages) { stage = 0; phase ^= 1; }
     }
   } else if (warp <= 2) {
@@ -129,12 +135,16 @@ stem_conv_pool_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv
     mbar_wait(&hd->b_full, 0);
     const int nmma = sh.nmma;
     const uint64_t b_add = (uint64_t)(smem_u32(bsm) >> 4);
+    // ring positions + phase bits instead of 64-bit divisions (the issuing warps' bookkeeping is on the critical path,
+    // see conv_tc_kernel); n_stages is a multiple of SP_NG, both are even
+    int stage = warp - 1, acc = warp - 1;
+    uint32_t full_par = 0, acc_par = 1;
+    const uint32_t a_base = smem_u32(asm0) >> 4, a_step = stage_bytes >> 4;
     for (long long it = warp - 1; it < nloc; it += 2) {
-      const int stage = (int)(it % n_stages), acc = (int)(it % SP_NG);
-      mbar_wait(&hd->acc_empty[acc], (uint32_t)((it / SP_NG) & 1) ^ 1);
-      mbar_wait(&hd->full[stage], (uint32_t)((it / n_stages) & 1));
+      mbar_wait(&hd->acc_empty[acc], acc_par);
+      mbar_wait(&hd->full[stage], full_par);
       tc_fence_after();
-      const uint64_t a_add = (uint64_t)(smem_u32(asm0 + (size_t)stage * stage_bytes) >> 4);
+      const uint64_t a_add = (uint64_t)(a_base + (uint32_t)stage * a_step);
       const uint32_t d = tmem_base + acc * acc_stride;
       if (elect_one()) {
 #pragma unroll 4
@@ -142,6 +152,10 @@ stem_conv_pool_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv
         umma_commit(&hd->empty[stage]);
       }
       __syncwarp();
+      stage += 2;
+      if (stage >= n_stages) { stage -= n_stages; full_par ^= 1; }
+      acc += 2;
+      if (acc >= SP_NG) { acc -= SP_NG; acc_par ^= 1; }
     }
   } else {
     // ===================== epilogue + pool: group eg takes the local tiles eg, eg + 2, ... =====================
@@ -150,6 +164,8 @@ stem_conv_pool_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv
     const int row = quarter * 32 + lane;  // pixel of the tile = TMEM lane
     const int wp = (int)gp.wp;
     const uint32_t NINF2 = 0xFF80FF80u;
+    int estage = eg;
+    uint32_t epar = 0;
     for (long long it = eg; it < nloc; it += SP_NG) {
       const long long q = (t_begin + it) * SP_M + row;
       const int n = (int)(q / gp.P);
@@ -159,8 +175,10 @@ stem_conv_pool_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv
       const bool live = in_range && y < gp.h && xo < gp.w;
       const int slot = (int)(it & 1);
       // 1. accumulator row out of TMEM, stage handed back at once
-      mbar_wait(&hd->empty[it % n_stages], (uint32_t)((it / n_stages) & 1));
+      mbar_wait(&hd->empty[estage], epar);
       tc_fence_after();
+      estage += SP_NG;
+      if (estage >= n_stages) { estage -= n_stages; epar ^= 1; }
       const uint32_t taddr = tmem_base + eg * acc_stride + ((uint32_t)(quarter * 32) << 16);
       float acc[SP_CB][8];
 #pragma unroll

@@ -80,20 +80,29 @@ stem_wgrad_kernel(const __nv_bfloat16* __restrict__ xs, MilPF8 gx, const __nv_bf
 
   if (warp == 0) {
     // ---- producer: xs planes, slots (c, dy) = the plane read from pixel q0 + dy * wp ----
+    // (running pointers advanced by constants: the 18 copies per tile are one serial instruction stream)
     int stage = 0;
     uint32_t phase = 0;
+    const uint32_t b0 = smem_u32(stage0) + SW_A_SLOTS * SW_PLANE, full0 = smem_u32(&hd->full[0]);
+    const char* src = reinterpret_cast<const char*>(xs) + (gx.G - wp + (long long)blockIdx.x * SW_TK) * 16;  // (c = 0, dy = -1)
+    const long long cstride = gx.PS * 16, tstride = (long long)gridDim.x * SW_TK * 16, rstride = (long long)wp * 16;
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       mbar_wait(&hd->empty[stage], phase ^ 1);
       if (elect_one()) {
-        mbar_expect_tx(&hd->full[stage], 3 * SW_CB * SW_PLANE);
-        const long long q0 = t * SW_TK;
-        unsigned char* bdst = stage0 + (size_t)stage * SW_STAGE + (size_t)SW_A_SLOTS * SW_PLANE;
-        for (int c = 0; c < SW_CB; ++c)
-          for (int d = 0; d < 3; ++d)
-            bulk_g2s(bdst + (size_t)(c * 3 + d) * SW_PLANE, xs + mil_pf8_off(gx, c, q0 + (long long)(d - 1) * wp), SW_PLANE,
-                     &hd->full[stage]);
+        const uint32_t bar = full0 + (uint32_t)stage * 8;
+        mbar_expect_tx_u32(bar, 3 * SW_CB * SW_PLANE);
+        uint32_t dst = b0 + (uint32_t)stage * SW_STAGE;
+        const char* sp = src;
+#pragma unroll
+        for (int c = 0; c < SW_CB; ++c, sp += cstride) {
+          bulk_g2s_u32(dst, sp, SW_PLANE, bar);
+          bulk_g2s_u32(dst + SW_PLANE, sp + rstride, SW_PLANE, bar);
+          bulk_g2s_u32(dst + 2 * SW_PLANE, sp + 2 * rstride, SW_PLANE, bar);
+          dst += 3 * SW_PLANE;
+        }
       }
       __syncwarp();
+      src += tstride;
       if (++stage == SW_STAGES) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {

@@ -103,27 +103,36 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
 
   if (warp == 0) {
     // producer: whole warp in uniform control flow, one elected lane issues the bulk copies
+    // (running pointers advanced by constants: one warp issues up to 38 copies per tile)
     int stage = 0;
     uint32_t phase = 0;
+    const uint32_t s0 = smem_u32(stage0), full0 = smem_u32(&hd->full[0]);
+    const uint32_t cba = (uint32_t)gz.cb, cbb = (uint32_t)gx.cb;
+    const char* srca = reinterpret_cast<const char*>(dz) + (gz.G + (long long)blockIdx.x * WG_TK) * 16;
+    const char* srcb = reinterpret_cast<const char*>(x) + (gx.G - back - (dxcat ? 1 : 0) + (long long)blockIdx.x * WG_TK) * 16;
+    const long long stra = gz.PS * 16, strb = gx.PS * 16, tstride = (long long)gridDim.x * WG_TK * 16;
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       mbar_wait(&hd->empty[stage], phase ^ 1);
       if (elect_one()) {
-        mbar_expect_tx(&hd->full[stage], load_bytes);
-        const long long q0 = t * WG_TK;
-        unsigned char* dst = stage0 + (size_t)stage * stage_bytes;
-        for (int c = 0; c < gz.cb; ++c)
-          bulk_g2s(dst + (size_t)c * WG_A_PLANE, dz + mil_pf8_off(gz, c, q0), WG_A_PLANE, &hd->full[stage]);
+        const uint32_t bar = full0 + (uint32_t)stage * 8;
+        mbar_expect_tx_u32(bar, load_bytes);
+        uint32_t dst = s0 + (uint32_t)stage * stage_bytes;
+        const char* sp = srca;
+        for (uint32_t c = 0; c < cba; ++c, dst += WG_A_PLANE, sp += stra) bulk_g2s_u32(dst, sp, WG_A_PLANE, bar);
+        sp = srcb;
         if (dxcat) {  // three shifted fetches of every plane, slots (chunk, dx)
-          for (int c = 0; c < gx.cb; ++c)
-            for (int dx = 0; dx < 3; ++dx)
-              bulk_g2s(dst + a_bytes + (size_t)(c * 3 + dx) * b_plane, x + mil_pf8_off(gx, c, q0 - back + dx - 1),
-                       b_plane, &hd->full[stage]);
+          for (uint32_t c = 0; c < cbb; ++c, sp += strb) {
+            bulk_g2s_u32(dst, sp, b_plane, bar);
+            bulk_g2s_u32(dst + b_plane, sp + 16, b_plane, bar);
+            bulk_g2s_u32(dst + 2 * b_plane, sp + 32, b_plane, bar);
+            dst += 3 * b_plane;
+          }
         } else {
-          for (int c = 0; c < gx.cb; ++c)
-            bulk_g2s(dst + a_bytes + (size_t)c * b_plane, x + mil_pf8_off(gx, c, q0 - back), b_plane, &hd->full[stage]);
+          for (uint32_t c = 0; c < cbb; ++c, dst += b_plane, sp += strb) bulk_g2s_u32(dst, sp, b_plane, bar);
         }
       }
       __syncwarp();
+      srca += tstride; srcb += tstride;
       if (++stage == n_stages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
@@ -242,7 +251,15 @@ struct WgsSmemHeader {
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(WG_THREADS, 1)
+// CBA / CBB: chunk counts of dz / x as compile-time facts (3 / 5 = layers 1 / 2; 0 = read them from the geometry) so that a
+// copy thread issues ALL of a tile's shared-memory loads before its first store.  Every ring stage has its OWN group of
+// four copy warps (group g serves stage g, i.e. the CTA's tiles g, g + n_stages, ...; a stage that changed hands
+// between groups would let a group wait on a phase parity that is still one revolution behind): the copy phase is a
+// chain of LDS -> STS latencies (profiles/r2_ncu_conv_wgrad_stalls.txt: the four warps of the first version were busy
+// 95 % of the time, the MMA warp waited on them a third of its time).
+#define WGS_THREADS(n_stages) (64 + 128 * (n_stages))  // warp 0 producer, warp 1 MMA issuer, 4 copy warps per stage (group 0: epilogue)
+template <int CBA, int CBB>
+__global__ void __launch_bounds__(WGS_THREADS(WGS_MAX_STAGES), 1)
 wgrad_sq_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat16* __restrict__ dz, MilPF8 gz,
                 float* __restrict__ partial, long long rec_stride, int npad, int n_stages) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -280,23 +297,30 @@ wgrad_sq_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
   const uint32_t tmem_base = hd->tmem_base;
 
   if (warp == 0) {
+    // running pointers advanced by constants (the producer is one serial instruction stream: see conv_tc_kernel)
     int stage = 0;
     uint32_t phase = 0;
+    const uint32_t s0 = smem_u32(stage0), full0 = smem_u32(&hd->full[0]);
+    const uint32_t cba = (uint32_t)gz.cb, cbb = (uint32_t)gx.cb;
+    const uint32_t sz_a = WG_A_PLANE + 2 * halo_a, sz_b = WG_A_PLANE + 2 * halo_b;
+    const char* srca = reinterpret_cast<const char*>(dz) + (gz.G - gz.wp + (long long)blockIdx.x * WG_TK) * 16;
+    const char* srcb = reinterpret_cast<const char*>(x) + (gx.G - 1 + (long long)blockIdx.x * WG_TK) * 16;
+    const long long stra = gz.PS * 16, strb = gx.PS * 16, tstride = (long long)gridDim.x * WG_TK * 16;
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       mbar_wait(&hd->empty[stage], phase ^ 1);
       if (elect_one()) {
-        mbar_expect_tx(&hd->full[stage], load_bytes);
-        const long long q0 = t * WG_TK;
-        unsigned char* bdst = stage0 + (size_t)stage * stage_bytes;
-        unsigned char* adst = bdst + b_bytes;
-        for (int c = 0; c < gz.cb; ++c)  // the unshifted window [q0, q0 + TK) lands in slot (c, dy = 0)
-          bulk_g2s(adst + (size_t)(c * 3 + 1) * pitch_a - halo_a, dz + mil_pf8_off(gz, c, q0 - gz.wp),
-                   WG_A_PLANE + 2 * halo_a, &hd->full[stage]);
-        for (int c = 0; c < gx.cb; ++c)
-          bulk_g2s(bdst + (size_t)(c * 3 + 1) * pitch_b - halo_b, x + mil_pf8_off(gx, c, q0 - 1),
-                   WG_A_PLANE + 2 * halo_b, &hd->full[stage]);
+        const uint32_t bar = full0 + (uint32_t)stage * 8;
+        mbar_expect_tx_u32(bar, load_bytes);
+        const uint32_t bdst = s0 + (uint32_t)stage * stage_bytes;
+        uint32_t da = bdst + b_bytes + pitch_a - halo_a;  // the unshifted window [q0, q0 + TK) lands in slot (c, dy = 0)
+        const char* sp = srca;
+        for (uint32_t c = 0; c < cba; ++c, da += 3 * pitch_a, sp += stra) bulk_g2s_u32(da, sp, sz_a, bar);
+        uint32_t db = bdst + pitch_b - halo_b;
+        sp = srcb;
+        for (uint32_t c = 0; c < cbb; ++c, db += 3 * pitch_b, sp += strb) bulk_g2s_u32(db, sp, sz_b, bar);
       }
       __syncwarp();
+      srca += tstride; srcb += tstride;
       if (++stage == n_stages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
@@ -328,32 +352,47 @@ wgrad_sq_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
     __syncwarp();
   } else {
     // ---- main loop: build the shifted planes (thread i of the four warps moves pixel i of every plane) ----
+    const int cg = (warp - 2) >> 2;                   // copy group = ring stage: the CTA's tiles cg, cg + n_stages, ...
     {
-      const int tid = threadIdx.x - 64;  // 0..127 = pixel of the K-tile
-      int stage = 0;
+      const int tid = (threadIdx.x - 64) & 127;       // 0..127 = pixel of the K-tile
+      const int stage = cg;
       uint32_t phase = 0;
-      for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      constexpr int MA = CBA ? CBA : 5, MB = CBB ? CBB : 5;
+      const int cba = CBA ? CBA : gz.cb, cbb = CBB ? CBB : gx.cb;
+      for (long long t = blockIdx.x + (long long)cg * gridDim.x; t < n_tiles; t += (long long)n_stages * gridDim.x) {
         mbar_wait(&hd->full[stage], phase);
         unsigned char* bdst = stage0 + (size_t)stage * stage_bytes;
-        unsigned char* adst = bdst + b_bytes;
-        for (int c = 0; c < gz.cb; ++c) {
-          unsigned char* mid = adst + (size_t)(c * 3 + 1) * pitch_a + (size_t)tid * 16;  // dz[q0 + tid]
-          const uint4 dn = *reinterpret_cast<const uint4*>(mid + halo_a);                 // dz[q + wp]: dy = -1
-          const uint4 up = *reinterpret_cast<const uint4*>(mid - halo_a);                 // dz[q - wp]: dy = +1
-          *reinterpret_cast<uint4*>(mid - pitch_a) = dn;
-          *reinterpret_cast<uint4*>(mid + pitch_a) = up;
-        }
-        for (int c = 0; c < gx.cb; ++c) {
-          unsigned char* mid = bdst + (size_t)(c * 3 + 1) * pitch_b + (size_t)tid * 16;  // x[q0 + tid]
-          const uint4 lf = *reinterpret_cast<const uint4*>(mid - 16);                     // x[q - 1]: dx = -1
-          const uint4 rt = *reinterpret_cast<const uint4*>(mid + 16);                     // x[q + 1]: dx = +1
-          *reinterpret_cast<uint4*>(mid - pitch_b) = lf;
-          *reinterpret_cast<uint4*>(mid + pitch_b) = rt;
-        }
+        unsigned char* amid = bdst + b_bytes + pitch_a + (size_t)tid * 16;  // dz[q0 + tid] of chunk 0
+        unsigned char* bmid = bdst + pitch_b + (size_t)tid * 16;            // x[q0 + tid] of chunk 0
+        uint4 dn[MA], up[MA], lf[MB], rt[MB];
+#pragma unroll
+        for (int c = 0; c < MA; ++c)
+          if (c < cba) {
+            dn[c] = *reinterpret_cast<const uint4*>(amid + (size_t)c * 3 * pitch_a + halo_a);  // dz[q + wp]: dy = -1
+            up[c] = *reinterpret_cast<const uint4*>(amid + (size_t)c * 3 * pitch_a - halo_a);  // dz[q - wp]: dy = +1
+          }
+#pragma unroll
+        for (int c = 0; c < MB; ++c)
+          if (c < cbb) {
+            lf[c] = *reinterpret_cast<const uint4*>(bmid + (size_t)c * 3 * pitch_b - 16);      // x[q - 1]: dx = -1
+            rt[c] = *reinterpret_cast<const uint4*>(bmid + (size_t)c * 3 * pitch_b + 16);      // x[q + 1]: dx = +1
+          }
+#pragma unroll
+        for (int c = 0; c < MA; ++c)
+          if (c < cba) {
+            *reinterpret_cast<uint4*>(amid + (size_t)c * 3 * pitch_a - pitch_a) = dn[c];
+            *reinterpret_cast<uint4*>(amid + (size_t)c * 3 * pitch_a + pitch_a) = up[c];
+          }
+#pragma unroll
+        for (int c = 0; c < MB; ++c)
+          if (c < cbb) {
+            *reinterpret_cast<uint4*>(bmid + (size_t)c * 3 * pitch_b - pitch_b) = lf[c];
+            *reinterpret_cast<uint4*>(bmid + (size_t)c * 3 * pitch_b + pitch_b) = rt[c];
+          }
         fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
         __syncwarp();
         if (lane == 0) mbar_arrive(&hd->ready[stage]);
-        if (++stage == n_stages) { stage = 0; phase ^= 1; }
+        phase ^= 1;
       }
     }
     // ---- epilogue: accumulator row (= TMEM lane) (c, e, j) -> output channel c * 8 + j, tap row dy = e - 1;
@@ -363,9 +402,9 @@ wgrad_sq_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
     const int g = row >> 3, c = g / 3, e = g - c * 3;
     const int co = c * 8 + (row & 7);
     const int coutp = gz.cb * 8, cinp = gx.cb * 8;
-    mbar_wait(&hd->done, 0);
+    if (cg == 0) mbar_wait(&hd->done, 0);  // (the second copy group has no epilogue share)
     tc_fence_after();
-    if (quarter * 32 < na * 8) {  // warp-uniform
+    if (cg == 0 && quarter * 32 < na * 8) {  // warp-uniform
       float* rec = partial + (size_t)blockIdx.x * rec_stride;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
       for (int p = 0; p < nb; ++p) {
@@ -477,9 +516,17 @@ int mil_launch_wgrad_tc_partials(const void* x, const MilPF8& gx, const void* dz
   const long long rec_sq = (long long)sh.ntaps * gx.cb * 8 * gz.cb * 8 + gz.cb * 8;
   if (c.sq) {
     MIL_REQUIRE(halo <= gz.G, "wgrad_tc: the window reaches %d pixels back but the gradient map's guard is %lld", halo, gz.G);
-    MIL_SET_SMEM((wgrad_sq_kernel), (int)c.smem);
-    wgrad_sq_kernel<<<c.ctas, WG_THREADS, c.smem, s>>>((const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)dz, gz, partial,
-                                                      rec_sq, c.npad, c.n_stages);
+#define MIL_WGS_LAUNCH(CBA, CBB)                                                                                       \
+  do {                                                                                                               \
+    MIL_SET_SMEM((wgrad_sq_kernel<CBA, CBB>), (int)c.smem);                                                          \
+    wgrad_sq_kernel<CBA, CBB><<<c.ctas, WGS_THREADS(c.n_stages), c.smem, s>>>((const __nv_bfloat16*)x, gx,                        \
+                                                                 (const __nv_bfloat16*)dz, gz, partial, rec_sq, c.npad, \
+                                                                 c.n_stages);                                        \
+  } while (0)
+    if (gz.cb == 3 && gx.cb == 3) MIL_WGS_LAUNCH(3, 3);
+    else if (gz.cb == 5 && gx.cb == 5) MIL_WGS_LAUNCH(5, 5);
+    else MIL_WGS_LAUNCH(0, 0);
+#undef MIL_WGS_LAUNCH
     MIL_LAUNCH_OK();
     *ctas_out = c.ctas;
     *rec_out = rec_sq;
