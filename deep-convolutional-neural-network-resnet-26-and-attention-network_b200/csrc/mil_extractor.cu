@@ -279,6 +279,34 @@ static void guard_add(GuardTable& t, void* buf, const MilPF8& g) {
   t.base[t.count] = buf; t.PS[t.count] = g.PS; t.G[t.count] = g.G; t.Q[t.count] = g.Q; t.cb[t.count] = g.cb;
   ++t.count;
 }
+// zero row / zero column of every image plus the guards: what a kernel that stores only the real pixels leaves undefined
+// (the stride-2 data gradient writes pixel pairs of the full-resolution map) -- instead of clearing the whole map
+__global__ void zero_pads_kernel(uint4* __restrict__ base, MilPF8 g, int unit) {
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  const int c = blockIdx.y;
+  uint4* plane = base + (size_t)c * g.PS * unit;
+  if (blockIdx.x == gridDim.x - 1) {  // guards
+    for (long long i = threadIdx.x; i < g.G * unit; i += blockDim.x) plane[i] = z;
+    for (long long i = (g.G + g.Q) * unit + threadIdx.x; i < g.PS * unit; i += blockDim.x) plane[i] = z;
+    return;
+  }
+  const int per = g.hp - 1 + g.wp;  // pad pixels per image: last column of rows 0..hp-2, then the whole last row
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)g.n * per;
+       i += (long long)(gridDim.x - 1) * blockDim.x) {
+    const int n = (int)(i / per), k = (int)(i - (long long)n * per);
+    const long long q = (long long)n * g.P + (k < g.hp - 1 ? (long long)k * g.wp + g.wp - 1 : (long long)(g.hp - 1) * g.wp + (k - (g.hp - 1)));
+    for (int u = 0; u < unit; ++u) plane[(g.G + q) * unit + u] = z;
+  }
+}
+int mil_zero_pads(int dtype, void* buf, const MilPF8& g, cudaStream_t s) {
+  const int unit = (int)(8 * mil_esize(dtype) / 16);
+  const long long items = (long long)g.n * (g.hp - 1 + g.wp);
+  const int blocks = (int)std::min<long long>(mil_cdiv(items, 256), 592) + 1;
+  zero_pads_kernel<<<dim3(blocks, g.cb), 256, 0, s>>>(reinterpret_cast<uint4*>(buf), g, unit);
+  MIL_LAUNCH_OK();
+  return 0;
+}
+
 int mil_zero_guards(int dtype, void* buf, const MilPF8& g, cudaStream_t s) {
   GuardTable t;
   t.count = 0;
@@ -590,7 +618,7 @@ int mil_extractor_backward_impl(const void* const* params, const float* bag, con
         void* xs2 = wsp(ws, pl.off_xs2[l]);
         void* t_sub = wsp(ws, pl.off_up[1]);
         MIL_TRY(mil_zero_guards(dt, t_sub, gts, s));
-        MIL_CHECK_CUDA(cudaMemsetAsync(dnew, 0, mil_pf8_bytes(gi, dt), s));  // pads + guards of the full-resolution map
+        MIL_TRY(mil_zero_pads(dt, dnew, gi, s));  // pads + guards of the full-resolution map (its pixels are all written below)
         MIL_TRY(mil_launch_wgrad_tc_s2(xs2, gs, dpre, go, partial, gptr(c1.p_w), gptr(c1.p_b), c1.cin, s));
         MIL_TRY(mil_wgrad_dispatch(dt, xs2, gxs, dz, go, partial, gptr(cd.p_w), nullptr, 1, 1, s));
         MIL_TRY(mil_conv_dispatch(dt, 1, dz, go, wpack + cd.wpt_off, TCW(cd, true), nullptr, nullptr, nullptr, t_sub, gts,

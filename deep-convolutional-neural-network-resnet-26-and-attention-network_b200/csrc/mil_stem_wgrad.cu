@@ -149,19 +149,35 @@ stem_wgrad_kernel(const __nv_bfloat16* __restrict__ xs, MilPF8 gx, const __nv_bf
     const bool st0 = i0 >= 0 && i0 < SW_TK, st1 = i1 >= 0 && i1 < SW_TK, st2 = i2 < SW_TK;
     int stage = 0;
     uint32_t phase = 0;
-    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    // The pooled gradient and the arg-max records of tile t + gridDim.x are fetched BEFORE tile t is worked on: the
+    // builders are the kernel's critical path, and without the prefetch they spent half of their time waiting for
+    // these eight loads (profiles/r2_ncu_stem_stalls.txt).
+    uint4 G00, G01, G10, G11;
+    uint2 A00, A01, A10, A11;
+    auto fetch = [&](long long t, bool& ok) {
       const long long q = t * SW_TK - 1 + j;
+      ok = t < n_tiles && j < SW_SPAN && q < gp.Q;  // (q = -1 reads the zero lead guard; beyond the bag: zeros)
+      if (ok) {
+        G00 = __ldg(gpl + q); G01 = __ldg(gpl + q + 1); G10 = __ldg(gpl + q + wp); G11 = __ldg(gpl + q + wp + 1);
+        A00 = __ldg(apl + q); A01 = __ldg(apl + q + 1); A10 = __ldg(apl + q + wp); A11 = __ldg(apl + q + wp + 1);
+      }
+    };
+    bool have;
+    fetch(blockIdx.x, have);
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       uint4 out[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) out[k] = make_uint4(0, 0, 0, 0);
-      if (j < SW_SPAN && q < gp.Q) {           // (q = -1 reads the zero lead guard; beyond the bag: zeros)
-        const uint4 G00 = __ldg(gpl + q), G01 = __ldg(gpl + q + 1), G10 = __ldg(gpl + q + wp), G11 = __ldg(gpl + q + wp + 1);
-        const uint2 A00 = __ldg(apl + q), A01 = __ldg(apl + q + 1), A10 = __ldg(apl + q + wp), A11 = __ldg(apl + q + wp + 1);
+      const uint4 g00 = G00, g01 = G01, g10 = G10, g11 = G11;
+      const uint2 a00 = A00, a01 = A01, a10 = A10, a11 = A11;
+      const bool cur = have;
+      fetch(t + gridDim.x, have);
+      if (cur) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           if (k < npair)
-            out[k] = mil_unpool_pair(mil_word(G00, k), mil_word(G01, k), mil_word(G10, k), mil_word(G11, k),
-                                     mil_am_lanes(A00, k), mil_am_lanes(A01, k), mil_am_lanes(A10, k), mil_am_lanes(A11, k));
+            out[k] = mil_unpool_pair(mil_word(g00, k), mil_word(g01, k), mil_word(g10, k), mil_word(g11, k),
+                                     mil_am_lanes(a00, k), mil_am_lanes(a01, k), mil_am_lanes(a10, k), mil_am_lanes(a11, k));
       }
       mbar_wait(&hd->empty[stage], phase ^ 1);  // (the loads and the arithmetic above overlap this wait)
       uint4* abase = reinterpret_cast<uint4*>(stage0 + (size_t)stage * SW_STAGE);

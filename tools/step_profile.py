@@ -61,3 +61,13 @@ print(f"# profiled: {span / steps / 1e3:.3f} ms per step wall on the device, {bu
 print(f"{'us/step':>10s} {'share':>7s} {'n/step':>6s}  kernel")
 for k, v in sorted(tot.items(), key=lambda kv: -kv[1])[:40]:
     print(f"{v / steps:10.1f} {100 * v / busy:6.1f}% {cnt[k] / steps:6.1f}  {k}")
+# idle gaps between consecutive kernels (where the device waited for the host or for a dependency)
+gaps = []
+for a, b in zip(evs[:-1], evs[1:]):
+    g = b.time_range.start - a.time_range.end
+    if g > 5:
+        gaps.append((g, a.name[:50], b.name[:50]))
+gaps.sort(reverse=True)
+print(f"# idle gaps > 5 us: {len(gaps) / steps:.1f} per step, {sum(g for g, _, _ in gaps) / steps:.1f} us per step")
+for g, a, b in gaps[:25]:
+    print(f"{g:9.1f} us  after {a}  before {b}")
