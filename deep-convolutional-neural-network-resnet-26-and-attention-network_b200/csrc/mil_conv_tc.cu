@@ -125,8 +125,21 @@ __device__ __forceinline__ void unpack8(const uint4& r, float v[8]) {
 // the tensor pipe, so they get 4 groups; the wide layers (more registers per thread) get 2.
 enum { TCM_GENERIC = 0, TCM_PLAIN, TCM_FWD, TCM_FWD_RES, TCM_DGRAD, TCM_DGRAD_RES };
 
+// Column split: with more than five output chunks a pixel's accumulator row goes to TWO epilogue threads (chunks
+// [0, 4) and [4, MAXCB); mask words are 4 chunks wide, so each half owns whole words).  The wide layers were bound by
+// the epilogue's instruction stream -- ~1000 dependent instructions per pixel on two warps per scheduler
+// (profiles/r2_ncu_conv_wide.txt: the epilogue warps waited for an accumulator 9 % of their time while the tensor pipe
+// sat at 50 %); twice the warps at half the registers each hide those latencies.
+template <int MAXCB, int MODE>
+struct TcSplit {
+  static constexpr int value = (MAXCB > 5 && MODE != TCM_GENERIC) ? 2 : 1;
+  static constexpr int at = value == 2 ? 4 : MAXCB;  // first chunk of the second half
+};
+template <int C>
+struct TcInt { static constexpr int value = C; };
+
 template <int MAXCB, int NG, int MODE>
-__global__ void __launch_bounds__(96 + NG * 128, 1)
+__global__ void __launch_bounds__(96 + NG * 128 * TcSplit<MAXCB, MODE>::value, 1)
 conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat16* __restrict__ wtc,
                const float* __restrict__ bias, const __nv_bfloat16* res, const __nv_bfloat16* act,
                __nv_bfloat16* out, MilPF8 go, MilTcShape sh, const __grid_constant__ TcIssue iss, int epi,
@@ -151,7 +164,7 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
   // ---- one-time setup ----
   if (threadIdx.x == 0) {
     for (int s = 0; s < n_stages; ++s) { mbar_init(&hd->full[s], 1); mbar_init(&hd->empty[s], 1); }
-    for (int a = 0; a < NG; ++a) mbar_init(&hd->acc_empty[a], 4);
+    for (int a = 0; a < NG; ++a) mbar_init(&hd->acc_empty[a], 4 * TcSplit<MAXCB, MODE>::value);
     mbar_init(&hd->b_full, 1);
     fence_barrier_init();
   }
@@ -255,7 +268,9 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
     // MODE != TCM_GENERIC: chunk count, epilogue kind and residual are compile-time facts -- the per-chunk branches
     // fold away (the generic form executes ~540 instructions per pixel on layer 1, the specialised one about a third)
     constexpr bool SPEC = MODE != TCM_GENERIC;
-    const int eg = (warp - 3) >> 2;
+    constexpr int CSPLIT = TcSplit<MAXCB, MODE>::value;
+    const int eg = ((warp - 3) >> 2) / CSPLIT;   // epilogue group = accumulator stage
+    const int csub = ((warp - 3) >> 2) % CSPLIT;  // which half of the chunk range this warp takes (warp-uniform)
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
     const int cbout = SPEC ? MAXCB : sh.cbout;
@@ -268,7 +283,6 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
     // This thread's pixel as (image n, in-plane offset r), advanced incrementally from tile to tile: the only
     // 64-bit divisions of the kernel happen here, once (the epilogue's instruction stream is what bounds the
     // small-channel layers, not the tensor pipe).
-    constexpr int HALF = MAXCB;  // chunks pulled from TMEM per batch: all at once, so the accumulator stage is handed back to the MMA warps before any arithmetic
     const long long step_q = (long long)NG * gridDim.x * TC_M;  // this group takes every NG-th tile of the CTA
     const int step_n = (int)(step_q / gx.P), step_r = (int)(step_q % gx.P);
     const long long q_first = ((long long)blockIdx.x + (long long)eg * gridDim.x) * TC_M + row;
@@ -278,6 +292,11 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
     const long long ostride = go.PS * 8, rstride = (res_half ? gr.PS : go.PS) * 8;  // elements between chunks
     // element offset of output chunk c: plane c, or in the stride-2 data-gradient mode plane c % cbh, pixel + c / cbh
 #define KOFF(c) (cbh == 0 ? (long long)(c) * ostride : (long long)((c) >= cbh ? (c) - cbh : (c)) * ostride + ((c) >= cbh ? 8 : 0))
+    // the whole per-tile loop, compiled per chunk range [C0, C1) of the accumulator row (all chunks are pulled from TMEM
+    // at once, so that the accumulator stage is handed back to the MMA warps before any arithmetic)
+    auto run = [&](auto c0_tag, auto c1_tag) {
+    constexpr int C0 = decltype(c0_tag)::value, C1 = decltype(c1_tag)::value, NC = C1 - C0;
+    constexpr int W0 = C0 / 4, W1 = (C1 + 3) / 4, MW = W1 - W0;  // sign-mask words of this range
     for (long long t = blockIdx.x + (long long)eg * gridDim.x; t < n_tiles; t += (long long)NG * gridDim.x) {
       // flat index q = n * P + r at the input resolution; qo = where the pixel is stored.  sub: the stride-2
       // convolutions are evaluated at full resolution and only the even (y, x) positions are kept.
@@ -322,8 +341,7 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
       // 1. residual / activation loads go out BEFORE we wait for the tensor core (the producer has already asked L2
       // for these rows).  Issuing them after the accumulator drain instead -- fewer live registers on the wide
       // layers -- was measured slower, even against a few spilled registers.
-      constexpr int MW = (MAXCB + 3) / 4;  // 32-bit sign-mask words per pixel
-      uint4 rres[MAXCB], ract[MAXCB];
+      uint4 rres[NC], ract[NC];
       uint32_t rmask[MW], wmask[MW];
 #pragma unroll
       for (int w = 0; w < MW; ++w) rmask[w] = wmask[w] = 0;
@@ -331,23 +349,23 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
         if (has_res) {
           const __nv_bfloat16* pr = res + ((res_half ? gr.G : go.G) + qres) * 8;
 #pragma unroll
-          for (int c = 0; c < MAXCB; ++c)
-            if (c < cbout) rres[c] = (res_ok && (cbh == 0 || c < cbh)) ? ld_nc16(pr + c * rstride) : make_uint4(0, 0, 0, 0);
+          for (int c = C0; c < C1; ++c)
+            if (c < cbout) rres[c - C0] = (res_ok && (cbh == 0 || c < cbh)) ? ld_nc16(pr + c * rstride) : make_uint4(0, 0, 0, 0);
         }
         if (has_act && mask_in == nullptr) {
           const __nv_bfloat16* pa = act + (go.G + qo) * 8;
 #pragma unroll
-          for (int c = 0; c < MAXCB; ++c)
-            if (c < cbout && (c < cbh || cbh == 0 || second_ok)) ract[c] = ld_nc16(pa + KOFF(c));
+          for (int c = C0; c < C1; ++c)
+            if (c < cbout && (c < cbh || cbh == 0 || second_ok)) ract[c - C0] = ld_nc16(pa + KOFF(c));
         }
         if (has_act && mask_in != nullptr) {
           // sign bits of the activation (written by the forward epilogue): 4 bytes per pixel and 4 chunks instead of
           // 16 bytes per pixel and chunk.  Stride-2 data gradient: chunks [cbh, 2 cbh) belong to the next pixel.
           const uint32_t* pm = mask_in + go.G + qo;
 #pragma unroll
-          for (int w = 0; w < MW; ++w) {
+          for (int w = W0; w < W1; ++w) {
             if (cbh == 0) {
-              if (w * 4 < cbout) rmask[w] = __ldg(pm + (long long)w * go.PS);
+              if (w * 4 < cbout) rmask[w - W0] = __ldg(pm + (long long)w * go.PS);
             } else {
               // word w covers kernel chunks 4w .. 4w+3 = (pixel b, map chunk c) pairs; gather their bytes
               uint32_t v = 0;
@@ -362,7 +380,7 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
                   }
                 }
               }
-              rmask[w] = v;
+              rmask[w - W0] = v;
             }
           }
         }
@@ -372,31 +390,27 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
       estage += NG;
       if (estage >= n_stages) { estage -= n_stages; epar ^= 1; }
       const uint32_t taddr = tmem_base + eg * acc_stride + ((uint32_t)(quarter * 32) << 16);
+      {
+        // 2. pull this thread's share of the accumulator row out of TMEM
+        float acc[NC][8];
 #pragma unroll
-      for (int half = 0; half < (MAXCB + HALF - 1) / HALF; ++half) {
-        if (half * HALF >= cbout) break;
-        // 2. pull this thread's accumulator row out of TMEM (5 chunks = 40 columns per batch)
-        float acc[HALF][8];
-#pragma unroll
-        for (int k = 0; k < HALF; ++k)
-          if (half * HALF + k < cbout) tmem_ld8(taddr + (half * HALF + k) * 8, acc[k]);
+        for (int k = 0; k < NC; ++k)
+          if (C0 + k < cbout) tmem_ld8(taddr + (C0 + k) * 8, acc[k]);
         tmem_ld_wait();
-        if ((half + 1) * HALF >= cbout) {
-          // 3. the accumulator stage is free again: the MMA warp can start the tile after next
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&hd->acc_empty[eg]);
-        }
+        // 3. the accumulator stage is free again: the MMA warp can start the tile after next
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&hd->acc_empty[eg]);
         // 4. arithmetic + stores: one divergent branch per batch, straight-line code inside
         if (live) {
 #pragma unroll
-          for (int k = 0; k < HALF; ++k) {
-            const int c = half * HALF + k;
+          for (int k = 0; k < NC; ++k) {
+            const int c = C0 + k;
             if (c < cbout) {
               float* v = acc[k];
               if (has_res) {
                 float rv[8];
-                unpack8(rres[c], rv);
+                unpack8(rres[k], rv);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] += rv[j];
               }
@@ -411,13 +425,13 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], MIL_SLOPE * v[j]);  // == x > 0 ? x : slope * x
               } else if (has_act && mask_in != nullptr) {
-                const uint32_t bits = rmask[c >> 2] >> ((c & 3) * 8);
+                const uint32_t bits = rmask[(c >> 2) - W0] >> ((c & 3) * 8);
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                   if (!((bits >> j) & 1u)) v[j] *= MIL_SLOPE;
               } else if (has_act) {
                 float av[8];
-                unpack8(ract[c], av);
+                unpack8(ract[k], av);
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                   if (!(av[j] > 0.f)) v[j] *= MIL_SLOPE;
@@ -432,7 +446,7 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
 #pragma unroll
                 for (int i = 0; i < 4; ++i) hp[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
                 const uint32_t bits = mil_positive_bits(pk);
-                wmask[c >> 2] |= bits << ((c & 3) * 8);
+                wmask[(c >> 2) - W0] |= bits << ((c & 3) * 8);
                 *reinterpret_cast<uint4*>(po + KOFF(c)) = pk;
               } else if (c < cbh || cbh == 0 || second_ok) {
                 mil_store8(po + KOFF(c), v);
@@ -442,17 +456,24 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
           if (do_lrelu && mask_out != nullptr) {
             uint32_t* pm = mask_out + go.G + qo;
 #pragma unroll
-            for (int w = 0; w < MW; ++w)
-              if (w * 4 < cbout) pm[(long long)w * go.PS] = wmask[w];
+            for (int w = W0; w < W1; ++w)
+              if (w * 4 < cbout) pm[(long long)w * go.PS] = wmask[w - W0];
           }
         } else if (in_range) {  // pad pixel of the output map: keep the zero row / column zero
 #pragma unroll
-          for (int k = 0; k < HALF; ++k) {
-            const int c = half * HALF + k;
+          for (int k = 0; k < NC; ++k) {
+            const int c = C0 + k;
             if (c < cbout) *reinterpret_cast<uint4*>(po + KOFF(c)) = make_uint4(0, 0, 0, 0);
           }
         }
       }
+    }
+    };  // run
+    if constexpr (CSPLIT == 1) {
+      run(TcInt<0>{}, TcInt<MAXCB>{});
+    } else {
+      if (csub == 0) run(TcInt<0>{}, TcInt<TcSplit<MAXCB, MODE>::at>{});
+      else run(TcInt<TcSplit<MAXCB, MODE>::at>{}, TcInt<MAXCB>{});
     }
   }
 #undef KOFF
@@ -682,7 +703,7 @@ int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const vo
 #define MIL_TC_LAUNCH1(MAXCB, NG, MODE)                                                                           \
   do {                                                                                                            \
     MIL_SET_SMEM((conv_tc_kernel<MAXCB, NG, MODE>), smem);                                                        \
-    conv_tc_kernel<MAXCB, NG, MODE><<<grid, 96 + NG * 128, smem, s>>>(                                            \
+    conv_tc_kernel<MAXCB, NG, MODE><<<grid, 96 + NG * 128 * TcSplit<MAXCB, MODE>::value, smem, s>>>(                                            \
         (const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)wtc, bias, (const __nv_bfloat16*)res,                  \
         (const __nv_bfloat16*)act, (__nv_bfloat16*)out, go, sh, iss, epi, sub, halo, n_stages,                    \
         gres_half ? *gres_half : go, gres_half ? 1 : 0, up_row + 1, up_row >= 0 ? go.cb : 0,                      \
