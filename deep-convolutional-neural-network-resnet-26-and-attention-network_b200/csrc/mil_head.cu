@@ -12,6 +12,12 @@
 //                            weight-gradient partials, sum dHz, sum dHz*xhat          -> bnsums[160] (AR-3)
 //   phase 5  head_bwd_b    : BatchNorm1d backward with the bag-wide sums -> dH [n,80]
 // All bag-wide sums are accumulated in double, in a fixed order (bit-reproducible).
+//
+// Work distribution (round 2): the per-tile kernels used to give ONE thread a whole tile (6400 dependent FMAs, 64 blocks of
+// 64 threads on a 148-SM part: 46 + 99 us at 4096 tiles, the same at 512).  Now eight threads share a tile -- each owns
+// five hidden units of both MLPs, the 3 + 1 outputs are finished with warp shuffles -- a group of 16 tiles is a block
+// of 128 threads (256 blocks at 4096 tiles), H rows are read with 128-bit loads, and the backward kernel is persistent
+// (<= 2 blocks per SM, parameter-gradient partials kept in registers across groups: one record per block).
 #include <algorithm>
 
 #include "mil_common.cuh"
@@ -20,46 +26,63 @@
 #define HL 80
 #define HD 40
 #define HK 3
-#define HT 64          // tiles per block (one thread per tile)
+#define HT 16          // tiles per group: a block of HTHREADS threads works on HT tiles at a time, HSUB threads per tile
+#define HSUB 8         // threads per tile: thread `sub` owns the hidden units sub, sub + 8, ..., sub + 32 of both MLPs
+#define HJ (HD / HSUB) // hidden units per thread (5)
+#define HTHREADS (HT * HSUB)
 #define HROW (HL + 1)  // padded smem row
 #define BN_EPS 1e-5
 
 // ---------------------------------------------------------------------------------------------------
 // phase 1
 // ---------------------------------------------------------------------------------------------------
-#define STATS_BLOCKS 128
-__global__ void __launch_bounds__(320)
+#define STATS_BLOCKS 148
+#define STATS_ROWS 16  // rows in flight per block: 16 x 20 threads, one float4 of a row each
+__global__ void __launch_bounds__(STATS_ROWS * (HL / 4))
 head_stats_kernel(const float* __restrict__ H, int n, double* __restrict__ part) {
-  __shared__ double s1[4][HL], s2[4][HL];
-  const int f = threadIdx.x % HL, r = threadIdx.x / HL;
+  __shared__ double s1[STATS_ROWS][HL], s2[STATS_ROWS][HL];
+  const int f4 = threadIdx.x % (HL / 4), r = threadIdx.x / (HL / 4);
   const int per = (int)mil_cdiv(n, (int)gridDim.x);
   const int n0 = blockIdx.x * per, n1 = min(n0 + per, n);
-  double a = 0.0, b = 0.0;
-  for (int i = n0 + r; i < n1; i += 4) {
-    const double v = (double)H[(size_t)i * HL + f];
-    a += v;
-    b += v * v;
+  double a[4] = {0.0, 0.0, 0.0, 0.0}, b[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int i = n0 + r; i < n1; i += STATS_ROWS) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(H + (size_t)i * HL) + f4);
+    const double x0 = v.x, x1 = v.y, x2 = v.z, x3 = v.w;
+    a[0] += x0; a[1] += x1; a[2] += x2; a[3] += x3;
+    b[0] += x0 * x0; b[1] += x1 * x1; b[2] += x2 * x2; b[3] += x3 * x3;
   }
-  s1[r][f] = a;
-  s2[r][f] = b;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { s1[r][f4 * 4 + k] = a[k]; s2[r][f4 * 4 + k] = b[k]; }
   __syncthreads();
-  if (r == 0) {
-    part[(size_t)blockIdx.x * 2 * HL + f] = s1[0][f] + s1[1][f] + s1[2][f] + s1[3][f];
-    part[(size_t)blockIdx.x * 2 * HL + HL + f] = s2[0][f] + s2[1][f] + s2[2][f] + s2[3][f];
+  if (threadIdx.x < HL) {
+    double x = 0.0, y = 0.0;
+    for (int k = 0; k < STATS_ROWS; ++k) { x += s1[k][threadIdx.x]; y += s2[k][threadIdx.x]; }
+    part[(size_t)blockIdx.x * 2 * HL + threadIdx.x] = x;
+    part[(size_t)blockIdx.x * 2 * HL + HL + threadIdx.x] = y;
   }
 }
-__global__ void reduce_double_kernel(const double* __restrict__ part, int nblk, int count, double* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
+// out[i] = sum over the nblk records of part[b][i]: one block per output, strided partial sums + a fixed tree
+// (the shape of the tree depends only on nblk: bit-reproducible)
+#define RD_THREADS 128
+__global__ void __launch_bounds__(RD_THREADS)
+reduce_double_kernel(const double* __restrict__ part, int nblk, int count, double* __restrict__ out) {
+  __shared__ double sh[RD_THREADS];
+  const int i = blockIdx.x;
   double a = 0.0;
-  for (int b = 0; b < nblk; ++b) a += part[(size_t)b * count + i];
-  out[i] = a;
+  for (int b = threadIdx.x; b < nblk; b += RD_THREADS) a += part[(size_t)b * count + i];
+  sh[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = RD_THREADS / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[i] = sh[0];
 }
 
 int mil_launch_head_stats(const float* H, int n, double* part_ws, double* stats, cudaStream_t s) {
-  head_stats_kernel<<<STATS_BLOCKS, 320, 0, s>>>(H, n, part_ws);
+  head_stats_kernel<<<STATS_BLOCKS, STATS_ROWS * (HL / 4), 0, s>>>(H, n, part_ws);
   MIL_LAUNCH_OK();
-  reduce_double_kernel<<<2, 128, 0, s>>>(part_ws, STATS_BLOCKS, 2 * HL, stats);
+  reduce_double_kernel<<<2 * HL, RD_THREADS, 0, s>>>(part_ws, STATS_BLOCKS, 2 * HL, stats);
   MIL_LAUNCH_OK();
   return 0;
 }
@@ -82,10 +105,9 @@ struct HeadSmem {
 __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
 
-// loads parameters + BN scale/shift and the block's H tile; fills hz / hm
-__device__ void head_load_tile(HeadSmem& S, const MilHeadParams& P, const float* __restrict__ H,
-                               const float* __restrict__ drop, int n, long long n_global,
-                               const double* __restrict__ stats, int i0) {
+// parameters + BN scale / shift of the bag (once per block)
+__device__ void head_load_params(HeadSmem& S, const MilHeadParams& P, long long n_global,
+                                 const double* __restrict__ stats) {
   for (int i = threadIdx.x; i < HL * HD; i += blockDim.x) {
     const int d = i / HL, f = i % HL;  // coalesced read of W[d][f]
     S.w1t[f][d] = P.att_w1[i];
@@ -114,48 +136,69 @@ __device__ void head_load_tile(HeadSmem& S, const MilHeadParams& P, const float*
     S.shift[f] = (float)((double)P.bn_b[f] - m * rs * (double)P.bn_w[f]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < HT * HL; i += blockDim.x) {
-    const int t = i / HL, f = i % HL;
-    float hz = 0.f, hm = 0.f;
-    if (i0 + t < n) {
-      const float h = H[(size_t)(i0 + t) * HL + f];
-      hz = fmaf(h, S.scale[f], S.shift[f]);
-      hm = mil_lrelu(h);
-      if (drop != nullptr) hm *= drop[(size_t)(i0 + t) * HL + f] * (1.f / 0.75f);
+}
+// the group's H rows (128-bit loads) -> hz (BN output) / hm (instance-path input, LeakyReLU + dropout)
+__device__ void head_load_rows(HeadSmem& S, const float* __restrict__ H, const float* __restrict__ drop, int n, int i0) {
+  for (int i = threadIdx.x; i < HT * (HL / 4); i += blockDim.x) {
+    const int t = i / (HL / 4), f = (i % (HL / 4)) * 4;
+    float4 h = make_float4(0.f, 0.f, 0.f, 0.f), dm = make_float4(1.f, 1.f, 1.f, 1.f);
+    const bool ok = i0 + t < n;
+    if (ok) {
+      h = __ldg(reinterpret_cast<const float4*>(H + (size_t)(i0 + t) * HL + f));
+      if (drop != nullptr) dm = __ldg(reinterpret_cast<const float4*>(drop + (size_t)(i0 + t) * HL + f));
     }
-    S.hz[t][f] = hz;
-    S.hm[t][f] = hm;
+    const float hv[4] = {h.x, h.y, h.z, h.w}, dv[4] = {dm.x, dm.y, dm.z, dm.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float hz = 0.f, hm = 0.f;
+      if (ok) {
+        hz = fmaf(hv[k], S.scale[f + k], S.shift[f + k]);
+        hm = mil_lrelu(hv[k]);
+        if (drop != nullptr) hm *= dv[k] * (1.f / 0.75f);
+      }
+      S.hz[t][f + k] = hz;
+      S.hm[t][f + k] = hm;
+    }
   }
   __syncthreads();
 }
 
-// per-tile forward of both MLPs; a[] = tanh(att pre-activation), u[] = buffer pre-activation (before lrelu)
-__device__ __forceinline__ void head_tile_forward(const HeadSmem& S, int t, float a[HD], float u[HD], float raw[HK],
-                                                  float& bval) {
+// forward of both MLPs for tile t, split over its HSUB threads: thread `sub` gets a[j] = tanh(att pre-activation) and
+// u[j] = buffer pre-activation (before lrelu) of its hidden units d = sub + HSUB * j; raw[] / bval are complete in EVERY
+// thread of the tile (xor-shuffle all-reduce over the 8 lanes, fixed order)
+__device__ __forceinline__ void head_tile_forward(const HeadSmem& S, int t, int sub, float a[HJ], float u[HJ],
+                                                  float raw[HK], float& bval) {
 #pragma unroll
-  for (int d = 0; d < HD; ++d) { a[d] = S.b1[d]; u[d] = S.c1[d]; }
+  for (int j = 0; j < HJ; ++j) { a[j] = S.b1[sub + HSUB * j]; u[j] = S.c1[sub + HSUB * j]; }
+#pragma unroll 4
   for (int f = 0; f < HL; ++f) {
     const float hz = S.hz[t][f], hm = S.hm[t][f];
 #pragma unroll
-    for (int d4 = 0; d4 < HD / 4; ++d4) {
-      const float4 w = *reinterpret_cast<const float4*>(&S.w1t[f][d4 * 4]);
-      const float4 v = *reinterpret_cast<const float4*>(&S.v1t[f][d4 * 4]);
-      a[d4 * 4 + 0] = fmaf(w.x, hz, a[d4 * 4 + 0]); a[d4 * 4 + 1] = fmaf(w.y, hz, a[d4 * 4 + 1]);
-      a[d4 * 4 + 2] = fmaf(w.z, hz, a[d4 * 4 + 2]); a[d4 * 4 + 3] = fmaf(w.w, hz, a[d4 * 4 + 3]);
-      u[d4 * 4 + 0] = fmaf(v.x, hm, u[d4 * 4 + 0]); u[d4 * 4 + 1] = fmaf(v.y, hm, u[d4 * 4 + 1]);
-      u[d4 * 4 + 2] = fmaf(v.z, hm, u[d4 * 4 + 2]); u[d4 * 4 + 3] = fmaf(v.w, hm, u[d4 * 4 + 3]);
+    for (int j = 0; j < HJ; ++j) {
+      a[j] = fmaf(S.w1t[f][sub + HSUB * j], hz, a[j]);
+      u[j] = fmaf(S.v1t[f][sub + HSUB * j], hm, u[j]);
     }
   }
 #pragma unroll
-  for (int k = 0; k < HK; ++k) raw[k] = S.b2[k];
-  bval = S.c2;
+  for (int k = 0; k < HK; ++k) raw[k] = 0.f;
+  bval = 0.f;
 #pragma unroll
-  for (int d = 0; d < HD; ++d) {
-    a[d] = tanhf(a[d]);
+  for (int j = 0; j < HJ; ++j) {
+    const int d = sub + HSUB * j;
+    a[j] = tanhf(a[j]);
 #pragma unroll
-    for (int k = 0; k < HK; ++k) raw[k] = fmaf(S.w2[k][d], a[d], raw[k]);
-    bval = fmaf(S.v2[d], mil_lrelu(u[d]), bval);
+    for (int k = 0; k < HK; ++k) raw[k] = fmaf(S.w2[k][d], a[j], raw[k]);
+    bval = fmaf(S.v2[d], mil_lrelu(u[j]), bval);
   }
+#pragma unroll
+  for (int o = 1; o < HSUB; o <<= 1) {
+#pragma unroll
+    for (int k = 0; k < HK; ++k) raw[k] += __shfl_xor_sync(0xffffffffu, raw[k], o);
+    bval += __shfl_xor_sync(0xffffffffu, bval, o);
+  }
+#pragma unroll
+  for (int k = 0; k < HK; ++k) raw[k] += S.b2[k];
+  bval += S.c2;
 }
 
 // block-wide sum of `cnt` doubles per thread (cnt <= 16), result in out[] of thread 0 .. written to dst
@@ -181,22 +224,23 @@ __device__ void block_sum_doubles(double v[CNT], double* s_red /*[blockDim.x/32]
 // ---------------------------------------------------------------------------------------------------
 // phase 2
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(HT)
+__global__ void __launch_bounds__(HTHREADS)
 head_scores_kernel(MilHeadParams P, const float* __restrict__ H, const float* __restrict__ drop, int n,
                    long long n_global, const double* __restrict__ stats, float* __restrict__ raw_o,
                    float* __restrict__ g_o, float* __restrict__ b_o, double* __restrict__ part) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   HeadSmem& S = *reinterpret_cast<HeadSmem*>(smem_raw);
-  __shared__ double s_red[(HT / 32) * MIL_HEAD_NSUMS];
+  __shared__ double s_red[(HTHREADS / 32) * MIL_HEAD_NSUMS];
   const int i0 = blockIdx.x * HT;
-  head_load_tile(S, P, H, drop, n, n_global, stats, i0);
-  const int t = threadIdx.x, i = i0 + t;
+  head_load_params(S, P, n_global, stats);
+  head_load_rows(S, H, drop, n, i0);
+  const int t = threadIdx.x / HSUB, sub = threadIdx.x % HSUB, i = i0 + t;
   double v[MIL_HEAD_NSUMS];
 #pragma unroll
   for (int k = 0; k < MIL_HEAD_NSUMS; ++k) v[k] = 0.0;
-  if (i < n) {
-    float a[HD], u[HD], raw[HK], bval;
-    head_tile_forward(S, t, a, u, raw, bval);
+  float a[HJ], u[HJ], raw[HK], bval;
+  head_tile_forward(S, t, sub, a, u, raw, bval);  // (whole warps: the shuffles need every lane)
+  if (i < n && sub == 0) {
     float g[HK];
 #pragma unroll
     for (int k = 0; k < HK; ++k) {
@@ -219,9 +263,9 @@ int mil_launch_head_scores(const MilHeadParams& P, const float* H, const float* 
                            cudaStream_t s) {
   const int nblk = (int)mil_cdiv(n, HT);
   MIL_SET_SMEM((head_scores_kernel), (int)sizeof(HeadSmem));
-  head_scores_kernel<<<nblk, HT, sizeof(HeadSmem), s>>>(P, H, drop, n, n_global, stats, raw, g, b, part_ws);
+  head_scores_kernel<<<nblk, HTHREADS, sizeof(HeadSmem), s>>>(P, H, drop, n, n_global, stats, raw, g, b, part_ws);
   MIL_LAUNCH_OK();
-  reduce_double_kernel<<<1, 32, 0, s>>>(part_ws, nblk, MIL_HEAD_NSUMS, sums);
+  reduce_double_kernel<<<MIL_HEAD_NSUMS, RD_THREADS, 0, s>>>(part_ws, nblk, MIL_HEAD_NSUMS, sums);
   MIL_LAUNCH_OK();
   return 0;
 }
@@ -324,8 +368,10 @@ int mil_launch_head_finalize(const double* sums, const double* stats, long long 
 #define HB_BNW (HB_WM + HK)           // context.bn.weight [80]  (local sum dHz*xhat)
 #define HB_BNB (HB_BNW + HL)          // context.bn.bias   [80]  (local sum dHz)
 #define HB_REC (HB_BNB + HL)
+#define HB_MAX_BLOCKS 296             // persistent grid: at most two blocks per SM
+#define HB_OUT (HD * HL / HTHREADS)   // lin1 weight-gradient elements per thread and matrix (25)
 
-__global__ void __launch_bounds__(HT)
+__global__ void __launch_bounds__(HTHREADS)
 head_bwd_a_kernel(MilHeadParams P, const float* __restrict__ H, const float* __restrict__ drop, int n,
                   long long n_global, const double* __restrict__ stats, const float* __restrict__ raw_i,
                   const float* __restrict__ g_i, const float* __restrict__ b_i, const float* __restrict__ scal,
@@ -338,138 +384,192 @@ head_bwd_a_kernel(MilHeadParams P, const float* __restrict__ H, const float* __r
   float(*s_t)[HD + 1] = s_dp + HT;                                                         // tanh output  [HT][41]
   float(*s_u)[HD + 1] = s_t + HT;                                                          // lrelu output [HT][41]
   float(*s_small)[8] = reinterpret_cast<float(*)[8]>(s_u + HT);                            // [HT][8]: draw[3], db, dwm[3]
-  const int i0 = blockIdx.x * HT;
-  head_load_tile(S, P, H, drop, n, n_global, stats, i0);
-  const int t = threadIdx.x, i = i0 + t;
-  float* rec = part + (size_t)blockIdx.x * HB_REC;
+  const int t = threadIdx.x / HSUB, sub = threadIdx.x % HSUB;
   const float gl = gloss ? gloss[0] : 1.f;
-
-  float a[HD], u[HD], raw[HK], bval;
-  float da[HD], dp[HD];
-  float draw[HK] = {0.f, 0.f, 0.f}, dwm[HK] = {0.f, 0.f, 0.f}, db = 0.f;
-  if (i < n) {
-    head_tile_forward(S, t, a, u, raw, bval);  // a = tanh(.), u = pre-activation of the instance MLP
+  head_load_params(S, P, n_global, stats);
+  float dMs[HK], Sk[HK], Mk[HK];
 #pragma unroll
-    for (int k = 0; k < HK; ++k) {
-      const float dM = gl * scal[MIL_SC_DM + k], Sk = scal[MIL_SC_S + k], Mk = scal[MIL_SC_M + k];
-      const float gk = g_i[(size_t)i * HK + k];
-      db = fmaf(dM, gk / Sk, db);                     // dL/db_n = sum_k dM_k A_kn
-      const float dg = dM * (bval - Mk) / Sk;         // L1-normalise backward (needs only S_k, M_k)
-      const float sg = raw[k] > 20.f ? 1.f : sigmoid_f(raw[k]);  // softplus'
-      draw[k] = dg * S.sneg[k] * sg;
-      const float sn = S.sneg[k], sp = S.spos[k];
-      dwm[k] = dg * (-10.f * sn * (1.f - sn) * softplus_f(raw[k]) + 10.f * sp * (1.f - sp));
+  for (int k = 0; k < HK; ++k) { dMs[k] = gl * scal[MIL_SC_DM + k]; Sk[k] = scal[MIL_SC_S + k]; Mk[k] = scal[MIL_SC_M + k]; }
+
+  // parameter-gradient partials of THIS BLOCK, kept in registers across its groups of tiles:
+  //   every thread: lin1 weight elements o = threadIdx.x + HTHREADS * k  (d = o / 80, f = o % 80) of both MLPs
+  //   threads < 40: hidden unit d = threadIdx.x -> b1, c1, v2, w2[3];  threads < 7: b2[3], c2, weight_mask[3]
+  //   threads < 80: feature f = threadIdx.x -> the local BatchNorm sums
+  float gw1[HB_OUT], gv1[HB_OUT];
+#pragma unroll
+  for (int k = 0; k < HB_OUT; ++k) gw1[k] = gv1[k] = 0.f;
+  float gb1 = 0.f, gc1 = 0.f, gv2 = 0.f, gw2[HK] = {0.f, 0.f, 0.f}, gsm = 0.f, gbnw = 0.f, gbnb = 0.f;
+
+  const int ngroups = (int)mil_cdiv(n, HT);
+  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    const int i0 = grp * HT, i = i0 + t;
+    head_load_rows(S, H, drop, n, i0);
+    float a[HJ], u[HJ], raw[HK], bval;
+    head_tile_forward(S, t, sub, a, u, raw, bval);  // a = tanh(.), u = pre-activation of the instance MLP
+    float da[HJ], dp[HJ];
+    float draw[HK] = {0.f, 0.f, 0.f}, dwm[HK] = {0.f, 0.f, 0.f}, db = 0.f;
+    const bool ok = i < n;
+    if (ok) {
+#pragma unroll
+      for (int k = 0; k < HK; ++k) {
+        const float gk = g_i[(size_t)i * HK + k];
+        db = fmaf(dMs[k], gk / Sk[k], db);                   // dL/db_n = sum_k dM_k A_kn
+        const float dg = dMs[k] * (bval - Mk[k]) / Sk[k];    // L1-normalise backward (needs only S_k, M_k)
+        const float sg = raw[k] > 20.f ? 1.f : sigmoid_f(raw[k]);  // softplus'
+        draw[k] = dg * S.sneg[k] * sg;
+        const float sn = S.sneg[k], sp = S.spos[k];
+        dwm[k] = dg * (-10.f * sn * (1.f - sn) * softplus_f(raw[k]) + 10.f * sp * (1.f - sp));
+      }
     }
 #pragma unroll
-    for (int d = 0; d < HD; ++d) {
+    for (int j = 0; j < HJ; ++j) {
+      const int d = sub + HSUB * j;
       float dt = 0.f;
 #pragma unroll
       for (int k = 0; k < HK; ++k) dt = fmaf(S.w2[k][d], draw[k], dt);
-      da[d] = dt * (1.f - a[d] * a[d]);
-      dp[d] = db * S.v2[d] * mil_lrelu_grad(u[d]);
+      da[j] = ok ? dt * (1.f - a[j] * a[j]) : 0.f;
+      dp[j] = ok ? db * S.v2[d] * mil_lrelu_grad(u[j]) : 0.f;
+      s_da[t][d] = da[j];
+      s_dp[t][d] = dp[j];
+      s_t[t][d] = ok ? a[j] : 0.f;
+      s_u[t][d] = ok ? mil_lrelu(u[j]) : 0.f;
     }
-  } else {
-#pragma unroll
-    for (int d = 0; d < HD; ++d) { a[d] = 0.f; u[d] = 0.f; da[d] = 0.f; dp[d] = 0.f; }
-  }
-#pragma unroll
-  for (int d = 0; d < HD; ++d) {
-    s_da[t][d] = da[d];
-    s_dp[t][d] = dp[d];
-    s_t[t][d] = a[d];
-    s_u[t][d] = (i < n) ? mil_lrelu(u[d]) : 0.f;
-  }
-  s_small[t][0] = draw[0]; s_small[t][1] = draw[1]; s_small[t][2] = draw[2]; s_small[t][3] = db;
-  s_small[t][4] = dwm[0]; s_small[t][5] = dwm[1]; s_small[t][6] = dwm[2]; s_small[t][7] = 0.f;
-  __syncthreads();
+    if (sub == 0) {
+      s_small[t][0] = draw[0]; s_small[t][1] = draw[1]; s_small[t][2] = draw[2]; s_small[t][3] = db;
+      s_small[t][4] = dwm[0]; s_small[t][5] = dwm[1]; s_small[t][6] = dwm[2]; s_small[t][7] = 0.f;
+    }
+    __syncthreads();
 
-  // ---- parameter-gradient partials of this block (outer products over its HT tiles) ----
-  for (int o = threadIdx.x; o < HD * HL; o += blockDim.x) {
-    const int d = o / HL, f = o % HL;
-    float w1 = 0.f, v1 = 0.f;
-    for (int tt = 0; tt < HT; ++tt) {
-      w1 = fmaf(s_da[tt][d], S.hz[tt][f], w1);
-      v1 = fmaf(s_dp[tt][d], S.hm[tt][f], v1);
-    }
-    rec[HB_W1 + o] = w1;
-    rec[HB_V1 + o] = v1;
-  }
-  for (int d = threadIdx.x; d < HD; d += blockDim.x) {
-    float sb1 = 0.f, sc1 = 0.f, sv2 = 0.f, w2k[HK] = {0.f, 0.f, 0.f};
-    for (int tt = 0; tt < HT; ++tt) {
-      sb1 += s_da[tt][d];
-      sc1 += s_dp[tt][d];
-      sv2 = fmaf(s_small[tt][3], s_u[tt][d], sv2);
+    // ---- parameter-gradient partials (outer products over the group's HT tiles) ----
 #pragma unroll
-      for (int k = 0; k < HK; ++k) w2k[k] = fmaf(s_small[tt][k], s_t[tt][d], w2k[k]);
-    }
-    rec[HB_B1 + d] = sb1;
-    rec[HB_C1 + d] = sc1;
-    rec[HB_V2 + d] = sv2;
+    for (int k = 0; k < HB_OUT; ++k) {
+      const int o = threadIdx.x + HTHREADS * k, d = o / HL, f = o % HL;
+      float w1 = gw1[k], v1 = gv1[k];
 #pragma unroll
-    for (int k = 0; k < HK; ++k) rec[HB_W2 + k * HD + d] = w2k[k];
-  }
-  if (threadIdx.x < 7) {
-    float sacc = 0.f;
-    for (int tt = 0; tt < HT; ++tt) sacc += s_small[tt][threadIdx.x];
-    if (threadIdx.x < 3) rec[HB_B2 + threadIdx.x] = sacc;
-    else if (threadIdx.x == 3) rec[HB_C2] = sacc;
-    else rec[HB_WM + threadIdx.x - 4] = sacc;
-  }
-  __syncthreads();  // everyone is done reading hz / hm as forward activations
-
-  // ---- input gradients: dHz = W1^T da  (kept for phase 5), instance path dH = lrelu'(H) * mask/0.75 * V1^T dp ----
-  // xhat is recovered from hz: xhat = (hz - beta) / gamma is ill-defined for gamma = 0 -> recompute from H instead.
-
-  for (int f = 0; f < HL; ++f) {
-    float dz = 0.f, dm = 0.f;
+      for (int tt = 0; tt < HT; ++tt) {
+        w1 = fmaf(s_da[tt][d], S.hz[tt][f], w1);
+        v1 = fmaf(s_dp[tt][d], S.hm[tt][f], v1);
+      }
+      gw1[k] = w1;
+      gv1[k] = v1;
+    }
+    if (threadIdx.x < HD) {
+      const int d = threadIdx.x;
 #pragma unroll
-    for (int d4 = 0; d4 < HD / 4; ++d4) {
-      const float4 w = *reinterpret_cast<const float4*>(&S.w1t[f][d4 * 4]);
-      const float4 v = *reinterpret_cast<const float4*>(&S.v1t[f][d4 * 4]);
-      dz = fmaf(w.x, da[d4 * 4 + 0], dz); dz = fmaf(w.y, da[d4 * 4 + 1], dz);
-      dz = fmaf(w.z, da[d4 * 4 + 2], dz); dz = fmaf(w.w, da[d4 * 4 + 3], dz);
-      dm = fmaf(v.x, dp[d4 * 4 + 0], dm); dm = fmaf(v.y, dp[d4 * 4 + 1], dm);
-      dm = fmaf(v.z, dp[d4 * 4 + 2], dm); dm = fmaf(v.w, dp[d4 * 4 + 3], dm);
-    }
-    S.hz[t][f] = dz;  // own row only: no hazard with other threads
-    S.hm[t][f] = dm;
-  }
-  __syncthreads();
-
-  for (int idx = threadIdx.x; idx < HT * HL; idx += blockDim.x) {
-    const int tt = idx / HL, f = idx % HL;
-    if (i0 + tt < n) {
-      const float h = H[(size_t)(i0 + tt) * HL + f];
-      float dmi = S.hm[tt][f] * mil_lrelu_grad(h);
-      if (drop != nullptr) dmi *= drop[(size_t)(i0 + tt) * HL + f] * (1.f / 0.75f);
-      dHz_o[(size_t)(i0 + tt) * HL + f] = S.hz[tt][f];
-      dHi_o[(size_t)(i0 + tt) * HL + f] = dmi;
-    }
-  }
-  // local BN sums: sum_t dHz, sum_t dHz * xhat  (per feature; fixed order over the block's tiles)
-  for (int f = threadIdx.x; f < HL; f += blockDim.x) {
-    float sb = 0.f, sw = 0.f;
-    for (int tt = 0; tt < HT; ++tt) {
-      if (i0 + tt < n) {
-        const float h = H[(size_t)(i0 + tt) * HL + f];
-        const float xh = (h - S.mean[f]) * S.rstd[f];
-        sb += S.hz[tt][f];
-        sw = fmaf(S.hz[tt][f], xh, sw);
+      for (int tt = 0; tt < HT; ++tt) {
+        gb1 += s_da[tt][d];
+        gc1 += s_dp[tt][d];
+        gv2 = fmaf(s_small[tt][3], s_u[tt][d], gv2);
+#pragma unroll
+        for (int k = 0; k < HK; ++k) gw2[k] = fmaf(s_small[tt][k], s_t[tt][d], gw2[k]);
       }
     }
-    rec[HB_BNW + f] = sw;
-    rec[HB_BNB + f] = sb;
+    if (threadIdx.x < 7)
+      for (int tt = 0; tt < HT; ++tt) gsm += s_small[tt][threadIdx.x];
+    __syncthreads();  // everyone is done reading hz / hm as forward activations
+
+    // ---- input gradients: dHz = W1^T da (kept for phase 5), instance path dH = lrelu'(H) * mask/0.75 * V1^T dp ----
+    // thread (t, sub) takes the features f = sub + HSUB * m of its tile
+#pragma unroll 2
+    for (int m = 0; m < HL / HSUB; ++m) {
+      const int f = sub + HSUB * m;
+      float dz = 0.f, dm = 0.f;
+#pragma unroll
+      for (int d4 = 0; d4 < HD / 4; ++d4) {
+        const float4 w = *reinterpret_cast<const float4*>(&S.w1t[f][d4 * 4]);
+        const float4 v = *reinterpret_cast<const float4*>(&S.v1t[f][d4 * 4]);
+        dz = fmaf(w.x, s_da[t][d4 * 4 + 0], dz); dz = fmaf(w.y, s_da[t][d4 * 4 + 1], dz);
+        dz = fmaf(w.z, s_da[t][d4 * 4 + 2], dz); dz = fmaf(w.w, s_da[t][d4 * 4 + 3], dz);
+        dm = fmaf(v.x, s_dp[t][d4 * 4 + 0], dm); dm = fmaf(v.y, s_dp[t][d4 * 4 + 1], dm);
+        dm = fmaf(v.z, s_dp[t][d4 * 4 + 2], dm); dm = fmaf(v.w, s_dp[t][d4 * 4 + 3], dm);
+      }
+      S.hz[t][f] = dz;  // own tile only: no hazard with the other tiles' threads
+      S.hm[t][f] = dm;
+    }
+    __syncthreads();
+
+    // xhat is recovered from H (xhat = (hz - beta) / gamma is ill-defined for gamma = 0)
+    for (int idx = threadIdx.x; idx < HT * (HL / 4); idx += HTHREADS) {
+      const int tt = idx / (HL / 4), f = (idx % (HL / 4)) * 4;
+      if (i0 + tt < n) {
+        const float4 h = __ldg(reinterpret_cast<const float4*>(H + (size_t)(i0 + tt) * HL + f));
+        float4 dm = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (drop != nullptr) dm = __ldg(reinterpret_cast<const float4*>(drop + (size_t)(i0 + tt) * HL + f));
+        const float hv[4] = {h.x, h.y, h.z, h.w}, dv[4] = {dm.x, dm.y, dm.z, dm.w};
+        float oz[4], oi[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float dmi = S.hm[tt][f + k] * mil_lrelu_grad(hv[k]);
+          if (drop != nullptr) dmi *= dv[k] * (1.f / 0.75f);
+          oz[k] = S.hz[tt][f + k];
+          oi[k] = dmi;
+        }
+        *reinterpret_cast<float4*>(dHz_o + (size_t)(i0 + tt) * HL + f) = make_float4(oz[0], oz[1], oz[2], oz[3]);
+        *reinterpret_cast<float4*>(dHi_o + (size_t)(i0 + tt) * HL + f) = make_float4(oi[0], oi[1], oi[2], oi[3]);
+      }
+    }
+    // local BN sums: sum_t dHz, sum_t dHz * xhat  (per feature; fixed order over the group's tiles)
+    if (threadIdx.x < HL) {
+      const int f = threadIdx.x;
+      for (int tt = 0; tt < HT; ++tt) {
+        if (i0 + tt < n) {
+          const float h = __ldg(H + (size_t)(i0 + tt) * HL + f);
+          const float xh = (h - S.mean[f]) * S.rstd[f];
+          gbnb += S.hz[tt][f];
+          gbnw = fmaf(S.hz[tt][f], xh, gbnw);
+        }
+      }
+    }
+    __syncthreads();  // hz / hm are rewritten by the next group's rows
+  }
+
+  // ---- this block's record ----
+  float* rec = part + (size_t)blockIdx.x * HB_REC;
+#pragma unroll
+  for (int k = 0; k < HB_OUT; ++k) {
+    const int o = threadIdx.x + HTHREADS * k;
+    rec[HB_W1 + o] = gw1[k];
+    rec[HB_V1 + o] = gv1[k];
+  }
+  if (threadIdx.x < HD) {
+    const int d = threadIdx.x;
+    rec[HB_B1 + d] = gb1;
+    rec[HB_C1 + d] = gc1;
+    rec[HB_V2 + d] = gv2;
+#pragma unroll
+    for (int k = 0; k < HK; ++k) rec[HB_W2 + k * HD + d] = gw2[k];
+  }
+  if (threadIdx.x < 3) rec[HB_B2 + threadIdx.x] = gsm;
+  else if (threadIdx.x == 3) rec[HB_C2] = gsm;
+  else if (threadIdx.x < 7) rec[HB_WM + threadIdx.x - 4] = gsm;
+  if (threadIdx.x < HL) {
+    rec[HB_BNW + threadIdx.x] = gbnw;
+    rec[HB_BNB + threadIdx.x] = gbnb;
   }
 }
 
-// fixed-order reduction of the per-block records: parameter gradients (+=, fp32) and BN sums (double)
-__global__ void head_bwd_reduce_kernel(const float* __restrict__ part, int nblk, MilHeadGrads G,
-                                       double* __restrict__ bnsums) {
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= HB_REC) return;
+// fixed-order reduction of the per-block records: parameter gradients (+=, fp32) and BN sums (double).
+// threadIdx.x walks the record (coalesced), threadIdx.y takes every HBR_PARTS-th record, four loads in flight
+#define HBR_PARTS 8
+__global__ void __launch_bounds__(32 * HBR_PARTS)
+head_bwd_reduce_kernel(const float* __restrict__ part, int nblk, MilHeadGrads G, double* __restrict__ bnsums) {
+  __shared__ double sh[HBR_PARTS][32];
+  const int o = blockIdx.x * 32 + threadIdx.x;
   double acc = 0.0;
-  for (int b = 0; b < nblk; ++b) acc += (double)part[(size_t)b * HB_REC + o];
+  if (o < HB_REC) {
+    int b = threadIdx.y;
+    for (; b + 3 * HBR_PARTS < nblk; b += 4 * HBR_PARTS) {
+      const float v0 = part[(size_t)b * HB_REC + o], v1 = part[(size_t)(b + HBR_PARTS) * HB_REC + o];
+      const float v2 = part[(size_t)(b + 2 * HBR_PARTS) * HB_REC + o], v3 = part[(size_t)(b + 3 * HBR_PARTS) * HB_REC + o];
+      acc += (double)v0; acc += (double)v1; acc += (double)v2; acc += (double)v3;
+    }
+    for (; b < nblk; b += HBR_PARTS) acc += (double)part[(size_t)b * HB_REC + o];
+  }
+  sh[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y != 0 || o >= HB_REC) return;
+#pragma unroll
+  for (int k = 1; k < HBR_PARTS; ++k) acc += sh[k][threadIdx.x];
   const float v = (float)acc;
   if (o < HB_B1) G.att_w1[o - HB_W1] += v;
   else if (o < HB_W2) G.att_b1[o - HB_B1] += v;
@@ -489,18 +589,19 @@ __global__ void head_bwd_reduce_kernel(const float* __restrict__ part, int nblk,
   }
 }
 
-size_t mil_head_bwd_partial_floats(int n) { return (size_t)mil_cdiv(n, HT) * HB_REC; }
+static int head_bwd_blocks(int n) { return (int)std::min<long long>(mil_cdiv(n, HT), HB_MAX_BLOCKS); }
+size_t mil_head_bwd_partial_floats(int n) { return (size_t)head_bwd_blocks(n) * HB_REC; }
 
 int mil_launch_head_bwd_a(const MilHeadParams& P, const MilHeadGrads& G, const float* H, const float* drop, int n,
                           long long n_global, const double* stats, const float* raw, const float* g, const float* b,
                           const float* scal, const float* gloss, float* dHz, float* dHi, float* part_ws,
                           double* bnsums, cudaStream_t s) {
-  const int nblk = (int)mil_cdiv(n, HT);
+  const int nblk = head_bwd_blocks(n);
   const size_t smem = sizeof(HeadSmem) + (size_t)4 * HT * (HD + 1) * sizeof(float) + (size_t)HT * 8 * sizeof(float);
   MIL_SET_SMEM((head_bwd_a_kernel), (int)smem);
-  head_bwd_a_kernel<<<nblk, HT, smem, s>>>(P, H, drop, n, n_global, stats, raw, g, b, scal, gloss, dHz, dHi, part_ws);
+  head_bwd_a_kernel<<<nblk, HTHREADS, smem, s>>>(P, H, drop, n, n_global, stats, raw, g, b, scal, gloss, dHz, dHi, part_ws);
   MIL_LAUNCH_OK();
-  head_bwd_reduce_kernel<<<(int)mil_cdiv(HB_REC, 128), 128, 0, s>>>(part_ws, nblk, G, bnsums);
+  head_bwd_reduce_kernel<<<(int)mil_cdiv(HB_REC, 32), dim3(32, HBR_PARTS), 0, s>>>(part_ws, nblk, G, bnsums);
   MIL_LAUNCH_OK();
   return 0;
 }
