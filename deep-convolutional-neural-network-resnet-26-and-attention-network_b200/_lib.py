@@ -72,6 +72,7 @@ PROTOTYPES = {
     "mil_minmax_normalize": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_void_p]),
     "mil_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float,
                               c_float, c_float, c_void_p]),
+    "mil_adam_step_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_void_p]),
 }
 
 

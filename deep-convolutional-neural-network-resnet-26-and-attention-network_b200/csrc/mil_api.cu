@@ -386,6 +386,16 @@ int mil_adam_step(float* params_flat, const float* grads_flat, float* exp_avg, f
   MIL_API_END
 }
 
+int mil_adam_step_dev(float* params_flat, const float* grads_flat, float* exp_avg, float* exp_avg_sq, long long count,
+                      const float* hyper, void* stream) {
+  MIL_API_BEGIN
+  MIL_TRY(require_device());
+  MIL_REQUIRE(params_flat && grads_flat && exp_avg && exp_avg_sq && hyper && count > 0,
+              "mil_adam_step_dev: null pointer argument");
+  return mil_launch_adam_step_dev(params_flat, grads_flat, exp_avg, exp_avg_sq, count, hyper, (cudaStream_t)stream);
+  MIL_API_END
+}
+
 size_t mil_conv_workspace_bytes(int n, int cin, int hi, int wi, int cout, int ho, int wo, int ks) {
   return conv_ws_layout(n, cin, hi, wi, cout, ho, wo, ks).total;
 }

@@ -177,6 +177,8 @@ int mil_raise_max_dynamic_smem(const void* func, int bytes);
 int mil_launch_minmax_normalize(const float* in, float* out, long long count, float* minmax, cudaStream_t s);
 int mil_launch_adam_step(float* p, const float* g, float* m, float* v, long long count, float step_size, float beta1,
                          float beta2, float bc2_sqrt, float eps, float weight_decay, cudaStream_t s);
+int mil_launch_adam_step_dev(float* p, const float* g, float* m, float* v, long long count, const float* hyper,
+                             cudaStream_t s);
 int mil_launch_reduce_partials(const float* partial, int nblk, long long stride, float* out, long long count,
                                cudaStream_t s);
 int mil_launch_reduce_conv_w(const float* partial, int nblk, long long stride, float* dw, float* db, int cout,

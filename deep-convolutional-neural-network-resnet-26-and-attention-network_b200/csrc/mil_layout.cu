@@ -189,6 +189,33 @@ __global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict_
     p[i] = pi - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
   }
 }
+// the same step with the six scalars read from DEVICE memory: hyper = {step_size, beta1, beta2, bc2_sqrt, eps,
+// weight_decay}.  A captured CUDA graph replays this launch while the host refreshes `hyper` between replays
+// (the bias corrections change with every step).
+__global__ void adam_step_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                     float* __restrict__ v, long long count, const float* __restrict__ hyper) {
+  const float step_size = hyper[0], beta1 = hyper[1], beta2 = hyper[2], bc2_sqrt = hyper[3], eps = hyper[4],
+              weight_decay = hyper[5];
+  const float w1 = 1.f - beta1, w2 = 1.f - beta2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float pi = p[i];
+    float gi = g[i];
+    if (weight_decay != 0.f) gi += weight_decay * pi;
+    const float mi = m[i] + w1 * (gi - m[i]);
+    const float vi = beta2 * v[i] + w2 * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = pi - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+  }
+}
+int mil_launch_adam_step_dev(float* p, const float* g, float* m, float* v, long long count, const float* hyper,
+                             cudaStream_t s) {
+  const int blocks = (int)std::min<long long>(mil_cdiv(count, 256), 148 * 8);
+  adam_step_dev_kernel<<<blocks, 256, 0, s>>>(p, g, m, v, count, hyper);
+  MIL_LAUNCH_OK();
+  return 0;
+}
 int mil_launch_adam_step(float* p, const float* g, float* m, float* v, long long count, float step_size, float beta1,
                          float beta2, float bc2_sqrt, float eps, float weight_decay, cudaStream_t s) {
   const int blocks = (int)std::min<long long>(mil_cdiv(count, 256), 148 * 8);

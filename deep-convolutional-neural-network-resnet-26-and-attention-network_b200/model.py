@@ -467,13 +467,23 @@ class Attention(nn.Module):
         group = self.bag_group
         if self.training:
             n_bag = bag.shape[0]
-            if self.subsample_indices is not None:
-                indices = torch.as_tensor(self.subsample_indices).long().cpu()
-                n_global = group.total(int(indices.numel()), device=dev)
+            si = self.subsample_indices
+            if isinstance(si, torch.Tensor) and si.is_cuda:
+                # a device-resident int32 index list is used as it is (no host round trip): what graph.GraphedStep
+                # refills before every replay of a captured step
+                if si.dtype != torch.int32 or not si.is_contiguous() or si.device != dev:
+                    raise ValueError("a CUDA subsample_indices tensor must be contiguous int32 on the bag's device")
+                idx = si
+                n = int(si.numel())
+                n_global = group.total(n, device=dev)
             else:
-                indices, n_global = group.subsample(n_bag, SUBSAMPLE, device=dev)     # gbm/model.py:193
-            idx = indices.to(torch.int32).to(dev, non_blocking=True)
-            n = int(indices.numel())
+                if si is not None:
+                    indices = torch.as_tensor(si).long().cpu()
+                    n_global = group.total(int(indices.numel()), device=dev)
+                else:
+                    indices, n_global = group.subsample(n_bag, SUBSAMPLE, device=dev)     # gbm/model.py:193
+                idx = indices.to(torch.int32).to(dev, non_blocking=True)
+                n = int(indices.numel())
             if self.drop_mask is not None:
                 drop = torch.as_tensor(self.drop_mask, dtype=torch.float32).to(dev).contiguous()
                 if tuple(drop.shape) != (n, 80):

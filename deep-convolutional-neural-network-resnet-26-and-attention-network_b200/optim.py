@@ -52,6 +52,13 @@ class FusedAdam(torch.optim.Optimizer):
         self._m = torch.zeros_like(self._flat)
         self._v = torch.zeros_like(self._flat)
         self._t = 0
+        self._hyper = None        # device float[6]: set by graph.GraphedStep (the captured step reads its scalars there)
+
+    def hyper_values(self, t):
+        """{step_size, beta1, beta2, bc2_sqrt, eps, weight_decay} of step number t (1-based), as mil_adam_step takes them."""
+        g = self.param_groups[0]
+        b1, b2 = g["betas"]
+        return [g["lr"] / (1.0 - b1 ** t), b1, b2, math.sqrt(1.0 - b2 ** t), g["eps"], g["weight_decay"]]
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -59,17 +66,21 @@ class FusedAdam(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        g = self.param_groups[0]
-        b1, b2 = g["betas"]
-        self._t += 1
-        step_size = g["lr"] / (1.0 - b1 ** self._t)
-        bc2_sqrt = math.sqrt(1.0 - b2 ** self._t)
         P = lambda t: C.c_void_p(t.data_ptr())
         st = C.c_void_p(torch.cuda.current_stream(self._flat.device).cuda_stream)
+        if self._hyper is not None:
+            # inside (the capture of) a graphed step: the scalars live in device memory, GraphedStep refreshes them
+            # and counts the steps
+            with torch.cuda.device(self._flat.device):
+                _lib.check(_lib.load().mil_adam_step_dev(P(self._flat), P(self._gflat), P(self._m), P(self._v),
+                                                         self._flat.numel(), P(self._hyper), st), "mil_adam_step_dev")
+            return loss
+        self._t += 1
+        step_size, b1, b2, bc2_sqrt, eps, wd = self.hyper_values(self._t)
         with torch.cuda.device(self._flat.device):
             _lib.check(_lib.load().mil_adam_step(P(self._flat), P(self._gflat), P(self._m), P(self._v),
-                                                 self._flat.numel(), step_size, b1, b2, bc2_sqrt, g["eps"],
-                                                 g["weight_decay"], st), "mil_adam_step")
+                                                 self._flat.numel(), step_size, b1, b2, bc2_sqrt, eps, wd, st),
+                       "mil_adam_step")
         return loss
 
     def zero_grad(self, set_to_none: bool = False):

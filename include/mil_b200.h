@@ -185,6 +185,11 @@ int mil_adam_step(float* params_flat, const float* grads_flat, float* exp_avg, f
                   float step_size, float beta1, float beta2, float bc2_sqrt, float eps, float weight_decay,
                   void* stream);
 
+/* The same step with the six scalars {step_size, beta1, beta2, bc2_sqrt, eps, weight_decay} read from DEVICE memory
+ * (float hyper[6]): the form a captured CUDA graph replays -- the host refreshes `hyper` between replays.        */
+int mil_adam_step_dev(float* params_flat, const float* grads_flat, float* exp_avg, float* exp_avg_sq, long long count,
+                      const float* hyper, void* stream);
+
 /* ---- attention-map export -------------------------------------------------------
  * out = (in - min(in)) / (max(in) - min(in)) over all `count` elements: the `plt.Normalize()(attn)` /
  * `(A - A.min()) / (A.max() - A.min())` scaling the reference applies to an attention map before writing the per-tile
