@@ -73,6 +73,8 @@ PROTOTYPES = {
     "mil_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float,
                               c_float, c_float, c_void_p]),
     "mil_adam_step_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_void_p]),
+    "mil_ingest_tiles_u8": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                                    c_void_p, c_void_p, c_void_p]),
 }
 
 

@@ -396,6 +396,18 @@ int mil_adam_step_dev(float* params_flat, const float* grads_flat, float* exp_av
   MIL_API_END
 }
 
+int mil_ingest_tiles_u8(const void* rois, int n_tiles, int roi, const int* crops, int pad, const unsigned char* flips,
+                        int side, const int* bounds, const int* coef, int ksize, const int* bounds_host, void* out,
+                        void* stream) {
+  MIL_API_BEGIN
+  MIL_TRY(require_device());
+  MIL_REQUIRE(rois && bounds && coef && bounds_host && out, "mil_ingest_tiles_u8: null pointer argument");
+  MIL_REQUIRE(pad >= 0 && (crops != nullptr || flips == nullptr || true), "mil_ingest_tiles_u8: bad arguments");
+  return mil_launch_ingest_u8((const uint8_t*)rois, n_tiles, roi, crops, pad, flips, side, bounds, coef, ksize,
+                              bounds_host, (uint8_t*)out, (cudaStream_t)stream);
+  MIL_API_END
+}
+
 size_t mil_conv_workspace_bytes(int n, int cin, int hi, int wi, int cout, int ho, int wo, int ks) {
   return conv_ws_layout(n, cin, hi, wi, cout, ho, wo, ks).total;
 }

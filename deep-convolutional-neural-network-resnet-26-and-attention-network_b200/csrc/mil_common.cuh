@@ -179,6 +179,10 @@ int mil_launch_adam_step(float* p, const float* g, float* m, float* v, long long
                          float beta2, float bc2_sqrt, float eps, float weight_decay, cudaStream_t s);
 int mil_launch_adam_step_dev(float* p, const float* g, float* m, float* v, long long count, const float* hyper,
                              cudaStream_t s);
+// mil_ingest.cu
+int mil_launch_ingest_u8(const uint8_t* rois, int T, int R, const int* crops, int pad, const uint8_t* flips, int S,
+                         const int* bounds, const int* coef, int ksize, const int* bounds_host, uint8_t* out,
+                         cudaStream_t s);
 int mil_launch_reduce_partials(const float* partial, int nblk, long long stride, float* out, long long count,
                                cudaStream_t s);
 int mil_launch_reduce_conv_w(const float* partial, int nblk, long long stride, float* dw, float* db, int cout,

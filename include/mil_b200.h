@@ -190,6 +190,21 @@ int mil_adam_step(float* params_flat, const float* grads_flat, float* exp_avg, f
 int mil_adam_step_dev(float* params_flat, const float* grads_flat, float* exp_avg, float* exp_avg_sq, long long count,
                       const float* hyper, void* stream);
 
+/* ---- tile ingest -----------------------------------------------------------------
+ * The per-tile finalisation of the reference's loader (RoiBuilder.py:193-210: ToPILImage, Pad(100), RandomCrop(roi),
+ * Resize(side), RandomHorizontalFlip, RandomVerticalFlip; :203-208 without the augmentations for validation) on the
+ * cached 8-bit tiles, bit-identical to Pillow's antialiased bilinear resampling:
+ *   rois   : device uint8 [n_tiles, roi, roi, 3] (HWC, the `.npy` tile cache, RoiBuilder.py:215-238)
+ *   crops  : device int32 [n_tiles, 2] = (top, left) of the crop inside the padded (roi + 2 pad) image, or NULL for
+ *            no pad / crop;  flips: device uint8 [n_tiles], bit 0 = horizontal, bit 1 = vertical flip, or NULL
+ *   bounds : device int32 [side, 2] = (first input pixel, count) and coef: device int32 [side, ksize] = Pillow's
+ *            fixed-point triangle weights (PRECISION_BITS = 22) per output position; bounds_host = host copy of bounds
+ *   out    : device uint8 [n_tiles, 3, side, side] -- the 8-bit bag mil_extractor_forward_u8 consumes (ToTensor +
+ *            Normalize(.5, .5) are fused into the stem's load)                                                     */
+int mil_ingest_tiles_u8(const void* rois, int n_tiles, int roi, const int* crops, int pad, const unsigned char* flips,
+                        int side, const int* bounds, const int* coef, int ksize, const int* bounds_host, void* out,
+                        void* stream);
+
 /* ---- attention-map export -------------------------------------------------------
  * out = (in - min(in)) / (max(in) - min(in)) over all `count` elements: the `plt.Normalize()(attn)` /
  * `(A - A.min()) / (A.max() - A.min())` scaling the reference applies to an attention map before writing the per-tile
