@@ -71,3 +71,10 @@ gaps.sort(reverse=True)
 print(f"# idle gaps > 5 us: {len(gaps) / steps:.1f} per step, {sum(g for g, _, _ in gaps) / steps:.1f} us per step")
 for g, a, b in gaps[:25]:
     print(f"{g:9.1f} us  after {a}  before {b}")
+# launches of the weight-gradient kernels in time order (first step): which layer costs what
+wg = [e for e in evs if "wgrad" in e.name]
+first = wg[: len(wg) // steps]
+print("# wgrad launches in order (us):", " ".join(f"{re.sub(r'_kernel.*', '', e.name.replace('void ', ''))[:9]}:{e.time_range.elapsed_us():.0f}" for e in first))
+cv = [e for e in evs if "conv_tc_kernel" in e.name]
+firstc = cv[: len(cv) // steps]
+print("# conv_tc launches in order (us):", " ".join(f"{re.sub(r'.*conv_tc_kernel<', '<', e.name)[:10].replace(' ', '')}:{e.time_range.elapsed_us():.0f}" for e in firstc))
