@@ -43,7 +43,10 @@ FLOP_FWD_BWD = {224: 1247.7e6, 256: 1629.9e6}      # algorithmic FLOP per tile (
 L1_CONV_FLOP_224 = 22.58e6                         # one layer1 3x3 conv, per tile
 # dram__bytes_read.sum + dram__bytes_write.sum of that kernel per launch size (tiles), from the ncu --set full
 # captures summarised in profiles/ (None = no capture for this launch size)
-L1_CONV_NCU_TRAFFIC = {4096: 1277668000 + 613048064}      # profiles/r1_ncu_tc_kernels_final.txt
+L1_CONV_NCU_TRAFFIC = {4096: 1284714000 + 665690112}      # profiles/r2_ncu_conv_wgrad_after.txt (in situ, with sign masks)
+# ncu, same capture: l1tex__data_pipe_tc_wavefronts_mem_shared (the tensor core's operand reads from shared memory) as
+# a fraction of its peak -- what actually bounds the thin-N implicit GEMMs of this network
+L1_CONV_NCU_TC_SMEM_PCT = {4096: 63.7}
 METRIC = "tiles/sec fwd+bwd ResNet-26+attention-MIL"
 
 
@@ -300,6 +303,9 @@ def kernel_rooflines(mil, lib, dev, n, side, precision, value_per_gpu):
             "traffic": L1_CONV_NCU_TRAFFIC.get(n), "peak_source": src,
             "algorithmic_bytes_per_launch": abytes, "tiles_per_launch": n, "ms_per_launch": kms,
             "tensor": {"achieved": ach, "peak": burst, "unit": "TFLOP/s", "frac": ach / burst},
+            "limiter": {"what": "shared-memory operand reads of the N = 32 MMAs (128 x 16 A block re-read per tap): "
+                                "ncu l1tex__data_pipe_tc_wavefronts_mem_shared, % of peak, in-situ capture",
+                        "pct": L1_CONV_NCU_TC_SMEM_PCT.get(n)},
             "whole_step_tensor_frac_of_sustained": value_per_gpu * FLOP_FWD_BWD.get(side, 0) / 1e12 / sustained}
     others = []
     # layer-1 weight + bias gradient (wgrad_sq_kernel + its 10-us record reduction): reads x and dz
@@ -454,6 +460,38 @@ def run_ours(args):
                       "tiles_through_cnn": n_cnn,
                       "note": "module in train(): randperm 20 % subsample gathered inside the stem load + Dropout(0.25)"}
 
+    # ---------------- small bags: the reference's live shape (<= 2 500 tiles per bag, 20 % through the CNN) ----------------
+    # eager launches vs the CUDA-graph replay of the whole step (graph.GraphedStep), fwd + bwd + FusedAdam
+    small_bag = None
+    if mode == "train" and world == 1 and n >= 2560:
+        sb = 2560
+        net2 = mil.Attention(n_classes=3).to(dev).train()
+        net2.precision = args.precision
+        opt2 = mil.FusedAdam(net2, lr=2e-4)
+        sbag = bag[:sb]
+
+        def eager_steps(k):
+            for _ in range(k):
+                opt2.zero_grad()
+                o = net2(sbag, Y)
+                o["loss"].backward()
+                opt2.step()
+        eager_steps(2)
+        ems_small, _ = timed(eager_steps, args.steps)
+        gstep = mil.GraphedStep(net2, sb, side, optimizer=opt2)
+        gstep.bag.copy_(sbag)
+
+        def graph_steps(k):
+            for _ in range(k):
+                gstep(gstep.bag, Y)
+        graph_steps(2)
+        gms_small, _ = timed(graph_steps, args.steps)
+        small_bag = {"bag_tiles": sb, "tiles_through_cnn": int(sb * 0.2), "eager_ms_per_step": ems_small,
+                     "graph_ms_per_step": gms_small, "bag_tiles_per_s_graph": sb / (gms_small * 1e-3),
+                     "note": "module in train(), fwd + bwd + FusedAdam; graph = one CUDA-graph replay per step "
+                             "(GraphedStep; the subsample indices are redrawn on the host before every replay)"}
+        del net2, opt2, gstep, sbag
+
     # ---------------- end to end from pinned host memory ----------------
     # Every step's bag starts in pinned HOST memory and is copied to the device inside the timed region; the result
     # is read back every step.  The copy of step k+1 is submitted (BagStager: side stream, double buffer) before
@@ -541,6 +579,8 @@ def run_ours(args):
         }
         if train_mode is not None:
             line["train_mode"] = train_mode
+        if small_bag is not None:
+            line["small_bag"] = small_bag
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

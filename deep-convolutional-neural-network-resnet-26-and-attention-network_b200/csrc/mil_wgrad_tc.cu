@@ -39,13 +39,18 @@ struct WgSmemHeader {
   uint64_t full[WG_MAX_STAGES], empty[WG_MAX_STAGES], done;
   uint32_t tmem_base;
 };
-// Explicit MMA list for the stride-2 3x3 convolution on its phase-split input (mil_tc_shape_s2): MMA i multiplies dz
-// with the `cb` planes starting at plane0[i], read `shift[i]` pixels away, and produces tap rtap[i] = ky * 3 + kx of
-// the 3x3 weight.  n = 0: the taps come from the window description `sh`.
+// Explicit MMA list for the stride-2 3x3 convolution on its phase-split input (mil_tc_shape_s2).  The nine taps fall
+// into FOUR groups by their pixel shift (0, -1, -wp, -wp-1); the taps of a group differ only in the parity phase they
+// read, and the phase planes sit at a uniform stride -- so ONE MMA per group covers all its taps: it multiplies dz with
+// the `nplanes[i]` planes starting at plane0[i] (N = 8 * nplanes, padded to 16), read `shift[i]` pixels away, into the
+// TMEM columns from col0[i].  Column block p of group i is plane plane0[i] + p = (phase, chunk); rtap[i][phase] is the
+// tap ky * 3 + kx it belongs to (0xFF: a phase that lies between two wanted ones -- computed, not stored).  A thin M = 64
+// MMA costs max(28, N / 2) cycles, so four wide MMAs (140 cycles per K-step on layer 2) replace nine thin ones (252).
+// n = 0: the taps come from the window description `sh`.
 struct WgCombo {
   int n, cb;
-  short shift[9];
-  unsigned char plane0[9], rtap[9];
+  short shift[4], col0[4], npad[4];
+  unsigned char plane0[4], nplanes[4], rtap[4][4];
 };
 
 // dxcat = 1: 3x3 window, taps grouped by dy, N = (dx, chunk) planes;  dxcat = 0: one tap per MMA (1x1 window, or the
@@ -155,11 +160,21 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
       const uint64_t ad0 = make_desc(a_base, 128, WG_A_PLANE);
       const uint32_t acc0 = first ? 0u : 1u;
       if (elect_one()) {
-        for (int tl = 0; tl < ntl; ++tl) {
+        if (cmb.n) {
+          for (int gi = 0; gi < cmb.n; ++gi) {
+            const uint64_t bd0 = make_desc(b_base + cmb.plane0[gi] * b_pitch + (uint32_t)(back + cmb.shift[gi]) * 16, 128, b_pitch);
+            const uint32_t idesc_g = idesc_base | ((uint32_t)(cmb.npad[gi] >> 3) << 17);
+            const uint32_t d = tmem_base + cmb.col0[gi];
+            umma_bf16(d, ad0, bd0, idesc_g, acc0);
+#pragma unroll
+            for (int kk = 1; kk < WG_TK / 16; ++kk) umma_bf16(d, ad0 + kk * 16, bd0 + kk * 16, idesc_g, 1u);
+          }
+        }
+        for (int tl = 0; tl < (cmb.n ? 0 : ntl); ++tl) {
           const int tap = tap_lo + tl;
           // pixel offset of this tap's window start inside a B plane
-          const int s = cmb.n ? back + cmb.shift[tap] : (dxcat ? tap * gx.wp : back + sh.t_dy[tap] * gx.wp + sh.t_dx[tap]);
-          const uint32_t p0 = cmb.n ? cmb.plane0[tap] * b_pitch : 0u;
+          const int s = dxcat ? tap * gx.wp : back + sh.t_dy[tap] * gx.wp + sh.t_dx[tap];
+          const uint32_t p0 = 0u;
           const uint64_t bd0 = make_desc(b_base + p0 + (uint32_t)s * 16, 128, b_pitch);
           // M = 64 accumulators occupy lanes 0-15 of every lane quarter only: lane_split = h > 0 parks the taps from
           // h on in lanes 16-31 of the same columns (TMEM holds twice as many M = 64 accumulators that way)
@@ -170,7 +185,7 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
           for (int kk = 1; kk < WG_TK / 16; ++kk) umma_bf16(d, ad0 + kk * 16, bd0 + kk * 16, idesc, 1u);
         }
         if (with_bias && !fold) {
-          const uint32_t d = tmem_base + ntl * npad;
+          const uint32_t d = tmem_base + (cmb.n ? cmb.col0[cmb.n - 1] + cmb.npad[cmb.n - 1] : ntl * npad);
           umma_bf16(d, ad0, ones_desc, idesc_b, acc0);
 #pragma unroll
           for (int kk = 1; kk < WG_TK / 16; ++kk) umma_bf16(d, ad0 + kk * 16, ones_desc, idesc_b, 1u);
@@ -198,7 +213,21 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
     if ((mma_m == 128 ? quarter * 32 : quarter * 16) < coutp) {  // warp-uniform
       float* rec = partial + (size_t)blockIdx.x * rec_stride;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-      const int ncol_taps = lane_split ? lane_split : ntl;  // accumulator column blocks to walk
+      if (cmb.n) {
+        for (int gi = 0; gi < cmb.n; ++gi)
+          for (int p = 0; p < cmb.nplanes[gi]; ++p) {
+            float v[8];
+            tmem_ld8(taddr + cmb.col0[gi] + p * 8, v);
+            tmem_ld_wait();
+            const int plane = cmb.plane0[gi] + p, ph = plane / cmb.cb, c = plane - ph * cmb.cb;
+            const int rtap = cmb.rtap[gi][ph];
+            if (co < coutp && rtap != 0xFF) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) rec[((size_t)rtap * cinp + c * 8 + j) * coutp + co] = v[j];
+            }
+          }
+      }
+      const int ncol_taps = cmb.n ? 0 : (lane_split ? lane_split : ntl);  // accumulator column blocks to walk
       for (int tc = 0; tc < ncol_taps; ++tc) {
         // the tap this LANE finds in column block tc
         const int tl = (lane_split && upper) ? lane_split + tc : tc;
@@ -207,7 +236,7 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
           tmem_ld8(taddr + tc * npad + p * 8, v);
           tmem_ld_wait();
           // record tap and input chunk of this column block
-          const int rtap = cmb.n ? cmb.rtap[tap_lo + tl] : (dxcat ? (tap_lo + tl) * 3 + p % 3 : tap_lo + tl);
+          const int rtap = dxcat ? (tap_lo + tl) * 3 + p % 3 : tap_lo + tl;
           const int c = dxcat ? p / 3 : p;
           if (co < coutp && tl < ntl) {
 #pragma unroll
@@ -217,7 +246,7 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
       }
       if (with_bias) {
         float v[8];
-        tmem_ld8(taddr + (fold ? nbp * 8 : ntl * npad), v);
+        tmem_ld8(taddr + (cmb.n ? cmb.col0[cmb.n - 1] + cmb.npad[cmb.n - 1] : (fold ? nbp * 8 : ntl * npad)), v);
         tmem_ld_wait();
         if (co < coutp && !(lane_split && upper)) rec[(size_t)ntaps * cinp * coutp + co] = v[0];
       }
@@ -554,25 +583,37 @@ int mil_launch_wgrad_tc_s2(const void* xs2, const MilPF8& gs, const void* dz, co
   MIL_REQUIRE(gs.n == gz.n && gs.h == gz.h && gs.w == gz.w && gs.wp == gz.wp && gs.cb == 4 * cb,
               "wgrad_tc_s2: geometry mismatch");
   WgCombo cmb;
-  cmb.n = 9;
+  cmb.n = 4;
   cmb.cb = cb;
-  for (int ky = 0; ky < 3; ++ky)
-    for (int kx = 0; kx < 3; ++kx) {
-      // w[ky][kx] multiplies phase (a, b) at pixel offset (dy, dx):  ky = 2 dy + a + 1,  kx = 2 dx + b + 1
-      const int a = (ky + 1) & 1, b = (kx + 1) & 1, dy = ky == 0 ? -1 : 0, dx = kx == 0 ? -1 : 0;
-      const int i = ky * 3 + kx;
-      cmb.shift[i] = (short)(dy * gs.wp + dx);
-      cmb.plane0[i] = (unsigned char)((a * 2 + b) * cb);
-      cmb.rtap[i] = (unsigned char)i;
+  int col = 0;
+  for (int gi = 0; gi < 4; ++gi) {
+    // group (dy, dx): w[ky][kx] multiplies phase (a, b) at pixel offset (dy, dx) with ky = 2 dy + a + 1, kx = 2 dx + b + 1,
+    // i.e. dy = -1 needs a = 1 (ky = 0), dy = 0 takes a = 0 (ky = 1) and a = 1 (ky = 2); the same for the columns
+    const int dy = gi >> 1 ? -1 : 0, dx = gi & 1 ? -1 : 0;
+    int first = 4, last = -1;
+    for (int ph = 0; ph < 4; ++ph) {
+      const int a = ph >> 1, b = ph & 1;
+      const bool ok = (dy == 0 || a == 1) && (dx == 0 || b == 1);
+      const int ky = dy == -1 ? 0 : a + 1, kx = dx == -1 ? 0 : b + 1;
+      cmb.rtap[gi][ph] = ok ? (unsigned char)(ky * 3 + kx) : 0xFF;
+      if (ok) { first = std::min(first, ph); last = std::max(last, ph); }
     }
+    cmb.shift[gi] = (short)(dy * gs.wp + dx);
+    cmb.plane0[gi] = (unsigned char)(first * cb);
+    cmb.nplanes[gi] = (unsigned char)((last - first + 1) * cb);
+    cmb.npad[gi] = (short)((cmb.nplanes[gi] * 8 + 15) / 16 * 16);
+    cmb.col0[gi] = (short)col;
+    col += cmb.npad[gi];
+  }
+  MIL_REQUIRE(col + 16 <= 512 && cmb.npad[0] <= 256, "wgrad_tc_s2: %d input channels need %d TMEM columns", cin, col + 16);
   MilTcShape sh;
   MIL_TRY(mil_tc_shape(cin, gz.c, 3, &sh));  // record layout: nine taps
   const int halo = gs.wp + 1;
   MIL_REQUIRE(halo <= gs.G, "wgrad_tc_s2: the window reaches %d pixels back but the map's guard is %lld", halo, gs.G);
   const int mma_m = gz.cb * 8 <= 64 ? 64 : 128;
   const int npad = (cb * 8 + 15) / 16 * 16;
-  const int groups = (9 * npad + 16 <= 512) ? 1 : 2;
-  const int tpg = (9 + groups - 1) / groups;
+  const int groups = 1;
+  const int tpg = 4;
   const long long n_tiles = mil_cdiv(gz.Q, WG_TK);
   const int ctas = (int)std::max<long long>(1, std::min<long long>(n_tiles, wg_sm_count() / groups));
   const size_t span = WG_TK + 2 * (size_t)halo;
