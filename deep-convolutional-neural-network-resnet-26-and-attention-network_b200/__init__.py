@@ -12,10 +12,10 @@ from .distributed import BagGroup, SlideGroup  # noqa: F401
 from .staging import BagStager  # noqa: F401
 from .graph import GraphedStep  # noqa: F401
 from .ingest import TileIngest  # noqa: F401
-from .optim import FusedAdam, flatten_parameters  # noqa: F401
+from .optim import FusedAdam, flatten_parameters, load_checkpoint, save_checkpoint, set_stage  # noqa: F401
 from .export import export_attention_maps, minmax_normalize, top_tiles, write_dla  # noqa: F401
 from .model import Attention, BasicResBlock, ContextLayer, CrossEntropyWithProbs, ResNet  # noqa: F401
 from . import _lib, model, synth  # noqa: F401
 
-__all__ = ["Attention", "BagGroup", "SlideGroup", "BagStager", "GraphedStep", "TileIngest", "FusedAdam", "flatten_parameters", "ResNet", "BasicResBlock", "ContextLayer", "CrossEntropyWithProbs", "build",
+__all__ = ["Attention", "BagGroup", "SlideGroup", "BagStager", "GraphedStep", "TileIngest", "FusedAdam", "flatten_parameters", "set_stage", "save_checkpoint", "load_checkpoint", "ResNet", "BasicResBlock", "ContextLayer", "CrossEntropyWithProbs", "build",
            "LIB_PATH"]

@@ -6,7 +6,7 @@
 // consumes (ToTensor + Normalize(.5, .5) are fused into that load: mil_extractor_forward_u8).
 //
 // The arithmetic is Pillow's antialiased bilinear resampling of 8-bit images, reproduced bit for bit
-// (libImaging/Resample.c, 8bpc path; restated and pinned against Pillow in oracle/ingest_oracle.py):
+// (libImaging/Resample.c, 8bpc path; the CPU restatement the tests compare against is pinned to Pillow itself):
 //   horizontal pass over the input rows, then vertical pass, each  out = clip((2^21 + sum_k pixel_k * coef_k) >> 22)
 // with the fixed-point triangle weights the HOST computes in double precision exactly as precompute_coeffs /
 // normalize_coeffs_8bpc do (ingest.py) -- square tiles, one table serves both passes.  Pad + crop are a source offset

@@ -97,3 +97,69 @@ class FusedAdam(torch.optim.Optimizer):
         self._v.copy_(sd["exp_avg_sq"])
         for g, s in zip(self.param_groups, sd["param_groups"]):
             g.update(s)
+
+
+# ---- the training driver's glue (gbm/classify_combined.py:110-138, 468-474, 521-535) ------------------------------
+STAGE_SCHEDULE = (0, 10, 150, 250, 340)      # epochs: warm-up | main | check | freeze | stop
+BASE_LR = 0.0002
+
+
+def set_stage(optimizer, model, epoch: int, test: bool = False, base_lr: float = BASE_LR, schedule=STAGE_SCHEDULE,
+              verbose: bool = True):
+    """The reference's `SetStage` (gbm/classify_combined.py:110-138): learning rate and train / eval mode of the epoch.
+    Warm-up: base_lr / (10 - epoch), train;  main: base_lr, train;  check: base_lr / 2;  freeze: base_lr / 10 (both:
+    eval when `test`, else train).  Past the schedule the reference saves `..._FINAL.model` and exits: here the stage is
+    returned as "Stop" and the caller decides (save_checkpoint(..., final=True)).  Returns (stage, lr).
+    Works with any optimizer that reads `param_groups[...]['lr']` at step time (FusedAdam does)."""
+    def set_lr(lr):
+        for g in optimizer.param_groups:
+            g["lr"] = lr
+    stage, lr = None, None
+    if schedule[0] <= epoch < schedule[1]:
+        stage, lr = "Warmup", base_lr / (schedule[1] - epoch)
+        set_lr(lr)
+        model.train()
+    if schedule[1] <= epoch < schedule[2]:
+        stage, lr = "Main", base_lr
+        set_lr(lr)
+        model.train()
+    if schedule[2] <= epoch < schedule[3]:
+        stage, lr = "Check", base_lr / 2.0
+        set_lr(lr)
+        model.eval() if test else model.train()
+    if schedule[3] <= epoch < schedule[4]:
+        stage, lr = "Freeze", base_lr / 10.0
+        set_lr(lr)
+        model.eval() if test else model.train()
+    if epoch > schedule[4]:
+        stage, lr = "Stop", 0.0
+    if stage is None:                      # epoch == schedule[4]: the reference falls through every branch
+        stage, lr = "Hold", optimizer.param_groups[0]["lr"]
+    if verbose:
+        print("Stage = [{0}], lr = [{1}], training mode = [{2}]".format(stage, lr, model.training))
+    return stage, lr
+
+
+def save_checkpoint(path, classifier, optimizer=None, final: bool = False):
+    """The reference's checkpoint file (gbm/classify_combined.py:468-474; :137 for the final one without the optimizer):
+    torch.save({'classifier': state_dict, 'optimizer': state_dict}).  The classifier's keys are the reference's own
+    (cnn.module.*, context.bn.*, ...), so the file loads into the reference model and vice versa."""
+    blob = {"classifier": {k: v.detach().cpu().clone() for k, v in classifier.state_dict().items()}}
+    if optimizer is not None and not final:
+        blob["optimizer"] = optimizer.state_dict()
+    torch.save(blob, path)
+    return path
+
+
+def load_checkpoint(path, classifier, optimizer=None, transfer: bool = False, map_location="cpu"):
+    """`--ckpt` of the reference (gbm/classify_combined.py:521-535): the full classifier (strict=False), or with
+    `transfer` only the extractor's convolutions (keys containing 'cnn' and 'conv').  The optimizer state is restored
+    when the file has one and an optimizer is given (the reference never reloads it)."""
+    ckpt = torch.load(path, map_location=map_location, weights_only=False)
+    sd = ckpt["classifier"]
+    if transfer:
+        sd = {k: v for k, v in sd.items() if "cnn" in k and "conv" in k}
+    missing = classifier.load_state_dict(sd, strict=False)
+    if optimizer is not None and "optimizer" in ckpt and not transfer:
+        optimizer.load_state_dict(ckpt["optimizer"])
+    return missing

@@ -243,3 +243,47 @@ def test_sharded_subsample_bookkeeping(mil):
             errs += 1
             assert "without a tile" in str(e)
     assert errs == 3
+
+
+def test_set_stage_follows_the_reference_schedule(mil):
+    """gbm/classify_combined.py:110-138: learning rate and train / eval mode per epoch."""
+    import torch
+    net = torch.nn.Linear(2, 2)
+    opt = torch.optim.SGD(net.parameters(), lr=1.0)
+    want = {0: ("Warmup", 0.0002 / 10, True), 9: ("Warmup", 0.0002, True), 10: ("Main", 0.0002, True),
+            149: ("Main", 0.0002, True), 150: ("Check", 0.0001, True), 250: ("Freeze", 0.00002, True),
+            339: ("Freeze", 0.00002, True)}
+    for epoch, (stage, lr, training) in want.items():
+        got = mil.set_stage(opt, net, epoch, verbose=False)
+        assert got[0] == stage and abs(got[1] - lr) < 1e-12 and net.training is training, (epoch, got)
+        assert all(abs(g["lr"] - lr) < 1e-12 for g in opt.param_groups)
+    mil.set_stage(opt, net, 200, test=True, verbose=False)
+    assert net.training is False                      # check / freeze stages evaluate when test=True
+    mil.set_stage(opt, net, 20, test=True, verbose=False)
+    assert net.training is True
+    assert mil.set_stage(opt, net, 341, verbose=False)[0] == "Stop"
+
+
+def test_checkpoint_file_round_trip_and_transfer_filter(tmp_path, mil):
+    """gbm/classify_combined.py:468-474 (save) and :521-535 (--ckpt / --transfer): the file holds the reference's
+    state-dict keys; `transfer` restores only the extractor's convolutions."""
+    import torch
+    torch.manual_seed(3)
+    a = mil.Attention(n_classes=3)
+    torch.manual_seed(4)
+    b = mil.Attention(n_classes=3)
+    path = mil.save_checkpoint(str(tmp_path / "train_step-007.model"), a)
+    blob = torch.load(path, weights_only=False)
+    assert set(blob) == {"classifier"} and "cnn.module.layer1.0.conv1.weight" in blob["classifier"]
+    mil.load_checkpoint(path, b)
+    for (k, p), (_, q) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert torch.equal(p, q), k
+    torch.manual_seed(5)
+    c = mil.Attention(n_classes=3)
+    before = {k: v.clone() for k, v in c.state_dict().items()}
+    mil.load_checkpoint(path, c, transfer=True)
+    for k, v in c.state_dict().items():
+        if "cnn" in k and "conv" in k:
+            assert torch.equal(v, a.state_dict()[k]), k
+        else:
+            assert torch.equal(v, before[k]), k

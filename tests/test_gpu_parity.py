@@ -536,3 +536,30 @@ def test_bag_stager_double_buffering():
             assert torch.equal(got[k], ref[k]), k
     with pytest.raises(ValueError):
         stager.submit(bags[0].cuda())
+
+
+def test_checkpoint_file_with_fused_adam_state(tmp_path):
+    """torch.save({'classifier', 'optimizer'}) as the reference writes every epoch (gbm/classify_combined.py:468-474):
+    training resumed from the file continues bit for bit."""
+    mil = G.pkg()
+    bag = torch.from_numpy(synth.make_bag(16, 64, seed=21)).cuda()
+    Y = torch.tensor([1]).cuda()
+
+    def steps(net, opt, k):
+        for _ in range(k):
+            opt.zero_grad()
+            net(bag, Y)["loss"].backward()
+            opt.step()
+
+    a = build_net("bf16")
+    oa = mil.FusedAdam(a, lr=1e-3)
+    steps(a, oa, 2)
+    path = mil.save_checkpoint(str(tmp_path / "train_step-002.model"), a, oa)
+    steps(a, oa, 2)
+    b = G.pkg().Attention(n_classes=3).cuda().eval()
+    b.precision = "bf16"
+    ob = mil.FusedAdam(b, lr=1e-3)
+    mil.load_checkpoint(path, b, ob)
+    assert ob._t == 2
+    steps(b, ob, 2)
+    assert torch.equal(oa._flat, ob._flat) and torch.equal(oa._m, ob._m) and torch.equal(oa._v, ob._v)
