@@ -69,6 +69,14 @@ PROTOTYPES = {
                                  c_void_p]),
     "mil_stem_backward": (c_int, [c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                   c_void_p]),
+    "mil_wide_conv_workspace_bytes": (c_size_t, [c_int] * 5),
+    "mil_wide_conv_pf8": (c_int, [c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p, c_size_t,
+                                  c_void_p]),
+    "mil_wide_wgrad_workspace_bytes": (c_size_t, [c_int] * 6),
+    "mil_wide_wgrad_pf8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                   c_size_t, c_void_p]),
+    "mil_split2_pf8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mil_minmax_normalize": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_void_p]),
     "mil_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float,
                               c_float, c_float, c_void_p]),

@@ -9,6 +9,7 @@
 #include "../../include/mil_b200.h"
 #include "mil_extractor.cuh"
 #include "mil_head.cuh"
+#include "mil_wide.cuh"
 
 static thread_local char g_err[1024] = "";
 void mil_set_error(const char* fmt, ...) {
@@ -586,6 +587,57 @@ int mil_stem_backward(int dtype, int impl, const float* bag, int n, int side, co
     return mil_launch_stem_bwd(dtype, bag, nullptr, n, side, g, gp, (const uint8_t*)(wsb + L.off_argmax), partial, dw, db, s);
   return mil_launch_stem_tc_bwd(wsb + L.off_xs, n, side, g, gp, (const uint8_t*)(wsb + L.off_argmax), wsb + L.off_cv, partial,
                                 dw, db, s);
+  MIL_API_END
+}
+
+// ---- wide-channel kernels at layer level (alt_resnet.py parameterisation; tests/test_gpu_wide.py) ----------------
+size_t mil_wide_conv_workspace_bytes(int mode, int transposed, int wcout, int wcin, int ks) {
+  MilWideShape sh;
+  if (mil_wide_shape(mode, transposed, wcout, wcin, ks, &sh) != 0) return 0;
+  return mil_wide_wpack_bytes(sh) + 256;
+}
+
+int mil_wide_conv_pf8(int mode, int transposed, const void* x, int n, int cx, int h, int w, const float* wt, int wcout,
+                      int wcin, int ks, const float* bias, const void* res, const void* act, void* out, int epi,
+                      float slope, int tm, void* ws, size_t ws_bytes, void* stream) {
+  MIL_API_BEGIN
+  MIL_TRY(require_device());
+  MIL_REQUIRE(x && wt && out && ws, "mil_wide_conv_pf8: null pointer argument");
+  MilWideShape sh;
+  MIL_TRY(mil_wide_shape(mode, transposed, wcout, wcin, ks, &sh));
+  MIL_REQUIRE(ws_bytes >= mil_wide_wpack_bytes(sh), "mil_wide_conv_pf8: workspace too small (%zu < %zu)", ws_bytes,
+              mil_wide_wpack_bytes(sh));
+  MIL_REQUIRE(cx == sh.kin * sh.ngroups, "mil_wide_conv_pf8: x has %d channels, expected %d", cx, sh.kin * sh.ngroups);
+  const MilPF8 gx = mil_pf8(n, cx, h, w), go = mil_pf8(n, sh.nout, h, w);
+  cudaStream_t s = (cudaStream_t)stream;
+  MIL_TRY(mil_launch_wide_pack(wt, ws, sh, s));
+  return mil_launch_wide_conv(x, gx, ws, sh, bias, res, act, out, go, epi, slope, tm, s);
+  MIL_API_END
+}
+
+size_t mil_wide_wgrad_workspace_bytes(int n, int cin, int cout, int h, int w, int ks) {
+  return mil_wide_wgrad_partial_floats(mil_pf8(n, cin, h, w), mil_pf8(n, cout, h, w), ks) * sizeof(float) + 256;
+}
+
+int mil_wide_wgrad_pf8(const void* x, int n, int cin, int h, int w, const void* dz, int cout, int ks, float* dw, void* ws,
+                       size_t ws_bytes, void* stream) {
+  MIL_API_BEGIN
+  MIL_TRY(require_device());
+  MIL_REQUIRE(x && dz && dw && ws, "mil_wide_wgrad_pf8: null pointer argument");
+  const MilPF8 gx = mil_pf8(n, cin, h, w), gz = mil_pf8(n, cout, h, w);
+  const size_t need = mil_wide_wgrad_partial_floats(gx, gz, ks) * sizeof(float);
+  MIL_REQUIRE(need > 0, "mil_wide_wgrad_pf8: unsupported shape cin=%d cout=%d ks=%d", cin, cout, ks);
+  MIL_REQUIRE(ws_bytes >= need, "mil_wide_wgrad_pf8: workspace too small (%zu < %zu)", ws_bytes, need);
+  return mil_launch_wide_wgrad(x, gx, dz, gz, (float*)ws, dw, nullptr, ks, (cudaStream_t)stream);
+  MIL_API_END
+}
+
+int mil_split2_pf8(const void* in, int n, int c, int h, int w, void* out, void* stream) {
+  MIL_API_BEGIN
+  MIL_TRY(require_device());
+  MIL_REQUIRE(in && out, "mil_split2_pf8: null pointer argument");
+  const MilPF8 gin = mil_pf8(n, c, h, w);
+  return mil_launch_split2(in, gin, out, mil_split2_geom(n, c, (h - 1) / 2 + 1), (cudaStream_t)stream);
   MIL_API_END
 }
 

@@ -174,6 +174,31 @@ int mil_stem_forward(int dtype, int impl, const float* bag, int n, int side, con
 int mil_stem_backward(int dtype, int impl, const float* bag, int n, int side, const void* g, float* dw, float* db, void* ws,
                       size_t ws_bytes, void* stream);
 
+/* ---- wide-channel kernel family at layer level -------------------------------------
+ * The alt_resnet.py parameterisation of the extractor (alt_resnet.py:24-32 conv3x3 / conv1x1 without bias, :35-67
+ * BasicBlock with ReLU, :70-145 widths 64/128/256/512) on its own tcgen05 kernels: the K loop streams weight slabs
+ * next to the input planes, output channels are tiled by 128.  bf16 only; PF8 buffers as above.
+ *   mode 0: ks = 1 / 3, stride 1 -- forward (transposed = 0) or data gradient (transposed = 1; x = the gradient
+ *           w.r.t. the conv's output);  mode 1: 3x3 / stride 2 forward, x = the phase-split input (mil_split2_pf8:
+ *           4 * cin channels at the OUTPUT resolution h x w);  mode 2: the 7x7 / stride-2 stem in space-to-depth-by-4
+ *           form, x = [n, 48, h, w] with x[(c,ry,rx)][Y][X] = tile[c][4Y+ry][4X+rx], out = [n, 4*wcout, h, w] with channel
+ *           (co, a, b) = conv1(tile)[co][2Y+a][2X+b].
+ * wt: PyTorch weight [wcout][wcin][ks][ks] fp32.  epi: 0 = act(acc + bias + res), 1 = (acc + res) * act'(act map),
+ * 2 = acc + bias + res;  slope: negative slope of the activation (0 = ReLU, alt_resnet.py:49).  tm: 128-pixel tiles per
+ * weight slab (0 = default).  The stride-2 data / weight gradients are the stride-1 ones of the zero-stuffed output
+ * gradient (mil_upsample2_pf8).                                                                                 */
+size_t mil_wide_conv_workspace_bytes(int mode, int transposed, int wcout, int wcin, int ks);
+int mil_wide_conv_pf8(int mode, int transposed, const void* x, int n, int cx, int h, int w, const float* wt, int wcout,
+                      int wcin, int ks, const float* bias, const void* res, const void* act, void* out, int epi,
+                      float slope, int tm, void* ws, size_t ws_bytes, void* stream);
+/* dw[cout][cin][ks][ks] += wgrad(x, dz) (no bias gradient: alt_resnet's convolutions have none); cout a multiple of
+ * 128; ks = 7: the stem form (x = [n,48,h,w] space-to-depth input, dz = [n, 4*C, h, w], dw = [C][3][7][7]).       */
+size_t mil_wide_wgrad_workspace_bytes(int n, int cin, int cout, int h, int w, int ks);
+int mil_wide_wgrad_pf8(const void* x, int n, int cin, int h, int w, const void* dz, int cout, int ks, float* dw, void* ws,
+                       size_t ws_bytes, void* stream);
+/* out = the four (row, column) parity phases of in at half resolution, as 4 * c channels (plane = phase * c/8 + chunk) */
+int mil_split2_pf8(const void* in, int n, int c, int h, int w, void* out, void* stream);
+
 /* ---- training-loop glue ------------------------------------------------------
  * One Adam step over the FLAT parameter / gradient buffers (state-dict order, mil_param_offset) in one launch:
  * what `optim.Adam(classifier.parameters(), lr=2e-4)` + `optimizer.step()` do tensor by tensor in the reference
