@@ -15,7 +15,8 @@ from .ingest import TileIngest  # noqa: F401
 from .optim import FusedAdam, flatten_parameters, load_checkpoint, save_checkpoint, set_stage  # noqa: F401
 from .export import export_attention_maps, minmax_normalize, top_tiles, write_dla  # noqa: F401
 from .model import Attention, BasicResBlock, ContextLayer, CrossEntropyWithProbs, ResNet  # noqa: F401
-from . import _lib, model, synth  # noqa: F401
+from .wide import AltBasicBlock, AltResNet, WideAttention  # noqa: F401
+from . import _lib, model, synth, wide  # noqa: F401
 
-__all__ = ["Attention", "BagGroup", "SlideGroup", "BagStager", "GraphedStep", "TileIngest", "FusedAdam", "flatten_parameters", "set_stage", "save_checkpoint", "load_checkpoint", "ResNet", "BasicResBlock", "ContextLayer", "CrossEntropyWithProbs", "build",
+__all__ = ["Attention", "WideAttention", "AltResNet", "AltBasicBlock", "BagGroup", "SlideGroup", "BagStager", "GraphedStep", "TileIngest", "FusedAdam", "flatten_parameters", "set_stage", "save_checkpoint", "load_checkpoint", "ResNet", "BasicResBlock", "ContextLayer", "CrossEntropyWithProbs", "build",
            "LIB_PATH"]

@@ -77,6 +77,13 @@ PROTOTYPES = {
     "mil_wide_wgrad_pf8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                    c_size_t, c_void_p]),
     "mil_split2_pf8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "mil_wide_param_count": (c_int, [c_void_p]),
+    "mil_wide_param_info": (c_int, [c_void_p, c_int, c_char_p, c_int, C.POINTER(c_int), C.POINTER(c_ll), C.POINTER(c_ll)]),
+    "mil_wide_param_total": (c_ll, [c_void_p]),
+    "mil_wide_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
+    "mil_wide_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p,
+                                 c_void_p]),
+    "mil_wide_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "mil_minmax_normalize": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_void_p]),
     "mil_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float,
                               c_float, c_float, c_void_p]),

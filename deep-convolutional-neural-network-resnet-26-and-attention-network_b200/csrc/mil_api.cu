@@ -10,6 +10,7 @@
 #include "mil_extractor.cuh"
 #include "mil_head.cuh"
 #include "mil_wide.cuh"
+#include "mil_wide_net.cuh"
 
 static thread_local char g_err[1024] = "";
 void mil_set_error(const char* fmt, ...) {
@@ -638,6 +639,62 @@ int mil_split2_pf8(const void* in, int n, int c, int h, int w, void* out, void* 
   MIL_REQUIRE(in && out, "mil_split2_pf8: null pointer argument");
   const MilPF8 gin = mil_pf8(n, c, h, w);
   return mil_launch_split2(in, gin, out, mil_split2_geom(n, c, (h - 1) / 2 + 1), (cudaStream_t)stream);
+  MIL_API_END
+}
+
+// ---- the wide extractor as a whole ------------------------------------------------------------------------------
+int mil_wide_param_count(const MilWideDesc* desc) {
+  if (desc == nullptr || mil_wide_check_desc(*desc) != 0) return 0;
+  return (int)mil_wide_param_table(*desc).size();
+}
+int mil_wide_param_info(const MilWideDesc* desc, int i, char* name_out, int name_cap, int* ndim, long long shape4[4],
+                        long long* offset) {
+  MIL_API_BEGIN
+  MIL_REQUIRE(desc && name_out && ndim && shape4 && offset && name_cap > 0, "mil_wide_param_info: null pointer argument");
+  MIL_TRY(mil_wide_check_desc(*desc));
+  const auto t = mil_wide_param_table(*desc);
+  MIL_REQUIRE(i >= 0 && i < (int)t.size(), "mil_wide_param_info: index %d out of range", i);
+  snprintf(name_out, (size_t)name_cap, "%s", t[i].name.c_str());
+  *ndim = t[i].ndim;
+  for (int k = 0; k < 4; ++k) shape4[k] = t[i].shape[k];
+  *offset = t[i].offset;
+  return 0;
+  MIL_API_END
+}
+long long mil_wide_param_total(const MilWideDesc* desc) {
+  if (desc == nullptr || mil_wide_check_desc(*desc) != 0) return 0;
+  const auto t = mil_wide_param_table(*desc);
+  return t.back().offset + t.back().numel;
+}
+size_t mil_wide_workspace_bytes(const MilWideDesc* desc, int n_tiles, int side) {
+  try {
+    MilWidePlan pl;
+    if (desc == nullptr || mil_wide_make_plan(*desc, n_tiles, side, &pl) != 0) return 0;
+    return pl.total_bytes;
+  } catch (...) {
+    return 0;
+  }
+}
+int mil_wide_forward(const MilWideDesc* desc, const void* const* params, const void* bag, int bag_is_u8, const int32_t* idx,
+                     int n_tiles, int side, void* ws, size_t ws_bytes, float* H, void* stream) {
+  MIL_API_BEGIN
+  MIL_TRY(require_device());
+  MIL_REQUIRE(desc && params && bag && ws && H, "mil_wide_forward: null pointer argument");
+  MilWidePlan pl;
+  MIL_TRY(mil_wide_make_plan(*desc, n_tiles, side, &pl));
+  MIL_REQUIRE(ws_bytes >= pl.total_bytes, "mil_wide_forward: workspace too small (%zu < %zu)", ws_bytes, pl.total_bytes);
+  return mil_wide_forward_impl(params, bag, bag_is_u8, idx, pl, ws, H, (cudaStream_t)stream);
+  MIL_API_END
+}
+int mil_wide_backward(const MilWideDesc* desc, const void* const* params, int n_tiles, int side, void* ws, size_t ws_bytes,
+                      const float* dH, float* grads_flat, void* stream) {
+  MIL_API_BEGIN
+  MIL_TRY(require_device());
+  MIL_REQUIRE(desc && params && ws && dH && grads_flat, "mil_wide_backward: null pointer argument");
+  MilWidePlan pl;
+  MIL_TRY(mil_wide_make_plan(*desc, n_tiles, side, &pl));
+  MIL_REQUIRE(ws_bytes >= pl.total_bytes, "mil_wide_backward: workspace too small (%zu < %zu)", ws_bytes, pl.total_bytes);
+  return mil_wide_backward_impl(params, pl, ws, dH, grads_flat, (cudaStream_t)stream);
   MIL_API_END
 }
 

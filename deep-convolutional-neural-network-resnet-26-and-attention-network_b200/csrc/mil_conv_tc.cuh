@@ -114,3 +114,10 @@ int mil_launch_stem_tc_fwd(const void* x, int x_u8, const int* idx, int n, int s
                            cudaStream_t s, void* pooled_mask = nullptr);
 int mil_launch_stem_tc_bwd(const void* xs, int n, int side, const void* g, const MilPF8& gp, const uint8_t* argmax,
                            void* dy, float* partial, float* dw, float* db, cudaStream_t s);
+
+// the stem's layout / pool kernels on their own, for any even channel count C (conv map = 4 * C channels (co, a, b) at
+// the pooled resolution; arg-max records of mil_stem_tc_argmax_bytes(gp) bytes)
+int mil_launch_stem_s2d4(const void* x, int x_u8, const int* idx, int side, void* xs, const MilPF8& gi, cudaStream_t s);
+int mil_launch_stem_pool4(const void* cv, const MilPF8& gc, int hc, void* pooled, const MilPF8& gp, void* argmax,
+                          cudaStream_t s);
+int mil_launch_stem_unpool4(const void* g, const MilPF8& gp, const void* argmax, void* dy, const MilPF8& gc, cudaStream_t s);

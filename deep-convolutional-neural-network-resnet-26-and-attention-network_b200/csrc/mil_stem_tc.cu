@@ -154,7 +154,7 @@ stem_pool4_kernel(const __nv_bfloat16* __restrict__ cv, MilPF8 gc, int hc, __nv_
     bool packed = false;
     if (py < gp.h && px < gp.w) {
       const long long qc = (long long)n * gc.P + (long long)py * gc.wp + px;
-      const int ncp = pc == 2 ? 2 : 4;  // channel pairs 8, 9 only in the last chunk (channels 20..23 are padding)
+      const int ncp = min(4, (gp.c >> 1) - 4 * pc);  // 20 channels: pairs 8, 9 only in the last chunk (20..23 are padding)
       const bool up_ok = py > 0, left_ok = px > 0;
       const bool all_phases = 2 * py + 1 < hc && 2 * px + 1 < hc;
       const uint4* ps = reinterpret_cast<const uint4*>(cv + mil_pf8_off(gc, pc * 4, qc));  // chunk cp: + j * gc.PS
@@ -226,7 +226,7 @@ stem_unpool4_kernel(const __nv_bfloat16* __restrict__ g, MilPF8 gp, const uint2*
     const long long q = (long long)n * gc.P + r;
     const int Y = r / gc.wp, X = r - Y * gc.wp;
     const bool inside = Y < gc.h && X < gc.w;
-    const int ncp = pc == 2 ? 2 : 4;
+    const int ncp = min(4, (gp.c >> 1) - 4 * pc);
     const int wp = gp.wp;
     uint4 out[4];
 #pragma unroll
@@ -303,7 +303,7 @@ size_t mil_stem_tc_partial_floats(int n, int side) {
   return std::max(mil_wgrad_tc_partial_floats(mil_stem_tc_geom_in(n, side), mil_stem_tc_geom_conv(n, side), 3),
                   mil_stem_wgrad_partial_floats());
 }
-size_t mil_stem_tc_argmax_bytes(const MilPF8& gp) { return (size_t)3 * gp.PS * sizeof(uint2); }
+size_t mil_stem_tc_argmax_bytes(const MilPF8& gp) { return (size_t)gp.cb * gp.PS * sizeof(uint2); }
 
 static int grid_for(long long work) { return (int)std::max<long long>(1, std::min<long long>(mil_cdiv(work, 256), 148 * 16)); }
 
@@ -334,7 +334,7 @@ int mil_launch_stem_tc_fwd(const void* x, int x_u8, const int* idx, int n, int s
   if (mil_stem_tc_fused_pool(gp, side))  // conv + pool in one kernel: the conv map never reaches HBM
     return mil_launch_stem_conv_pool(xs, gi, wtc, bias4, pooled, gp, argmax, pooled_mask, hc, s);
   MIL_TRY(mil_launch_conv_tc(0, xs, gi, wtc, sh, bias4, nullptr, nullptr, convout, gc, MIL_EPI_FWD, 0, s));
-  stem_pool4_kernel<<<dim3(gp.n, (unsigned)mil_cdiv(gp.P, 256), 3), 256, 0, s>>>((const __nv_bfloat16*)convout, gc, hc, (__nv_bfloat16*)pooled,
+  stem_pool4_kernel<<<dim3(gp.n, (unsigned)mil_cdiv(gp.P, 256), gp.cb), 256, 0, s>>>((const __nv_bfloat16*)convout, gc, hc, (__nv_bfloat16*)pooled,
                                                         gp, argmax);
   MIL_LAUNCH_OK();
   return 0;
@@ -351,12 +351,39 @@ int mil_launch_stem_tc_bwd(const void* xs, int n, int side, const void* g, const
     // built inside the weight-gradient kernel, tile by tile, straight into its A-operand planes
     MIL_TRY(mil_launch_stem_wgrad(xs, gi, g, gp, argmax, partial, &ctas, &rec, s));
   } else {
-    stem_unpool4_kernel<<<dim3(gc.n, (unsigned)mil_cdiv(gc.P, 256), 3), 256, 0, s>>>((const __nv_bfloat16*)g, gp, argmax,
+    stem_unpool4_kernel<<<dim3(gc.n, (unsigned)mil_cdiv(gc.P, 256), gp.cb), 256, 0, s>>>((const __nv_bfloat16*)g, gp, argmax,
                                                                                    (__nv_bfloat16*)dy, gc);
     MIL_LAUNCH_OK();
     MIL_TRY(mil_launch_wgrad_tc_partials(xs, gi, dy, gc, partial, 3, &ctas, &rec, s));
   }
   stem_reduce4_kernel<<<(int)mil_cdiv(STC_CO * 147 + STC_CO, 32), dim3(32, SR4_PARTS), 0, s>>>(partial, ctas, rec, dw, db);
+  MIL_LAUNCH_OK();
+  return 0;
+}
+
+// ---- the stem's layout / pool kernels on their own (the wide parameterisation, mil_wide_net.cu: any even channel
+// count C, conv map = 4 * C channels (co, a, b) at the pooled resolution) ------------------------------------------
+int mil_launch_stem_s2d4(const void* x, int x_u8, const int* idx, int side, void* xs, const MilPF8& gi, cudaStream_t s) {
+  if (x_u8)
+    stem_s2d4_kernel<uint8_t><<<grid_for(6 * gi.Q), 256, 0, s>>>((const uint8_t*)x, idx, side, (__nv_bfloat16*)xs, gi);
+  else
+    stem_s2d4_kernel<float><<<grid_for(6 * gi.Q), 256, 0, s>>>((const float*)x, idx, side, (__nv_bfloat16*)xs, gi);
+  MIL_LAUNCH_OK();
+  return 0;
+}
+int mil_launch_stem_pool4(const void* cv, const MilPF8& gc, int hc, void* pooled, const MilPF8& gp, void* argmax,
+                          cudaStream_t s) {
+  MIL_REQUIRE(gc.c == 4 * gp.c && (gp.c & 1) == 0 && gc.wp == gp.wp && gc.n == gp.n,
+              "stem_pool4: geometry mismatch");
+  stem_pool4_kernel<<<dim3(gp.n, (unsigned)mil_cdiv(gp.P, 256), gp.cb), 256, 0, s>>>((const __nv_bfloat16*)cv, gc, hc,
+                                                                                     (__nv_bfloat16*)pooled, gp, (uint2*)argmax);
+  MIL_LAUNCH_OK();
+  return 0;
+}
+int mil_launch_stem_unpool4(const void* g, const MilPF8& gp, const void* argmax, void* dy, const MilPF8& gc, cudaStream_t s) {
+  MIL_REQUIRE(gc.c == 4 * gp.c && (gp.c & 1) == 0 && gc.wp == gp.wp && gc.n == gp.n, "stem_unpool4: geometry mismatch");
+  stem_unpool4_kernel<<<dim3(gc.n, (unsigned)mil_cdiv(gc.P, 256), gp.cb), 256, 0, s>>>((const __nv_bfloat16*)g, gp,
+                                                                                       (const uint2*)argmax, (__nv_bfloat16*)dy, gc);
   MIL_LAUNCH_OK();
   return 0;
 }

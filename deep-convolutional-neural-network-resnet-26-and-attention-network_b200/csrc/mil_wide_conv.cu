@@ -404,7 +404,9 @@ int mil_launch_wide_conv(const void* x, const MilPF8& gx, const void* wpk, const
   const size_t hdr = (sizeof(WideSmemHeader) + 127) / 128 * 128;
   const size_t budget = 227 * 1024 - hdr;
   auto stage_of = [&](int t) { return (size_t)2 * (t * 128 + 2 * halo) * 16 + (size_t)max_taps * kp.b_tap; };
-  if (tm <= 0) tm = 4;
+  // default: two accumulator sets (the epilogue of a unit overlaps the next unit's MMAs; measured on the layer shapes,
+  // profiles/r2_wide_kernel_timings.txt): 4 M-tiles of 64 channels, 2 of 128
+  if (tm <= 0) tm = 512 / (2 * sh.nt);
   tm = (int)std::min<long long>(tm, n_tiles);
   while (tm * sh.nt > 512) --tm;
   while (tm > 1 && stage_of(tm) * 2 > budget) --tm;

@@ -53,8 +53,12 @@ wide_wgrad_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfl
   for (int t = 1; t < ntaps; ++t) { smin = min(smin, pr.shift[tap0 + t]); smax = max(smax, pr.shift[tap0 + t]); }
   const int span = WW_TK + (smax - smin);
   const int ncic = pr.cit >> 3;
+  // output-channel tile: 16 chunk planes of dz, fewer in the last tile of a 64-channel layer (the MMA still reads 128
+  // rows: whatever the missing planes' slots hold lands in accumulator rows nobody reads)
+  const int ncoc = min(16, gz.cb - cot_i * 16);
   const uint32_t a_bytes = 16 * WW_A_PLANE, b_plane = (uint32_t)span * 16;
   const uint32_t stage_bytes = a_bytes + (uint32_t)ncic * b_plane;
+  const uint32_t load_bytes = (uint32_t)ncoc * WW_A_PLANE + (uint32_t)ncic * b_plane;
   const long long n_tiles = mil_cdiv(gz.Q, WW_TK);
 
   if (threadIdx.x == 0) {
@@ -79,10 +83,11 @@ wide_wgrad_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfl
       mbar_wait(&hd->empty[stage], phase ^ 1);
       if (elect_one()) {
         const uint32_t bar = full0 + (uint32_t)stage * 8;
-        mbar_expect_tx_u32(bar, stage_bytes);
+        mbar_expect_tx_u32(bar, load_bytes);
         uint32_t dst = s0 + (uint32_t)stage * stage_bytes;
         const char* sp = srca;
-        for (int c = 0; c < 16; ++c, dst += WW_A_PLANE, sp += stra) bulk_g2s_u32(dst, sp, WW_A_PLANE, bar);
+        for (int c = 0; c < ncoc; ++c, dst += WW_A_PLANE, sp += stra) bulk_g2s_u32(dst, sp, WW_A_PLANE, bar);
+        dst = s0 + (uint32_t)stage * stage_bytes + a_bytes;
         sp = srcb;
         for (int c = 0; c < ncic; ++c, dst += b_plane, sp += strb) bulk_g2s_u32(dst, sp, b_plane, bar);
       }
@@ -221,7 +226,7 @@ static int ww_config(const MilPF8& gx, const MilPF8& gz, int ks, WwConfig* out) 
   c = WwConfig{};
   const int cin = gx.cb * 8, cout = gz.cb * 8;
   MIL_REQUIRE(ks == 1 || ks == 3 || ks == 7, "wide_wgrad: unsupported window %d", ks);
-  MIL_REQUIRE(cout % 128 == 0, "wide_wgrad: %d output channels (need a multiple of 128)", cout);
+  MIL_REQUIRE(cout % 64 == 0, "wide_wgrad: %d output channels (need a multiple of 64)", cout);
   const int r = ks == 1 ? 0 : 1;  // ks = 7: the stem's space-to-depth form has 3x3 taps
   int nt = 0;
   for (int a = -r; a <= r; ++a)
@@ -237,7 +242,7 @@ static int ww_config(const MilPF8& gx, const MilPF8& gz, int ks, WwConfig* out) 
     c.p.n_tg = ks == 3 ? 3 : 1;
     for (int g = 0; g < c.p.n_tg; ++g) { c.p.tg_ntaps[g] = ks == 3 ? 3 : 1; c.p.tg_tap0[g] = 3 * g; }
   }
-  c.p.n_cot = cout / 128;
+  c.p.n_cot = (cout + 127) / 128;
   c.kinds = c.p.n_cot * c.p.n_cit * c.p.n_tg;
   c.p.rec_floats = (long long)c.p.tg_ntaps[0] * c.p.cit * 128;
   const long long n_tiles = mil_cdiv(gz.Q, WW_TK);

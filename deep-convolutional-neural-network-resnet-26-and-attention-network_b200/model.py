@@ -360,7 +360,7 @@ class Attention(nn.Module):
         else:
             self.loss = CrossEntropyWithProbs(classes=3, smoothing=0.25)
 
-        self.cnn = _ModuleHolder(ResNet(block=BasicResBlock, layers=[3, 3, 3, 3], num_classes=self.L))
+        self.cnn = _ModuleHolder(self._make_extractor())
         self.context = ContextLayer(self.L)
         self.attention = nn.Sequential(OrderedDict([
             ('lin1', nn.Linear(self.L, self.D)),
@@ -385,6 +385,10 @@ class Attention(nn.Module):
         self._param_list_cache = None
         self._gflat = None            # set by optim.flatten_parameters: flat gradient buffer the .grad tensors view
         self.reset_params()
+
+    def _make_extractor(self):
+        """The tile feature extractor's parameter holder (gbm/model.py:132); wide.WideAttention substitutes alt_resnet's."""
+        return ResNet(block=BasicResBlock, layers=[3, 3, 3, 3], num_classes=self.L)
 
     # ---- init: identical distributions to gbm/model.py:161-187 ----
     def weight_init(self, m, name=''):

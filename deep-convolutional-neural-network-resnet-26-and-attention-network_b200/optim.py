@@ -25,7 +25,7 @@ def flatten_parameters(model):
     dev = next(iter(params.values())).device
     if dev.type != "cuda":
         raise RuntimeError("flatten_parameters: move the module to a CUDA device first (no CPU fallback)")
-    total = int(_lib.load().mil_param_total())
+    total = max(off + params[name].numel() for name, _, off in table)     # the model's own table (ResNet-26 or wide)
     flat = torch.zeros(total, dtype=torch.float32, device=dev)
     gflat = torch.zeros(total, dtype=torch.float32, device=dev)
     with torch.no_grad():

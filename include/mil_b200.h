@@ -199,6 +199,32 @@ int mil_wide_wgrad_pf8(const void* x, int n, int cin, int h, int w, const void* 
 /* out = the four (row, column) parity phases of in at half resolution, as 4 * c channels (plane = phase * c/8 + chunk) */
 int mil_split2_pf8(const void* in, int n, int c, int h, int w, void* out, void* stream);
 
+/* ---- the wide extractor as a whole --------------------------------------------------
+ * alt_resnet.py's ResNet as the tile feature extractor of the same MIL head: conv1 7x7/2 (3 -> stem, no bias), ReLU,
+ * max-pool 3x3/2, four layers of BasicBlocks (alt_resnet.py:35-67; 1x1/2 projections where the shape changes, :107-123),
+ * average pool, fc widths[3] -> features WITH bias (:90).  `slope` is the activation's negative slope (0 = ReLU, :49).
+ * resnet18 of alt_resnet.py:157-165 = layers {2,2,2,2}, widths {64,128,256,512}, stem 64; features must be 80 (L).
+ * Parameters: the state dict of Attention with cnn = DataParallel(alt_resnet.ResNet(BasicBlock, layers, num_classes=80)),
+ * in its own order (mil_wide_param_*), fp32; gradients accumulate into one flat buffer like the ResNet-26 entry points.
+ * bf16 only (bag: fp32 or uint8 NCHW).  The head's entry points (mil_head_*) are shared: hand them an array of
+ * MIL_NUM_PARAMS pointers with the head's tensors at their ResNet-26 indices.                                      */
+typedef struct MilWideDesc {
+  int layers[4];
+  int widths[4];
+  int stem;
+  int features;
+  float slope;
+} MilWideDesc;
+int mil_wide_param_count(const MilWideDesc* desc);
+int mil_wide_param_info(const MilWideDesc* desc, int i, char* name_out, int name_cap, int* ndim, long long shape4[4],
+                        long long* offset);
+long long mil_wide_param_total(const MilWideDesc* desc);
+size_t mil_wide_workspace_bytes(const MilWideDesc* desc, int n_tiles, int side);
+int mil_wide_forward(const MilWideDesc* desc, const void* const* params_host, const void* bag, int bag_is_u8,
+                     const int32_t* idx, int n_tiles, int side, void* ws, size_t ws_bytes, float* H, void* stream);
+int mil_wide_backward(const MilWideDesc* desc, const void* const* params_host, int n_tiles, int side, void* ws,
+                      size_t ws_bytes, const float* dH, float* grads_flat, void* stream);
+
 /* ---- training-loop glue ------------------------------------------------------
  * One Adam step over the FLAT parameter / gradient buffers (state-dict order, mil_param_offset) in one launch:
  * what `optim.Adam(classifier.parameters(), lr=2e-4)` + `optimizer.step()` do tensor by tensor in the reference

@@ -1,4 +1,4 @@
-"""Recipe for oracle/_ref: byte-for-byte copies of the two reference source files on the hot path, so that the
+"""Recipe for oracle/_ref: byte-for-byte copies of the three reference source files on the hot path, so that the
 UNMODIFIED reference can be timed (bench.py --impl reference / cpu_baseline, kind "reference") and used as a checker
 on the GPU box, where /root/reference does not exist.  TEST / BENCH INFRASTRUCTURE ONLY.
 
@@ -15,7 +15,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 DEST = os.path.join(HERE, "_ref")
-FILES = ("gbm/model.py", "nnBlocks.py")      # Attention / ResNet / ContextLayer; BasicResBlock / CrossEntropyWithProbs
+FILES = ("gbm/model.py", "nnBlocks.py", "alt_resnet.py")   # Attention / ResNet / ContextLayer; BasicResBlock / CrossEntropyWithProbs; the wide extractor
 
 
 def make(reference_root=None, quiet=False) -> bool:

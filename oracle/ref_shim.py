@@ -87,3 +87,47 @@ def build_reference(class_weights=None, seed: int = 0, quiet: bool = True):
     with ctx:
         net = ref_model.Attention(n_classes=3, class_weights=class_weights)
     return net
+
+
+def alt_resnet_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "alt_resnet.py"))
+
+
+def load_reference_alt_resnet():
+    """The reference's UNMODIFIED `alt_resnet.py`.  It cannot be imported as it stands -- line 3 is the relative import
+    `from .utils import load_state_dict_from_url` and the checkout has neither a package nor a `utils` module (SURVEY.md
+    section 2) -- so it is loaded as the submodule of a stub package whose `utils` provides that one name (only used
+    by `pretrained=True`, which nothing here asks for).  Harness code, not a restatement."""
+    import importlib.util
+    name = "_mil_altpkg.alt_resnet"
+    if name in sys.modules:
+        return sys.modules[name]
+    path = os.path.join(REFERENCE_ROOT, "alt_resnet.py")
+    if not os.path.isfile(path):
+        raise FileNotFoundError(f"{path} not found")
+    pkg = types.ModuleType("_mil_altpkg")
+    pkg.__path__ = []
+    utils = types.ModuleType("_mil_altpkg.utils")
+
+    def load_state_dict_from_url(*a, **k):  # pragma: no cover
+        raise RuntimeError("no network: pretrained weights are not available")
+    utils.load_state_dict_from_url = load_state_dict_from_url
+    sys.modules["_mil_altpkg"] = pkg
+    sys.modules["_mil_altpkg.utils"] = utils
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    mod.__package__ = "_mil_altpkg"
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def build_reference_wide(layers=(2, 2, 2, 2), class_weights=None, seed: int = 0, quiet: bool = True):
+    """The reference's `Attention` with its `cnn` replaced by the reference's own alt ResNet:
+    `nn.DataParallel(alt_resnet.ResNet(alt_resnet.BasicBlock, layers, num_classes=80))` (gbm/model.py:132-135 with
+    alt_resnet.py:70-145 in place of gbm/model.py:14-61) -- both classes unmodified."""
+    from torch import nn
+    net = build_reference(class_weights, seed, quiet)
+    alt = load_reference_alt_resnet()
+    net.cnn = nn.DataParallel(alt.ResNet(alt.BasicBlock, list(layers), num_classes=net.L))
+    return net

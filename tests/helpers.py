@@ -58,3 +58,34 @@ def perturbed_weights(seed=0, conv_bias=True):
         elif k.startswith(("attention.", "buffer.")):
             sd[k] = v * (1.0 + 0.3 * torch.randn(v.shape, generator=g))
     return sd
+
+
+def wide_golden_cases():
+    """Golden cases of the wide (alt_resnet.py) parameterisation: tests/golden/make_wide_golden.py."""
+    out = []
+    for f in sorted(glob.glob(os.path.join(GOLDEN, "wide_*.npz"))):
+        z = np.load(f)
+        meta = json.loads(bytes(z["meta"]).decode())
+        out.append((meta, {k: z[k] for k in z.files if k != "meta"}))
+    return out
+
+
+def wide_case_inputs(meta, rec):
+    """(params, bag, Y, class weights, training kwargs) of a wide golden case, regenerated deterministically."""
+    from oracle import synth, wide_oracle
+    p = wide_oracle.init_params(meta["wseed"], meta["layers"])
+    p["weight_mask"] = torch.tensor(meta["wm"])
+    bag = torch.from_numpy(synth.make_bag(meta["n"], meta["side"], seed=meta.get("seed", 1)))
+    cw = None if meta["cw"] is None else torch.tensor(meta["cw"])
+    kw = {}
+    if meta["training"]:
+        idx = torch.from_numpy(rec["extra.indices"])
+        kw = dict(training=True, indices=idx, drop_mask=torch.from_numpy(synth.make_drop_mask(len(idx), seed=2)))
+    return p, bag, torch.tensor([meta["Y"]]), cw, kw
+
+
+def grad_sample(t, n=2048):
+    """The strided sample make_wide_golden.py stores for the large gradient tensors."""
+    f = torch.as_tensor(t).flatten()
+    step = max(1, f.numel() // n)
+    return f[::step][:n]
