@@ -48,6 +48,45 @@ L1_CONV_NCU_TRAFFIC = {4096: 1284714000 + 665690112}      # profiles/r2_ncu_conv
 # a fraction of its peak -- what actually bounds the thin-N implicit GEMMs of this network
 L1_CONV_NCU_TC_SMEM_PCT = {4096: 63.7}
 METRIC = "tiles/sec fwd+bwd ResNet-26+attention-MIL"
+WIDE_LAYERS = {"wide18": (2, 2, 2, 2), "wide34": (3, 4, 6, 3)}      # alt_resnet.py:157-165 (resnet18) and torchvision's resnet34
+WIDE_WIDTHS = (64, 128, 256, 512)                                    # alt_resnet.py:87-90
+
+
+def metric_name(model, mode):
+    net = "ResNet-26" if model == "resnet26" else f"alt-ResNet-{model[4:]} (alt_resnet.py, 64-512 channels)"
+    if mode == "inference":
+        return f"tiles/sec forward-only {net}+attention-MIL (attention-map extraction)"
+    return f"tiles/sec fwd+bwd {net}+attention-MIL"
+
+
+def make_net(mil, model, precision="bf16"):
+    """The module under test: the reference's Attention (gbm/model.py:114-264), or the same module with alt_resnet.py's
+    network as extractor."""
+    if model == "resnet26":
+        net = mil.Attention(n_classes=3)
+        net.precision = precision
+        return net
+    return mil.WideAttention(n_classes=3, layers=WIDE_LAYERS[model], widths=WIDE_WIDTHS)
+
+
+def wide_flop_fwd_bwd(side, layers, widths=WIDE_WIDTHS):
+    """Algorithmic FLOP per tile of the wide extractor, forward + data gradient + weight gradient (2 FLOP per MAC; the
+    stem has no data gradient: the bag is detached; head and fc are negligible)."""
+    hc = (side - 1) // 2 + 1
+    h = [(hc - 1) // 2 + 1]
+    for _ in range(3):
+        h.append((h[-1] - 1) // 2 + 1)
+    f = 2.0 * 2 * widths[0] * 147 * hc * hc
+    inpl = widths[0]
+    for l in range(4):
+        w = widths[l]
+        for b in range(layers[l]):
+            cin = inpl if b == 0 else w
+            f += 3 * 2.0 * (cin * w * 9 + w * w * 9) * h[l] * h[l]
+            if b == 0 and l > 0:
+                f += 3 * 2.0 * cin * w * h[l] * h[l]
+        inpl = w
+    return f
 
 
 def peaks():
@@ -124,7 +163,7 @@ def bind_to_gpu_numa_node(index):
     return None
 
 
-def cpu_arm(side, forward_only=False):
+def cpu_arm(side, forward_only=False, model="resnet26"):
     """fwd+bwd (or forward only, under no_grad) of the reference path on the CPU.  Returns (step(bag, Y), kind, description): the UNMODIFIED reference
     source under the import shim when it is available (build container: /root/reference; GPU box: the copies
     oracle/make_ref.py left under oracle/_ref), else the oracle restatement."""
@@ -132,6 +171,31 @@ def cpu_arm(side, forward_only=False):
     from oracle import mil_oracle, ref_shim
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
+    if model != "resnet26":
+        from oracle import wide_oracle
+        layers = WIDE_LAYERS[model]
+        if ref_shim.reference_available() and ref_shim.alt_resnet_available():
+            net = ref_shim.build_reference_wide(layers, seed=0).eval()     # unmodified Attention + unmodified alt_resnet.ResNet
+
+            def step(bag, Y):
+                if forward_only:
+                    with torch.no_grad():
+                        return float(net(bag, Y)["loss"])
+                net.zero_grad(set_to_none=True)
+                out = net(bag, Y)
+                out["loss"].backward()
+                return float(out["loss"].detach())
+            return step, "reference", ("unmodified gbm/model.py Attention with alt_resnet.py's ResNet as cnn, under "
+                                       f"oracle/ref_shim.py ({ref_shim.REFERENCE_ROOT})"), cores
+        p = wide_oracle.init_params(0, layers)
+
+        def step(bag, Y):
+            if forward_only:
+                with torch.no_grad():
+                    return float(wide_oracle.attention_forward(p, bag, Y, layers)["loss"])
+            out, _ = wide_oracle.forward_backward(p, bag, Y, layers)
+            return float(out["loss"])
+        return step, "port", "oracle/wide_oracle.py restatement (oracle/_ref missing)", cores
     if ref_shim.reference_available():
         net = ref_shim.build_reference(seed=0).eval()      # eval: every tile goes through the CNN (gbm/model.py:196)
 
@@ -165,11 +229,11 @@ def cpu_model_name():
     return "unknown CPU"
 
 
-def cpu_reference_throughput(side, sample_tiles, reps, warmup=1, seed=1, forward_only=False):
+def cpu_reference_throughput(side, sample_tiles, reps, warmup=1, seed=1, forward_only=False, model="resnet26"):
     """(best tiles/s, median tiles/s, cores, kind, description, times) of the CPU arm on a bounded sample."""
     import torch
     mil = importlib.import_module(PKG)
-    step, kind, what, cores = cpu_arm(side, forward_only)
+    step, kind, what, cores = cpu_arm(side, forward_only, model)
     bag = torch.from_numpy(mil.synth.make_bag(sample_tiles, side, seed=seed))
     Y = torch.tensor([1])
     for _ in range(warmup):
@@ -183,7 +247,12 @@ def cpu_reference_throughput(side, sample_tiles, reps, warmup=1, seed=1, forward
     return sample_tiles / srt[0], sample_tiles / srt[len(srt) // 2], cores, kind, what, times
 
 
-def workload_string(n, side, world, mode="train"):
+def workload_string(n, side, world, mode="train", model="resnet26"):
+    if model != "resnet26":
+        return (f"{model}: bag of {n} RGB {side}x{side} tiles per GPU through the alt_resnet.py extractor "
+                f"(layers {list(WIDE_LAYERS[model])}, widths {list(WIDE_WIDTHS)}, ReLU) + the MIL head, "
+                f"{'forward only' if mode == 'inference' else 'fwd+bwd'}, 3 classes (SURVEY.md section 8f N4; the shape of "
+                f"BASELINE.json configs[1])")
     if mode == "multi-slide":
         return (f"{world} bag(s) of {n} RGB {side}x{side} tiles per step, one per GPU, all tiles through the CNN, fwd+bwd, "
                 f"gradients summed over the bags (BASELINE.json configs[4])")
@@ -202,7 +271,7 @@ def run_reference(args):
     t_all0 = time.perf_counter()
     import torch
     mil = importlib.import_module(PKG)
-    step, kind, what, cores = cpu_arm(args.side, forward_only=args.mode == "inference")
+    step, kind, what, cores = cpu_arm(args.side, forward_only=args.mode == "inference", model=args.model)
     bag = torch.from_numpy(mil.synth.make_bag(sample, args.side, seed=1))
     Y = torch.tensor([1])
     for _ in range(args.warmup):
@@ -217,12 +286,12 @@ def run_reference(args):
     srt = sorted(times)
     line = {
         "impl": "reference",
-        "metric": METRIC if args.mode != "inference" else "tiles/sec forward-only ResNet-26+attention-MIL (attention-map extraction)",
+        "metric": metric_name(args.model, args.mode),
         "value": v, "unit": "tiles/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_string(args.tiles, args.side, max(1, args.gpus), args.mode),
-                   "tiles_per_step_timed": sample, "mode": args.mode},
+        "config": {"workload": workload_string(args.tiles, args.side, max(1, args.gpus), args.mode, args.model),
+                   "tiles_per_step_timed": sample, "mode": args.mode, "extractor": args.model},
         "cpu_baseline": {"value": v, "unit": "tiles/s", "cores": cores, "kind": kind, "cpu": cpu_model_name(),
                          "best": sample / srt[0], "median": sample / srt[len(srt) // 2],
                          "sample": f"{sample} of the {args.tiles} tiles per step (throughput per tile, extrapolated "
@@ -360,6 +429,64 @@ def kernel_rooflines(mil, lib, dev, n, side, precision, value_per_gpu):
     return roof
 
 
+def wide_rooflines(mil, lib, dev, n, side, model, value_per_gpu):
+    """The wide extractor's convolutions are tensor-bound (N = 128 MMAs at the pipe's full rate): the 3x3 convolution of
+    layer 2 (128 channels) timed alone at the step's launch size against the measured dense bf16 peak; `kernels` lists
+    the other layers' convolutions and weight gradients the same way."""
+    import ctypes as C
+    import torch
+    burst, sustained, hbm, how = peaks()
+    P = lambda t: C.c_void_p(t.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ck = mil._lib.check
+    hc = (side - 1) // 2 + 1
+    hs = [(hc - 1) // 2 + 1]
+    for _ in range(3):
+        hs.append((hs[-1] - 1) // 2 + 1)
+    rows = []
+    for C_, H in zip(WIDE_WIDTHS, hs):
+        nb = int(lib.mil_pf8_bytes(n, C_, H, H, 1))
+        X = torch.zeros(nb, dtype=torch.uint8, device=dev)
+        R = torch.zeros(nb, dtype=torch.uint8, device=dev)
+        O = torch.zeros(nb, dtype=torch.uint8, device=dev)
+        xin = torch.randn(n, C_, H, H, device=dev)
+        ck(lib.mil_to_pf8(1, P(xin), P(X), n, C_, H, H, None), "mil_to_pf8")
+        ck(lib.mil_to_pf8(1, P(xin), P(R), n, C_, H, H, None), "mil_to_pf8")
+        del xin
+        w = torch.randn(C_, C_, 3, 3, device=dev) / (C_ * 9) ** 0.5
+        wsb = int(lib.mil_wide_conv_workspace_bytes(0, 0, C_, C_, 3))
+        wsk = torch.zeros(wsb, dtype=torch.uint8, device=dev)
+        flop = 2.0 * C_ * C_ * 9 * H * H * n
+
+        def conv_once():
+            ck(lib.mil_wide_conv_pf8(0, 0, P(X), n, C_, H, H, P(w), C_, C_, 3, None, P(R), None, P(O), 0, C.c_float(0.0), 0,
+                                     P(wsk), wsb, st), "mil_wide_conv_pf8")
+        kms = time_calls(conv_once, 5)
+        rows.append({"kernel": f"conv3x3 {C_}->{C_} @ {H}x{H} + identity + ReLU (wide_conv_kernel)", "bound": "tensor",
+                     "achieved": flop / (kms * 1e-3) / 1e12, "peak": burst, "unit": "TFLOP/s",
+                     "frac": flop / (kms * 1e-3) / 1e12 / burst, "ms_per_launch": kms, "flop_per_launch": flop,
+                     "tiles_per_launch": n})
+        gsb = int(lib.mil_wide_wgrad_workspace_bytes(n, C_, C_, H, H, 3))
+        gsk = torch.zeros(gsb, dtype=torch.uint8, device=dev)
+        dw = torch.zeros(C_, C_, 3, 3, device=dev)
+
+        def wgrad_once():
+            ck(lib.mil_wide_wgrad_pf8(P(X), n, C_, H, H, P(R), C_, 3, P(dw), P(gsk), gsb, st), "mil_wide_wgrad_pf8")
+        gms = time_calls(wgrad_once, 5)
+        rows.append({"kernel": f"weight gradient 3x3 {C_}->{C_} @ {H}x{H} (wide_wgrad_kernel + reduction)", "bound": "tensor",
+                     "achieved": flop / (gms * 1e-3) / 1e12, "peak": burst, "unit": "TFLOP/s",
+                     "frac": flop / (gms * 1e-3) / 1e12 / burst, "ms_per_launch": gms, "flop_per_launch": flop,
+                     "tiles_per_launch": n})
+        del X, R, O, wsk, gsk
+    top = dict(rows[2])          # the layer-2 convolution: 128 channels, the shape with the most pixels at N = 128
+    top["peak_source"] = f"MEASURED_PEAKS.json bf16_tflops ({how}, burst cuBLAS 8192^3)"
+    top["traffic"] = None
+    top["whole_step_tensor_frac_of_sustained"] = value_per_gpu * wide_flop_fwd_bwd(side, WIDE_LAYERS[model]) / 1e12 / sustained
+    top["whole_step_tflops"] = value_per_gpu * wide_flop_fwd_bwd(side, WIDE_LAYERS[model]) / 1e12
+    top["kernels"] = rows
+    return top
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -382,8 +509,7 @@ def run_ours(args):
     lib = mil._lib.load()
 
     torch.manual_seed(0)
-    net = mil.Attention(n_classes=3).to(dev).eval()      # eval => every tile goes through the CNN (gbm/model.py:196)
-    net.precision = args.precision
+    net = make_net(mil, args.model, args.precision).to(dev).eval()      # eval => every tile goes through the CNN (gbm/model.py:196)
     net.bag_group = group
     n, side = args.tiles, args.side
     bag = make_device_bag(mil, n, side, dev, seed=1 + rank)
@@ -463,10 +589,9 @@ def run_ours(args):
     # ---------------- small bags: the reference's live shape (<= 2 500 tiles per bag, 20 % through the CNN) ----------------
     # eager launches vs the CUDA-graph replay of the whole step (graph.GraphedStep), fwd + bwd + FusedAdam
     small_bag = None
-    if mode == "train" and world == 1 and n >= 2560:
+    if mode == "train" and world == 1 and n >= 2560 and args.model == "resnet26":
         sb = 2560
-        net2 = mil.Attention(n_classes=3).to(dev).train()
-        net2.precision = args.precision
+        net2 = make_net(mil, args.model, args.precision).to(dev).train()
         opt2 = mil.FusedAdam(net2, lr=2e-4)
         sbag = bag[:sb]
 
@@ -542,13 +667,16 @@ def run_ours(args):
     # ---------------- heavy kernels alone (rank 0) ----------------
     roofline = None
     if rank == 0:
-        roofline = kernel_rooflines(mil, lib, dev, n, side, args.precision, value / world)
+        if args.model == "resnet26":
+            roofline = kernel_rooflines(mil, lib, dev, n, side, args.precision, value / world)
+        else:
+            roofline = wide_rooflines(mil, lib, dev, n, side, args.model, value / world)
 
     # ---------------- CPU baseline (rank 0, N=1 only): the unmodified reference, BASELINE.md section 4 protocol ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         best, med, cores, kind, what, times = cpu_reference_throughput(side, args.ref_tiles, reps=5, warmup=1,
-                                                                       forward_only=mode == "inference")
+                                                                       forward_only=mode == "inference", model=args.model)
         cpu = {"value": best, "unit": "tiles/s", "cores": cores, "kind": kind, "cpu": cpu_model_name(), "best": best,
                "median": med,
                "sample": f"{args.ref_tiles} tiles of the same synthetic workload (per-tile throughput, extrapolated linearly "
@@ -560,11 +688,11 @@ def run_ours(args):
         par = {"train": f"bag-sharded x{world}", "multi-slide": f"slide-parallel x{world} (gradient all-reduce only)",
                "inference": f"slide-parallel x{world} (no collective)"}[mode]
         line = {
-            "metric": METRIC if mode != "inference" else "tiles/sec forward-only ResNet-26+attention-MIL (attention-map extraction)",
+            "metric": metric_name(args.model, mode),
             "value": value, "unit": "tiles/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": workload_string(n, side, world, mode), "mode": mode,
+            "config": {"workload": workload_string(n, side, world, mode, args.model), "mode": mode, "extractor": args.model,
                        "tiles_per_gpu": n, "side": side, "parallelism": par, "host_cores_per_rank": numa,
                        "l2": f"inputs larger than L2 ({bag_bytes * 4 / 1e6:.0f} MB bag per GPU per step)",
                        "slides_per_s": value / n if mode != "train" else value / (n * world), "loss": loss_val},
@@ -598,6 +726,9 @@ def main():
     ap.add_argument("--mode", default="train", choices=["train", "multi-slide", "inference"])
     ap.add_argument("--ref-tiles", type=int, default=256, help="tiles per step of the CPU arm (bounded sample)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--model", default="resnet26", choices=["resnet26", "wide18", "wide34"],
+                    help="resnet26: the reference's live extractor (gbm/model.py:14-61; BASELINE.json's metric); wide18 / "
+                         "wide34: alt_resnet.py's network (64-512 channels) as extractor (SURVEY.md section 8f N4)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -76,6 +76,10 @@ PROTOTYPES = {
     "mil_wide_wgrad_workspace_bytes": (c_size_t, [c_int] * 6),
     "mil_wide_wgrad_pf8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                    c_size_t, c_void_p]),
+    "mil_merge2_pf8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "mil_wide_wgrad_s2_workspace_bytes": (c_size_t, [c_int] * 5),
+    "mil_wide_wgrad_s2_pf8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_size_t,
+                                      c_void_p]),
     "mil_split2_pf8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mil_wide_param_count": (c_int, [c_void_p]),
     "mil_wide_param_info": (c_int, [c_void_p, c_int, c_char_p, c_int, C.POINTER(c_int), C.POINTER(c_ll), C.POINTER(c_ll)]),

@@ -633,6 +633,32 @@ int mil_wide_wgrad_pf8(const void* x, int n, int cin, int h, int w, const void* 
   MIL_API_END
 }
 
+size_t mil_wide_wgrad_s2_workspace_bytes(int n, int cin, int cout, int ho, int wo) {
+  return mil_wide_wgrad_partial_floats(mil_split2_geom(n, cin, ho), mil_pf8(n, cout, ho, wo), 3, 1) * sizeof(float) + 256;
+}
+
+int mil_wide_wgrad_s2_pf8(const void* xs2, int n, int cin, int ho, int wo, const void* dz, int cout, float* dw, void* ws,
+                          size_t ws_bytes, void* stream) {
+  MIL_API_BEGIN
+  MIL_TRY(require_device());
+  MIL_REQUIRE(xs2 && dz && dw && ws, "mil_wide_wgrad_s2_pf8: null pointer argument");
+  MIL_REQUIRE(ho == wo, "mil_wide_wgrad_s2_pf8: square maps only");
+  const MilPF8 gs = mil_split2_geom(n, cin, ho), gz = mil_pf8(n, cout, ho, wo);
+  const size_t need = mil_wide_wgrad_partial_floats(gs, gz, 3, 1) * sizeof(float);
+  MIL_REQUIRE(need > 0, "mil_wide_wgrad_s2_pf8: unsupported shape cin=%d cout=%d", cin, cout);
+  MIL_REQUIRE(ws_bytes >= need, "mil_wide_wgrad_s2_pf8: workspace too small (%zu < %zu)", ws_bytes, need);
+  return mil_launch_wide_wgrad(xs2, gs, dz, gz, (float*)ws, dw, nullptr, 3, (cudaStream_t)stream, 1);
+  MIL_API_END
+}
+
+int mil_merge2_pf8(const void* in, int n, int c, int h, int w, void* out, void* stream) {
+  MIL_API_BEGIN
+  MIL_TRY(require_device());
+  MIL_REQUIRE(in && out, "mil_merge2_pf8: null pointer argument");
+  return mil_launch_merge2(in, mil_split2_geom(n, c, (h - 1) / 2 + 1), out, mil_pf8(n, c, h, w), (cudaStream_t)stream);
+  MIL_API_END
+}
+
 int mil_split2_pf8(const void* in, int n, int c, int h, int w, void* out, void* stream) {
   MIL_API_BEGIN
   MIL_TRY(require_device());

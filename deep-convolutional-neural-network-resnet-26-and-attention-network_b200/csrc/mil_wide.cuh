@@ -18,7 +18,9 @@
 //   phase-split input of a stride-2 3x3 convolution); K-step = (group, pair of chunks): one K = 16 MMA per tap
 struct MilWideShape {
   int mode;        // 0: ks = 1 / 3, stride 1 (forward or data gradient);  1: 3x3 / stride 2 forward on the phase-split
-                   // input (mil_launch_split2);  2: stem 7x7 / stride 2 in space-to-depth-by-4 form (3x3 taps, 48 -> 4*C)
+                   // input (mil_launch_split2);  2: stem 7x7 / stride 2 in space-to-depth-by-4 form (3x3 taps, 48 -> 4*C);
+                   // 3 + 2a + b: data gradient of the 3x3 / stride-2 convolution for the input pixels of parity phase (a, b)
+                   // (x = the output gradient, out = that phase of the input gradient, both at the OUTPUT resolution)
   int transposed;  // mode 0: data gradient (kernel input = the conv's output channels, taps mirrored)
   int wcout, wcin, ks;  // the PyTorch weight [wcout][wcin][ks][ks]
   int kin, nout;        // kernel-side input channels PER GROUP / output channels
@@ -41,7 +43,12 @@ int mil_launch_wide_conv(const void* x, const MilPF8& gx, const void* wpk, const
 
 // weight gradient dW[co][ci][tap] += sum_q x[q + shift_tap][ci] * dz[q][co] (stride 1; a stride-2 convolution hands in
 // the zero-stuffed dz), db[co] += sum_q dz[q][co] (db may be NULL).  ks = 1 / 3, or 7 with x = the stem's
-// space-to-depth input (48 channels) and dz = the four-phase gradient map (4 * C channels).
-size_t mil_wide_wgrad_partial_floats(const MilPF8& gx, const MilPF8& gz, int ks);
+// space-to-depth input (48 channels) and dz = the four-phase gradient map (4 * C channels).  s2 = 1: the 3x3 / stride-2
+// convolution on its phase-split input (x = mil_launch_split2's 4 * cb planes, dz at the output resolution).
+size_t mil_wide_wgrad_partial_floats(const MilPF8& gx, const MilPF8& gz, int ks, int s2 = 0);
 int mil_launch_wide_wgrad(const void* x, const MilPF8& gx, const void* dz, const MilPF8& gz, float* partial, float* dw,
-                          float* db, int ks, cudaStream_t s);
+                          float* db, int ks, cudaStream_t s, int s2 = 0);
+
+// out (full resolution) = the four parity phases in `in` (4 * cb planes at half resolution, mil_launch_split2's layout)
+// interleaved back; pad pixels of `out` are written as zeros (bf16)
+int mil_launch_merge2(const void* in, const MilPF8& gin, void* out, const MilPF8& gout, cudaStream_t s);

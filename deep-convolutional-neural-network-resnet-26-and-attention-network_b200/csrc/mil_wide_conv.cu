@@ -286,6 +286,10 @@ __global__ void wide_pack_kernel(const float* __restrict__ w, __nv_bfloat16* __r
     } else if (sh.mode == 1) {
       const int ky = 2 * dy + sh.ga[g] + 1, kx = 2 * dx + sh.gb[g] + 1;
       if (nc < sh.wcout && kc < sh.wcin) v = w[((size_t)nc * sh.wcin + kc) * 9 + ky * 3 + kx];
+    } else if (sh.mode >= 3) {
+      // stride-2 data gradient, output phase (a, b): tap (dY, dX) in {0, 1}^2 carries w[a + 1 - 2 dY][b + 1 - 2 dX]^T
+      const int ky = sh.ga[g] + 1 - 2 * dy, kx = sh.gb[g] + 1 - 2 * dx;
+      if (kc < sh.wcout && nc < sh.wcin) v = w[((size_t)kc * sh.wcin + nc) * 9 + ky * 3 + kx];
     } else {
       // stem: kernel input (c, ry, rx), output (co, a, b):  w[co][c][4 dy + ry - 2a + 3][4 dx + rx - 2b + 3]
       const int c = kc >> 4, ry = (kc >> 2) & 3, rx = kc & 3;
@@ -337,6 +341,20 @@ int mil_wide_shape(int mode, int transposed, int wcout, int wcin, int ks, MilWid
     int t = 0;
     for (int a = -1; a <= 1; ++a)
       for (int b = -1; b <= 1; ++b) { sh.tdy[0][t] = (signed char)a; sh.tdx[0][t] = (signed char)b; ++t; }
+    sh.gntaps[0] = t;
+  } else if (mode >= 3 && mode <= 6) {
+    // data gradient of the 3x3 / stride-2 convolution for the input pixels of parity phase (a, b):
+    //   dx[2Y + a][2X + b] = sum over ky = a + 1 (mod 2), kx = b + 1 (mod 2) of w[ky][kx]^T dz[Y + dY][X + dX],
+    //   dY = (a + 1 - ky) / 2, dX = (b + 1 - kx) / 2   -- 1 / 2 / 2 / 4 taps at the OUTPUT resolution, no zero-stuffing
+    MIL_REQUIRE(ks == 3 && !transposed, "wide_conv: the phase-wise form is the 3x3 / stride-2 data gradient");
+    const int a = (mode - 3) >> 1, b = (mode - 3) & 1;
+    sh.kin = wcout;
+    sh.nout = wcin;
+    sh.ngroups = 1;
+    sh.ga[0] = a; sh.gb[0] = b;
+    int t = 0;
+    for (int dY = 0; dY <= a; ++dY)
+      for (int dX = 0; dX <= b; ++dX) { sh.tdy[0][t] = (signed char)dY; sh.tdx[0][t] = (signed char)dX; ++t; }
     sh.gntaps[0] = t;
   } else {
     MIL_REQUIRE(false, "wide_conv: unknown mode %d", mode);

@@ -121,6 +121,12 @@ int mil_wide_make_plan(const MilWideDesc& d, int n, int side, MilWidePlan* plan)
     MIL_TRY(mil_wide_shape(0, 1, cout, cin, ks, &st));
     c.wf_off = wofs; wofs += walign(mil_wide_wpack_bytes(sf));
     c.wt_off = wofs; wofs += walign(mil_wide_wpack_bytes(st));
+    if (ks == 3 && stride == 2)
+      for (int ph = 0; ph < 4; ++ph) {
+        MilWideShape sp;
+        MIL_TRY(mil_wide_shape(3 + ph, 0, cout, cin, 3, &sp));
+        pl.s2_wt_off[l][ph] = wofs; wofs += walign(mil_wide_wpack_bytes(sp));
+      }
     pl.convs.push_back(c);
     return 0;
   };
@@ -167,7 +173,7 @@ int mil_wide_make_plan(const MilWideDesc& d, int n, int side, MilWidePlan* plan)
   size_t gmax = 0, upmax = 0, tmax = 0;
   for (int l = 0; l < 4; ++l) gmax = std::max(gmax, mil_pf8_bytes(pl.g[l], MIL_BF16));
   for (int l = 1; l < 4; ++l) {
-    upmax = std::max(upmax, mil_pf8_bytes(mil_pf8(n, d.widths[l], pl.h[l - 1], pl.h[l - 1]), MIL_BF16));
+    upmax = std::max(upmax, mil_pf8_bytes(mil_split2_geom(n, d.widths[l - 1], pl.h[l]), MIL_BF16));   // phase-split gradient
     tmax = std::max(tmax, mil_pf8_bytes(mil_pf8(n, d.widths[l - 1], pl.h[l], pl.h[l]), MIL_BF16));
   }
   const size_t cvb = mil_pf8_bytes(pl.gcv, MIL_BF16);
@@ -175,15 +181,14 @@ int mil_wide_make_plan(const MilWideDesc& d, int n, int side, MilWidePlan* plan)
   pl.off_up = pl.off_cv;
   pl.off_tsub = pl.off_cv + walign(upmax);
   for (int i = 0; i < 3; ++i) pl.off_grad[i] = take(gmax);
-  pl.off_tfull = take(gmax);
+  pl.off_tfull = 0;
   pl.off_wpack = take(pl.wpack_bytes);
   size_t pf = (size_t)64 * d.features * d.widths[3] + 64 * d.features;  // tail
   pf = std::max(pf, wgrad_partial_floats(pl.gxs, pl.gcv, 7));
   for (const auto& c : pl.convs) {
     const MilPF8& go = pl.g[c.layer];
     if (c.stride == 2 && c.ks == 3) {
-      const MilPF8& gi = pl.g[c.layer - 1];
-      pf = std::max(pf, wgrad_partial_floats(gi, mil_pf8(n, c.cout, gi.h, gi.w), 3));
+      pf = std::max(pf, mil_wide_wgrad_partial_floats(mil_split2_geom(n, c.cin, go.h), go, 3, 1));
     } else {
       pf = std::max(pf, wgrad_partial_floats(mil_pf8(n, c.cin, go.h, go.w), go, c.ks));
     }
@@ -287,6 +292,38 @@ wide_tail_w_kernel(const float* __restrict__ avg, const float* __restrict__ dH, 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// phase merge (inverse of split2_kernel): out(n, 2Y + a, 2X + b) = in plane (2a + b) * cb + c at (Y, X)
+// grid = (image, pixel block of the HALF-resolution map incl. its pad row / column, output chunk): a thread writes a
+// 2x2 block of the full-resolution map, zeros on its pad row / column
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) merge2_kernel(const uint4* __restrict__ in, MilPF8 gin, uint4* __restrict__ out,
+                                                     MilPF8 gout) {
+  const int n = blockIdx.x, c = blockIdx.z;
+  const int r = blockIdx.y * blockDim.x + threadIdx.x;
+  if (r >= (int)gin.P) return;
+  const int Y = r / gin.wp, X = r - Y * gin.wp;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  const bool inside = Y < gin.h && X < gin.w;
+  const size_t i0 = gin.G + (size_t)n * gin.P + r;
+  uint4* po = out + (size_t)c * gout.PS + gout.G + (size_t)n * gout.P;
+#pragma unroll
+  for (int ph = 0; ph < 4; ++ph) {
+    const int y = 2 * Y + (ph >> 1), x = 2 * X + (ph & 1);
+    if (y >= gout.hp || x >= gout.wp) continue;
+    uint4 v = zero;
+    if (inside && y < gout.h && x < gout.w) v = in[(size_t)(ph * gout.cb + c) * gin.PS + i0];
+    po[(size_t)y * gout.wp + x] = v;
+  }
+}
+int mil_launch_merge2(const void* in, const MilPF8& gin, void* out, const MilPF8& gout, cudaStream_t s) {
+  MIL_REQUIRE(gin.n == gout.n && gin.cb == 4 * gout.cb && gin.h == (gout.h - 1) / 2 + 1 && gin.w == (gout.w - 1) / 2 + 1,
+              "merge2: geometry mismatch");
+  merge2_kernel<<<dim3(gout.n, (unsigned)mil_cdiv(gin.P, 256), gout.cb), 256, 0, s>>>((const uint4*)in, gin, (uint4*)out, gout);
+  MIL_LAUNCH_OK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // forward / backward
 // ---------------------------------------------------------------------------------------------------
 static inline char* wsp(void* ws, size_t off) { return reinterpret_cast<char*>(ws) + off; }
@@ -297,6 +334,13 @@ static int pack_all(const void* const* params, const MilWidePlan& pl, void* ws, 
   char* area = wsp(ws, pl.off_wpack);
   for (const auto& c : pl.convs) {
     MilWideShape sh;
+    if (transposed && c.ks == 3 && c.stride == 2) {
+      for (int ph = 0; ph < 4; ++ph) {
+        MIL_TRY(mil_wide_shape(3 + ph, 0, c.cout, c.cin, 3, &sh));
+        MIL_TRY(mil_launch_wide_pack((const float*)params[c.p_w], area + pl.s2_wt_off[c.layer][ph], sh, s));
+      }
+      continue;
+    }
     if (transposed) MIL_TRY(mil_wide_shape(0, 1, c.cout, c.cin, c.ks, &sh));
     else MIL_TRY(mil_wide_shape(c.ks == 3 && c.stride == 2 ? 1 : 0, 0, c.cout, c.cin, c.ks, &sh));
     MIL_TRY(mil_launch_wide_pack((const float*)params[c.p_w], area + (transposed ? c.wt_off : c.wf_off), sh, s));
@@ -436,27 +480,30 @@ int mil_wide_backward_impl(const void* const* params, const MilWidePlan& pl, voi
         MIL_TRY(mil_wide_shape(0, 1, c1.cout, c1.cin, 3, &sh));
         MIL_TRY(mil_launch_wide_conv(dpre, go, wpk + c1.wt_off, sh, nullptr, dz, xin, dnew, gi, MIL_EPI_DGRAD, slope, 0, s));
       } else {
-        // stride-2 block: zero-stuff the gradient of the 3x3 convolution's output to the input resolution, after which
-        // its gradients are stride-1 problems; the 1x1 projection's gradients are computed at the OUTPUT resolution
-        // (weight gradient against phase (0, 0) of the saved split input) and its data gradient is zero-stuffed too
+        // stride-2 block: every gradient is computed at the OUTPUT resolution.
+        //   conv1 wgrad : the nine taps grouped by the parity phase of the saved split input they read
+        //   projection  : 1x1 weight gradient against phase (0, 0); data gradient into t_sub (= phase (0, 0) only)
+        //   conv1 dgrad : one launch per INPUT parity phase (1 / 2 / 2 / 4 taps of the output gradient), activation mask
+        //                 from the same phase of the split input, written into a phase-split gradient map, which is then
+        //                 interleaved back to the full resolution
         const MilWideConv& cd = pl.convs[ci + 2];
-        const MilPF8 gu = mil_pf8(pl.n, go.c, gi.h, gi.w);     // zero-stuffed dpre
-        const MilPF8 gts = mil_pf8(pl.n, gi.c, go.h, go.w);    // projection data gradient, output resolution
+        const MilPF8 gts = mil_pf8(pl.n, gi.c, go.h, go.w);    // one phase / the projection's data gradient
         const MilPF8 gs = mil_split2_geom(pl.n, gi.c, go.h);
-        void* up_pre = wsp(ws, pl.off_up);
+        const char* xs2 = wsp(ws, pl.off_xs2[l]);
+        char* dsplit = wsp(ws, pl.off_up);
         void* t_sub = wsp(ws, pl.off_tsub);
-        void* t_full = wsp(ws, pl.off_tfull);
-        MIL_TRY(zg(up_pre, gu, s));
         MIL_TRY(zg(t_sub, gts, s));
-        MIL_TRY(zg(t_full, gi, s));
-        MIL_TRY(mil_launch_upsample2(dpre, go, up_pre, gu, s));
-        MIL_TRY(wide_wgrad(xin, gi, up_pre, gu, partial, gptr(c1.p_w), 3, s));
-        MIL_TRY(wide_wgrad(wsp(ws, pl.off_xs2[l]), mil_split2_phase0(gs, gi.c), dz, go, partial, gptr(cd.p_w), 1, s));
+        MIL_TRY(mil_launch_wide_wgrad(xs2, gs, dpre, go, partial, gptr(c1.p_w), nullptr, 3, s, 1));
+        MIL_TRY(wide_wgrad(xs2, mil_split2_phase0(gs, gi.c), dz, go, partial, gptr(cd.p_w), 1, s));
         MIL_TRY(mil_wide_shape(0, 1, cd.cout, cd.cin, 1, &sh));
         MIL_TRY(mil_launch_wide_conv(dz, go, wpk + cd.wt_off, sh, nullptr, nullptr, nullptr, t_sub, gts, MIL_EPI_PLAIN, slope, 0, s));
-        MIL_TRY(mil_launch_upsample2(t_sub, gts, t_full, gi, s));
-        MIL_TRY(mil_wide_shape(0, 1, c1.cout, c1.cin, 3, &sh));
-        MIL_TRY(mil_launch_wide_conv(up_pre, gu, wpk + c1.wt_off, sh, nullptr, t_full, xin, dnew, gi, MIL_EPI_DGRAD, slope, 0, s));
+        const size_t phase_bytes = (size_t)gts.cb * gs.PS * 16;
+        for (int ph = 0; ph < 4; ++ph) {
+          MIL_TRY(mil_wide_shape(3 + ph, 0, c1.cout, c1.cin, 3, &sh));
+          MIL_TRY(mil_launch_wide_conv(dpre, go, wpk + pl.s2_wt_off[l][ph], sh, nullptr, ph == 0 ? t_sub : nullptr,
+                                       xs2 + ph * phase_bytes, dsplit + ph * phase_bytes, gts, MIL_EPI_DGRAD, slope, 0, s));
+        }
+        MIL_TRY(mil_launch_merge2(dsplit, gs, dnew, gi, s));
       }
       std::swap(dz, dnew);
     }

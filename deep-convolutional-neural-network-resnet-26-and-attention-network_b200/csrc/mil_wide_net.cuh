@@ -26,6 +26,7 @@ struct MilWidePlan {
   std::vector<std::vector<size_t>> off_h, off_y;
   size_t off_xs, off_pooled, off_argmax, off_xs2[4], off_avg, off_cv, off_up, off_tsub, off_tfull, off_grad[3], off_wpack,
       off_partial, stem_w_off;
+  size_t s2_wt_off[4][4];   // [layer][input parity phase]: operand blocks of the stride-2 convolution's phase-wise data gradient
   size_t wpack_bytes, partial_floats, total_bytes;
 };
 

@@ -28,13 +28,21 @@ struct WwSmemHeader {
   uint32_t tmem_base;
 };
 
+struct WwGroup {
+  int ntaps;           // B-side taps = MMAs per K-step
+  int plane0;          // first x chunk plane of the group (a parity phase of the split input; 0 otherwise)
+  int bshift[9];       // pixel shift of each tap's x window
+  int nslots;          // A-side slots = shifted copies of the dz tile on the M axis (2 for 64-channel layers: two tap rows)
+  int ashift[2];       // pixel shift of each slot's dz window
+  short tapid[2][9];   // weight tap ky * ks + kx of (slot, tap)
+};
 struct WwParams {
   int n_cot, n_cit, n_tg;  // kinds = output-channel tiles x input-channel tiles x tap groups (blockIdx.y)
   int cit;                 // input channels per tile (N of the MMAs, a multiple of 16)
-  int tg_ntaps[3], tg_tap0[3];  // taps of each group: tg_tap0 .. tg_tap0 + tg_ntaps - 1 of the shift table
-  int shift[9];            // pixel shift of every tap
+  int a_chunks;            // dz chunk planes per A slot: 16 (128 output channels), 8 when two slots share the M axis
   int n_stages;
   long long rec_floats;    // floats per partial record
+  WwGroup g[4];
 };
 
 __global__ void __launch_bounds__(WW_THREADS, 1)
@@ -48,17 +56,19 @@ wide_wgrad_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfl
   // kind -> (output tile, input tile, tap group)
   const int kind = blockIdx.y;
   const int tg = kind % pr.n_tg, cit_i = (kind / pr.n_tg) % pr.n_cit, cot_i = kind / (pr.n_tg * pr.n_cit);
-  const int ntaps = pr.tg_ntaps[tg], tap0 = pr.tg_tap0[tg];
-  int smin = pr.shift[tap0], smax = pr.shift[tap0];
-  for (int t = 1; t < ntaps; ++t) { smin = min(smin, pr.shift[tap0 + t]); smax = max(smax, pr.shift[tap0 + t]); }
+  const WwGroup& gr = pr.g[tg];
+  const int ntaps = gr.ntaps;
+  int smin = gr.bshift[0], smax = gr.bshift[0];
+  for (int t = 1; t < ntaps; ++t) { smin = min(smin, gr.bshift[t]); smax = max(smax, gr.bshift[t]); }
   const int span = WW_TK + (smax - smin);
   const int ncic = pr.cit >> 3;
-  // output-channel tile: 16 chunk planes of dz, fewer in the last tile of a 64-channel layer (the MMA still reads 128
-  // rows: whatever the missing planes' slots hold lands in accumulator rows nobody reads)
-  const int ncoc = min(16, gz.cb - cot_i * 16);
+  // A side: nslots shifted copies of the output-channel tile's planes (fewer planes in the last tile of a layer whose
+  // width is not a multiple of 128; the MMA still reads 128 rows: whatever the missing planes' slots hold lands in
+  // accumulator rows nobody reads)
+  const int ncoc = min(pr.a_chunks, gz.cb - cot_i * pr.a_chunks);
   const uint32_t a_bytes = 16 * WW_A_PLANE, b_plane = (uint32_t)span * 16;
   const uint32_t stage_bytes = a_bytes + (uint32_t)ncic * b_plane;
-  const uint32_t load_bytes = (uint32_t)ncoc * WW_A_PLANE + (uint32_t)ncic * b_plane;
+  const uint32_t load_bytes = (uint32_t)(gr.nslots * ncoc) * WW_A_PLANE + (uint32_t)ncic * b_plane;
   const long long n_tiles = mil_cdiv(gz.Q, WW_TK);
 
   if (threadIdx.x == 0) {
@@ -76,19 +86,23 @@ wide_wgrad_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfl
     int stage = 0;
     uint32_t phase = 0;
     const uint32_t s0 = smem_u32(stage0), full0 = smem_u32(&hd->full[0]);
-    const char* srca = reinterpret_cast<const char*>(dz) + ((long long)cot_i * 16 * gz.PS + gz.G + (long long)blockIdx.x * WW_TK) * 16;
-    const char* srcb = reinterpret_cast<const char*>(x) + ((long long)cit_i * ncic * gx.PS + gx.G + smin + (long long)blockIdx.x * WW_TK) * 16;
+    const char* srca = reinterpret_cast<const char*>(dz) + ((long long)cot_i * pr.a_chunks * gz.PS + gz.G + (long long)blockIdx.x * WW_TK) * 16;
+    const char* srcb = reinterpret_cast<const char*>(x) +
+                       ((long long)(gr.plane0 + cit_i * ncic) * gx.PS + gx.G + smin + (long long)blockIdx.x * WW_TK) * 16;
     const long long stra = gz.PS * 16, strb = gx.PS * 16, tstride = (long long)gridDim.x * WW_TK * 16;
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       mbar_wait(&hd->empty[stage], phase ^ 1);
       if (elect_one()) {
         const uint32_t bar = full0 + (uint32_t)stage * 8;
         mbar_expect_tx_u32(bar, load_bytes);
-        uint32_t dst = s0 + (uint32_t)stage * stage_bytes;
-        const char* sp = srca;
-        for (int c = 0; c < ncoc; ++c, dst += WW_A_PLANE, sp += stra) bulk_g2s_u32(dst, sp, WW_A_PLANE, bar);
-        dst = s0 + (uint32_t)stage * stage_bytes + a_bytes;
-        sp = srcb;
+        const uint32_t sb = s0 + (uint32_t)stage * stage_bytes;
+        for (int sl = 0; sl < gr.nslots; ++sl) {
+          uint32_t dst = sb + (uint32_t)(sl * pr.a_chunks) * WW_A_PLANE;
+          const char* sp = srca + (long long)gr.ashift[sl] * 16;
+          for (int c = 0; c < ncoc; ++c, dst += WW_A_PLANE, sp += stra) bulk_g2s_u32(dst, sp, WW_A_PLANE, bar);
+        }
+        uint32_t dst = sb + a_bytes;
+        const char* sp = srcb;
         for (int c = 0; c < ncic; ++c, dst += b_plane, sp += strb) bulk_g2s_u32(dst, sp, b_plane, bar);
       }
       __syncwarp();
@@ -111,7 +125,7 @@ wide_wgrad_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfl
       const uint32_t acc0 = first ? 0u : 1u;
       if (elect_one()) {
         for (int tl = 0; tl < ntaps; ++tl) {
-          const uint64_t bd0 = make_desc(b_base + (uint32_t)(pr.shift[tap0 + tl] - smin) * 16, 128, b_plane);
+          const uint64_t bd0 = make_desc(b_base + (uint32_t)(gr.bshift[tl] - smin) * 16, 128, b_plane);
           const uint32_t d = tmem_base + (uint32_t)(tl * pr.cit);
           umma_bf16(d, ad0, bd0, idesc, acc0);
 #pragma unroll
@@ -126,9 +140,9 @@ wide_wgrad_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfl
     if (elect_one()) umma_commit(&hd->done);
     __syncwarp();
   } else {
-    // epilogue: TMEM lane = output channel of the tile, columns = (local tap, input channel of the tile)
+    // epilogue: TMEM lane = accumulator row (slot, output channel of the tile), columns = (local tap, input channel)
     const int quarter = warp & 3;
-    const int co = quarter * 32 + lane;
+    const int row = quarter * 32 + lane;
     mbar_wait(&hd->done, 0);
     tc_fence_after();
     float* rec = partial + ((size_t)kind * gridDim.x + blockIdx.x) * pr.rec_floats;
@@ -140,7 +154,7 @@ wide_wgrad_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfl
         tmem_ld8(taddr + (uint32_t)(tl * pr.cit + c * 8), v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) rec[((size_t)tl * pr.cit + c * 8 + j) * 128 + co] = any ? v[j] : 0.f;
+        for (int j = 0; j < 8; ++j) rec[((size_t)tl * pr.cit + c * 8 + j) * 128 + row] = any ? v[j] : 0.f;
       }
   }
   tc_fence_before();
@@ -163,18 +177,22 @@ wide_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ 
   const WwParams& pr = rp.p;
   const int kind = blockIdx.y;
   const int tg = kind % pr.n_tg, cit_i = (kind / pr.n_tg) % pr.n_cit, cot_i = kind / (pr.n_tg * pr.n_cit);
-  const int ntaps = pr.tg_ntaps[tg], tap0 = pr.tg_tap0[tg];
-  const int per = ntaps * pr.cit * 128;
+  const WwGroup& gr = pr.g[tg];
+  const int per = gr.ntaps * pr.cit * 128;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= per) return;
-  const int col = i & 127, cl = (i >> 7) % pr.cit, tl = (i >> 7) / pr.cit;
+  const int row = i & 127, cl = (i >> 7) % pr.cit, tl = (i >> 7) / pr.cit;
+  const int rows_per_slot = pr.a_chunks * 8;
+  const int slot = row / rows_per_slot, r = row - slot * rows_per_slot;
+  if (slot >= gr.nslots) return;
+  const int tap = gr.tapid[slot][tl];
+  const int kc = cit_i * pr.cit + cl;                 // kernel-side input channel
+  const int nc = cot_i * rows_per_slot + r;           // kernel-side output channel
+  if (tap < 0 || nc >= rp.cout || kc >= rp.cin) return;
   const float* src = partial + (size_t)kind * rp.nsplit * pr.rec_floats + i;
   float acc = 0.f;
   for (int k = 0; k < rp.nsplit; ++k) acc += src[(size_t)k * pr.rec_floats];
-  const int tap = tap0 + tl;
-  const int kc = cit_i * pr.cit + cl;  // kernel-side input channel
-  const int nc = cot_i * 128 + col;    // kernel-side output channel
-  if (nc < rp.cout && kc < rp.cin) dw[((size_t)nc * rp.cin + kc) * (rp.ks * rp.ks) + tap] += acc;
+  dw[((size_t)nc * rp.cin + kc) * (rp.ks * rp.ks) + tap] += acc;
 }
 
 // stem: the records hold the space-to-depth form [tap (dy, dx)][(c, ry, rx)][(co, a, b)]; weight element
@@ -221,41 +239,88 @@ struct WwConfig {
   size_t smem;
 };
 
-static int ww_config(const MilPF8& gx, const MilPF8& gz, int ks, WwConfig* out) {
+// s2 = 1: x is the PHASE-SPLIT input of a 3x3 / stride-2 convolution (mil_launch_split2: 4 * cb planes at the output
+// resolution) and dz its output gradient -- the nine taps grouped by the parity phase they read (4 + 2 + 2 + 1)
+static int ww_config(const MilPF8& gx, const MilPF8& gz, int ks, int s2, WwConfig* out) {
   WwConfig& c = *out;
   c = WwConfig{};
-  const int cin = gx.cb * 8, cout = gz.cb * 8;
+  const int cin = s2 ? gx.cb * 2 : gx.cb * 8, cout = gz.cb * 8;
   MIL_REQUIRE(ks == 1 || ks == 3 || ks == 7, "wide_wgrad: unsupported window %d", ks);
+  MIL_REQUIRE(!s2 || ks == 3, "wide_wgrad: the phase-split form is the 3x3 / stride-2 convolution");
   MIL_REQUIRE(cout % 64 == 0, "wide_wgrad: %d output channels (need a multiple of 64)", cout);
-  const int r = ks == 1 ? 0 : 1;  // ks = 7: the stem's space-to-depth form has 3x3 taps
-  int nt = 0;
-  for (int a = -r; a <= r; ++a)
-    for (int b = -r; b <= r; ++b) c.p.shift[nt++] = a * gx.wp + b;
+  const int wp = gx.wp;
+  for (int g = 0; g < 4; ++g)
+    for (int sl = 0; sl < 2; ++sl)
+      for (int t = 0; t < 9; ++t) c.p.g[g].tapid[sl][t] = -1;
+  c.p.a_chunks = 16;
   if (ks == 7) {
     MIL_REQUIRE(cin == 48, "wide_wgrad: the stem form reads the 48-channel space-to-depth input");
     c.p.cit = 48; c.p.n_cit = 1; c.p.n_tg = 1;
-    c.p.tg_ntaps[0] = 9; c.p.tg_tap0[0] = 0;
+    WwGroup& g = c.p.g[0];
+    g.ntaps = 9; g.plane0 = 0; g.nslots = 1; g.ashift[0] = 0;
+    for (int t = 0; t < 9; ++t) { g.bshift[t] = (t / 3 - 1) * wp + (t % 3 - 1); g.tapid[0][t] = (short)t; }
   } else {
     c.p.cit = cin >= 128 ? 128 : cin;
     MIL_REQUIRE(cin % c.p.cit == 0 && c.p.cit % 16 == 0, "wide_wgrad: %d input channels", cin);
     c.p.n_cit = cin / c.p.cit;
-    c.p.n_tg = ks == 3 ? 3 : 1;
-    for (int g = 0; g < c.p.n_tg; ++g) { c.p.tg_ntaps[g] = ks == 3 ? 3 : 1; c.p.tg_tap0[g] = 3 * g; }
-  }
-  c.p.n_cot = (cout + 127) / 128;
-  c.kinds = c.p.n_cot * c.p.n_cit * c.p.n_tg;
-  c.p.rec_floats = (long long)c.p.tg_ntaps[0] * c.p.cit * 128;
-  const long long n_tiles = mil_cdiv(gz.Q, WW_TK);
-  c.nsplit = (int)std::max<long long>(1, std::min<long long>(n_tiles, ww_sm_count() / c.kinds));
-  int span_max = 0;
-  for (int g = 0; g < c.p.n_tg; ++g) {
-    int lo = c.p.shift[c.p.tg_tap0[g]], hi = lo;
-    for (int t = 1; t < c.p.tg_ntaps[g]; ++t) {
-      lo = std::min(lo, c.p.shift[c.p.tg_tap0[g] + t]);
-      hi = std::max(hi, c.p.shift[c.p.tg_tap0[g] + t]);
+    if (s2) {
+      // phase (a, b): tap (dy, dx) in {-1, 0}^2 carries w[2 dy + a + 1][2 dx + b + 1]; dy = -1 needs a = 1
+      c.p.n_tg = 4;
+      for (int ph = 0; ph < 4; ++ph) {
+        const int a = ph >> 1, b = ph & 1;
+        WwGroup& g = c.p.g[ph];
+        g.plane0 = ph * (cin / 8); g.nslots = 1; g.ashift[0] = 0; g.ntaps = 0;
+        for (int dy = -1; dy <= 0; ++dy)
+          for (int dx = -1; dx <= 0; ++dx) {
+            if ((dy == -1 && a == 0) || (dx == -1 && b == 0)) continue;
+            g.bshift[g.ntaps] = dy * wp + dx;
+            g.tapid[0][g.ntaps] = (short)((2 * dy + a + 1) * 3 + (2 * dx + b + 1));
+            ++g.ntaps;
+          }
+      }
+    } else if (ks == 3 && cout == 64) {
+      // 64 output channels fill half of the M = 128 rows: two tap ROWS share the M axis (slot = the dz tile shifted by
+      // -dy * wp), the three dx taps are the MMAs -- dW[dy][dx] = sum_q' x[q' + dx] dz[q' - dy wp]
+      c.p.a_chunks = 8;
+      c.p.n_tg = 2;
+      for (int gi = 0; gi < 2; ++gi) {
+        WwGroup& g = c.p.g[gi];
+        g.ntaps = 3; g.plane0 = 0;
+        g.nslots = gi == 0 ? 2 : 1;
+        const int dys[2] = {gi == 0 ? -1 : 1, 0};
+        for (int sl = 0; sl < g.nslots; ++sl) {
+          g.ashift[sl] = -dys[sl] * wp;
+          for (int t = 0; t < 3; ++t) g.tapid[sl][t] = (short)((dys[sl] + 1) * 3 + t);
+        }
+        for (int t = 0; t < 3; ++t) g.bshift[t] = t - 1;
+      }
+    } else {
+      c.p.n_tg = ks == 3 ? 3 : 1;
+      for (int gi = 0; gi < c.p.n_tg; ++gi) {
+        WwGroup& g = c.p.g[gi];
+        g.ntaps = ks == 3 ? 3 : 1; g.plane0 = 0; g.nslots = 1; g.ashift[0] = 0;
+        for (int t = 0; t < g.ntaps; ++t) {
+          g.bshift[t] = ks == 3 ? (gi - 1) * wp + (t - 1) : 0;
+          g.tapid[0][t] = (short)(ks == 3 ? gi * 3 + t : 0);
+        }
+      }
     }
+  }
+  c.p.n_cot = (cout + c.p.a_chunks * 8 - 1) / (c.p.a_chunks * 8);
+  if (c.p.a_chunks == 8) c.p.n_cot = 1;
+  c.kinds = c.p.n_cot * c.p.n_cit * c.p.n_tg;
+  int max_taps = 0, span_max = 0;
+  for (int g = 0; g < c.p.n_tg; ++g) {
+    const WwGroup& gr = c.p.g[g];
+    max_taps = std::max(max_taps, gr.ntaps);
+    int lo = gr.bshift[0], hi = lo;
+    for (int t = 1; t < gr.ntaps; ++t) { lo = std::min(lo, gr.bshift[t]); hi = std::max(hi, gr.bshift[t]); }
     span_max = std::max(span_max, WW_TK + hi - lo);
   }
+  MIL_REQUIRE(max_taps * c.p.cit <= 512, "wide_wgrad: %d taps x %d input channels exceed the 512 TMEM columns", max_taps, c.p.cit);
+  c.p.rec_floats = (long long)max_taps * c.p.cit * 128;
+  const long long n_tiles = mil_cdiv(gz.Q, WW_TK);
+  c.nsplit = (int)std::max<long long>(1, std::min<long long>(n_tiles, ww_sm_count() / c.kinds));
   const size_t stage = (size_t)16 * WW_A_PLANE + (size_t)(c.p.cit / 8) * span_max * 16;
   c.p.n_stages = WW_MAX_STAGES;
   while (c.p.n_stages > 1 && 128 + c.p.n_stages * stage > 224 * 1024) --c.p.n_stages;
@@ -264,18 +329,18 @@ static int ww_config(const MilPF8& gx, const MilPF8& gz, int ks, WwConfig* out) 
   return 0;
 }
 
-size_t mil_wide_wgrad_partial_floats(const MilPF8& gx, const MilPF8& gz, int ks) {
+size_t mil_wide_wgrad_partial_floats(const MilPF8& gx, const MilPF8& gz, int ks, int s2) {
   WwConfig c;
-  if (ww_config(gx, gz, ks, &c) != 0) return 0;
+  if (ww_config(gx, gz, ks, s2, &c) != 0) return 0;
   return (size_t)c.kinds * c.nsplit * c.p.rec_floats;
 }
 
 int mil_launch_wide_wgrad(const void* x, const MilPF8& gx, const void* dz, const MilPF8& gz, float* partial, float* dw,
-                          float* db, int ks, cudaStream_t s) {
+                          float* db, int ks, cudaStream_t s, int s2) {
   MIL_REQUIRE(gx.n == gz.n && gx.h == gz.h && gx.w == gz.w && gx.wp == gz.wp && gx.hp == gz.hp, "wide_wgrad: geometry mismatch");
   MIL_REQUIRE(db == nullptr, "wide_wgrad: the wide parameterisation has no convolution bias (alt_resnet.py:24-32)");
   WwConfig c;
-  MIL_TRY(ww_config(gx, gz, ks, &c));
+  MIL_TRY(ww_config(gx, gz, ks, s2, &c));
   MIL_REQUIRE(gx.wp + 1 <= gx.G, "wide_wgrad: the window reaches %d pixels back but the map's guard is %lld", gx.wp + 1, gx.G);
   MIL_SET_SMEM(wide_wgrad_kernel, c.smem);
   wide_wgrad_kernel<<<dim3(c.nsplit, c.kinds), WW_THREADS, c.smem, s>>>((const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)dz,
@@ -286,11 +351,11 @@ int mil_launch_wide_wgrad(const void* x, const MilPF8& gx, const void* dz, const
   rp.nsplit = c.nsplit;
   rp.ks = ks;
   if (ks == 7) { rp.cout = gz.cb * 8 / 4; rp.cin = 3; }
-  else { rp.cout = gz.cb * 8; rp.cin = gx.cb * 8; }
+  else { rp.cout = gz.cb * 8; rp.cin = s2 ? gx.cb * 2 : gx.cb * 8; }
   if (ks == 7) {
     wide_stem_reduce_kernel<<<(unsigned)mil_cdiv(rp.cout * 147, 256), 256, 0, s>>>(partial, dw, rp);
   } else {
-    const int per = c.p.tg_ntaps[0] * c.p.cit * 128;
+    const int per = (int)c.p.rec_floats;
     wide_wgrad_reduce_kernel<<<dim3((unsigned)mil_cdiv(per, 256), c.kinds), 256, 0, s>>>(partial, dw, rp);
   }
   MIL_LAUNCH_OK();

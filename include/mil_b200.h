@@ -198,6 +198,15 @@ int mil_wide_wgrad_pf8(const void* x, int n, int cin, int h, int w, const void* 
                        size_t ws_bytes, void* stream);
 /* out = the four (row, column) parity phases of in at half resolution, as 4 * c channels (plane = phase * c/8 + chunk) */
 int mil_split2_pf8(const void* in, int n, int c, int h, int w, void* out, void* stream);
+/* the inverse: out [n, c, h, w] = the phases of in interleaved back (pad pixels zero) */
+int mil_merge2_pf8(const void* in, int n, int c, int h, int w, void* out, void* stream);
+/* The stride-2 3x3 convolution's gradients at the OUTPUT resolution ho x wo (no zero-stuffing):
+ *   weight gradient from the phase-split input xs2 (mil_split2_pf8) and the output gradient dz;
+ *   data gradient: mil_wide_conv_pf8 with mode = 3 + 2a + b computes input parity phase (a, b) from x = dz
+ *   (cx = wcout channels), out = [n, wcin, ho, wo]; act / res are maps of that phase.                               */
+size_t mil_wide_wgrad_s2_workspace_bytes(int n, int cin, int cout, int ho, int wo);
+int mil_wide_wgrad_s2_pf8(const void* xs2, int n, int cin, int ho, int wo, const void* dz, int cout, float* dw, void* ws,
+                          size_t ws_bytes, void* stream);
 
 /* ---- the wide extractor as a whole --------------------------------------------------
  * alt_resnet.py's ResNet as the tile feature extractor of the same MIL head: conv1 7x7/2 (3 -> stem, no bias), ReLU,

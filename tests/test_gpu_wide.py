@@ -314,3 +314,58 @@ def test_wide_attention_with_fused_adam_and_uint8_tiles():
     f32 = ((u8.cpu().float() / 255.0 - 0.5) / 0.5).cuda()      # ToTensor() + Normalize(.5, .5) as the loader does it, on the CPU
     with torch.no_grad():
         assert torch.equal(a(u8, Y)["Fterm"], a(f32, Y)["Fterm"])
+
+
+@pytest.mark.parametrize("cin,cout,H,n", [(64, 128, 14, 3), (128, 256, 28, 2), (256, 512, 7, 5), (64, 128, 13, 2), (64, 128, 56, 2)])
+def test_wide_stride2_gradients_at_the_output_resolution(cin, cout, H, n):
+    """Weight gradient from the phase-split input, data gradient per input parity phase + merge (no zero-stuffing)."""
+    lib = G.lib()
+    gen = torch.Generator(device="cuda").manual_seed(19)
+    x = q(torch.randn(n, cin, H, H, device="cuda", generator=gen))
+    w = torch.randn(cout, cin, 3, 3, device="cuda", generator=gen) / (cin * 9) ** 0.5
+    Ho = (H - 1) // 2 + 1
+    dz = q(torch.randn(n, cout, Ho, Ho, device="cuda", generator=gen))
+    X, DZ = G.PF8.from_nchw(x, "bf16"), G.PF8.from_nchw(dz, "bf16")
+    XS = G.PF8(n, 4 * cin, Ho, Ho, "bf16")
+    G.check(lib.mil_split2_pf8(G._p(X.buf), n, cin, H, H, G._p(XS.buf), G._s()), "mil_split2_pf8")
+    # weight gradient
+    dw = torch.zeros(cout, cin, 3, 3, device="cuda")
+    nbytes = int(lib.mil_wide_wgrad_s2_workspace_bytes(n, cin, cout, Ho, Ho))
+    ws = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    G.check(lib.mil_wide_wgrad_s2_pf8(G._p(XS.buf), n, cin, Ho, Ho, G._p(DZ.buf), cout, G._p(dw), G._p(ws), nbytes, G._s()),
+            "mil_wide_wgrad_s2_pf8")
+    gw = torch.nn.grad.conv2d_weight(x, w.shape, dz, stride=2, padding=1)
+    assert G.relerr(dw, gw) < 3e-3
+    # data gradient: (conv_transpose(dz) + projection gradient at the even positions) * relu'(x)
+    tsub = q(torch.randn(n, cin, Ho, Ho, device="cuda", generator=gen))
+    TS = G.PF8.from_nchw(tsub, "bf16")
+    DS = G.PF8(n, 4 * cin, Ho, Ho, "bf16")
+    plane_bytes = DS.buf.numel() // (4 * cin // 8)
+    phase_bytes = plane_bytes * (cin // 8)
+
+    class View:
+        def __init__(self, t, ph):
+            self.buf = t.buf[ph * phase_bytes:(ph + 1) * phase_bytes]
+
+    for ph in range(4):
+        nb = int(lib.mil_wide_conv_workspace_bytes(3 + ph, 0, cout, cin, 3))
+        wsk = torch.zeros(nb, dtype=torch.uint8, device="cuda")
+        G.check(lib.mil_wide_conv_pf8(3 + ph, 0, G._p(DZ.buf), n, cout, Ho, Ho, G._p(w.contiguous()), cout, cin, 3, None,
+                                      G._p(TS.buf) if ph == 0 else None, G._p(View(XS, ph).buf), G._p(View(DS, ph).buf), 1,
+                                      C.c_float(0.0), 0, G._p(wsk), nb, G._s()), "mil_wide_conv_pf8")
+    OUT = G.PF8(n, cin, H, H, "bf16")
+    OUT.buf.fill_(0x7F)      # the merge must overwrite every pixel, pads with zeros
+    G.check(lib.mil_merge2_pf8(G._p(DS.buf), n, cin, H, H, G._p(OUT.buf), G._s()), "mil_merge2_pf8")
+    gi = torch.nn.grad.conv2d_input(x.shape, q(w), dz, stride=2, padding=1)
+    gi[:, :, ::2, ::2] += tsub
+    assert G.relerr(OUT.to_nchw(), gi * (x > 0).float()) < 1.2e-2
+    # every pixel of the map (incl. the pad row / column) was written: only the guards still hold the fill pattern
+    ref = G.PF8.from_nchw(OUT.to_nchw(), "bf16")
+    g0 = int(lib.mil_pf8_bytes(n, cin, H, H, 1))
+    assert g0 == OUT.buf.numel()
+    a = OUT.raw().float().view(cin // 8, -1, 8)
+    b = ref.raw().float().view(cin // 8, -1, 8)
+    Hp = H + 1
+    lead = ((Hp + 1) + 7) // 8 * 8
+    body = slice(lead, lead + n * Hp * Hp)
+    assert torch.equal(a[:, body], b[:, body])

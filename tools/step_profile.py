@@ -1,6 +1,6 @@
 """In-situ kernel times of the bench step (torch.profiler / CUPTI, kernels back to back at the step's real clocks and
 cache state -- unlike an ncu launch list, which serialises and cools the GPU between launches).
-usage: python tools/step_profile.py [tiles] [side] [steps]"""
+usage: [MIL_MODEL=wide18] python tools/step_profile.py [tiles] [side] [steps]"""
 import collections
 import importlib
 import os
@@ -19,7 +19,8 @@ side = int(sys.argv[2]) if len(sys.argv) > 2 else 224
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)
-net = mil.Attention(n_classes=3).to(dev).eval()
+model = os.environ.get("MIL_MODEL", "resnet26")      # resnet26 | wide18 | wide34 (bench.py --model)
+net = bench.make_net(mil, model).to(dev).eval()
 bag = bench.make_device_bag(mil, n, side, dev, seed=1)
 Y = torch.tensor([1], device=dev)
 
