@@ -20,7 +20,8 @@ struct MilWideShape {
   int mode;        // 0: ks = 1 / 3, stride 1 (forward or data gradient);  1: 3x3 / stride 2 forward on the phase-split
                    // input (mil_launch_split2);  2: stem 7x7 / stride 2 in space-to-depth-by-4 form (3x3 taps, 48 -> 4*C);
                    // 3 + 2a + b: data gradient of the 3x3 / stride-2 convolution for the input pixels of parity phase (a, b)
-                   // (x = the output gradient, out = that phase of the input gradient, both at the OUTPUT resolution)
+                   // (x = the output gradient, out = that phase of the input gradient, both at the OUTPUT resolution);
+                   // 7: the same for ALL four phases at once, as 4 * wcin output channels (phase, ci) = the phase-split map
   int transposed;  // mode 0: data gradient (kernel input = the conv's output channels, taps mirrored)
   int wcout, wcin, ks;  // the PyTorch weight [wcout][wcin][ks][ks]
   int kin, nout;        // kernel-side input channels PER GROUP / output channels
@@ -39,7 +40,7 @@ int mil_launch_wide_pack(const float* w, void* wpk, const MilWideShape& sh, cuda
 // tm = 128-pixel M-tiles per weight slab (0 = choose)
 int mil_launch_wide_conv(const void* x, const MilPF8& gx, const void* wpk, const MilWideShape& sh, const float* bias,
                          const void* res, const void* act, void* out, const MilPF8& go, int epi, float slope, int tm,
-                         cudaStream_t s);
+                         cudaStream_t s, int res_chunks = 0);  // res_chunks > 0: the residual covers only the first chunks
 
 // weight gradient dW[co][ci][tap] += sum_q x[q + shift_tap][ci] * dz[q][co] (stride 1; a stride-2 convolution hands in
 // the zero-stuffed dz), db[co] += sum_q dz[q][co] (db may be NULL).  ks = 1 / 3, or 7 with x = the stem's

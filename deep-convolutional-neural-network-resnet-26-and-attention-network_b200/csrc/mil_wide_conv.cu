@@ -41,6 +41,13 @@ struct WideKParams {
   uint32_t a_plane, b_tap, stage_bytes, wtile_bytes;
   int epi, has_bias;
   float slope;
+  // per_tile = 1 (single group): N-tile nti issues only the taps tile_tap[nti][0 .. tile_ntaps[nti]) -- the weight blocks
+  // of the others are all zero for that tile (the phase-wise stride-2 data gradient)
+  int per_tile;
+  int tile_ntaps[8];
+  int tile_shift[8][4];   // pixel shift of the tile's t-th tap
+  int tile_blk[8][4];     // which tap block of the slab it multiplies with
+  int res_chunks;         // the residual exists for the first res_chunks output chunks only (all: go.cb)
 };
 
 __device__ __forceinline__ uint4 wide_ld16(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
@@ -72,7 +79,7 @@ wide_conv_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bflo
     for (int a = 0; a < kp.nsets; ++a) { mbar_init(&hd->acc_full[a], 1); mbar_init(&hd->acc_empty[a], 8); }
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < 512; i += blockDim.x) hd->bias[i] = (kp.has_bias && i < go.c) ? bias[i] : 0.f;
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) hd->bias[i] = (kp.has_bias && i < go.c) ? bias[i] : 0.f;  // (<= 512 channels with a bias)
   if (warp == 1) tmem_alloc(&hd->tmem_base, 512);
   tc_fence_before();
   __syncthreads();
@@ -131,6 +138,8 @@ wide_conv_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bflo
       const int tm_eff = (int)(left < kp.tm ? left : kp.tm);
       mbar_wait(&hd->acc_empty[set], set_par ^ 1);
       tc_fence_after();
+      const int nti_m = (int)(u % kp.n_ntiles) & 7;
+      const int tile_nt = kp.tile_ntaps[nti_m];
       const uint32_t d0 = tmem_base + (uint32_t)set * set_cols;
       bool first = true;
       for (int g = 0; g < kp.ngroups; ++g) {
@@ -144,9 +153,15 @@ wide_conv_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bflo
             for (int m = 0; m < tm_eff; ++m) {
               const uint32_t ab = (sb + (uint32_t)(m * 128 + kp.halo) * 16) >> 4;
               const uint32_t d = d0 + (uint32_t)(m * kp.nt);
-              for (int t = 0; t < ntaps; ++t)
-                umma_bf16(d, a_hi + (uint64_t)(ab + kp.shift[g][t]), b_hi + (uint64_t)(bb + (uint32_t)t * (kp.b_tap >> 4)), idesc,
-                          (first && t == 0) ? 0u : 1u);
+              if (!kp.per_tile) {
+                for (int t = 0; t < ntaps; ++t)
+                  umma_bf16(d, a_hi + (uint64_t)(ab + kp.shift[g][t]), b_hi + (uint64_t)(bb + (uint32_t)t * (kp.b_tap >> 4)), idesc,
+                            (first && t == 0) ? 0u : 1u);
+              } else {
+                for (int t = 0; t < tile_nt; ++t)
+                  umma_bf16(d, a_hi + (uint64_t)(ab + kp.tile_shift[nti_m][t]),
+                            b_hi + (uint64_t)(bb + (uint32_t)kp.tile_blk[nti_m][t] * (kp.b_tap >> 4)), idesc, (first && t == 0) ? 0u : 1u);
+              }
             }
             umma_commit(&hd->empty[stage]);
           }
@@ -195,7 +210,8 @@ wide_conv_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bflo
           if (live) {
             if (res != nullptr) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) rr[k] = wide_ld16(res + e0 + (long long)(cb + k) * go.PS * 8);
+              for (int k = 0; k < 4; ++k)
+                rr[k] = (nti * nc + cb + k < kp.res_chunks) ? wide_ld16(res + e0 + (long long)(cb + k) * go.PS * 8) : make_uint4(0, 0, 0, 0);
             }
             if (kp.epi == MIL_EPI_DGRAD) {
 #pragma unroll
@@ -286,6 +302,13 @@ __global__ void wide_pack_kernel(const float* __restrict__ w, __nv_bfloat16* __r
     } else if (sh.mode == 1) {
       const int ky = 2 * dy + sh.ga[g] + 1, kx = 2 * dx + sh.gb[g] + 1;
       if (nc < sh.wcout && kc < sh.wcin) v = w[((size_t)nc * sh.wcin + kc) * 9 + ky * 3 + kx];
+    } else if (sh.mode == 7) {
+      // stride-2 data gradient, all four input phases as output channels (phase, ci): tap (dY, dX) in {0, 1}^2 carries
+      // w[a + 1 - 2 dY][b + 1 - 2 dX]^T where dY <= a and dX <= b, zero otherwise
+      const int ph = nc / sh.wcin, ci = nc - ph * sh.wcin;
+      const int a = ph >> 1, bq = ph & 1;
+      if (ph < 4 && dy <= a && dx <= bq && kc < sh.wcout)
+        v = w[((size_t)kc * sh.wcin + ci) * 9 + (a + 1 - 2 * dy) * 3 + (bq + 1 - 2 * dx)];
     } else if (sh.mode >= 3) {
       // stride-2 data gradient, output phase (a, b): tap (dY, dX) in {0, 1}^2 carries w[a + 1 - 2 dY][b + 1 - 2 dX]^T
       const int ky = sh.ga[g] + 1 - 2 * dy, kx = sh.gb[g] + 1 - 2 * dx;
@@ -356,11 +379,22 @@ int mil_wide_shape(int mode, int transposed, int wcout, int wcin, int ks, MilWid
     for (int dY = 0; dY <= a; ++dY)
       for (int dX = 0; dX <= b; ++dX) { sh.tdy[0][t] = (signed char)dY; sh.tdx[0][t] = (signed char)dX; ++t; }
     sh.gntaps[0] = t;
+  } else if (mode == 7) {
+    // the same data gradient with the four input phases as OUTPUT CHANNELS (phase, ci): a 2x2-window convolution of the
+    // output gradient whose weight blocks are zero where a phase does not use a tap (the kernel skips those MMAs)
+    MIL_REQUIRE(ks == 3 && !transposed, "wide_conv: the phase-wise form is the 3x3 / stride-2 data gradient");
+    sh.kin = wcout;
+    sh.nout = 4 * wcin;
+    sh.ngroups = 1;
+    int t = 0;
+    for (int dY = 0; dY <= 1; ++dY)
+      for (int dX = 0; dX <= 1; ++dX) { sh.tdy[0][t] = (signed char)dY; sh.tdx[0][t] = (signed char)dX; ++t; }
+    sh.gntaps[0] = t;
   } else {
     MIL_REQUIRE(false, "wide_conv: unknown mode %d", mode);
   }
   MIL_REQUIRE(sh.kin % 16 == 0, "wide_conv: %d input channels (need a multiple of 16)", sh.kin);
-  MIL_REQUIRE(sh.nout % 64 == 0 && sh.nout <= 512, "wide_conv: %d output channels (need a multiple of 64, at most 512)", sh.nout);
+  MIL_REQUIRE(sh.nout % 64 == 0 && sh.nout <= 1024, "wide_conv: %d output channels (need a multiple of 64, at most 1024)", sh.nout);
   sh.npairs = sh.kin / 16;
   sh.nt = sh.nout % 128 == 0 ? 128 : 64;
   sh.n_ntiles = sh.nout / sh.nt;
@@ -390,7 +424,7 @@ int mil_launch_wide_pack(const float* w, void* wpk, const MilWideShape& sh, cuda
 
 int mil_launch_wide_conv(const void* x, const MilPF8& gx, const void* wpk, const MilWideShape& sh, const float* bias,
                          const void* res, const void* act, void* out, const MilPF8& go, int epi, float slope, int tm,
-                         cudaStream_t s) {
+                         cudaStream_t s, int res_chunks) {
   MIL_REQUIRE(gx.n == go.n && gx.h == go.h && gx.w == go.w && gx.wp == go.wp && gx.hp == go.hp && gx.Q == go.Q,
               "wide_conv: input and output maps must share their pixel geometry");
   MIL_REQUIRE(gx.cb * 8 == sh.kin * sh.ngroups, "wide_conv: x has %d chunk planes, the packed weights expect %d", gx.cb,
@@ -434,6 +468,28 @@ int mil_launch_wide_conv(const void* x, const MilPF8& gx, const void* wpk, const
   kp.stage_bytes = (uint32_t)stage_of(tm);
   kp.n_stages = (int)std::min<size_t>(WIDE_MAX_STAGES, budget / kp.stage_bytes);
   kp.nsets = std::min(WIDE_MAX_SETS, 512 / (tm * sh.nt));
+  kp.per_tile = 0;
+  if (sh.mode == 7) {
+    MIL_REQUIRE(sh.n_ntiles <= 8, "wide_conv: %d output tiles in the phase-wise data gradient", sh.n_ntiles);
+    kp.per_tile = 1;
+    // N-tile -> the phases whose channels it holds -> the taps any of them uses (tap 2 dY + dX; phase (a, b): dY <= a, dX <= b)
+    for (int nti = 0; nti < sh.n_ntiles; ++nti) {
+      const int c0 = nti * sh.nt, c1 = c0 + sh.nt;
+      int cnt = 0;
+      for (int t = 0; t < 4; ++t) {
+        bool used = false;
+        for (int ph = 0; ph < 4; ++ph)
+          if (c0 < (ph + 1) * sh.wcin && c1 > ph * sh.wcin && (t >> 1) <= (ph >> 1) && (t & 1) <= (ph & 1)) used = true;
+        if (used) {
+          kp.tile_shift[nti][cnt] = kp.shift[0][t];
+          kp.tile_blk[nti][cnt] = t;
+          ++cnt;
+        }
+      }
+      kp.tile_ntaps[nti] = cnt;
+    }
+  }
+  kp.res_chunks = res_chunks > 0 ? res_chunks : go.cb;
   kp.epi = epi;
   kp.has_bias = (bias != nullptr && epi != MIL_EPI_DGRAD) ? 1 : 0;
   kp.slope = slope;

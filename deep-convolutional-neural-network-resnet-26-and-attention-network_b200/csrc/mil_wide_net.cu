@@ -121,12 +121,11 @@ int mil_wide_make_plan(const MilWideDesc& d, int n, int side, MilWidePlan* plan)
     MIL_TRY(mil_wide_shape(0, 1, cout, cin, ks, &st));
     c.wf_off = wofs; wofs += walign(mil_wide_wpack_bytes(sf));
     c.wt_off = wofs; wofs += walign(mil_wide_wpack_bytes(st));
-    if (ks == 3 && stride == 2)
-      for (int ph = 0; ph < 4; ++ph) {
-        MilWideShape sp;
-        MIL_TRY(mil_wide_shape(3 + ph, 0, cout, cin, 3, &sp));
-        pl.s2_wt_off[l][ph] = wofs; wofs += walign(mil_wide_wpack_bytes(sp));
-      }
+    if (ks == 3 && stride == 2) {
+      MilWideShape sp;
+      MIL_TRY(mil_wide_shape(7, 0, cout, cin, 3, &sp));
+      pl.s2_wt_off[l][0] = wofs; wofs += walign(mil_wide_wpack_bytes(sp));
+    }
     pl.convs.push_back(c);
     return 0;
   };
@@ -335,10 +334,8 @@ static int pack_all(const void* const* params, const MilWidePlan& pl, void* ws, 
   for (const auto& c : pl.convs) {
     MilWideShape sh;
     if (transposed && c.ks == 3 && c.stride == 2) {
-      for (int ph = 0; ph < 4; ++ph) {
-        MIL_TRY(mil_wide_shape(3 + ph, 0, c.cout, c.cin, 3, &sh));
-        MIL_TRY(mil_launch_wide_pack((const float*)params[c.p_w], area + pl.s2_wt_off[c.layer][ph], sh, s));
-      }
+      MIL_TRY(mil_wide_shape(7, 0, c.cout, c.cin, 3, &sh));
+      MIL_TRY(mil_launch_wide_pack((const float*)params[c.p_w], area + pl.s2_wt_off[c.layer][0], sh, s));
       continue;
     }
     if (transposed) MIL_TRY(mil_wide_shape(0, 1, c.cout, c.cin, c.ks, &sh));
@@ -497,12 +494,11 @@ int mil_wide_backward_impl(const void* const* params, const MilWidePlan& pl, voi
         MIL_TRY(wide_wgrad(xs2, mil_split2_phase0(gs, gi.c), dz, go, partial, gptr(cd.p_w), 1, s));
         MIL_TRY(mil_wide_shape(0, 1, cd.cout, cd.cin, 1, &sh));
         MIL_TRY(mil_launch_wide_conv(dz, go, wpk + cd.wt_off, sh, nullptr, nullptr, nullptr, t_sub, gts, MIL_EPI_PLAIN, slope, 0, s));
-        const size_t phase_bytes = (size_t)gts.cb * gs.PS * 16;
-        for (int ph = 0; ph < 4; ++ph) {
-          MIL_TRY(mil_wide_shape(3 + ph, 0, c1.cout, c1.cin, 3, &sh));
-          MIL_TRY(mil_launch_wide_conv(dpre, go, wpk + pl.s2_wt_off[l][ph], sh, nullptr, ph == 0 ? t_sub : nullptr,
-                                       xs2 + ph * phase_bytes, dsplit + ph * phase_bytes, gts, MIL_EPI_DGRAD, slope, 0, s));
-        }
+        // all four phases in one launch: output channels (phase, ci) = the planes of the phase-split map; the projection's
+        // gradient t_sub is the residual of phase (0, 0) = the first cb planes
+        MIL_TRY(mil_wide_shape(7, 0, c1.cout, c1.cin, 3, &sh));
+        MIL_TRY(mil_launch_wide_conv(dpre, go, wpk + pl.s2_wt_off[l][0], sh, nullptr, t_sub, xs2, dsplit, gs, MIL_EPI_DGRAD,
+                                     slope, 0, s, gts.cb));
         MIL_TRY(mil_launch_merge2(dsplit, gs, dnew, gi, s));
       }
       std::swap(dz, dnew);

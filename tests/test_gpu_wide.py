@@ -353,6 +353,15 @@ def test_wide_stride2_gradients_at_the_output_resolution(cin, cout, H, n):
         G.check(lib.mil_wide_conv_pf8(3 + ph, 0, G._p(DZ.buf), n, cout, Ho, Ho, G._p(w.contiguous()), cout, cin, 3, None,
                                       G._p(TS.buf) if ph == 0 else None, G._p(View(XS, ph).buf), G._p(View(DS, ph).buf), 1,
                                       C.c_float(0.0), 0, G._p(wsk), nb, G._s()), "mil_wide_conv_pf8")
+    # the same four phases in ONE launch (mode 7: output channels = (phase, ci); what the extractor runs)
+    DS7 = G.PF8(n, 4 * cin, Ho, Ho, "bf16")
+    nb = int(lib.mil_wide_conv_workspace_bytes(7, 0, cout, cin, 3))
+    wsk = torch.zeros(nb, dtype=torch.uint8, device="cuda")
+    TS4 = G.PF8(n, 4 * cin, Ho, Ho, "bf16")          # residual: phase (0, 0) = the projection's gradient, zero elsewhere
+    TS4.buf[:phase_bytes] = TS.buf[:phase_bytes]
+    G.check(lib.mil_wide_conv_pf8(7, 0, G._p(DZ.buf), n, cout, Ho, Ho, G._p(w.contiguous()), cout, cin, 3, None, G._p(TS4.buf),
+                                  G._p(XS.buf), G._p(DS7.buf), 1, C.c_float(0.0), 0, G._p(wsk), nb, G._s()), "mil_wide_conv_pf8")
+    assert torch.equal(DS7.buf, DS.buf)
     OUT = G.PF8(n, cin, H, H, "bf16")
     OUT.buf.fill_(0x7F)      # the merge must overwrite every pixel, pads with zeros
     G.check(lib.mil_merge2_pf8(G._p(DS.buf), n, cin, H, H, G._p(OUT.buf), G._s()), "mil_merge2_pf8")

@@ -79,3 +79,6 @@ print("# wgrad launches in order (us):", " ".join(f"{re.sub(r'_kernel.*', '', e.
 cv = [e for e in evs if "conv_tc_kernel" in e.name]
 firstc = cv[: len(cv) // steps]
 print("# conv_tc launches in order (us):", " ".join(f"{re.sub(r'.*conv_tc_kernel<', '<', e.name)[:10].replace(' ', '')}:{e.time_range.elapsed_us():.0f}" for e in firstc))
+wc = [e for e in evs if "wide_conv_kernel" in e.name]
+if wc:
+    print("# wide_conv launches in order (us):", " ".join(f"{e.time_range.elapsed_us():.0f}" for e in wc[: len(wc) // steps]))
