@@ -617,6 +617,32 @@ def run_ours(args):
                              "(GraphedStep; the subsample indices are redrawn on the host before every replay)"}
         del net2, opt2, gstep, sbag
 
+    # ---------------- the wide parameterisation of the extractor, same bag, same step ----------------
+    # alt_resnet.py's network (resnet18 layout, 64-512 channels, ReLU) in front of the same head: the shape where the
+    # north star's tensor-pipe target is physically reachable (N = 128 MMAs run at the pipe's full rate; the 20-80
+    # channel network above is bound by its operand reads).  Full line: bench.py --model wide18.
+    wide_extra = None
+    if mode == "train" and world == 1 and args.model == "resnet26" and args.precision == "bf16" and not args.no_wide:
+        netw = make_net(mil, "wide18").to(dev).eval()
+
+        def wide_steps(k):
+            for _ in range(k):
+                netw.zero_grad(set_to_none=True)
+                o = netw(bag, Y)
+                o["loss"].backward()
+        wide_steps(2)
+        wms, _ = timed(wide_steps, max(3, args.steps // 2))
+        wflop = wide_flop_fwd_bwd(side, WIDE_LAYERS["wide18"])
+        burst, sustained, _, _ = peaks()
+        wide_extra = {"extractor": "alt_resnet.ResNet(BasicBlock, [2,2,2,2]) (alt_resnet.py:70-165), widths 64/128/256/512",
+                      "tiles_per_s": n / (wms * 1e-3), "ms_per_step": wms, "flop_per_tile_fwd_bwd": wflop,
+                      "tflops": n / (wms * 1e-3) * wflop / 1e12,
+                      "tensor_frac_of_sustained": n / (wms * 1e-3) * wflop / 1e12 / sustained,
+                      "tensor_frac_of_burst": n / (wms * 1e-3) * wflop / 1e12 / burst,
+                      "note": "fwd + bwd of WideAttention on the same 4096-tile bag, bf16, all tiles through the CNN"}
+        del netw
+        torch.cuda.empty_cache()
+
     # ---------------- end to end from pinned host memory ----------------
     # Every step's bag starts in pinned HOST memory and is copied to the device inside the timed region; the result
     # is read back every step.  The copy of step k+1 is submitted (BagStager: side stream, double buffer) before
@@ -709,6 +735,8 @@ def run_ours(args):
             line["train_mode"] = train_mode
         if small_bag is not None:
             line["small_bag"] = small_bag
+        if wide_extra is not None:
+            line["alt_resnet18"] = wide_extra
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -726,6 +754,7 @@ def main():
     ap.add_argument("--mode", default="train", choices=["train", "multi-slide", "inference"])
     ap.add_argument("--ref-tiles", type=int, default=256, help="tiles per step of the CPU arm (bounded sample)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-wide", action="store_true", help="skip the alt_resnet18 extra of the default line")
     ap.add_argument("--model", default="resnet26", choices=["resnet26", "wide18", "wide34"],
                     help="resnet26: the reference's live extractor (gbm/model.py:14-61; BASELINE.json's metric); wide18 / "
                          "wide34: alt_resnet.py's network (64-512 channels) as extractor (SURVEY.md section 8f N4)")
