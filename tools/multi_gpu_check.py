@@ -32,13 +32,21 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     ok = True
-    for precision, tol in (("fp32", 2e-5), ("bf16", 2e-5)):   # same kernels, same inputs: only summation order differs
+    def build(kind, precision):
+        if kind == "wide":      # alt_resnet.py's network as extractor, one block per layer
+            return mil.WideAttention(n_classes=3, layers=(1, 1, 1, 1)).to(dev).eval()
+        m = mil.Attention(n_classes=3).to(dev).eval()
+        m.precision = precision
+        return m
+
+    # same kernels, same inputs: only summation order differs (the wide weight gradient accumulates a whole shard in TMEM:
+    # its split over the CTAs changes with the shard size -> 1e-4 on the gradients there)
+    for kind, precision, tol in (("resnet26", "fp32", 2e-5), ("resnet26", "bf16", 2e-5), ("wide", "bf16", 3e-4)):
         n, side = 96, 64
         bag = torch.from_numpy(mil.synth.make_bag(n, side, seed=5)).to(dev)
         Y = torch.tensor([2], device=dev)
         torch.manual_seed(0)
-        ref = mil.Attention(n_classes=3).to(dev).eval()
-        ref.precision = precision
+        ref = build(kind, precision)
         with torch.no_grad():
             ref.weight_mask.copy_(torch.tensor([-1.0, 0.25, -0.5]))
         out1 = ref(bag, Y)
@@ -48,8 +56,7 @@ def main():
         cuts = [0] + [int(n * (r + 1) / world + (3 if r == 0 and world > 1 else 0)) for r in range(world - 1)] + [n]
         lo, hi = cuts[rank], cuts[rank + 1]
         torch.manual_seed(0)
-        net = mil.Attention(n_classes=3).to(dev).eval()
-        net.precision = precision
+        net = build(kind, precision)
         with torch.no_grad():
             net.weight_mask.copy_(torch.tensor([-1.0, 0.25, -0.5]))
         net.bag_group = mil.BagGroup(dist.group.WORLD, seed=3)
@@ -63,7 +70,7 @@ def main():
             "Aterm_var": rel(out["Aterm_var"], out1["Aterm_var"]), "grads": rel(g, g1),
         }
         bad = {k: v for k, v in errs.items() if not v < tol}
-        print(f"rank {rank} {precision} shard [{lo},{hi}) " + " ".join(f"{k}={v:.1e}" for k, v in errs.items())
+        print(f"rank {rank} {kind} {precision} shard [{lo},{hi}) " + " ".join(f"{k}={v:.1e}" for k, v in errs.items())
               + ("  FAIL " + str(bad) if bad else "  ok"), flush=True)
         ok = ok and not bad
         # train mode: shared-seed subsample + dropout; ranks must agree on the bag-level results
@@ -77,18 +84,17 @@ def main():
         agree = all(torch.equal(vs[0], t) for t in vs)
         cnt = torch.tensor([outt["Aterm"].shape[1]], device=dev)
         dist.all_reduce(cnt)
-        print(f"rank {rank} {precision} train: local tiles {outt['Aterm'].shape[1]} total {int(cnt)} (expect {int(n * 0.2)}) "
+        print(f"rank {rank} {kind} {precision} train: local tiles {outt['Aterm'].shape[1]} total {int(cnt)} (expect {int(n * 0.2)}) "
               f"ranks agree: {agree} finite: {bool(torch.isfinite(v).all())}", flush=True)
         ok = ok and agree and int(cnt) == int(n * 0.2) and bool(torch.isfinite(v).all())
     # ---- multi-slide data parallelism (BASELINE configs[4]): every rank its own bag; only the gradients cross ranks ----
-    for precision, tol in (("fp32", 2e-5), ("bf16", 2e-5)):
+    for kind, precision, tol in (("resnet26", "fp32", 2e-5), ("resnet26", "bf16", 2e-5), ("wide", "bf16", 3e-4)):
         side = 64
         sizes = [40 + 8 * r for r in range(world)]                      # slides differ in size
         bags = [torch.from_numpy(mil.synth.make_bag(sizes[r], side, seed=20 + r)).to(dev) for r in range(world)]
         labels = [torch.tensor([r % 3], device=dev) for r in range(world)]
         torch.manual_seed(0)
-        ref = mil.Attention(n_classes=3).to(dev).eval()
-        ref.precision = precision
+        ref = build(kind, precision)
         outs = []
         for r in range(world):                                          # the reference's loop: one slide after the other,
             o = ref(bags[r], labels[r])                                 # gradients accumulate (gbm/classify_combined.py:446-454)
@@ -96,8 +102,7 @@ def main():
             outs.append(o)
         g1 = torch.cat([p.grad.flatten() for p in ref.parameters()])
         torch.manual_seed(0)
-        net = mil.Attention(n_classes=3).to(dev).eval()
-        net.precision = precision
+        net = build(kind, precision)
         net.bag_group = mil.SlideGroup(dist.group.WORLD)
         out = net(bags[rank], labels[rank])
         out["loss"].backward()
@@ -106,7 +111,7 @@ def main():
                 "Aterm(own slide)": rel(out["Aterm"], outs[rank]["Aterm"]), "grads(sum over slides)": rel(g, g1)}
         same = torch.equal(out["Aterm"], outs[rank]["Aterm"]) and torch.equal(out["Fterm"], outs[rank]["Fterm"])
         bad = {k: v for k, v in errs.items() if not v < tol}
-        print(f"rank {rank} {precision} multi-slide: " + " ".join(f"{k}={v:.1e}" for k, v in errs.items())
+        print(f"rank {rank} {kind} {precision} multi-slide: " + " ".join(f"{k}={v:.1e}" for k, v in errs.items())
               + f" own-slide outputs bit-identical: {same}" + ("  FAIL " + str(bad) if bad else "  ok"), flush=True)
         ok = ok and not bad and same
     dist.barrier()
