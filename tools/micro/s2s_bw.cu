@@ -5,9 +5,11 @@
 #include "mil_tc_ptx.cuh"
 
 __device__ __forceinline__ void bulk_s2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "r"(smem_u32(src)), "r"(bytes), "r"(smem_u32(bar))
+  uint32_t d32 = smem_u32(dst), b32 = smem_u32(bar), dc, bc;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(dc) : "r"(d32));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(bc) : "r"(b32));
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dc),
+               "r"(smem_u32(src)), "r"(bytes), "r"(bc)
                : "memory");
 }
 
@@ -40,7 +42,12 @@ int main() {
   struct { int cb, ps, shift; } cs[] = {{2048, 1, 0}, {2048, 6, 16}, {2048, 12, 16}, {4096, 6, 16}, {4096, 12, 16}, {16384, 4, 16}};
   for (auto& c : cs) {
     const int iters = 2000;
-    k<<<148, 128, 200 * 1024>>>(c.cb, c.ps, iters, c.shift, d);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(148); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 200 * 1024;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, k, c.cb, c.ps, iters, c.shift, d);
     cudaError_t e = cudaDeviceSynchronize();
     long long h[2] = {0, 0}; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
     const double bytes = (double)iters * c.cb * c.ps;
