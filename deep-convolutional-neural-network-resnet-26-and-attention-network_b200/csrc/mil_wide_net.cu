@@ -241,32 +241,35 @@ wide_fc_kernel(const float* __restrict__ avg, const float* __restrict__ w, const
 __global__ void __launch_bounds__(256)
 wide_tail_dz_kernel(const __nv_bfloat16* __restrict__ y, MilPF8 g, const float* __restrict__ w, const float* __restrict__ dH,
                     int Fo, float slope, __nv_bfloat16* __restrict__ dz) {
-  extern __shared__ float s_dh[];
+  // one block per tile: (1) d[c] = sum_f dH[n][f] W[f][c], threads along c (coalesced weight rows); (2) the tile's
+  // (chunk, pixel) items with the pixel index fastest, so that a warp loads / stores 512 contiguous bytes of a chunk plane
+  extern __shared__ float s_mem[];
+  float* s_dh = s_mem;       // [Fo]
+  float* s_d = s_mem + Fo;   // [g.cb * 8] (channels past g.c: zero)
   const int n = blockIdx.x;
   for (int f = threadIdx.x; f < Fo; f += blockDim.x) s_dh[f] = dH[(size_t)n * Fo + f];
   __syncthreads();
   const float inv = 1.f / (float)(g.h * g.w);
-  for (int cb = threadIdx.x; cb < g.cb; cb += blockDim.x) {
-    float d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int f = 0; f < Fo; ++f) {
-      // scalar loads: inside FusedAdam's flat buffer a parameter tensor is only 4-byte aligned
-      const float* wr = w + (size_t)f * g.c + cb * 8;
-      const float h = s_dh[f];
+  for (int c = threadIdx.x; c < g.cb * 8; c += blockDim.x) {
+    float d = 0.f;
+    if (c < g.c)
+      for (int f = 0; f < Fo; ++f) d = fmaf(s_dh[f], __ldg(w + (size_t)f * g.c + c), d);
+    s_d[c] = d * inv;
+  }
+  __syncthreads();
+  const int P = (int)g.P, total = g.cb * P;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int cb = i / P, p = i - cb * P;
+    const int yy = p / g.wp, xx = p - yy * g.wp;
+    const long long o = mil_pf8_off(g, cb, (long long)n * g.P + p);
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (yy < g.h && xx < g.w) {
+      float a[8];
+      mil_load8(y + o, a);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) d[j] = fmaf(h, __ldg(wr + j), d[j]);
+      for (int j = 0; j < 8; ++j) v[j] = s_d[cb * 8 + j] * (a[j] > 0.f ? 1.f : slope);
     }
-    for (int yy = 0; yy < g.hp; ++yy)
-      for (int xx = 0; xx < g.wp; ++xx) {
-        const long long o = mil_pf8_off(g, cb, (long long)n * g.P + (long long)yy * g.wp + xx);
-        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (yy < g.h && xx < g.w) {
-          float a[8];
-          mil_load8(y + o, a);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = d[j] * inv * (a[j] > 0.f ? 1.f : slope);
-        }
-        mil_store8(dz + o, v);
-      }
+    mil_store8(dz + o, v);
   }
 }
 // partial[blk][f][c] = sum over the block's tiles of dH[n][f] avg[n][c]  (+ [f] bias sums); fixed-order reduction after
@@ -445,7 +448,7 @@ int mil_wide_backward_impl(const void* const* params, const MilWidePlan& pl, voi
     const int p_fw = pindex(pl.params, "cnn.module.fc.weight"), p_fb = pindex(pl.params, "cnn.module.fc.bias");
     const float* avg = (const float*)wsp(ws, pl.off_avg);
     const MilPF8& g3 = pl.g[3];
-    wide_tail_dz_kernel<<<pl.n, 64, Fo * sizeof(float), s>>>((const __nv_bfloat16*)wsp(ws, pl.off_y[3].back()), g3,
+    wide_tail_dz_kernel<<<pl.n, 256, (Fo + g3.cb * 8) * sizeof(float), s>>>((const __nv_bfloat16*)wsp(ws, pl.off_y[3].back()), g3,
                                                              (const float*)params[p_fw], dH, Fo, slope, (__nv_bfloat16*)dz);
     MIL_LAUNCH_OK();
     const int total = Fo * C + Fo;
