@@ -63,8 +63,6 @@ void mil_count_launch();
 enum MilOpt {
   MIL_OPT_DISABLE_TC = 0,    // 1: CUDA-core kernels only (cross-check of the tcgen05 path, same rounding points)
   MIL_OPT_STEM_UNFUSED = 1,  // 1: stem as separate conv / pool / unpool / wgrad kernels (cross-check of the fused ones)
-  MIL_OPT_COMPACT = 2,       // 10 * a + b > 0: small-footprint forms of the thin layers' kernels (a ring stages in wgrad_sq_kernel, two accumulator
-                             // stages + b ring stages in conv_tc_kernel) so that a convolution and a weight gradient fit on one SM together
   MIL_OPT_COUNT
 };
 int mil_opt(int id);

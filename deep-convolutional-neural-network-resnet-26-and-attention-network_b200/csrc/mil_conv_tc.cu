@@ -682,9 +682,8 @@ int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const vo
   // ring depth: as deep as shared memory allows, and a MULTIPLE of the accumulator ring (the one `empty[stage]`
   // barrier per tile is waited on by the producer and by the epilogue group of that accumulator: with
   // n_stages % NG == 0 the next completion of a stage's barrier needs this epilogue group to have moved on)
-  const int compact = sh.cbout <= 5 ? mil_opt(MIL_OPT_COMPACT) % 10 : 0;  // small-footprint form (see MIL_OPT_COMPACT)
-  const int ng = (sh.cbout <= 5 && !compact) ? 4 : 2;
-  int n_stages = compact ? std::max(2, compact / 2 * 2) : TC_MAX_STAGES;
+  const int ng = sh.cbout <= 5 ? 4 : 2;
+  int n_stages = TC_MAX_STAGES;
   while (n_stages > ng && tc_smem_bytes(halo, sh, n_stages) > 200 * 1024) n_stages -= ng;
   const size_t smem = tc_smem_bytes(halo, sh, n_stages);
   MIL_REQUIRE(smem <= 227 * 1024, "conv_tc: tile width %d needs %zu bytes of shared memory", gx.w, smem);
@@ -726,9 +725,7 @@ int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const vo
       default: MIL_TC_LAUNCH1(MAXCB, NG, TCM_GENERIC); break;                                                     \
     }                                                                                                             \
   } while (0)
-  if (sh.cbout <= 3 && compact) MIL_TC_LAUNCH(3, 2);
-  else if (sh.cbout <= 3) MIL_TC_LAUNCH(3, 4);
-  else if (sh.cbout <= 5 && compact) MIL_TC_LAUNCH(5, 2);
+  if (sh.cbout <= 3) MIL_TC_LAUNCH(3, 4);
   else if (sh.cbout <= 5) MIL_TC_LAUNCH(5, 4);
   else if (sh.cbout == 6) MIL_TC_LAUNCH(6, 2);
   else if (sh.cbout <= 8) MIL_TC_LAUNCH(8, 2);

@@ -327,8 +327,8 @@ int mil_wgrad_dispatch(int dtype, const void* x, const MilPF8& gi, const void* d
 
 // runtime switches: initial value from the environment, changed through mil_set_option (tests flip them to run the
 // same bag through the tcgen05 and the CUDA-core kernels, the fused and the un-fused stem)
-static const char* const kOptNames[MIL_OPT_COUNT] = {"disable_tc", "stem_unfused", "compact"};
-static const char* const kOptEnv[MIL_OPT_COUNT] = {"MIL_B200_DISABLE_TC", "MIL_B200_STEM_UNFUSED", "MIL_B200_COMPACT"};
+static const char* const kOptNames[MIL_OPT_COUNT] = {"disable_tc", "stem_unfused"};
+static const char* const kOptEnv[MIL_OPT_COUNT] = {"MIL_B200_DISABLE_TC", "MIL_B200_STEM_UNFUSED"};
 static std::atomic<int>* opt_slots() {
   static std::atomic<int> v[MIL_OPT_COUNT];
   static const bool init = [] {

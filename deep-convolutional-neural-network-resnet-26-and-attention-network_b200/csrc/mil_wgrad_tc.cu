@@ -493,7 +493,6 @@ static WgConfig wg_config(const MilPF8& gx, const MilPF8& gz, int ks) {
     const size_t stage = (size_t)(3 * gx.cb + 1) * pitch_b + (size_t)3 * gz.cb * pitch_a;
     const size_t tail = (size_t)(16 - 3 * gz.cb) * pitch_a + 128;
     c.n_stages = WGS_MAX_STAGES;
-    if (mil_opt(MIL_OPT_COMPACT) >= 10) c.n_stages = std::min(c.n_stages, mil_opt(MIL_OPT_COMPACT) / 10);
     while (c.n_stages > 1 && 128 + c.n_stages * stage + tail > 220 * 1024) --c.n_stages;
     c.smem = 128 + c.n_stages * stage + tail;
     return c;
