@@ -172,27 +172,60 @@ struct WwReduceParams {
   int nsplit;        // records per kind
   int cout, cin, ks; // the PyTorch weight [cout][cin][ks][ks];  ks = 7: stem, folded back from the space-to-depth form
 };
+// Block = (32 output channels, 8 input channels: one per warp) of one (output tile, input tile): it walks over ALL tap groups / slots / taps
+// of that pair -- a warp reads 32 consecutive accumulator rows (= output channels) of one (tap, input channel) from every
+// split-K record (coalesced, all loads of the fixed-order sum in flight) -- parks the sums in shared memory as
+// [output channel][input channel][tap] and adds each output channel's 8 * ks * ks contiguous floats to dw in one coalesced run
+// (the first version wrote one float per thread at a stride of cin * ks * ks: 123 us for 38 MB on the 512-channel layers,
+// profiles/r2_ncu_wide_small_kernels.txt).
+#define WWR_T 32   // output channels per block
+#define WWR_K 8    // input channels per block = warps
 __global__ void __launch_bounds__(256)
 wide_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, const __grid_constant__ WwReduceParams rp) {
+  __shared__ float tile[WWR_T * (WWR_K * 9 + 1)];
   const WwParams& pr = rp.p;
-  const int kind = blockIdx.y;
-  const int tg = kind % pr.n_tg, cit_i = (kind / pr.n_tg) % pr.n_cit, cot_i = kind / (pr.n_tg * pr.n_cit);
-  const WwGroup& gr = pr.g[tg];
-  const int per = gr.ntaps * pr.cit * 128;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= per) return;
-  const int row = i & 127, cl = (i >> 7) % pr.cit, tl = (i >> 7) / pr.cit;
+  const int kk = rp.ks * rp.ks, pitch = WWR_K * kk + 1;
   const int rows_per_slot = pr.a_chunks * 8;
-  const int slot = row / rows_per_slot, r = row - slot * rows_per_slot;
-  if (slot >= gr.nslots) return;
-  const int tap = gr.tapid[slot][tl];
-  const int kc = cit_i * pr.cit + cl;                 // kernel-side input channel
-  const int nc = cot_i * rows_per_slot + r;           // kernel-side output channel
-  if (tap < 0 || nc >= rp.cout || kc >= rp.cin) return;
-  const float* src = partial + (size_t)kind * rp.nsplit * pr.rec_floats + i;
-  float acc = 0.f;
-  for (int k = 0; k < rp.nsplit; ++k) acc += src[(size_t)k * pr.rec_floats];
-  dw[((size_t)nc * rp.cin + kc) * (rp.ks * rp.ks) + tap] += acc;
+  const int nct = rows_per_slot / WWR_T;                 // output-channel tiles per slot
+  const int j = blockIdx.x % nct, c0 = (blockIdx.x / nct) * WWR_K;
+  const int cit_i = blockIdx.y % pr.n_cit, cot_i = blockIdx.y / pr.n_cit;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < WWR_T * pitch; i += blockDim.x) tile[i] = 0.f;
+  __syncthreads();
+  for (int tg = 0; tg < pr.n_tg; ++tg) {
+    const WwGroup& gr = pr.g[tg];
+    const int kind = (cot_i * pr.n_cit + cit_i) * pr.n_tg + tg;
+    const float* base = partial + (size_t)kind * rp.nsplit * pr.rec_floats;
+    for (int slot = 0; slot < gr.nslots; ++slot) {
+      const int row = slot * rows_per_slot + j * WWR_T + lane;
+      for (int tl = 0; tl < gr.ntaps; ++tl) {
+        const int tap = gr.tapid[slot][tl];
+        if (tap < 0) continue;
+        const int cl = c0 + warp;
+        if (cl < pr.cit) {
+          const float* src = base + (((size_t)tl * pr.cit + cl) << 7) + row;
+          float acc = 0.f;
+          int k = 0;
+          for (; k + 4 <= rp.nsplit; k += 4) {
+            const float v0 = src[(size_t)k * pr.rec_floats], v1 = src[(size_t)(k + 1) * pr.rec_floats],
+                        v2 = src[(size_t)(k + 2) * pr.rec_floats], v3 = src[(size_t)(k + 3) * pr.rec_floats];
+            acc += v0; acc += v1; acc += v2; acc += v3;
+          }
+          for (; k < rp.nsplit; ++k) acc += src[(size_t)k * pr.rec_floats];
+          tile[lane * pitch + (cl - c0) * kk + tap] += acc;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int kc0 = cit_i * pr.cit + c0;
+  const int ncols = min(WWR_K, min(pr.cit - c0, rp.cin - kc0)) * kk;  // this block's contiguous floats per output channel
+  for (int r = warp; r < WWR_T; r += 8) {
+    const int nc = cot_i * rows_per_slot + j * WWR_T + r;
+    if (nc >= rp.cout) break;
+    float* dst = dw + ((size_t)nc * rp.cin + kc0) * kk;
+    for (int i = lane; i < ncols; i += 32) dst[i] += tile[r * pitch + i];
+  }
 }
 
 // stem: the records hold the space-to-depth form [tap (dy, dx)][(c, ry, rx)][(co, a, b)]; weight element
@@ -355,8 +388,9 @@ int mil_launch_wide_wgrad(const void* x, const MilPF8& gx, const void* dz, const
   if (ks == 7) {
     wide_stem_reduce_kernel<<<(unsigned)mil_cdiv(rp.cout * 147, 256), 256, 0, s>>>(partial, dw, rp);
   } else {
-    const int per = (int)c.p.rec_floats;
-    wide_wgrad_reduce_kernel<<<dim3((unsigned)mil_cdiv(per, 256), c.kinds), 256, 0, s>>>(partial, dw, rp);
+    MIL_REQUIRE(c.p.a_chunks * 8 % WWR_T == 0 && ks * ks <= 9, "wide_wgrad: reduction tile does not divide the slot (%d rows)", c.p.a_chunks * 8);
+    const int nct = c.p.a_chunks * 8 / WWR_T;
+    wide_wgrad_reduce_kernel<<<dim3((unsigned)(nct * mil_cdiv(c.p.cit, WWR_K)), c.p.n_cot * c.p.n_cit), 256, 0, s>>>(partial, dw, rp);
   }
   MIL_LAUNCH_OK();
   return 0;
