@@ -187,6 +187,13 @@ int mil_launch_reduce_partials(const float* partial, int nblk, long long stride,
                                cudaStream_t s);
 int mil_launch_reduce_conv_w(const float* partial, int nblk, long long stride, float* dw, float* db, int cout,
                              int cin, int ks, cudaStream_t s);
+// deferred form (mil_layout.cu): between begin and end, a weight gradient that put its partial records at
+// mil_reduce_batch_cursor() has its reduction recorded instead of launched; flush sums all recorded jobs in one launch.
+// max_need = the largest partial-record area one weight gradient may write (floats).
+void mil_reduce_batch_begin(float* arena, size_t arena_floats, size_t max_need);
+float* mil_reduce_batch_cursor(float* fallback, cudaStream_t s);  // nullptr: a flush failed (mil_last_error)
+int mil_reduce_batch_flush(cudaStream_t s);
+int mil_reduce_batch_end(cudaStream_t s);
 // mil_conv_direct.cu
 int mil_launch_conv_direct(int dtype, int transposed, const void* x, const MilPF8& gi, const float* wp,
                            const float* bias, const void* res, const void* act, void* out, const MilPF8& go, int ks,

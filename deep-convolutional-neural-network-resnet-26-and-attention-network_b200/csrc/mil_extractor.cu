@@ -216,7 +216,10 @@ int mil_make_plan(int n, int side, int dtype, MilPlan* plan, bool infer) {
   if (pl.stem_tc) pf = std::max(pf, mil_stem_tc_partial_floats(n, side));
   if (infer) pf = 64;
   pl.partial_floats = pf;
-  pl.off_partial = take(pf * sizeof(float));
+  // room for the partial records of a whole layer's weight gradients (5 stride-1 convolutions + the stride-2 pair): their
+  // reductions run as ONE launch per layer (mil_reduce_batch_*)
+  pl.partial_arena_floats = infer ? pf : 8 * mil_rup((long long)pf, 64);
+  pl.off_partial = take(pl.partial_arena_floats * sizeof(float));
   pl.total_bytes = off;
   return 0;
 }
@@ -449,6 +452,8 @@ int mil_extractor_forward_impl(const void* const* params, const void* bag, int b
   auto TCW = [&](const MilConvDesc& c, bool tr) -> const void* {
     return c.tc ? wsp(ws, pl.off_wtc) + (tr ? c.wtct_off : c.wtc_off) : nullptr;
   };
+#undef MIL_PBUF
+  MIL_TRY(mil_reduce_batch_end(s));
   const int p_c1w = mil_param_index("cnn.module.conv1.weight"), p_c1b = mil_param_index("cnn.module.conv1.bias");
   if (pl.stem_tc)
     MIL_TRY(mil_launch_stem_tc_fwd(bag, bag_u8, idx, pl.n, pl.side, (const float*)params[p_c1w], (const float*)params[p_c1b],
@@ -570,6 +575,14 @@ int mil_extractor_backward_impl(const void* const* params, const float* bag, con
   }
   MIL_TRY(mil_launch_tail_bwd(dt, wsp(ws, pl.off_y[11]), pl.g[3], (const float*)params[p_fc],
                               (const float*)wsp(ws, pl.off_avg), dH, dz, partial, gptr(p_fc), s));
+  // the reductions of a layer's weight gradients are recorded and run as one launch at the end of the layer
+  struct BatchScope {
+    ~BatchScope() { mil_reduce_batch_begin(nullptr, 0, 0); }  // closes the batch on every exit path
+  } batch_scope;
+  mil_reduce_batch_begin(partial, pl.partial_arena_floats, pl.partial_floats);
+#define MIL_PBUF(var)                                         \
+  float* var = mil_reduce_batch_cursor(partial, s);           \
+  if (var == nullptr) return 1
   // index of the first conv descriptor of (l, b)
   auto conv_base = [&](int l, int b) {
     size_t i = 0;
@@ -596,14 +609,20 @@ int mil_extractor_backward_impl(const void* const* params, const float* bag, con
       const MilConvDesc& c1 = pl.convs[cb];
       const MilConvDesc& c2 = pl.convs[cb + 1];
       // conv2: weight gradient, then data gradient through conv2 and the first LeakyReLU
-      MIL_TRY(mil_wgrad_dispatch(dt, h, go, dz, go, partial, gptr(c2.p_w), gptr(c2.p_b), 3, 1, s));
+      {
+        MIL_PBUF(pb);
+        MIL_TRY(mil_wgrad_dispatch(dt, h, go, dz, go, pb, gptr(c2.p_w), gptr(c2.p_b), 3, 1, s));
+      }
       MIL_TRY(mil_conv_dispatch(dt, 1, dz, go, wpack + c2.wpt_off, TCW(c2, true), nullptr, nullptr, h, dpre, go, 3, 1,
                                 MIL_EPI_DGRAD, s, c2.tc ? mh : nullptr));
       // which 1: gradient w.r.t. the pre-activation of this block's first conv (geometry go)
       if (g_dump.dst != nullptr && g_dump.layer == l && g_dump.block == b && g_dump.which == 1)
         MIL_TRY(mil_launch_from_pf8(dt, dpre, g_dump.dst, go.n, go.c, go.h, go.w, s));
       // conv1: weight gradient (the stride-2 blocks do it inside their own branch below)
-      if (!down) MIL_TRY(mil_wgrad_dispatch(dt, xin, gi, dpre, go, partial, gptr(c1.p_w), gptr(c1.p_b), 3, 1, s));
+      if (!down) {
+        MIL_PBUF(pb);
+        MIL_TRY(mil_wgrad_dispatch(dt, xin, gi, dpre, go, pb, gptr(c1.p_w), gptr(c1.p_b), 3, 1, s));
+      }
       if (down && c1.tc && pl.s2_split[l]) {
         // stride-2 block, phase-split form: every gradient of the block is computed at the OUTPUT resolution.
         //   conv1 wgrad : nine single-tap MMAs over the saved phase-split input
@@ -619,8 +638,14 @@ int mil_extractor_backward_impl(const void* const* params, const float* bag, con
         void* t_sub = wsp(ws, pl.off_up[1]);
         MIL_TRY(mil_zero_guards(dt, t_sub, gts, s));
         MIL_TRY(mil_zero_pads(dt, dnew, gi, s));  // pads + guards of the full-resolution map (its pixels are all written below)
-        MIL_TRY(mil_launch_wgrad_tc_s2(xs2, gs, dpre, go, partial, gptr(c1.p_w), gptr(c1.p_b), c1.cin, s));
-        MIL_TRY(mil_wgrad_dispatch(dt, xs2, gxs, dz, go, partial, gptr(cd.p_w), nullptr, 1, 1, s));
+        {
+          MIL_PBUF(pb);
+          MIL_TRY(mil_launch_wgrad_tc_s2(xs2, gs, dpre, go, pb, gptr(c1.p_w), gptr(c1.p_b), c1.cin, s));
+        }
+        {
+          MIL_PBUF(pb);
+          MIL_TRY(mil_wgrad_dispatch(dt, xs2, gxs, dz, go, pb, gptr(cd.p_w), nullptr, 1, 1, s));
+        }
         MIL_TRY(mil_conv_dispatch(dt, 1, dz, go, wpack + cd.wpt_off, TCW(cd, true), nullptr, nullptr, nullptr, t_sub, gts,
                                   1, 1, MIL_EPI_PLAIN, s));
         for (int a = 0; a < 2; ++a) {
@@ -659,8 +684,14 @@ int mil_extractor_backward_impl(const void* const* params, const float* bag, con
           MIL_TRY(launch_guards(t, s));
         }
         MIL_TRY(mil_launch_upsample2(dpre, go, up_pre, gu, s));
-        MIL_TRY(mil_wgrad_dispatch(dt, xin, gi, up_pre, gu, partial, gptr(c1.p_w), gptr(c1.p_b), 3, 1, s));
-        MIL_TRY(mil_wgrad_dispatch(dt, wsp(ws, pl.off_xs2[l]), gxs, dz, go, partial, gptr(cd.p_w), nullptr, 1, 1, s));
+        {
+          MIL_PBUF(pb);
+          MIL_TRY(mil_wgrad_dispatch(dt, xin, gi, up_pre, gu, pb, gptr(c1.p_w), gptr(c1.p_b), 3, 1, s));
+        }
+        {
+          MIL_PBUF(pb);
+          MIL_TRY(mil_wgrad_dispatch(dt, wsp(ws, pl.off_xs2[l]), gxs, dz, go, pb, gptr(cd.p_w), nullptr, 1, 1, s));
+        }
         MIL_TRY(mil_conv_dispatch(dt, 1, dz, go, wpack + cd.wpt_off, TCW(cd, true), nullptr, nullptr, nullptr, t_sub, gts,
                                   1, 1, MIL_EPI_PLAIN, s));
         {
@@ -680,8 +711,14 @@ int mil_extractor_backward_impl(const void* const* params, const float* bag, con
       } else if (down) {
         // CUDA-core path (fp32 check mode): strided weight gradients and transposed stride-2 convolutions
         const MilConvDesc& cd = pl.convs[cb + 2];
-        MIL_TRY(mil_wgrad_dispatch(dt, xin, gi, dpre, go, partial, gptr(c1.p_w), gptr(c1.p_b), 3, c1.stride, s));
-        MIL_TRY(mil_wgrad_dispatch(dt, xin, gi, dz, go, partial, gptr(cd.p_w), nullptr, 1, 2, s));
+        {
+          MIL_PBUF(pb);
+          MIL_TRY(mil_wgrad_dispatch(dt, xin, gi, dpre, go, pb, gptr(c1.p_w), gptr(c1.p_b), 3, c1.stride, s));
+        }
+        {
+          MIL_PBUF(pb);
+          MIL_TRY(mil_wgrad_dispatch(dt, xin, gi, dz, go, pb, gptr(cd.p_w), nullptr, 1, 2, s));
+        }
         {
           GuardTable t;
           t.count = 0;
@@ -710,6 +747,7 @@ int mil_extractor_backward_impl(const void* const* params, const float* bag, con
         MIL_TRY(mil_launch_from_pf8(dt, dnew, g_dump.dst, gi.n, gi.c, gi.h, gi.w, s));
       std::swap(dz, dnew);
     }
+    MIL_TRY(mil_reduce_batch_flush(s));
     // every gradient of layer l+1 (and, for l = 3, of fc and the head) is final: let the caller start reducing it
     if (layer_events != nullptr && layer_events[l] != nullptr) MIL_CHECK_CUDA(cudaEventRecord(layer_events[l], s));
   }

@@ -54,7 +54,7 @@ struct MilPlan {
   bool pool_mask;    // the fused stem kernel also writes the sign mask of the pooled map (off_mpool)
   bool masks;        // sign masks of the saved activations exist (bf16 tensor-core path): off_mh / off_my
   bool s2_split[4];  // stride-2 block of layer l runs on the phase-split input (else: full-resolution evaluation)
-  size_t wpack_floats, wtc_bytes, partial_floats, grad_bytes, up_bytes;
+  size_t wpack_floats, wtc_bytes, partial_floats, partial_arena_floats, grad_bytes, up_bytes;
   size_t total_bytes;
 };
 int mil_make_plan(int n, int side, int dtype, MilPlan* plan, bool infer = false);

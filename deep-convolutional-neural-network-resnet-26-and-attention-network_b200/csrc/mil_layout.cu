@@ -125,9 +125,8 @@ int mil_launch_reduce_partials(const float* partial, int nblk, long long stride,
 // partial[b][tap][cin_pad][cout_pad] (+ [cout_pad] bias sums at the end of each record) ->
 //   dw[cout][cin][tap] += ... ,  db[cout] += ...      (PyTorch parameter layout)
 #define RCW_PARTS 8
-__global__ void __launch_bounds__(32 * RCW_PARTS)
-reduce_conv_w_kernel(const float* __restrict__ partial, int nblk, long long stride, float* __restrict__ dw,
-                     float* __restrict__ db, int cout, int cin, int ks) {
+__device__ __forceinline__ void reduce_conv_w_body(const float* __restrict__ partial, int nblk, long long stride,
+                                                   float* __restrict__ dw, float* __restrict__ db, int cout, int cin, int ks) {
   // threadIdx.x walks the RECORD layout (coalesced reads of every partial record), threadIdx.y takes every
   // RCW_PARTS-th record; the parts are then summed in a fixed order (bit-reproducible) and scattered into the
   // parameter layout
@@ -162,10 +161,89 @@ reduce_conv_w_kernel(const float* __restrict__ partial, int nblk, long long stri
     if (co < cout) db[co] += acc;
   }
 }
+__global__ void __launch_bounds__(32 * RCW_PARTS)
+reduce_conv_w_kernel(const float* __restrict__ partial, int nblk, long long stride, float* __restrict__ dw,
+                     float* __restrict__ db, int cout, int cin, int ks) {
+  reduce_conv_w_body(partial, nblk, stride, dw, db, cout, cin, ks);
+}
+// ---- deferred reductions -------------------------------------------------------------------------------
+// A backward pass makes 27 of these reductions, each a ~7 us latency-bound launch whatever the bag size (7 % of the step
+// at the reference's live bag shape of ~500 tiles through the CNN).  While a batch is open on the calling thread,
+// mil_launch_reduce_conv_w only RECORDS the job -- the weight-gradient kernels of a layer write their partial records one
+// after the other into an arena instead of sharing one buffer -- and mil_reduce_batch_flush sums all recorded jobs in ONE
+// launch (blockIdx.y = job).  Per output element the summation order is the same as in the immediate form.
+#define MIL_RB_MAX 8
+struct ReduceJob {
+  const float* partial;
+  float *dw, *db;
+  long long stride;
+  int nblk, cout, cin, ks;
+};
+struct ReduceTable {
+  ReduceJob job[MIL_RB_MAX];
+};
+__global__ void __launch_bounds__(32 * RCW_PARTS)
+reduce_conv_w_table_kernel(const __grid_constant__ ReduceTable t) {
+  const ReduceJob& j = t.job[blockIdx.y];
+  const int cop = (j.cout + 7) / 8 * 8, cip = (j.cin + 7) / 8 * 8;
+  const int total = j.ks * j.ks * cip * cop + (j.db != nullptr ? cop : 0);
+  if (blockIdx.x * 32 >= total) return;  // block-uniform: the grid is sized for the largest job
+  reduce_conv_w_body(j.partial, j.nblk, j.stride, j.dw, j.db, j.cout, j.cin, j.ks);
+}
+
+namespace {
+struct ReduceBatch {
+  bool open = false;
+  float* arena = nullptr;
+  size_t arena_floats = 0, max_need = 0, used = 0;
+  int count = 0, max_total = 0;
+  ReduceTable table;
+};
+thread_local ReduceBatch g_rb;
+}  // namespace
+
+void mil_reduce_batch_begin(float* arena, size_t arena_floats, size_t max_need) {
+  g_rb.open = arena != nullptr && arena_floats >= 2 * max_need;  // too small an arena: stay in the immediate form
+  g_rb.arena = arena;
+  g_rb.arena_floats = arena_floats;
+  g_rb.max_need = max_need;
+  g_rb.used = 0;
+  g_rb.count = 0;
+  g_rb.max_total = 0;
+}
+int mil_reduce_batch_flush(cudaStream_t s) {
+  if (g_rb.count > 0) {
+    reduce_conv_w_table_kernel<<<dim3((unsigned)mil_cdiv(g_rb.max_total, 32), g_rb.count), dim3(32, RCW_PARTS), 0, s>>>(g_rb.table);
+    MIL_LAUNCH_OK();
+  }
+  g_rb.used = 0;
+  g_rb.count = 0;
+  g_rb.max_total = 0;
+  return 0;
+}
+int mil_reduce_batch_end(cudaStream_t s) {
+  const int rc = mil_reduce_batch_flush(s);
+  g_rb.open = false;
+  return rc;
+}
+float* mil_reduce_batch_cursor(float* fallback, cudaStream_t s) {
+  if (!g_rb.open) return fallback;
+  if (g_rb.arena_floats - g_rb.used < g_rb.max_need && mil_reduce_batch_flush(s) != 0) return nullptr;
+  return g_rb.arena + g_rb.used;
+}
+
 int mil_launch_reduce_conv_w(const float* partial, int nblk, long long stride, float* dw, float* db, int cout,
                              int cin, int ks, cudaStream_t s) {
   const int cop = (cout + 7) / 8 * 8;
   const int total = ks * ks * ((cin + 7) / 8 * 8) * cop + cop;
+  if (g_rb.open && partial == g_rb.arena + g_rb.used) {
+    ReduceJob& j = g_rb.table.job[g_rb.count++];
+    j.partial = partial; j.dw = dw; j.db = db; j.stride = stride; j.nblk = nblk; j.cout = cout; j.cin = cin; j.ks = ks;
+    g_rb.max_total = std::max(g_rb.max_total, total);
+    g_rb.used += (size_t)mil_rup((long long)nblk * stride, 64);
+    if (g_rb.count == MIL_RB_MAX) return mil_reduce_batch_flush(s);
+    return 0;
+  }
   reduce_conv_w_kernel<<<(int)mil_cdiv(total, 32), dim3(32, RCW_PARTS), 0, s>>>(partial, nblk, stride, dw, db, cout, cin,
                                                                                ks);
   MIL_LAUNCH_OK();
