@@ -58,16 +58,67 @@ void mil_count_launch();
     if (_rc != 0) return _rc; \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
+// A step is ~140 dependent launches; at the reference's live bag shape (~500 tiles through the CNN) every one of them
+// costs ~6 us of launch latency + prologue (barrier init, TMEM allocation, shared-memory set-up) + drain against 5-40 us of
+// work.  Kernels launched through MIL_LAUNCH_PDL may START while their predecessor in the stream is still running: the
+// prologue overlaps the predecessor's tail, and mil_pdl_wait() blocks until the predecessor has completed and its memory
+// is visible.  Rules that keep this equivalent to stream order:
+//   * a kernel touches NO global memory before mil_pdl_wait() (shared memory, TMEM, barriers, kernel parameters only);
+//   * it calls mil_pdl_trigger() only AFTER its own wait, so a dependent can overlap its immediate predecessor only -- by
+//     then everything older has completed -- and LATE: when its producer warp has issued the CTA's last loads.  (Triggering
+//     at the start parks the dependent's CTAs next to the running kernel for its whole duration wherever both fit on an
+//     SM: measured 2.5 % slower on 4096-tile bags);
+//   * only the persistent tcgen05 kernels are launched this way: small many-CTA kernels (layout passes, reductions) waiting
+//     next to a running convolution slowed it down more than their launch latency is worth;
+//   * kernels launched the ordinary way (torch's, NCCL's, ours) remain fully ordered; for them both calls are no-ops.
+__device__ __forceinline__ void mil_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void mil_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- runtime switches (mil_set_option / mil_get_option of the C ABI; the environment variables of the same
 // meaning -- MIL_B200_DISABLE_TC, MIL_B200_STEM_UNFUSED, ... -- only give the initial values) -------------------
 enum MilOpt {
   MIL_OPT_DISABLE_TC = 0,    // 1: CUDA-core kernels only (cross-check of the tcgen05 path, same rounding points)
   MIL_OPT_STEM_UNFUSED = 1,  // 1: stem as separate conv / pool / unpool / wgrad kernels (cross-check of the fused ones)
+  MIL_OPT_NO_PDL = 2,        // 1: plain stream-ordered launches (cross-check of the programmatic dependent launches below)
   MIL_OPT_COUNT
 };
 int mil_opt(int id);
 int mil_opt_set(const char* name, int value);  // 0 = ok
 int mil_opt_get(const char* name, int* value);
+
+// The extractor drivers switch PDL off for large bags (measured: -7 % step time at ~500 tiles through the CNN, neutral
+// around 2500, +1.5 % at 4096 tiles x 224^2, tools/pdl_ab.py): thread-local, on by default (layer-level entry points).
+bool mil_pdl_allowed();
+void mil_pdl_allow(bool on);
+struct MilPdlScope {
+  bool prev;
+  // pixels = tiles x side^2 of the bag this call works on
+  explicit MilPdlScope(long long pixels) : prev(mil_pdl_allowed()) { mil_pdl_allow(pixels <= 1536LL * 224 * 224); }
+  ~MilPdlScope() { mil_pdl_allow(prev); }
+};
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t mil_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                         Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = (mil_opt(MIL_OPT_NO_PDL) || !mil_pdl_allowed()) ? 0 : 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// launch + count + error check, in place of kernel<<<grid, block, smem, s>>>(args...); MIL_LAUNCH_OK();
+#define MIL_LAUNCH_PDL(kernel, grid, block, smem, s, ...)                                   \
+  do {                                                                                      \
+    MIL_CHECK_CUDA(mil_launch_pdl(kernel, dim3(grid), dim3(block), smem, s, __VA_ARGS__)); \
+    mil_count_launch();                                                                     \
+  } while (0)
 
 __host__ __device__ static inline long long mil_cdiv(long long a, long long b) { return (a + b - 1) / b; }
 __host__ __device__ static inline long long mil_rup(long long a, long long b) { return mil_cdiv(a, b) * b; }

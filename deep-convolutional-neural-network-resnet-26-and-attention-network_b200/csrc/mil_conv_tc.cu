@@ -168,14 +168,16 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
     mbar_init(&hd->b_full, 1);
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < 96; i += blockDim.x)
-    hd->bias[i] = (bias != nullptr && i < go.c) ? bias[i] : 0.f;
   for (int s = 0; s < n_stages; ++s) {  // zero plane of every stage
     uint4* zp = reinterpret_cast<uint4*>(asm0 + (size_t)s * stage_bytes + (size_t)sh.cbin * plane);
     for (int i = threadIdx.x; i < span; i += blockDim.x) zp[i] = make_uint4(0, 0, 0, 0);
   }
   fence_proxy_async();  // generic-proxy writes (zero planes) -> visible to the tensor-core (async) proxy
   if (warp == 1) tmem_alloc(&hd->tmem_base, tmem_cols);
+  // everything above overlaps the previous kernel's tail; global memory only from here on (mil_common.cuh, PDL)
+  mil_pdl_wait();
+  for (int i = threadIdx.x; i < 96; i += blockDim.x)
+    hd->bias[i] = (bias != nullptr && i < go.c) ? bias[i] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -228,6 +230,7 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloat
       src += tstride; pres += tstride; pact += tstride;
       if (++stage == n_stages) { stage = 0; phase ^= 1; }
     }
+    mil_pdl_trigger();  // all of this CTA's loads are issued: the next kernel may start its prologue (PDL, mil_common.cuh)
   } else if (warp <= 2) {
     // ===================== MMA issuers: two warps take alternate tiles (uniform control flow, one elected lane) ====
     // The per-tile fixed cost of an issuing warp (two mbarrier waits, fence, elect, commit) is ~1/3 of its loop on
@@ -703,11 +706,12 @@ int mil_launch_conv_tc(int transposed, const void* x, const MilPF8& gx, const vo
 #define MIL_TC_LAUNCH1(MAXCB, NG, MODE)                                                                           \
   do {                                                                                                            \
     MIL_SET_SMEM((conv_tc_kernel<MAXCB, NG, MODE>), smem);                                                        \
-    conv_tc_kernel<MAXCB, NG, MODE><<<grid, 96 + NG * 128 * TcSplit<MAXCB, MODE>::value, smem, s>>>(                                            \
+    MIL_CHECK_CUDA(mil_launch_pdl((conv_tc_kernel<MAXCB, NG, MODE>), dim3(grid),                                  \
+                                  dim3(96 + NG * 128 * TcSplit<MAXCB, MODE>::value), smem, s,                     \
         (const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)wtc, bias, (const __nv_bfloat16*)res,                  \
         (const __nv_bfloat16*)act, (__nv_bfloat16*)out, go, sh, iss, epi, sub, halo, n_stages,                    \
         gres_half ? *gres_half : go, gres_half ? 1 : 0, up_row + 1, up_row >= 0 ? go.cb : 0,                      \
-        (const uint32_t*)mask_in, (uint32_t*)mask_out);                                                           \
+        (const uint32_t*)mask_in, (uint32_t*)mask_out));                                                          \
   } while (0)
   // the network's layers (3 / 5 / 8 / 10 output chunks, five epilogue kinds) run specialised instantiations
 #define MIL_TC_LAUNCH(MAXCB, NG)                                                                                  \

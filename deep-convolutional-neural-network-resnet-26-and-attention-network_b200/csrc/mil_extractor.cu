@@ -206,19 +206,24 @@ int mil_make_plan(int n, int side, int dtype, MilPlan* plan, bool infer) {
   pl.off_wpack = take(pl.wpack_floats * sizeof(float));
   pl.off_wtc = take(pl.wtc_bytes + 256);
   size_t pf = std::max(mil_stem_bwd_partial_floats(), mil_tail_bwd_partial_floats());
+  size_t layer_sum[4] = {0, 0, 0, 0};
   for (const auto& c : pl.convs) {
     const MilPF8& go = pl.g[c.layer];
     const MilPF8 gi = (c.stride == 2) ? pl.g[c.layer - 1] : mil_pf8(n, c.cin, go.h, go.w);
-    pf = std::max(pf, mil_wgrad_direct_partial_floats(gi, go, c.ks));
+    size_t need = mil_wgrad_direct_partial_floats(gi, go, c.ks);
     if (mil_tc_enabled() && mil_wgrad_tc_supported(dtype, c.ks, 1, c.cin, c.cout))
-      pf = std::max(pf, mil_wgrad_tc_partial_floats(gi, mil_pf8(n, c.cout, gi.h, gi.w), c.ks));
+      need = std::max(need, mil_wgrad_tc_partial_floats(gi, mil_pf8(n, c.cout, gi.h, gi.w), c.ks));
+    pf = std::max(pf, need);
+    layer_sum[c.layer] += (size_t)mil_rup((long long)need, 64);
   }
   if (pl.stem_tc) pf = std::max(pf, mil_stem_tc_partial_floats(n, side));
   if (infer) pf = 64;
   pl.partial_floats = pf;
-  // room for the partial records of a whole layer's weight gradients (5 stride-1 convolutions + the stride-2 pair): their
-  // reductions run as ONE launch per layer (mil_reduce_batch_*)
-  pl.partial_arena_floats = infer ? pf : 8 * mil_rup((long long)pf, 64);
+  // room for the partial records of a whole layer's weight gradients, written one after the other: their reductions run
+  // as ONE launch per layer (mil_reduce_batch_*; a layer that does not fit is flushed in two launches)
+  size_t arena = (size_t)mil_rup((long long)pf, 64);
+  for (int l = 0; l < 4; ++l) arena = std::max(arena, layer_sum[l] + (size_t)mil_rup((long long)pf, 64));
+  pl.partial_arena_floats = infer ? pf : arena;
   pl.off_partial = take(pl.partial_arena_floats * sizeof(float));
   pl.total_bytes = off;
   return 0;
@@ -330,8 +335,8 @@ int mil_wgrad_dispatch(int dtype, const void* x, const MilPF8& gi, const void* d
 
 // runtime switches: initial value from the environment, changed through mil_set_option (tests flip them to run the
 // same bag through the tcgen05 and the CUDA-core kernels, the fused and the un-fused stem)
-static const char* const kOptNames[MIL_OPT_COUNT] = {"disable_tc", "stem_unfused"};
-static const char* const kOptEnv[MIL_OPT_COUNT] = {"MIL_B200_DISABLE_TC", "MIL_B200_STEM_UNFUSED"};
+static const char* const kOptNames[MIL_OPT_COUNT] = {"disable_tc", "stem_unfused", "no_pdl"};
+static const char* const kOptEnv[MIL_OPT_COUNT] = {"MIL_B200_DISABLE_TC", "MIL_B200_STEM_UNFUSED", "MIL_B200_NO_PDL"};
 static std::atomic<int>* opt_slots() {
   static std::atomic<int> v[MIL_OPT_COUNT];
   static const bool init = [] {
@@ -365,6 +370,9 @@ int mil_opt_get(const char* name, int* value) {
 }
 
 bool mil_tc_enabled() { return mil_opt(MIL_OPT_DISABLE_TC) == 0; }
+static thread_local bool g_pdl_allowed = true;
+bool mil_pdl_allowed() { return g_pdl_allowed; }
+void mil_pdl_allow(bool on) { g_pdl_allowed = on; }
 
 int mil_conv_dispatch(int dtype, int transposed, const void* x, const MilPF8& gi, const float* wp, const void* wtc,
                       const float* bias, const void* res, const void* act, void* out, const MilPF8& go, int ks,
@@ -421,6 +429,7 @@ static int pack_weights(const void* const* params, const MilPlan& pl, void* ws, 
 int mil_extractor_forward_impl(const void* const* params, const void* bag, int bag_u8, const int* idx,
                                const MilPlan& pl, void* ws, float* H, cudaStream_t s) {
   MIL_REQUIRE(!bag_u8 || pl.stem_tc, "extractor: 8-bit tiles need the bf16 tensor-core stem (dtype bf16)");
+  const MilPdlScope pdl_scope((long long)pl.n * pl.side * pl.side);
   const int dt = pl.dtype;
   // guards of every saved activation buffer (cheap, makes the workspace self-initialising)
   {
@@ -550,6 +559,7 @@ void mil_debug_request_dump(int layer, int block, int which, float* dst) {
 int mil_extractor_backward_impl(const void* const* params, const float* bag, const int* idx, const MilPlan& pl,
                                 void* ws, const float* dH, float* grads, cudaStream_t s,
                                 const cudaEvent_t* layer_events) {
+  const MilPdlScope pdl_scope((long long)pl.n * pl.side * pl.side);
   const int dt = pl.dtype;
   const auto& pt = mil_param_table();
   MIL_TRY(pack_weights(params, pl, ws, true, s));

@@ -91,13 +91,14 @@ stem_conv_pool_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv
     mbar_init(&hd->b_full, 1);
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < 80; i += blockDim.x) hd->bias[i] = bias4[i];
   for (int s = 0; s < n_stages; ++s) {
     uint4* zp = reinterpret_cast<uint4*>(asm0 + (size_t)s * stage_bytes + (size_t)sh.cbin * plane);
     for (int i = threadIdx.x; i < span; i += blockDim.x) zp[i] = make_uint4(0, 0, 0, 0);
   }
   fence_proxy_async();
   if (warp == 1) tmem_alloc(&hd->tmem_base, 256);
+  mil_pdl_wait();   // everything above overlaps the previous kernel's tail; global memory only from here on (PDL, mil_common.cuh)
+  for (int i = threadIdx.x; i < 80; i += blockDim.x) hd->bias[i] = bias4[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -129,6 +130,7 @@ stem_conv_pool_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv
       src += SP_M * 16;
       if (++stage == n_stages) { stage = 0; phase ^= 1; }
     }
+    mil_pdl_trigger();  // all of this CTA's loads are issued: the next kernel may start its prologue (PDL, mil_common.cuh)
   } else if (warp <= 2) {
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(sh.npad >> 3) << 17) |
                            ((uint32_t)(SP_M >> 4) << 24);
@@ -309,9 +311,8 @@ int mil_launch_stem_conv_pool(const void* xs, const MilPF8& gi, const void* wtc,
   const int grid = (int)std::min<long long>(n_tiles, n_sm);
   const long long chunk = mil_cdiv(n_tiles, grid);
   MIL_SET_SMEM(stem_conv_pool_kernel, smem);
-  stem_conv_pool_kernel<<<grid, 96 + SP_NG * 128, smem, s>>>((const __nv_bfloat16*)xs, gi, (const __nv_bfloat16*)wtc, bias4,
+  MIL_LAUNCH_PDL(stem_conv_pool_kernel, grid, 96 + SP_NG * 128, smem, s, (const __nv_bfloat16*)xs, gi, (const __nv_bfloat16*)wtc, bias4,
                                                           (__nv_bfloat16*)pooled, gp, (uint2*)argmax, (uint32_t*)mask_out, sh, iss,
                                                           halo, n_stages, chunk);
-  MIL_LAUNCH_OK();
   return 0;
 }

@@ -73,6 +73,7 @@ stem_wgrad_kernel(const __nv_bfloat16* __restrict__ xs, MilPF8 gx, const __nv_bf
   }
   fence_proxy_async();
   if (warp == 1) tmem_alloc(&hd->tmem_base, 512);
+  mil_pdl_wait();   // everything above overlaps the previous kernel's tail; global memory only from here on (PDL, mil_common.cuh)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -105,6 +106,7 @@ stem_wgrad_kernel(const __nv_bfloat16* __restrict__ xs, MilPF8 gx, const __nv_bf
       src += tstride;
       if (++stage == SW_STAGES) { stage = 0; phase ^= 1; }
     }
+    mil_pdl_trigger();  // all of this CTA's loads are issued: the next kernel may start its prologue (PDL, mil_common.cuh)
   } else if (warp == 1) {
     // ---- MMA issuer: D = f32, A = B = bf16, both MN-major, M = 128, N = 160.  Half h multiplies A slots 15 h ..
     // 15 h + 15 (its 16th slot is the other half's first one, or the first B slot: rows nobody reads) ----
@@ -259,9 +261,8 @@ int mil_launch_stem_wgrad(const void* xs, const MilPF8& gx, const void* g, const
   const size_t smem = 128 + (size_t)SW_STAGES * SW_STAGE + SW_PLANE;  // + one slot read past the last stage's A half
   const long long rec = (long long)9 * SW_CB * 8 * SW_CA * 8 + SW_CA * 8;
   MIL_SET_SMEM(stem_wgrad_kernel, smem);
-  stem_wgrad_kernel<<<ctas, SW_THREADS, smem, s>>>((const __nv_bfloat16*)xs, gx, (const __nv_bfloat16*)g, gp,
+  MIL_LAUNCH_PDL(stem_wgrad_kernel, ctas, SW_THREADS, smem, s, (const __nv_bfloat16*)xs, gx, (const __nv_bfloat16*)g, gp,
                                                    (const uint2*)am, partial, rec);
-  MIL_LAUNCH_OK();
   *ctas_out = ctas;
   *rec_out = rec;
   return 0;

@@ -101,6 +101,7 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
     }
   fence_proxy_async();
   if (warp == 1) tmem_alloc(&hd->tmem_base, 512);
+  mil_pdl_wait();   // everything above overlaps the previous kernel's tail; global memory only from here on (PDL, mil_common.cuh)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -140,6 +141,7 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
       srca += tstride; srcb += tstride;
       if (++stage == n_stages) { stage = 0; phase ^= 1; }
     }
+    mil_pdl_trigger();  // all of this CTA's loads are issued: the next kernel may start its prologue (PDL, mil_common.cuh)
   } else if (warp == 1) {
     // MMA issuer: uniform control flow (descriptors stay in uniform registers), one elected lane issues.
     // M = 64 when the output channels fit (the accumulator rows then sit in 16 lanes of every lane quarter).
@@ -320,6 +322,7 @@ wgrad_sq_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
   }
   fence_proxy_async();
   if (warp == 1) tmem_alloc(&hd->tmem_base, tmem_cols);
+  mil_pdl_wait();   // everything above overlaps the previous kernel's tail; global memory only from here on (PDL, mil_common.cuh)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -352,6 +355,7 @@ wgrad_sq_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfloa
       srca += tstride; srcb += tstride;
       if (++stage == n_stages) { stage = 0; phase ^= 1; }
     }
+    mil_pdl_trigger();  // all of this CTA's loads are issued: the next kernel may start its prologue (PDL, mil_common.cuh)
   } else if (warp == 1) {
     // D = f32, A = B = bf16, both MN-major, M = 128 (the M-groups past 3 * cb read whatever follows in shared
     // memory -- the next stage or the tail pad: values landing in accumulator rows nobody reads)
@@ -548,9 +552,9 @@ int mil_launch_wgrad_tc_partials(const void* x, const MilPF8& gx, const void* dz
 #define MIL_WGS_LAUNCH(CBA, CBB)                                                                                       \
   do {                                                                                                               \
     MIL_SET_SMEM((wgrad_sq_kernel<CBA, CBB>), (int)c.smem);                                                          \
-    wgrad_sq_kernel<CBA, CBB><<<c.ctas, WGS_THREADS(c.n_stages), c.smem, s>>>((const __nv_bfloat16*)x, gx,                        \
-                                                                 (const __nv_bfloat16*)dz, gz, partial, rec_sq, c.npad, \
-                                                                 c.n_stages);                                        \
+    MIL_CHECK_CUDA(mil_launch_pdl((wgrad_sq_kernel<CBA, CBB>), dim3(c.ctas), dim3(WGS_THREADS(c.n_stages)), c.smem, s,   \
+                                  (const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)dz, gz, partial, rec_sq, c.npad,  \
+                                  c.n_stages));                                                                      \
   } while (0)
     if (gz.cb == 3 && gx.cb == 3) MIL_WGS_LAUNCH(3, 3);
     else if (gz.cb == 5 && gx.cb == 5) MIL_WGS_LAUNCH(5, 5);
@@ -566,10 +570,9 @@ int mil_launch_wgrad_tc_partials(const void* x, const MilPF8& gx, const void* dz
   MIL_REQUIRE(c.smem <= 227 * 1024, "wgrad_tc: tile width %d needs %zu bytes of shared memory", gx.w, c.smem);
   MIL_SET_SMEM((wgrad_tc_kernel), (int)c.smem);
   const long long rec = (long long)sh.ntaps * gx.cb * 8 * gz.cb * 8 + gz.cb * 8;
-  wgrad_tc_kernel<<<dim3(c.ctas, c.groups), WG_THREADS, c.smem, s>>>(
+  MIL_LAUNCH_PDL(wgrad_tc_kernel, dim3(c.ctas, c.groups), WG_THREADS, c.smem, s, 
       (const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)dz, gz, partial, rec, sh, halo, c.tpg, c.npad, c.mma_m, c.dxcat,
       c.fold, c.n_stages, WgCombo{}, c.lane_split);
-  MIL_LAUNCH_OK();
   *ctas_out = c.ctas;
   *rec_out = rec;
   return 0;
@@ -624,9 +627,8 @@ int mil_launch_wgrad_tc_s2(const void* xs2, const MilPF8& gs, const void* dz, co
   MIL_REQUIRE(smem <= 227 * 1024, "wgrad_tc_s2: tile width %d needs %zu bytes of shared memory", gs.w, smem);
   MIL_SET_SMEM((wgrad_tc_kernel), (int)smem);
   const long long rec = (long long)9 * cb * 8 * gz.cb * 8 + gz.cb * 8;
-  wgrad_tc_kernel<<<dim3(ctas, groups), WG_THREADS, smem, s>>>((const __nv_bfloat16*)xs2, gs, (const __nv_bfloat16*)dz, gz,
+  MIL_LAUNCH_PDL(wgrad_tc_kernel, dim3(ctas, groups), WG_THREADS, smem, s, (const __nv_bfloat16*)xs2, gs, (const __nv_bfloat16*)dz, gz,
                                                               partial, rec, sh, halo, tpg, npad, mma_m, 0, 0, n_stages, cmb, 0);
-  MIL_LAUNCH_OK();
   return mil_launch_reduce_conv_w(partial, ctas, rec, dw, db, gz.c, cin, 3, s);
 }
 

@@ -79,8 +79,9 @@ wide_conv_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bflo
     for (int a = 0; a < kp.nsets; ++a) { mbar_init(&hd->acc_full[a], 1); mbar_init(&hd->acc_empty[a], 8); }
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < 512; i += blockDim.x) hd->bias[i] = (kp.has_bias && i < go.c) ? bias[i] : 0.f;  // (<= 512 channels with a bias)
   if (warp == 1) tmem_alloc(&hd->tmem_base, 512);
+  mil_pdl_wait();   // everything above overlaps the previous kernel's tail; global memory only from here on (PDL, mil_common.cuh)
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) hd->bias[i] = (kp.has_bias && i < go.c) ? bias[i] : 0.f;  // (<= 512 channels with a bias)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -123,6 +124,7 @@ wide_conv_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bflo
         }
       }
     }
+    mil_pdl_trigger();  // all of this CTA's loads are issued: the next kernel may start its prologue (PDL, mil_common.cuh)
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     // instruction descriptor: D = f32, A = B = bf16, both K-major, N = nt, M = 128
@@ -503,9 +505,8 @@ int mil_launch_wide_conv(const void* x, const MilPF8& gx, const void* wpk, const
   const int grid = (int)std::min<long long>(n_units, n_sm);
   const size_t smem = hdr + (size_t)kp.n_stages * kp.stage_bytes;
   MIL_SET_SMEM(wide_conv_kernel, smem);
-  wide_conv_kernel<<<grid, WIDE_THREADS, smem, s>>>((const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)wpk, bias,
+  MIL_LAUNCH_PDL(wide_conv_kernel, grid, WIDE_THREADS, smem, s, (const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)wpk, bias,
                                                     (const __nv_bfloat16*)res, (const __nv_bfloat16*)act,
                                                     (__nv_bfloat16*)out, go, kp);
-  MIL_LAUNCH_OK();
   return 0;
 }

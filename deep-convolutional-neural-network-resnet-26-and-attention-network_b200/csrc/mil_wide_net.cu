@@ -355,6 +355,7 @@ static int pack_all(const void* const* params, const MilWidePlan& pl, void* ws, 
 
 int mil_wide_forward_impl(const void* const* params, const void* bag, int bag_u8, const int* idx, const MilWidePlan& pl,
                           void* ws, float* H, cudaStream_t s) {
+  const MilPdlScope pdl_scope((long long)pl.n * pl.side * pl.side);
   const MilWideDesc& d = pl.d;
   const float slope = d.slope;
   char* wpk = wsp(ws, pl.off_wpack);
@@ -432,6 +433,7 @@ static int wide_wgrad(const void* x, const MilPF8& gx, const void* dz, const Mil
 
 int mil_wide_backward_impl(const void* const* params, const MilWidePlan& pl, void* ws, const float* dH, float* grads,
                            cudaStream_t s) {
+  const MilPdlScope pdl_scope((long long)pl.n * pl.side * pl.side);
   const MilWideDesc& d = pl.d;
   const float slope = d.slope;
   char* wpk = wsp(ws, pl.off_wpack);

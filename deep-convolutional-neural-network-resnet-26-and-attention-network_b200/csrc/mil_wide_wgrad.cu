@@ -77,6 +77,7 @@ wide_wgrad_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfl
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&hd->tmem_base, 512);
+  mil_pdl_wait();   // everything above overlaps the previous kernel's tail; global memory only from here on (PDL, mil_common.cuh)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -109,6 +110,7 @@ wide_wgrad_kernel(const __nv_bfloat16* __restrict__ x, MilPF8 gx, const __nv_bfl
       srca += tstride; srcb += tstride;
       if (++stage == pr.n_stages) { stage = 0; phase ^= 1; }
     }
+    mil_pdl_trigger();  // all of this CTA's loads are issued: the next kernel may start its prologue (PDL, mil_common.cuh)
   } else if (warp == 1) {
     // D = f32, A = B = bf16, both MN-major (bits 15, 16), M = 128, N = cit
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 4) << 24) |
@@ -376,9 +378,8 @@ int mil_launch_wide_wgrad(const void* x, const MilPF8& gx, const void* dz, const
   MIL_TRY(ww_config(gx, gz, ks, s2, &c));
   MIL_REQUIRE(gx.wp + 1 <= gx.G, "wide_wgrad: the window reaches %d pixels back but the map's guard is %lld", gx.wp + 1, gx.G);
   MIL_SET_SMEM(wide_wgrad_kernel, c.smem);
-  wide_wgrad_kernel<<<dim3(c.nsplit, c.kinds), WW_THREADS, c.smem, s>>>((const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)dz,
+  MIL_LAUNCH_PDL(wide_wgrad_kernel, dim3(c.nsplit, c.kinds), WW_THREADS, c.smem, s, (const __nv_bfloat16*)x, gx, (const __nv_bfloat16*)dz,
                                                                         gz, partial, c.p);
-  MIL_LAUNCH_OK();
   WwReduceParams rp;
   rp.p = c.p;
   rp.nsplit = c.nsplit;

@@ -50,6 +50,9 @@ class GraphedStep:
                 raise ValueError(f"a {n_bag}-tile bag leaves {k} tiles after the 20 % subsample: BatchNorm1d needs 2")
             self.idx = torch.arange(k, dtype=torch.int32, device=dev)
             self._idx_host = torch.empty(k, dtype=torch.int32).pin_memory()
+        if optimizer is None and getattr(net, "_gflat", None) is not None:
+            raise ValueError("this module's gradients accumulate into a FusedAdam flat buffer: pass that optimizer to "
+                             "GraphedStep (its zero_grad / step become part of the graph)")
         self._fused = optimizer is not None and hasattr(optimizer, "hyper_values")
         if optimizer is not None and not self._fused:
             raise TypeError("GraphedStep captures FusedAdam (or no optimizer): the warm-up steps of another optimizer "

@@ -52,7 +52,8 @@ def test_workspace_sizes_are_sane(mil):
     lib = mil._lib.load()
     b64 = lib.mil_extractor_workspace_bytes(64, 224, 1)
     b128 = lib.mil_extractor_workspace_bytes(128, 224, 1)
-    assert 1.5e6 * 64 < b64 < 6e6 * 64 and 1.8 * b64 < b128 < 2.1 * b64 + 5e8   # ~4.2 MB per tile in bf16
+    # ~4 MB per tile in bf16 + a fixed part (packed weights, the split-K partial records of a layer's weight gradients)
+    assert 1.5e6 * 64 < b64 < 6e6 * 64 and 2.5e6 * 64 < b128 - b64 < 6e6 * 64
     assert lib.mil_extractor_workspace_bytes(64, 224, 0) > 1.2 * b64 - 5e8      # fp32: no tensor-core staging buffers
     assert lib.mil_extractor_workspace_bytes(0, 224, 1) == 0       # rejected, message set
     assert b"at least one tile" in lib.mil_last_error()

@@ -70,7 +70,7 @@ def dist(ga, gb):
 
 def test_options_round_trip():
     lib = G.pkg()._lib
-    for name in ("disable_tc", "stem_unfused"):
+    for name in ("disable_tc", "stem_unfused", "no_pdl"):
         old = lib.get_option(name)
         lib.set_option(name, 1)
         assert lib.get_option(name) == 1
@@ -141,6 +141,27 @@ def test_fused_stem_vs_unfused_stem(option, n, side):
             assert l2rel(g_f[k], g_u[k].cpu()) < 2e-6, (k, l2rel(g_f[k], g_u[k].cpu()))
         else:
             assert torch.equal(g_f[k], g_u[k]), k
+
+
+@pytest.mark.parametrize("n,side", [(40, 64), (7, 96), (96, 224)])
+def test_programmatic_dependent_launches_equal_plain_launches(option, n, side):
+    """The persistent tcgen05 kernels are launched with programmatic stream serialisation (their prologue overlaps the
+    previous kernel's tail, griddepcontrol.wait before the first global access); `no_pdl` launches them the ordinary way.
+    Same kernels, same order: every output and every gradient must be bit-identical -- a kernel that touched global memory
+    before its wait, or a missing wait, shows up here as a difference (run three times: such races are timing-dependent)."""
+    net = build_net("bf16")
+    net.load_state_dict(perturbed_weights(3))
+    bag = torch.from_numpy(synth.make_bag(n, side, seed=4)).cuda()
+    Y = torch.tensor([1]).cuda()
+    option("no_pdl", 1)
+    out_p, g_p = run(net, bag, Y)
+    option("no_pdl", 0)
+    for _ in range(3):
+        out_d, g_d = run(net, bag, Y)
+        for k in ("Fterm", "Aterm", "Bterm", "Mterm", "loss", "y_pred"):
+            assert torch.equal(out_p[k], out_d[k]), k
+        for k in g_p:
+            assert torch.equal(g_p[k], g_d[k]), k
 
 
 BIG = [c for c in CASES if not c[0]["training"] and c[0]["n"] >= 32]

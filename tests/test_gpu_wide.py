@@ -417,3 +417,35 @@ def test_wide_full_size_bag_properties():
     net(bag, Y)["loss"].backward()
     for k, p in net.named_parameters():
         assert torch.equal(p.grad, grads[k]), k
+
+
+def test_wide_programmatic_dependent_launches_equal_plain_launches():
+    """`no_pdl` (ordinary launches) against the default programmatic dependent launches of wide_conv_kernel /
+    wide_wgrad_kernel: bit-identical outputs and gradients (see tests/test_gpu_crosscheck.py)."""
+    lib = G.pkg()._lib
+    from oracle import synth
+    layers = (1, 1, 1, 1)
+    net = build_wide(dict(cw=None, layers=list(layers)), wide_oracle.init_params(5, layers)).eval()
+    bag = torch.from_numpy(synth.make_bag(24, 96, seed=6)).cuda()
+    Y = torch.tensor([2]).cuda()
+
+    def run():
+        net.zero_grad(set_to_none=True)
+        out = net(bag, Y)
+        out["loss"].backward()
+        torch.cuda.synchronize()
+        return out, {k: p.grad.clone() for k, p in net.named_parameters()}
+
+    old = lib.get_option("no_pdl")
+    try:
+        lib.set_option("no_pdl", 1)
+        out_p, g_p = run()
+        lib.set_option("no_pdl", 0)
+        for _ in range(3):
+            out_d, g_d = run()
+            for k in ("Fterm", "Aterm", "Mterm", "loss"):
+                assert torch.equal(out_p[k], out_d[k]), k
+            for k in g_p:
+                assert torch.equal(g_p[k], g_d[k]), k
+    finally:
+        lib.set_option("no_pdl", old)
