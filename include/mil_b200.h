@@ -59,6 +59,7 @@ long long mil_param_total(void);                  /* 640967 */
 /* Runtime switches (cross-checks; the environment variables MIL_B200_<NAME> give the initial values):
  *   "disable_tc"   1 = CUDA-core (FFMA) kernels only, with the tensor-core path's bf16 rounding points
  *   "stem_unfused" 1 = stem as separate conv / pool / unpool / weight-gradient kernels
+ *   "no_pdl"       1 = ordinary stream-ordered launches instead of programmatic dependent launches of the tcgen05 kernels
  * A forward pass and its backward pass must run under the same settings (they size the workspace). */
 int mil_set_option(const char* name, int value);
 int mil_get_option(const char* name, int* value);
