@@ -62,6 +62,9 @@ struct TcPackEntry {
   unsigned char s2cb;       // != 0: phase-split stride-2 forward, chunk planes = phase * s2cb + chunk
   unsigned char pair_cbh;   // != 0: stride-2 data gradient of row parity pair_a, output rows n = (b, ci)
   unsigned char pair_a;
+  unsigned char fold_cbm;   // != 0: folded form, K-groups of chunks >= fold_cbm read the projection weight w2 [cout][cin2]
+  short cin2;
+  const float* w2;
   signed char t_dy[MIL_TC_MAX_TAPS], t_dx[MIL_TC_MAX_TAPS];
   unsigned char g_tap[2 * MIL_TC_MAX_MMA], g_chunk[2 * MIL_TC_MAX_MMA];
 };
@@ -92,7 +95,10 @@ __global__ void pack_tc_table_kernel(const __grid_constant__ TcPackTable t) {
       stap = ky * 3 + kx;
     }
     float v = 0.f;
-    if (tap != 0xFF && ok && nn < nout && k < kin) {
+    if (p.fold_cbm != 0 && tap != 0xFF && p.g_chunk[g] >= p.fold_cbm) {
+      const int k2 = (p.g_chunk[g] - p.fold_cbm) * 8 + e;
+      if (nn < nout && k2 < p.cin2) v = p.w2[(size_t)nn * p.cin2 + k2];
+    } else if (tap != 0xFF && ok && nn < nout && k < kin) {
       const int co = p.transposed ? k : nn, ci = p.transposed ? nn : k;
       v = p.w[((size_t)co * p.cin + ci) * p.taps + stap];
     }
@@ -532,6 +538,35 @@ int mil_tc_shape(int cin, int cout, int ks, MilTcShape* out) {
   return 0;
 }
 
+int mil_tc_shape_fold(int cmain, int cproj, int cout, MilTcShape* out) {
+  MIL_TRY(mil_tc_shape(cmain, cout, 3, out));
+  MilTcShape& sh = *out;
+  const int cbm = sh.cbin, cbp = (cproj + 7) / 8;
+  int ng = 9 * cbm;
+  // undo the pair ordering of mil_tc_shape, append the projection's groups (centre tap = 4), then order every pair by
+  // shared-memory address again: (chunk plane, shift) ascending, so that the descriptor's unsigned LBO stays positive
+  for (int g = 0; g < ng; ++g) { sh.g_tap[g] = (unsigned char)(g / cbm); sh.g_chunk[g] = (unsigned char)(g % cbm); }
+  for (int c = 0; c < cbp; ++c, ++ng) {
+    MIL_REQUIRE(ng < 2 * MIL_TC_MAX_MMA, "conv_tc: too many K groups (folded projection)");
+    sh.g_tap[ng] = 4;
+    sh.g_chunk[ng] = (unsigned char)(cbm + c);
+  }
+  sh.cbin = cbm + cbp;
+  sh.nmma = (ng + 1) / 2;
+  MIL_REQUIRE(sh.nmma <= MIL_TC_MAX_MMA, "conv_tc: too many K groups (%d)", ng);
+  for (int g = ng; g < 2 * MIL_TC_MAX_MMA; ++g) sh.g_tap[g] = sh.g_chunk[g] = 0xFF;
+  for (int j = 0; j < sh.nmma; ++j) {
+    const int a = 2 * j, b = 2 * j + 1;
+    if (sh.g_tap[b] == 0xFF) continue;
+    const bool swap = sh.g_chunk[a] > sh.g_chunk[b] || (sh.g_chunk[a] == sh.g_chunk[b] && sh.g_tap[a] > sh.g_tap[b]);
+    if (swap) {
+      std::swap(sh.g_tap[a], sh.g_tap[b]);
+      std::swap(sh.g_chunk[a], sh.g_chunk[b]);
+    }
+  }
+  return 0;
+}
+
 int mil_tc_shape_s2(int cin, int cout, MilTcShape* out) {
   MilTcShape& sh = *out;
   const int cb = (cin + 7) / 8;
@@ -603,7 +638,8 @@ int mil_launch_pack_tc_table(const MilTcPackJob* jobs, int count, cudaStream_t s
     for (int i = 0; i < m; ++i) {
       const MilTcPackJob& j = jobs[base + i];
       MilTcShape sh;
-      if (j.s2 == 1) MIL_TRY(mil_tc_shape_s2(j.cin, j.cout, &sh));
+      if (j.w2 != nullptr) MIL_TRY(mil_tc_shape_fold(j.cin, j.cin2, j.cout, &sh));
+      else if (j.s2 == 1) MIL_TRY(mil_tc_shape_s2(j.cin, j.cout, &sh));
       else if (j.s2 >= 2) MIL_TRY(mil_tc_shape_s2_dgrad(j.cout, j.cin, j.s2 - 2, &sh));
       else MIL_TRY(mil_tc_shape(j.transposed ? j.cout : j.cin, j.transposed ? j.cin : j.cout, j.ks, &sh));
       TcPackEntry& e = t.e[i];
@@ -612,6 +648,9 @@ int mil_launch_pack_tc_table(const MilTcPackJob* jobs, int count, cudaStream_t s
       e.pair_a = j.s2 >= 2 ? (unsigned char)(j.s2 - 2) : 0;
       for (int q = 0; q < MIL_TC_MAX_TAPS; ++q) { e.t_dy[q] = sh.t_dy[q]; e.t_dx[q] = sh.t_dx[q]; }
       e.w = j.w;
+      e.w2 = j.w2;
+      e.cin2 = (short)j.cin2;
+      e.fold_cbm = j.w2 != nullptr ? (unsigned char)((j.cin + 7) / 8) : 0;
       e.wtc = (__nv_bfloat16*)j.wtc;
       e.cout = (short)j.cout; e.cin = (short)j.cin;
       e.taps = (unsigned char)(j.ks * j.ks); e.transposed = j.transposed ? 1 : 0;

@@ -2,7 +2,7 @@
 #pragma once
 #include "mil_common.cuh"
 
-#define MIL_TC_MAX_MMA 46  // ceil(9 taps * 10 chunks / 2) + 1
+#define MIL_TC_MAX_MMA 50  // ceil((9 taps * 10 chunks + 8 projection chunks) / 2) + 1
 
 #define MIL_TC_MAX_TAPS 16
 // Window + K-loop description shared by the weight pre-pack and the kernels.  A tap is an offset (dy, dx) of the
@@ -44,6 +44,11 @@ int mil_tc_shape(int cin, int cout, int ks, MilTcShape* out);  // cin/cout = the
 // (-1..0) in which tap (dy, dx) of phase (a, b) carries the weight w[2 dy + a + 1][2 dx + b + 1] -- the same nine
 // K-groups per chunk as a stride-1 3x3 convolution, evaluated at a quarter of the pixels.
 int mil_tc_shape_s2(int cin, int cout, MilTcShape* out);
+// conv2 of a stride-2 block with the block's 1x1 projection folded in as extra K-groups (nnBlocks.py:183-187):
+// the kernel's input is the map h (cmain channels) FOLLOWED IN MEMORY by the projection's input (cproj channels, the even
+// positions of the block input = the first planes of the phase-split copy) at the same geometry; K-groups = nine taps x
+// the chunks of h + the centre tap x the projection chunks.  out = conv3x3(h) + conv1x1(x_even) in one accumulator.
+int mil_tc_shape_fold(int cmain, int cproj, int cout, MilTcShape* out);
 // data gradient of that convolution for the input rows of parity a, BOTH column parities at once: the kernel's output
 // chunks are (column parity b, input chunk) = 2 * cb chunks, so that a thread stores the two neighbouring pixels
 // (2Y + a, 2X) and (2Y + a, 2X + 1) together; taps (dY, dX) in {0, a} x {0, 1} of the output gradient, with
@@ -68,6 +73,8 @@ struct MilTcPackJob {
   void* wtc;
   int cout, cin, ks, transposed;
   int s2;  // 0: plain;  1: forward of the stride-2 3x3 on the phase-split input;  2 + a: its data gradient, rows a
+  const float* w2;  // != NULL: folded form (mil_tc_shape_fold): the 1x1 projection weight [cout][cin2][1][1]
+  int cin2;
 };
 int mil_launch_pack_tc_table(const MilTcPackJob* jobs, int count, cudaStream_t s);
 // out = the four (row parity, column parity) phases of `in` at half resolution, as 4 * cb chunk planes (bf16)

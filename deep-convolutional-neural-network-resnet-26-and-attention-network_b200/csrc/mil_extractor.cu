@@ -109,12 +109,24 @@ int mil_make_plan(int n, int side, int dtype, MilPlan* plan, bool infer) {
         c.wpt_off = wofs; wofs += sz;
         c.tc = mil_tc_enabled() && mil_tc_supported(dtype, c.ks, c.stride, c.cin, c.cout);
         c.wtc_off = c.wtct_off = 0;
+        c.fold = false;
+        c.wtc_fold_off = 0;
         if (c.tc) {
           MilTcShape sf, sb;
           MIL_TRY(mil_tc_shape(c.cin, c.cout, c.ks, &sf));
           MIL_TRY(mil_tc_shape(c.cout, c.cin, c.ks, &sb));
           c.wtc_off = tcofs; tcofs += align_up(mil_tc_wpack_bytes(sf), 256);
           c.wtct_off = tcofs; tcofs += align_up(mil_tc_wpack_bytes(sb), 256);
+          c.fold = false;
+          c.wtc_fold_off = 0;
+          if (which == 1 && b == 0 && l > 0) {
+            MilTcShape sf2;
+            MIL_TRY(mil_tc_shape_fold(c.cin, inpl, c.cout, &sf2));
+            if (mil_conv_tc_fits(sf2, pl.g[l].wp)) {
+              c.fold = true;
+              c.wtc_fold_off = tcofs; tcofs += align_up(mil_tc_wpack_bytes(sf2), 256);
+            }
+          }
           for (int a = 0; a < 2; ++a) c.wtct_s2_off[a] = 0;
           if (c.ks == 3 && c.stride == 2 && 2 * ((c.cin + 7) / 8) <= 10)
             for (int a = 0; a < 2; ++a) {
@@ -131,6 +143,17 @@ int mil_make_plan(int n, int side, int dtype, MilPlan* plan, bool infer) {
   pl.wpack_floats = wofs;
   pl.wtc_bytes = tcofs;
 
+  // which stride-2 blocks run in the phase-split form (decides the geometry of their saved input copies, mil_xs2_geom)
+  for (int l = 0; l < 4; ++l) { pl.off_xs2[l] = 0; pl.s2_split[l] = false; }
+  if (dtype == MIL_BF16 && mil_tc_enabled())
+    for (int l = 1; l < 4; ++l) {
+      MilTcShape sh;
+      MIL_TRY(mil_tc_shape_s2(kMilWidths[l - 1], kMilWidths[l], &sh));
+      pl.s2_split[l] = mil_conv_tc_fits(sh, pl.g[l].wp) && 2 * ((kMilWidths[l - 1] + 7) / 8) <= 10;  // dgrad: 2 * cb output chunks
+    }
+  bool fold_l[4] = {false, false, false, false};
+  for (const auto& c : pl.convs) if (c.fold) fold_l[c.layer] = true;
+
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   pl.off_pooled = take(mil_pf8_bytes(pl.g[0], dtype));
@@ -141,7 +164,15 @@ int mil_make_plan(int n, int side, int dtype, MilPlan* plan, bool infer) {
   if (!infer) {
     for (int l = 0; l < 4; ++l)
       for (int b = 0; b < 3; ++b) {
-        pl.off_h[l * 3 + b] = take(mil_pf8_bytes(pl.g[l], dtype));
+        if (b == 0 && fold_l[l]) {
+          // folded projection: conv2 reads [h | even positions of the block input] as ONE map -- the saved input copy
+          // (phase (0,0) first) follows h without a gap (same geometry => same plane stride)
+          const size_t hb = mil_pf8_bytes(pl.g[l], dtype);
+          pl.off_h[l * 3] = take(hb + mil_pf8_bytes(mil_xs2_geom(pl, l), dtype));
+          pl.off_xs2[l] = pl.off_h[l * 3] + hb;
+        } else {
+          pl.off_h[l * 3 + b] = take(mil_pf8_bytes(pl.g[l], dtype));
+        }
         pl.off_y[l * 3 + b] = take(mil_pf8_bytes(pl.g[l], dtype));
       }
   } else {
@@ -156,6 +187,19 @@ int mil_make_plan(int n, int side, int dtype, MilPlan* plan, bool infer) {
         pl.off_y[l * 3 + b] = rot[(cur + 2) % 3];
         cur = (cur + 2) % 3;
       }
+    // folded projections: [h | saved input copy] of a stride-2 block must be ONE run of planes -- an area of its own,
+    // shared by the three blocks (sized for the largest)
+    size_t fold_bytes = 0;
+    for (int l = 1; l < 4; ++l)
+      if (fold_l[l]) fold_bytes = std::max(fold_bytes, mil_pf8_bytes(pl.g[l], dtype) + mil_pf8_bytes(mil_xs2_geom(pl, l), dtype));
+    if (fold_bytes > 0) {
+      const size_t area = take(fold_bytes);
+      for (int l = 1; l < 4; ++l)
+        if (fold_l[l]) {
+          pl.off_h[l * 3] = area;
+          pl.off_xs2[l] = area + mil_pf8_bytes(pl.g[l], dtype);
+        }
+    }
   }
   // 1-bit sign masks of every saved activation map: what the data-gradient epilogues read in place of the map
   pl.masks = dtype == MIL_BF16 && mil_tc_enabled() && !infer;
@@ -186,12 +230,9 @@ int mil_make_plan(int n, int side, int dtype, MilPlan* plan, bool infer) {
   // the backward pass
   // (a layer whose split form does not fit the convolution kernel's shared memory -- 32 input planes on the way into
   // layer 4 -- keeps the full-resolution evaluation and stores only the even positions here)
-  for (int l = 0; l < 4; ++l) { pl.off_xs2[l] = 0; pl.s2_split[l] = false; }
   if (dtype == MIL_BF16 && mil_tc_enabled())
     for (int l = 1; l < 4; ++l) {
-      MilTcShape sh;
-      MIL_TRY(mil_tc_shape_s2(kMilWidths[l - 1], kMilWidths[l], &sh));
-      pl.s2_split[l] = mil_conv_tc_fits(sh, pl.g[l].wp) && 2 * ((kMilWidths[l - 1] + 7) / 8) <= 10;  // dgrad: 2 * cb output chunks
+      if (fold_l[l]) continue;  // allocated behind h above
       pl.off_xs2[l] = (infer && l > 1) ? pl.off_xs2[1] : take(mil_pf8_bytes(mil_xs2_geom(pl, l), dtype));  // layer 2's is the largest
     }
   pl.stem_tc = (dtype == MIL_BF16) && mil_tc_enabled();
@@ -421,6 +462,14 @@ static int pack_weights(const void* const* params, const MilPlan& pl, void* ws, 
       continue;
     }
     jobs.push_back({w, tca + (transposed ? c.wtct_off : c.wtc_off), c.cout, c.cin, c.ks, transposed ? 1 : 0, 0});
+    if (c.fold && !transposed) {
+      // conv2 + the block's 1x1 projection as one operand (the projection is the next descriptor of the block)
+      const MilConvDesc& cd = *(&c + 1);
+      MilTcPackJob j = {w, tca + c.wtc_fold_off, c.cout, c.cin, 3, 0, 0};
+      j.w2 = reinterpret_cast<const float*>(params[cd.p_w]);
+      j.cin2 = cd.cin;
+      jobs.push_back(j);
+    }
   }
   if (!jobs.empty()) MIL_TRY(mil_launch_pack_tc_table(jobs.data(), (int)jobs.size(), s));
   return 0;
@@ -461,8 +510,6 @@ int mil_extractor_forward_impl(const void* const* params, const void* bag, int b
   auto TCW = [&](const MilConvDesc& c, bool tr) -> const void* {
     return c.tc ? wsp(ws, pl.off_wtc) + (tr ? c.wtct_off : c.wtc_off) : nullptr;
   };
-#undef MIL_PBUF
-  MIL_TRY(mil_reduce_batch_end(s));
   const int p_c1w = mil_param_index("cnn.module.conv1.weight"), p_c1b = mil_param_index("cnn.module.conv1.bias");
   if (pl.stem_tc)
     MIL_TRY(mil_launch_stem_tc_fwd(bag, bag_u8, idx, pl.n, pl.side, (const float*)params[p_c1w], (const float*)params[p_c1b],
@@ -485,6 +532,9 @@ int mil_extractor_forward_impl(const void* const* params, const void* bag, int b
       t.esize = (int)mil_esize(dt);
       guard_add(t, wsp(ws, pl.off_h[l * 3]), pl.g[l]);
       guard_add(t, wsp(ws, pl.off_y[l * 3]), pl.g[l]);
+      // block 1 writes its y into the second free rotating buffer: block 0's h unless that lives behind a folded projection's
+      // input (then nothing has given this buffer the layer's geometry yet)
+      if (pl.off_y[l * 3 + 1] != pl.off_h[l * 3]) guard_add(t, wsp(ws, pl.off_y[l * 3 + 1]), pl.g[l]);
       if (pl.dtype == MIL_BF16 && mil_tc_enabled()) guard_add(t, wsp(ws, pl.off_xs2[l]), mil_xs2_geom(pl, l));
       MIL_TRY(launch_guards(t, s));
     }
@@ -523,6 +573,24 @@ int mil_extractor_forward_impl(const void* const* params, const void* bag, int b
         MIL_TRY(mil_conv_dispatch(dt, 0, X, gx, wpack + c1.wp_off, TCW(c1, false), (const float*)params[c1.p_b], nullptr, nullptr,
                                   h, go, 3, c1.stride, MIL_EPI_FWD, s, nullptr, c1.tc ? mh : nullptr));
       const void* res = X;
+      if (b == 0 && l > 0 && c2.fold) {
+        // the 1x1 / stride-2 projection shortcut as extra K-groups of conv2: the kernel reads h and the
+        // even positions of the block input (the first planes of the saved copy, which follows h in memory) as one map;
+        // no projection launch, no residual map
+        const MilConvDesc& cd = pl.convs[ci++];
+        MilTcShape shf;
+        MIL_TRY(mil_tc_shape_fold(c2.cin, cd.cin, c2.cout, &shf));
+        MilPF8 gf = go;
+        gf.cb = shf.cbin;
+        gf.c = shf.cbin * 8;
+        MIL_REQUIRE(pl.off_xs2[l] == pl.off_h[l * 3] + mil_pf8_bytes(go, dt) && mil_xs2_geom(pl, l).PS == go.PS,
+                    "extractor: folded projection needs its input behind h");
+        MIL_TRY(mil_launch_conv_tc(0, h, gf, wsp(ws, pl.off_wtc) + c2.wtc_fold_off, shf, (const float*)params[c2.p_b], nullptr,
+                                   nullptr, y, go, MIL_EPI_FWD, 0, s, nullptr, -1, nullptr, my));
+        X = y;
+        gx = go;
+        continue;
+      }
       if (b == 0 && l > 0) {
         const MilConvDesc& cd = pl.convs[ci++];
         // projection shortcut (1x1 / stride 2, no bias) written into y, then consumed in place as the residual
@@ -762,6 +830,8 @@ int mil_extractor_backward_impl(const void* const* params, const float* bag, con
     if (layer_events != nullptr && layer_events[l] != nullptr) MIL_CHECK_CUDA(cudaEventRecord(layer_events[l], s));
   }
 
+#undef MIL_PBUF
+  MIL_TRY(mil_reduce_batch_end(s));
   const int p_c1w = mil_param_index("cnn.module.conv1.weight"), p_c1b = mil_param_index("cnn.module.conv1.bias");
   if (pl.stem_tc)  // the conv-map buffer of the forward pass is free by now: it takes the dense conv-resolution gradient
     return mil_launch_stem_tc_bwd(wsp(ws, pl.off_xs), pl.n, pl.side, dz, pl.g[0],

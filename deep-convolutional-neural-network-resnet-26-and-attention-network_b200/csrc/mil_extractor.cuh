@@ -28,6 +28,8 @@ struct MilConvDesc {
   bool tc;                 // forward and data gradient run on the tcgen05 kernel (bf16 mode, 3x3 stride 1)
   size_t wtc_off, wtct_off;  // byte offsets of the bf16 UMMA-layout weights (normal / transposed) in the tc area
   size_t wtct_s2_off[2];     // stride-2 3x3 only: the data-gradient weights of the two input row parities
+  bool fold;                 // conv2 of a stride-2 block: the block's 1x1 projection runs as extra K-groups of this convolution
+  size_t wtc_fold_off;       //   (mil_tc_shape_fold); its operand blocks
 };
 
 // the phase-split copy of a c-channel map whose stride-2 output is ho x ho: 4 * cb chunk planes at that resolution

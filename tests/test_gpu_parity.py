@@ -563,3 +563,32 @@ def test_checkpoint_file_with_fused_adam_state(tmp_path):
     assert ob._t == 2
     steps(b, ob, 2)
     assert torch.equal(oa._flat, ob._flat) and torch.equal(oa._m, ob._m) and torch.equal(oa._v, ob._v)
+
+
+@pytest.mark.parametrize("n,side", [(20, 224), (7, 129), (33, 64)])
+def test_workspace_reuse_leaves_no_state(n, side):
+    """A module keeps its extractor workspaces (training and forward-only) between calls, and their buffers rotate / are
+    shared between layers: a second bag through the SAME workspaces must give the bits of a fresh module -- guards, pad
+    pixels and pad channels that one call leaves dirty show up here (first / last tile of the bag)."""
+    bag1 = torch.from_numpy(synth.make_bag(n, side, seed=21)).cuda()
+    bag2 = torch.from_numpy(synth.make_bag(n, side, seed=22)).cuda() * 0.7
+    Y = torch.tensor([2]).cuda()
+    used, fresh = build_net("bf16"), build_net("bf16")
+    for _ in range(2):                      # training workspace, forward-only workspace, features()
+        used(bag1, Y)["loss"].backward()
+        with torch.no_grad():
+            used(bag1, Y)
+        used.features(bag1)
+    used.zero_grad(set_to_none=True)
+    a = used(bag2, Y)
+    a["loss"].backward()
+    b = fresh(bag2, Y)
+    b["loss"].backward()
+    for k in ("Fterm", "Aterm", "Bterm", "Mterm", "loss", "y_pred"):
+        assert torch.equal(a[k], b[k]), k
+    for (k, pa), (_, pb) in zip(used.named_parameters(), fresh.named_parameters()):
+        assert torch.equal(pa.grad, pb.grad), k
+    with torch.no_grad():
+        assert torch.equal(used(bag2, Y)["Fterm"], b["Fterm"])
+    assert torch.equal(used.features(bag2), b["Fterm"])
+    assert torch.equal(fresh.features(bag2), b["Fterm"])

@@ -449,3 +449,28 @@ def test_wide_programmatic_dependent_launches_equal_plain_launches():
                 assert torch.equal(g_p[k], g_d[k]), k
     finally:
         lib.set_option("no_pdl", old)
+
+
+def test_wide_workspace_reuse_leaves_no_state():
+    """A second bag through the workspaces a first bag used gives the bits of a fresh module (tests/test_gpu_parity.py)."""
+    from oracle import synth
+    layers = (2, 2, 2, 2)
+    params = wide_oracle.init_params(13, layers)
+    bag1 = torch.from_numpy(synth.make_bag(9, 96, seed=31)).cuda()
+    bag2 = torch.from_numpy(synth.make_bag(9, 96, seed=32)).cuda() * 0.6
+    Y = torch.tensor([1]).cuda()
+    used = build_wide(dict(cw=None, layers=list(layers)), params).eval()
+    fresh = build_wide(dict(cw=None, layers=list(layers)), params).eval()
+    for _ in range(2):
+        used(bag1, Y)["loss"].backward()
+        with torch.no_grad():
+            used(bag1, Y)
+    used.zero_grad(set_to_none=True)
+    a = used(bag2, Y)
+    a["loss"].backward()
+    b = fresh(bag2, Y)
+    b["loss"].backward()
+    for k in ("Fterm", "Aterm", "Mterm", "loss"):
+        assert torch.equal(a[k], b[k]), k
+    for (k, pa), (_, pb) in zip(used.named_parameters(), fresh.named_parameters()):
+        assert torch.equal(pa.grad, pb.grad), k
