@@ -32,22 +32,58 @@
 __device__ __forceinline__ float stem_norm(float v) { return v; }
 __device__ __forceinline__ float stem_norm(uint8_t v) { return ((float)v / 255.0f - 0.5f) / 0.5f; }
 
+template <typename TIn> struct StemIsU8 { static constexpr bool value = false; };
+template <> struct StemIsU8<uint8_t> { static constexpr bool value = true; };
+
 template <typename TIn>
 __global__ void __launch_bounds__(256)
 stem_s2d4_kernel(const TIn* __restrict__ x, const int* __restrict__ idx, int side, __nv_bfloat16* __restrict__ xs,
                  MilPF8 g) {
   // one thread per (pixel, chunk k of 6): chunk k = channels (c, ry, rx) with c = k/2, ry = 2(k&1) + {0,1}, rx = 0..3
   // -> two 4-element row segments in (one vector load each when aligned), ONE 16-byte chunk out
-  const long long total = 6 * g.Q;
+  // 8-bit tiles: the normalised value is rounded to bf16 on its way out, and for all 256 byte values
+  // bf16(fma(u, 2/255, -1)) == bf16(((float)u / 255 - 0.5) / 0.5) (checked exhaustively, tests/test_gpu_parity.py) -- one FMA
+  // instead of an IEEE division per element (with eight divisions per thread the kernel was bound by its instruction
+  // stream and SLOWER than the fp32 form, 908 vs 623 us at 4096 tiles, although it reads a quarter of the bytes)
+  // grid = (image, pixel block, chunk): no 64-bit division per thread (with a flat index the kernel executed ~175
+  // instructions per thread, two thirds of them index arithmetic, and was bound by its instruction stream:
+  // smsp__issue_active 65-68 %, DRAM 33 % for 8-bit tiles)
   const bool vec = (side & 3) == 0;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(i / g.Q);
-    const long long q = i - (long long)k * g.Q;
-    const int n = (int)(q / g.P);
-    const int r = (int)(q - (long long)n * g.P);
+  const int n = blockIdx.x, k = blockIdx.z;
+  for (int r = blockIdx.y * blockDim.x + threadIdx.x; r < (int)g.P; r += gridDim.y * blockDim.x) {
+    const long long q = (long long)n * g.P + r;
     const int Y = r / g.wp, X = r - Y * g.wp;
     float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (StemIsU8<TIn>::value) {
+      uint32_t w[4] = {0u, 0u, 0u, 0u};  // the chunk as packed bf16 pairs: word h * 2 + (rx >> 1)
+      if (Y < g.h && X < g.w) {
+        const int c = k >> 1;
+        const int src_n = idx ? idx[n] : n;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int iy = 4 * Y + 2 * (k & 1) + h;
+          if (iy < side) {
+            const uint8_t* row = reinterpret_cast<const uint8_t*>(x) + (((size_t)src_n * 3 + c) * side + iy) * side + 4 * X;
+            uint32_t f = 0u;
+            int valid = 4;
+            if (vec) f = *reinterpret_cast<const uint32_t*>(row);
+            else {
+              valid = min(4, side - 4 * X);
+              for (int rx = 0; rx < valid; ++rx) f |= (uint32_t)row[rx] << (8 * rx);
+            }
+            float e[4];
+#pragma unroll
+            for (int rx = 0; rx < 4; ++rx)
+              e[rx] = rx < valid ? fmaf((float)((f >> (8 * rx)) & 0xFFu), 2.0f / 255.0f, -1.0f) : 0.f;
+            const __nv_bfloat162 p0 = __floats2bfloat162_rn(e[0], e[1]), p1 = __floats2bfloat162_rn(e[2], e[3]);
+            w[h * 2] = *reinterpret_cast<const uint32_t*>(&p0);
+            w[h * 2 + 1] = *reinterpret_cast<const uint32_t*>(&p1);
+          }
+        }
+      }
+      *reinterpret_cast<uint4*>(xs + mil_pf8_off(g, k, q)) = make_uint4(w[0], w[1], w[2], w[3]);
+      continue;
+    }
     if (Y < g.h && X < g.w) {
       const int c = k >> 1;
       const int src_n = idx ? idx[n] : n;
@@ -305,8 +341,6 @@ size_t mil_stem_tc_partial_floats(int n, int side) {
 }
 size_t mil_stem_tc_argmax_bytes(const MilPF8& gp) { return (size_t)gp.cb * gp.PS * sizeof(uint2); }
 
-static int grid_for(long long work) { return (int)std::max<long long>(1, std::min<long long>(mil_cdiv(work, 256), 148 * 16)); }
-
 // true when the forward pass runs the fused conv + pool kernel (which also writes the pooled map's sign mask);
 // MIL_B200_STEM_UNFUSED=1 forces the two-kernel path
 bool mil_stem_tc_fused_pool(const MilPF8& gp, int side) {
@@ -321,9 +355,9 @@ int mil_launch_stem_tc_fwd(const void* x, int x_u8, const int* idx, int n, int s
   const int hc = (side - 1) / 2 + 1;
   MIL_REQUIRE(gp.h == gi.h && gp.w == gi.w && gp.c == STC_CO && gp.n == n, "stem_tc_fwd: geometry mismatch");
   if (x_u8)
-    stem_s2d4_kernel<uint8_t><<<grid_for(6 * gi.Q), 256, 0, s>>>((const uint8_t*)x, idx, side, (__nv_bfloat16*)xs, gi);
+    stem_s2d4_kernel<uint8_t><<<dim3((unsigned)gi.n, (unsigned)std::min<long long>(mil_cdiv(gi.P, 256), 65535), 6), 256, 0, s>>>((const uint8_t*)x, idx, side, (__nv_bfloat16*)xs, gi);
   else
-    stem_s2d4_kernel<float><<<grid_for(6 * gi.Q), 256, 0, s>>>((const float*)x, idx, side, (__nv_bfloat16*)xs, gi);
+    stem_s2d4_kernel<float><<<dim3((unsigned)gi.n, (unsigned)std::min<long long>(mil_cdiv(gi.P, 256), 65535), 6), 256, 0, s>>>((const float*)x, idx, side, (__nv_bfloat16*)xs, gi);
   MIL_LAUNCH_OK();
   float* bias4 = wp + (size_t)9 * STC_CI * STC_CO4;
   stem_pack_w4_kernel<<<64, 256, 0, s>>>(w, b, wp, bias4);
@@ -365,9 +399,9 @@ int mil_launch_stem_tc_bwd(const void* xs, int n, int side, const void* g, const
 // count C, conv map = 4 * C channels (co, a, b) at the pooled resolution) ------------------------------------------
 int mil_launch_stem_s2d4(const void* x, int x_u8, const int* idx, int side, void* xs, const MilPF8& gi, cudaStream_t s) {
   if (x_u8)
-    stem_s2d4_kernel<uint8_t><<<grid_for(6 * gi.Q), 256, 0, s>>>((const uint8_t*)x, idx, side, (__nv_bfloat16*)xs, gi);
+    stem_s2d4_kernel<uint8_t><<<dim3((unsigned)gi.n, (unsigned)std::min<long long>(mil_cdiv(gi.P, 256), 65535), 6), 256, 0, s>>>((const uint8_t*)x, idx, side, (__nv_bfloat16*)xs, gi);
   else
-    stem_s2d4_kernel<float><<<grid_for(6 * gi.Q), 256, 0, s>>>((const float*)x, idx, side, (__nv_bfloat16*)xs, gi);
+    stem_s2d4_kernel<float><<<dim3((unsigned)gi.n, (unsigned)std::min<long long>(mil_cdiv(gi.P, 256), 65535), 6), 256, 0, s>>>((const float*)x, idx, side, (__nv_bfloat16*)xs, gi);
   MIL_LAUNCH_OK();
   return 0;
 }

@@ -592,3 +592,21 @@ def test_workspace_reuse_leaves_no_state(n, side):
         assert torch.equal(used(bag2, Y)["Fterm"], b["Fterm"])
     assert torch.equal(used.features(bag2), b["Fterm"])
     assert torch.equal(fresh.features(bag2), b["Fterm"])
+
+
+def test_uint8_tiles_every_byte_value():
+    """The 8-bit stem load normalises with one FMA (bf16(fma(u, 2/255, -1))) instead of the reference's two divisions
+    ((u / 255 - 0.5) / 0.5, RoiBuilder.py:199-202): the bf16 results are the same for ALL 256 byte values -- checked on
+    the host bit for bit, and through the network with tiles that contain every value."""
+    u = torch.arange(256, dtype=torch.float32)
+    ref = ((u / 255.0 - 0.5) / 0.5).to(torch.bfloat16)
+    fma = (u.double() * float(torch.tensor(2.0 / 255.0, dtype=torch.float32)) - 1.0).float().to(torch.bfloat16)
+    assert torch.equal(ref, fma)
+    net = build_net("bf16")
+    g = torch.Generator().manual_seed(3)
+    u8 = torch.stack([torch.arange(256, dtype=torch.uint8)[torch.randperm(256, generator=g)].repeat(3 * 96 * 96 // 256)
+                      .reshape(3, 96, 96) for _ in range(6)]).cuda()
+    f32 = ((u8.cpu().float() / 255.0 - 0.5) / 0.5).cuda()
+    with torch.no_grad():
+        assert torch.equal(net.features(u8), net.features(f32))
+        assert torch.equal(net(u8, torch.tensor([1]).cuda())["Fterm"], net(f32, torch.tensor([1]).cuda())["Fterm"])
